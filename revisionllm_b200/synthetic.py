@@ -1,0 +1,236 @@
+"""Deterministic synthetic weights / features / prompts for tests and the benchmark.
+
+There is no network in the build or GPU containers, so neither Vicuna-7B /
+CLIP checkpoints nor a sentencepiece vocabulary are available: everything on
+the hot path is exercised with random-init weights of the right architecture
+and N(0,1) features.
+
+Token-identity on pure N(0, 0.02) weights is ill-posed (the 32000 logits are a
+near-uniform Gaussian race whose top-2 margin is below bf16 noise, SURVEY.md
+H1), so the generator can *plant* structure: `lm_head` carries, on top of its
+random part, a copy of the token-embedding table shifted by a fixed
+permutation, and `embed_tokens` gets unit scale so the current token stays
+visible in the residual stream.  The greedy continuation is then the
+permutation chain of the last prompt token with a margin far above bf16 noise,
+while every logit still depends on all 32 layers' arithmetic.
+All values are rounded to bf16 so the fp32 oracle and the bf16 CUDA path share
+bit-identical parameters.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from dataclasses import dataclass, asdict
+from typing import Dict, Optional, Tuple
+
+import torch
+
+
+@dataclass
+class SynthConfig:
+    hidden: int = 4096
+    n_layers: int = 32
+    n_heads: int = 32
+    head_dim: int = 128
+    intermediate: int = 11008
+    vocab: int = 32000
+    adapter_dim: int = 768
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    max_pos: int = 4096
+    # init
+    init_std: float = 0.02
+    embed_std: float = 1.0
+    norm_jitter: float = 0.1
+    plant_gain: float = 1.0         # 0 disables the planted successor structure
+    perm_mult: int = 7919           # successor(t) = 3 + ((t-3)*mult + add) mod (vocab-3)
+    perm_add: int = 104729
+
+    def dict(self):
+        return asdict(self)
+
+
+VICUNA_7B = SynthConfig()
+TINY = SynthConfig(hidden=256, n_layers=2, n_heads=2, head_dim=128, intermediate=512, vocab=512, max_pos=1024)
+SMALL = SynthConfig(hidden=512, n_layers=4, n_heads=4, head_dim=128, intermediate=1024, vocab=2048, max_pos=2048)
+
+
+def successor_table(cfg: SynthConfig) -> torch.Tensor:
+    """successor[t] for t in [0, vocab): a permutation of [3, vocab) (ids 0..2 =
+    unk/bos/eos map to 3 and are never produced), so greedy decode never hits EOS."""
+    n = cfg.vocab - 3
+    mult = cfg.perm_mult
+    while math.gcd(mult, n) != 1:
+        mult += 1
+    t = torch.arange(cfg.vocab, dtype=torch.int64)
+    succ = 3 + ((t - 3).clamp(min=0) * mult + cfg.perm_add) % n
+    succ[:3] = 3
+    return succ
+
+
+def _randn(shape, std, gen, device, dtype=torch.bfloat16):
+    return (torch.randn(shape, generator=gen, device=device, dtype=torch.float32) * std).to(dtype)
+
+
+def make_llama_weights(cfg: SynthConfig, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Tensor]:
+    """HF-named state dict (bf16) of a random-init Llama + Linear mm_projector.
+
+    Names follow the reference's checkpoint layout:
+    `model.embed_tokens.weight`, `model.layers.{i}.self_attn.{q,k,v,o}_proj.weight`,
+    `model.layers.{i}.mlp.{gate,up,down}_proj.weight`, `...input_layernorm.weight`,
+    `...post_attention_layernorm.weight`, `model.norm.weight`, `lm_head.weight`,
+    `model.mm_projector.{weight,bias}`.
+    The stream of random numbers depends on `device` (torch CPU and CUDA
+    generators differ): generate once and copy when two devices must agree.
+    """
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    H, I, V = cfg.hidden, cfg.intermediate, cfg.vocab
+    w: Dict[str, torch.Tensor] = {}
+    w["model.embed_tokens.weight"] = _randn((V, H), cfg.embed_std, gen, device)
+    for i in range(cfg.n_layers):
+        p = f"model.layers.{i}."
+        for n in ("q", "k", "v", "o"):
+            w[p + f"self_attn.{n}_proj.weight"] = _randn((H, H), cfg.init_std, gen, device)
+        w[p + "mlp.gate_proj.weight"] = _randn((I, H), cfg.init_std, gen, device)
+        w[p + "mlp.up_proj.weight"] = _randn((I, H), cfg.init_std, gen, device)
+        w[p + "mlp.down_proj.weight"] = _randn((H, I), cfg.init_std, gen, device)
+        w[p + "input_layernorm.weight"] = (1.0 + _randn((H,), cfg.norm_jitter, gen, device, torch.float32)).to(torch.bfloat16)
+        w[p + "post_attention_layernorm.weight"] = (1.0 + _randn((H,), cfg.norm_jitter, gen, device, torch.float32)).to(torch.bfloat16)
+    w["model.norm.weight"] = (1.0 + _randn((H,), cfg.norm_jitter, gen, device, torch.float32)).to(torch.bfloat16)
+    head = torch.randn((V, H), generator=gen, device=device, dtype=torch.float32)
+    if cfg.plant_gain != 0.0:
+        succ = successor_table(cfg).to(device)
+        src = torch.zeros(V, dtype=torch.int64, device=device)
+        src[succ[3:]] = torch.arange(3, V, device=device)        # src[j] = token whose successor is j
+        planted = w["model.embed_tokens.weight"].float()[src] / cfg.embed_std
+        planted[:3] = 0
+        head = head + cfg.plant_gain * planted
+    w["lm_head.weight"] = (head * cfg.init_std).to(torch.bfloat16)
+    w["model.mm_projector.weight"] = _randn((H, cfg.adapter_dim), 1.0 / math.sqrt(cfg.adapter_dim), gen, device)
+    w["model.mm_projector.bias"] = _randn((H,), 0.1, gen, device)
+    return w
+
+
+CLIP_D, CLIP_FFN, CLIP_LAYERS = 768, 2048, 2
+
+
+def make_clip_encoder_weights(hidden: int, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Tensor]:
+    """State dict of the stage-2 `ClipEncoder` adapter, keys below
+    `model.mm_projector.` (reference module tree:
+    /root/reference/revisionllm/model/adapter/transformer.py:60-92)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 1000003)
+    d = CLIP_D
+    p: Dict[str, torch.Tensor] = {}
+    p["global_rep_token"] = _randn((d,), 1.0, gen, device)
+    p["global_rep_pos"] = _randn((d,), 1.0, gen, device)
+
+    def layer(pre):
+        p[pre + "self_attn.in_proj_weight"] = _randn((3 * d, d), 1.0 / math.sqrt(d), gen, device)
+        p[pre + "self_attn.in_proj_bias"] = _randn((3 * d,), 0.02, gen, device)
+        p[pre + "self_attn.out_proj.weight"] = _randn((d, d), 1.0 / math.sqrt(d), gen, device)
+        p[pre + "self_attn.out_proj.bias"] = _randn((d,), 0.02, gen, device)
+        p[pre + "linear1.weight"] = _randn((CLIP_FFN, d), 1.0 / math.sqrt(d), gen, device)
+        p[pre + "linear1.bias"] = _randn((CLIP_FFN,), 0.02, gen, device)
+        p[pre + "linear2.weight"] = _randn((d, CLIP_FFN), 1.0 / math.sqrt(CLIP_FFN), gen, device)
+        p[pre + "linear2.bias"] = _randn((d,), 0.02, gen, device)
+        for n in ("norm1", "norm2"):
+            p[pre + n + ".weight"] = (1.0 + _randn((d,), 0.1, gen, device, torch.float32)).to(torch.bfloat16)
+            p[pre + n + ".bias"] = _randn((d,), 0.05, gen, device)
+
+    for i in range(CLIP_LAYERS):
+        layer(f"t2v_encoder.layers.{i}.")
+    for i in range(CLIP_LAYERS):
+        layer(f"encoder.layers.{i}.")
+    p["mm_projector.weight"] = _randn((hidden, d), 1.0 / math.sqrt(d), gen, device)
+    p["mm_projector.bias"] = _randn((hidden,), 0.1, gen, device)
+    return p
+
+
+def make_features(n_segments: int, n_frames: int, dim: int = 768, seed: int = 0, device: str = "cpu") -> torch.Tensor:
+    """Synthetic CLIP frame features ~ N(0,1), bf16."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 17)
+    return torch.randn((n_segments, n_frames, dim), generator=gen, device=device, dtype=torch.float32).to(torch.bfloat16)
+
+
+def make_prompt_ids(cfg: SynthConfig, n_pre: int = 38, n_post: int = 46, seed: int = 0) -> torch.Tensor:
+    """BOS + (n_pre-1) text ids + IMAGE placeholder (-200) + n_post text ids.
+    Defaults give Ltxt = 85 and, with 100 frames, a spliced length of 184
+    (BASELINE.md section 4)."""
+    gen = torch.Generator()
+    gen.manual_seed(seed + 29)
+    pre = torch.randint(3, cfg.vocab, (n_pre - 1,), generator=gen)
+    post = torch.randint(3, cfg.vocab, (n_post,), generator=gen)
+    return torch.cat([torch.tensor([1]), pre, torch.tensor([-200]), post]).to(torch.int64)
+
+
+def weights_digest(w: Dict[str, torch.Tensor]) -> str:
+    """sha256 over names + raw bytes - fixtures store it to detect generator drift."""
+    h = hashlib.sha256()
+    for k in sorted(w):
+        h.update(k.encode())
+        t = w[k].detach().cpu().contiguous()
+        h.update(t.view(torch.uint8).numpy().tobytes() if t.dtype != torch.bfloat16 else t.view(torch.int16).numpy().tobytes())
+    return h.hexdigest()
+
+
+class StubTokenizer:
+    """Minimal whitespace tokenizer with the sentencepiece-Llama surface the
+    reference's `inference()` touches (`__call__().input_ids`, `bos_token_id`,
+    `batch_decode`).  Used only because no real vocabulary is available offline.
+    Words are hashed into [3 + n_special, vocab); digits and the answer words
+    have fixed ids so `"From 12 to 34."` / `"Not Present"` round-trip."""
+
+    bos_token_id = 1
+    eos_token_id = 2
+    pad_token_id = 0
+    SPECIAL = ["From", "to", "Not", "Present", ".", "and"] + [str(d) for d in range(10)]
+
+    def __init__(self, vocab: int = 32000):
+        self.vocab = vocab
+        self.fixed = {s: 3 + i for i, s in enumerate(self.SPECIAL)}
+        self.inv = {v: k for k, v in self.fixed.items()}
+
+    def _word(self, wd: str) -> int:
+        if wd in self.fixed:
+            return self.fixed[wd]
+        hv = int(hashlib.md5(wd.encode()).hexdigest()[:8], 16)
+        base = 3 + len(self.SPECIAL)
+        return base + hv % (self.vocab - base)
+
+    def __call__(self, text: str):
+        ids = [self.bos_token_id]
+        for wd in text.replace("\n", " \n ").split(" "):
+            if wd == "":
+                continue
+            if wd.isdigit():
+                ids.extend(self.fixed[c] for c in wd)
+            else:
+                ids.append(self._word(wd))
+
+        class _R:
+            pass
+
+        r = _R()
+        r.input_ids = ids
+        return r
+
+    def batch_decode(self, ids, skip_special_tokens: bool = True):
+        out = []
+        for row in ids.tolist():
+            s, prev_digit = "", False
+            for t in row:
+                if skip_special_tokens and t in (0, 1, 2):
+                    continue
+                tok = self.inv.get(t, f"<{t}>")
+                if tok.isdigit() and prev_digit:
+                    s += tok
+                elif tok == ".":
+                    s += tok
+                else:
+                    s += (" " if s else "") + tok
+                prev_digit = tok.isdigit()
+            out.append(s)
+        return out

@@ -1,0 +1,182 @@
+"""Generate the committed golden fixtures from the REFERENCE ITSELF.
+
+Run in the authoring container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own modules through `oracle/ref_shim.py`
+(`prepare_inputs_labels_for_multimodal`, `VTimeLLMLlamaForCausalLM.forward`,
+`ClipEncoder`, `_topk_pooling`, `get_entropy_statistics`,
+`tokenizer_image_token`, `conv_templates['v1']`, `pad_sequences_1d`) plus the
+installed `transformers` Llama (eager attention, fp32), runs them on seeded
+synthetic inputs from `revisionllm_b200.synthetic`, and writes input/output
+vectors to `tests/golden/*.npz`.  Weights are regenerated from the seed by the
+tests; each fixture stores their sha256 so generator drift is detected.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from revisionllm_b200 import synthetic as syn  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def greedy_via_reference(model, inputs_embeds, attention_mask, steps):
+    """Manual greedy loop around the reference model's forward (its
+    `generate()` breaks at the first decode step under transformers 5.x,
+    SURVEY.md section 8c).  Right-padded rows: the step-t position is the number of
+    valid tokens so far (vtimellm_arch.py:88-100)."""
+    B, L, _ = inputs_embeds.shape
+    lens = attention_mask.sum(1)
+    pos = (attention_mask.long().cumsum(1) - 1).clamp(min=0)
+    out = model(inputs_embeds=inputs_embeds, attention_mask=attention_mask.long(), position_ids=pos, use_cache=True)
+    logits_all = out.logits.float()
+    last = logits_all[torch.arange(B), lens - 1]
+    cache = out.past_key_values
+    am = attention_mask.long()
+    toks, scores = [], []
+    for t in range(steps):
+        scores.append(last.clone())
+        nxt = last.argmax(-1)
+        toks.append(nxt)
+        if t == steps - 1:
+            break
+        am = torch.cat([am, torch.ones(B, 1, dtype=am.dtype)], dim=1)
+        pid = am.sum(1, keepdim=True) - 1
+        emb = model.get_model().embed_tokens(nxt)[:, None]
+        out = model(inputs_embeds=emb, attention_mask=am, position_ids=pid, past_key_values=cache, use_cache=True)
+        cache = out.past_key_values
+        last = out.logits[:, -1].float()
+    return logits_all, torch.stack(toks, 1), torch.stack(scores, 0)
+
+
+def case_stage1(ref, name, cfg, n_seg, n_frames, n_pre, n_post, steps, ragged=False):
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    feats = syn.make_features(n_seg, n_frames, cfg.adapter_dim, seed=1).float()
+    base = syn.make_prompt_ids(cfg, n_pre, n_post, seed=2)
+    ids = base[None].repeat(n_seg, 1)
+    attn = None
+    if ragged:
+        # rows get different numbers of trailing text tokens (right padded with 0)
+        Ltxt = ids.shape[1]
+        attn = torch.ones(n_seg, Ltxt, dtype=torch.bool)
+        for b in range(n_seg):
+            cut = (b * 3) % 7
+            if cut:
+                attn[b, Ltxt - cut:] = False
+                ids[b, Ltxt - cut:] = 0
+    with torch.inference_mode():
+        r = model.prepare_inputs_labels_for_multimodal(
+            ids, None, attn, None, None, feats, None, None, None, None)
+        _, pos, am, _, embeds, _ = r
+        if am is None:
+            am = torch.ones(embeds.shape[:2], dtype=torch.bool)
+        logits_all, toks, scores = greedy_via_reference(model, embeds, am.bool(), steps)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        cfg=np.array(list(cfg.dict().items()), dtype=object), digest=syn.weights_digest(w),
+        feats=feats.numpy(), ids=ids.numpy(), attn=(attn.numpy() if attn is not None else np.zeros(0)),
+        embeds=embeds.numpy(), embeds_mask=am.bool().numpy(),
+        prefill_logits=logits_all.numpy().astype(np.float32), tokens=toks.numpy(), scores=scores.numpy(),
+    )
+    print(name, "embeds", tuple(embeds.shape), "tokens", toks[0].tolist())
+
+
+def case_clip_encoder(ref, name, cfg, V, T, Lq):
+    w = syn.make_llama_weights(cfg, seed=0)
+    cw = syn.make_clip_encoder_weights(cfg.hidden, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w, clip_weights=cw)
+    frames = syn.make_features(V, T, 768, seed=3).float()
+    g = torch.Generator().manual_seed(5)
+    q_tok = torch.randn(Lq, 768, generator=g).to(torch.bfloat16).float()
+    q, qmask = ref.tensor_utils.pad_sequences_1d([q_tok, q_tok[: Lq - 2]], dtype=torch.float32)
+    ids = syn.make_prompt_ids(cfg, 5, 8, seed=4)[None]
+    with torch.inference_mode():
+        enc = model.get_model().mm_projector
+        # direct adapter call on V segments, ragged text mask (row 1 of the padded pair)
+        txt = q[1:2].repeat(V, 1, 1)
+        msk = qmask[1:2].repeat(V, 1)
+        cls_out = enc(frames, txt, msk, None)                 # [V, 1, hidden]
+        r = model.prepare_inputs_labels_for_multimodal(
+            ids, None, None, None, None, frames[None], (q[0:1], qmask[0:1]), None, None, None)
+        embeds = r[4]
+        logits = model(inputs_embeds=embeds).logits[:, -1].float()
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        digest=syn.weights_digest(w), clip_digest=syn.weights_digest(cw),
+        frames=frames.numpy(), q=q.numpy(), qmask=qmask.numpy(), ids=ids.numpy(),
+        cls_out=cls_out[:, 0].numpy(), embeds=embeds.numpy(), last_logits=logits.numpy(),
+    )
+    print(name, "cls_out", tuple(cls_out.shape), "embeds", tuple(embeds.shape))
+
+
+def case_scoring(ref, name):
+    g = torch.Generator().manual_seed(11)
+    text = torch.randn(2, 768, generator=g)
+    video = torch.randn(3, 9, 768, generator=g)
+    pooled = ref.similarity._topk_pooling(text, video, 3)
+    # stage-1 caller arithmetic (eval_nlq_negative.py:309-316) and stage-2 (e2e2:380-386)
+    cls = torch.randn(768, generator=g)
+    prop = torch.randn(17, 768, generator=g)
+    pf0 = prop / prop.norm(dim=0, keepdim=True)
+    s0 = torch.einsum("bd,d->b", ref.similarity._topk_pooling(cls[None], pf0[None], 3)[0], cls)
+    pf1 = prop[None] / prop[None].norm(dim=1, keepdim=True)      # e2e2 quirk: dim=1 of [1,n,d] is the frame axis too
+    s1 = torch.einsum("bd,d->b", ref.similarity._topk_pooling(cls[None], pf1, 3)[:, 0], cls)
+    pf2 = prop / prop.norm(dim=1, keepdim=True)                  # similarity.py:61 per-frame normalisation
+    s2 = torch.einsum("ld,d->l", ref.similarity._topk_pooling(cls[None], pf2[None], 3)[0], cls)
+    logits = torch.randn(3, 5, 512, generator=g) * 3
+    ent = ref.entropy.get_entropy_statistics(logits, 0, 5)
+    ent1 = ref.entropy.get_entropy_statistics(logits[:, :1], 0, 1)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        text=text.numpy(), video=video.numpy(), pooled=pooled.numpy(),
+        cls=cls.numpy(), prop=prop.numpy(), s_norm0=s0.numpy(), s_norm1_batched=s1.numpy(), s_perframe=s2.numpy(),
+        logits=logits.numpy(), ent=ent.numpy(), ent1=ent1.float().numpy(),
+    )
+    print(name, "ok")
+
+
+def case_prompt(ref, name):
+    tok = syn.StubTokenizer(32000)
+    rows = {}
+    for key, q in (("stage1", "<video>\nDuring which frames can we see a man opens the door?"),
+                   ("stage2", "<video>\nDuring which video can we see she picks up 2 cups?")):
+        conv = ref.conversation.conv_templates["v1"].copy()
+        conv.append_message(conv.roles[0], q)
+        conv.append_message(conv.roles[1], None)
+        prompt = conv.get_prompt()
+        ids = ref.mm_utils.tokenizer_image_token(prompt, tok, ref.constants.IMAGE_TOKEN_INDEX, return_tensors="pt")
+        rows[key + "_prompt"] = np.array(prompt)
+        rows[key + "_ids"] = ids.numpy()
+    # memory variant (inference.py:29-30)
+    conv = ref.conversation.conv_templates["v1"].copy()
+    conv.append_message(conv.roles[0], "<video>\nWhere is the cat?<memory>")
+    conv.append_message(conv.roles[1], None)
+    prompt = conv.get_prompt()
+    rows["memory_prompt"] = np.array(prompt)
+    rows["memory_ids"] = ref.mm_utils.tokenizer_image_token(prompt, tok, -200, return_tensors="pt").numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rows)
+    print(name, {k: (v.shape if v.ndim else str(v)[:40]) for k, v in rows.items()})
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ref = ref_shim.load()
+    case_stage1(ref, "stage1_tiny", syn.TINY, n_seg=3, n_frames=20, n_pre=6, n_post=9, steps=6)
+    case_stage1(ref, "stage1_ragged", syn.TINY, n_seg=4, n_frames=12, n_pre=5, n_post=11, steps=4, ragged=True)
+    case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
+    case_scoring(ref, "scoring")
+    case_prompt(ref, "prompt")
+
+
+if __name__ == "__main__":
+    main()

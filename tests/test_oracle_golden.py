@@ -1,0 +1,128 @@
+"""Pin the CPU oracle (oracle/) against vectors produced by the reference itself
+(tests/golden/make_golden.py ran the reference's own modules from /root/reference)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import clip_encoder_ref, llama_ref, scoring_ref, splice_ref
+from revisionllm_b200 import synthetic as syn
+
+
+def _shape(cfg):
+    return llama_ref.LlamaShape(cfg.hidden, cfg.n_layers, cfg.n_heads, cfg.head_dim, cfg.intermediate,
+                                cfg.vocab, cfg.rms_eps, cfg.rope_theta, cfg.adapter_dim)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=True)
+
+
+def test_weights_generator_is_stable(golden_dir):
+    g = _load(golden_dir, "stage1_tiny")
+    w = syn.make_llama_weights(syn.TINY, seed=0)
+    assert syn.weights_digest(w) == str(g["digest"])
+
+
+def test_stage1_splice_prefill_and_greedy_match_reference(golden_dir):
+    g = _load(golden_dir, "stage1_tiny")
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    feats, ids = torch.from_numpy(g["feats"]), torch.from_numpy(g["ids"])
+    img = splice_ref.mm_projector_linear(w, feats)
+    emb = splice_ref.splice(w, ids, img)
+    x = torch.stack(emb)
+    np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)
+    hidden = llama_ref.decoder_stack(w, _shape(cfg), x)
+    logits = llama_ref.lm_head(w, hidden)
+    np.testing.assert_allclose(logits.numpy(), g["prefill_logits"], rtol=2e-4, atol=2e-4)
+    steps = g["tokens"].shape[1]
+    toks, scores = llama_ref.greedy_decode(w, _shape(cfg), x, steps, stop_on_eos=False)
+    assert toks.tolist() == g["tokens"].tolist()
+    np.testing.assert_allclose(torch.stack(scores).numpy(), g["scores"], rtol=2e-4, atol=2e-4)
+    # planted successor chain (size-independent property used at full size on the GPU)
+    succ = syn.successor_table(cfg)
+    cur = int(ids[0, -1])
+    for t in range(steps):
+        cur = int(succ[cur])
+        assert int(toks[0, t]) == cur
+
+
+def test_ragged_batch_matches_reference_right_padding(golden_dir):
+    g = _load(golden_dir, "stage1_ragged")
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    feats, ids, attn = torch.from_numpy(g["feats"]), torch.from_numpy(g["ids"]), torch.from_numpy(g["attn"])
+    emb = splice_ref.splice(w, ids, splice_ref.mm_projector_linear(w, feats), attention_mask=attn)
+    x, m, p = splice_ref.right_pad(emb)
+    np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)
+    assert m.numpy().tolist() == g["embeds_mask"].tolist()
+    steps = g["tokens"].shape[1]
+    toks, scores = llama_ref.forward_ragged(w, _shape(cfg), emb, steps, stop_on_eos=False)
+    assert torch.stack(toks).tolist() == g["tokens"].tolist()
+    sc = torch.stack([torch.stack(s) for s in scores], dim=1)      # [T, B, V]
+    np.testing.assert_allclose(sc.numpy(), g["scores"], rtol=2e-4, atol=2e-4)
+    am, pos = splice_ref.decode_step_fixup(m.long(), x.shape[1])
+    assert pos[:, 0].tolist() == [e.shape[0] for e in emb]
+
+
+def test_clip_encoder_and_hierarchy_splice_match_reference(golden_dir):
+    g = _load(golden_dir, "clip_encoder_tiny")
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    cw = syn.make_clip_encoder_weights(cfg.hidden, seed=0)
+    assert syn.weights_digest(cw) == str(g["clip_digest"])
+    frames, q, qmask = torch.from_numpy(g["frames"]), torch.from_numpy(g["q"]), torch.from_numpy(g["qmask"])
+    V = frames.shape[0]
+    out = clip_encoder_ref.clip_encoder_cls(cw, frames, q[1:2].repeat(V, 1, 1), qmask[1:2].repeat(V, 1))
+    np.testing.assert_allclose(out.numpy(), g["cls_out"], rtol=2e-4, atol=2e-4)
+    feats = clip_encoder_ref.hierarchy_features(cw, frames[None], (q[0:1], qmask[0:1]))
+    emb = splice_ref.splice(w, torch.from_numpy(g["ids"]), feats)
+    np.testing.assert_allclose(torch.stack(emb).numpy(), g["embeds"], rtol=2e-4, atol=2e-4)
+    hidden = llama_ref.decoder_stack(w, _shape(cfg), torch.stack(emb))
+    np.testing.assert_allclose(llama_ref.lm_head(w, hidden[:, -1]).numpy(), g["last_logits"], rtol=5e-4, atol=5e-4)
+
+
+def test_topk_pooling_and_entropy_match_reference(golden_dir):
+    g = _load(golden_dir, "scoring")
+    pooled = scoring_ref.topk_pooling(torch.from_numpy(g["text"]), torch.from_numpy(g["video"]), 3)
+    np.testing.assert_allclose(pooled.numpy(), g["pooled"], rtol=1e-5, atol=1e-5)
+    cls, prop = torch.from_numpy(g["cls"]), torch.from_numpy(g["prop"])
+    s0, _, _ = scoring_ref.cosine_topk_score(prop, cls, 3, norm_axis=0)
+    np.testing.assert_allclose(s0, g["s_norm0"][0], rtol=1e-5)
+    np.testing.assert_allclose(s0, g["s_norm1_batched"][0], rtol=1e-5)   # e2e2's dim=1 on [1,n,d] is the same axis
+    s2, _, _ = scoring_ref.cosine_topk_score(prop, cls, 3, norm_axis=1)
+    np.testing.assert_allclose(s2, g["s_perframe"][0], rtol=1e-5)
+    ent = scoring_ref.get_entropy_statistics(torch.from_numpy(g["logits"]))
+    np.testing.assert_allclose(ent.numpy(), g["ent"], rtol=1e-5, atol=1e-6)
+    ent1 = scoring_ref.get_entropy_statistics(torch.from_numpy(g["logits"])[:, :1])
+    np.testing.assert_allclose(ent1.numpy(), g["ent1"], rtol=1e-5, atol=1e-6)
+
+
+def test_prompt_and_placeholder_tokenisation_match_reference(golden_dir):
+    g = _load(golden_dir, "prompt")
+    tok = syn.StubTokenizer(32000)
+    for key, q in (("stage1", "<video>\nDuring which frames can we see a man opens the door?"),
+                   ("stage2", "<video>\nDuring which video can we see she picks up 2 cups?")):
+        prompt = splice_ref.vicuna_v1_prompt(q)
+        assert prompt == str(g[key + "_prompt"])
+        assert splice_ref.tokenizer_image_token(prompt, tok) == g[key + "_ids"].tolist()
+    prompt = splice_ref.vicuna_v1_prompt("<video>\nWhere is the cat?<memory>")
+    assert prompt == str(g["memory_prompt"])
+    assert splice_ref.tokenizer_image_token(prompt, tok) == g["memory_ids"].tolist()
+
+
+def test_windows_and_selection_rules():
+    # eval_nlq_negative.py:224-235 on a 1 h MAD movie: 18000 feats, 625-feat windows -> 57 windows
+    w = scoring_ref.stage1_windows(18000, 625, 250)
+    assert w.shape == (57, 250)
+    assert w[1, 0] == 312 and w[0, -1] == 625
+    w2, times = scoring_ref.stage2_windows(18000, 625, 250, stride=5)
+    assert w2.shape == (143, 250)
+    assert all(e - s == 625 for s, e in times)
+    assert scoring_ref.nonoverlap_segments(18000, 100).shape == (180, 100)
+    sel = scoring_ref.stage2_select_windows(["Not Present", "From 3 to 9.", "Not Present", "From 1 to 2."], 40, 10)
+    assert len(sel) == 10 and sel == sorted(sel)
+    assert scoring_ref.parse_span("From 12 to 34.") == (12, 34)
+    assert scoring_ref.parse_span("Not Present") is None
+    assert scoring_ref.select_topk_segments(np.array([1.0, 3.0, 3.0, 2.0], np.float32), 2).tolist() == [1, 2]
