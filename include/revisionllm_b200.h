@@ -1,0 +1,224 @@
+/*
+ * revisionllm_b200 - C ABI of the Blackwell (sm_100a) kernels behind the
+ * ReVisionLLM recursive segment-scoring inference path.
+ *
+ * The reference (Tanveer81/ReVisionLLM) has no FFI boundary of its own: its hot
+ * path is Python calling HuggingFace `transformers` / torch.
+ * This header is the boundary a maintainer binds (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference code it replaces.
+ * All paths below are relative to the reference tree.
+ *
+ * Conventions
+ *  - plain C, no C++ types, no exceptions across the boundary;
+ *  - every function returns RVL_OK (0) or a negative rvl_status; the message is
+ *    available from rvl_last_error(h) (or rvl_last_error(NULL) for handle-less calls);
+ *  - every tensor is allocated and owned by the caller (PyTorch): the library
+ *    receives raw device pointers + sizes, never frees them, and keeps pointers
+ *    past a call only for bound weights, the workspace and the KV pages;
+ *  - every call enqueues work on the caller's cudaStream_t and returns without
+ *    synchronising; no host allocation or cudaMalloc on the hot path;
+ *  - one handle per (process, GPU); a handle is not thread-safe;
+ *  - there is NO CPU fallback: without an sm_100 device the calls fail.
+ */
+#ifndef REVISIONLLM_B200_H
+#define REVISIONLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RVL_API __attribute__((visibility("default")))
+#else
+#define RVL_API
+#endif
+
+typedef enum rvl_status {
+  RVL_OK = 0,
+  RVL_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  RVL_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  RVL_ERR_STATE = -3,       /* weights / workspace / kv not bound */
+  RVL_ERR_UNSUPPORTED = -4  /* device is not sm_100 */
+} rvl_status;
+
+typedef struct rvl_handle rvl_handle;
+typedef void* rvl_stream; /* cudaStream_t */
+
+/* Llama-2-7B / Vicuna-7B-v1.5 shape by default. head_dim must be 128. */
+typedef struct rvl_config {
+  int32_t hidden;        /* 4096 */
+  int32_t n_layers;      /* 32 */
+  int32_t n_heads;       /* 32 (no GQA) */
+  int32_t head_dim;      /* 128 */
+  int32_t intermediate;  /* 11008 */
+  int32_t vocab;         /* 32000 */
+  int32_t adapter_dim;   /* 768 (CLIP ViT-L/14) */
+  int32_t max_pos;       /* 4096 */
+  int32_t kv_page_size;  /* tokens per KV page; 32 */
+  int32_t device;        /* CUDA device ordinal */
+  float rms_eps;         /* 1e-5 */
+  float rope_theta;      /* 10000 */
+} rvl_config;
+
+/* Per-layer weights, all bf16 row-major [out_features, in_features] like the HF
+ * state dict; q/k/v and gate/up are concatenated along out_features by the host
+ * once at load time:
+ *   wqkv  = cat(self_attn.{q,k,v}_proj.weight)        [3*hidden, hidden]
+ *   wo    = self_attn.o_proj.weight                   [hidden, hidden]
+ *   wgu   = cat(mlp.gate_proj.weight, up_proj.weight) [2*intermediate, hidden]
+ *   wdown = mlp.down_proj.weight                      [hidden, intermediate]
+ *   ln1   = input_layernorm.weight, ln2 = post_attention_layernorm.weight  [hidden] */
+typedef struct rvl_layer_weights {
+  const void* wqkv;
+  const void* wo;
+  const void* wgu;
+  const void* wdown;
+  const void* ln1;
+  const void* ln2;
+} rvl_layer_weights;
+
+typedef struct rvl_weights {
+  const void* embed_tokens;        /* model.embed_tokens.weight [vocab, hidden] bf16 */
+  const void* final_norm;          /* model.norm.weight [hidden] bf16 */
+  const void* lm_head;             /* lm_head.weight [vocab, hidden] bf16 */
+  const void* proj_w;              /* model.mm_projector.weight [hidden, adapter_dim] bf16 (stage 1) */
+  const void* proj_b;              /* model.mm_projector.bias [hidden] bf16 */
+  const rvl_layer_weights* layers; /* n_layers entries (host array, copied) */
+} rvl_weights;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+RVL_API int rvl_abi_version(void);
+RVL_API const char* rvl_last_error(const rvl_handle* h);
+RVL_API int rvl_create(const rvl_config* cfg, rvl_handle** out);
+RVL_API void rvl_destroy(rvl_handle* h);
+/* Replaces builder.py:21-67 `load_pretrained_model` at the device boundary: borrows the pointers. */
+RVL_API int rvl_bind_weights(rvl_handle* h, const rvl_weights* w);
+/* Scratch for up to max_tokens packed prompt tokens and max_seqs sequences. */
+RVL_API size_t rvl_workspace_bytes(const rvl_handle* h, int64_t max_tokens, int32_t max_seqs);
+RVL_API int rvl_set_workspace(rvl_handle* h, void* ws, size_t bytes, int64_t max_tokens, int32_t max_seqs);
+/* Paged KV cache: [layer][k|v][page][head][slot][head_dim] bf16. */
+RVL_API size_t rvl_kv_bytes(const rvl_handle* h, int32_t n_pages);
+RVL_API int rvl_set_kv(rvl_handle* h, void* kv, int32_t n_pages);
+
+/* ---- hot path --------------------------------------------------------------------------- */
+
+/* Projector GEMM fused with the embedding splice.
+ * Replaces vtimellm_arch.py:42,125 (`mm_projector`) + :149-244 (split ids at the
+ * placeholder, embed text chunks, concat) of `prepare_inputs_labels_for_multimodal`.
+ *   feats        [n_feat_rows, adapter_dim] bf16, all segments' frames concatenated
+ *   feat_dst     [n_feat_rows] int32: destination row of each frame in the packed stream
+ *   text_ids     [n_text] int32 token ids (placeholders removed)
+ *   text_dst     [n_text] int32 destination rows
+ *   hidden_out   [total_tokens, hidden] fp32 packed residual stream (written at the dst rows) */
+RVL_API int rvl_project_splice(rvl_handle* h, const void* feats, const int32_t* feat_dst, int32_t n_feat_rows,
+                       const int32_t* text_ids, const int32_t* text_dst, int32_t n_text,
+                       float* hidden_out, int64_t total_tokens, rvl_stream stream);
+
+/* Same splice for already-projected visual rows (stage-2: one ClipEncoder CLS row per segment,
+ * vtimellm_arch.py:114-121): vis [n_vis, hidden] bf16 scattered to vis_dst rows. */
+RVL_API int rvl_splice_rows(rvl_handle* h, const void* vis, const int32_t* vis_dst, int32_t n_vis,
+                    const int32_t* text_ids, const int32_t* text_dst, int32_t n_text,
+                    float* hidden_out, int64_t total_tokens, rvl_stream stream);
+
+/* Varlen causal prefill of the decoder stack over a packed token stream.
+ * Replaces transformers LlamaModel/LlamaForCausalLM.forward reached from
+ * vtimellm_llama.py:79-90 at step 0 (RMSNorm, QKV, RoPE, KV write, causal attention,
+ * O, SwiGLU MLP, final norm, lm_head).
+ *   hidden       [total_tokens, hidden] fp32 in/out (residual stream, overwritten)
+ *   cu_seqlens   [n_seq+1] int32 device
+ *   page_table   [n_seq, max_pages] int32 device (KV page ids per sequence)
+ *   logits_out   fp32 [n_seq, vocab] (last token of each sequence) or, when all_logits != 0,
+ *                [total_tokens, vocab] */
+RVL_API int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t n_seq,
+                int64_t total_tokens, int32_t max_seqlen, const int32_t* page_table, int32_t max_pages,
+                float* logits_out, int32_t all_logits, rvl_stream stream);
+
+/* One KV-cached decode step for n_seq sequences (one new token each).
+ * Replaces the step t>0 forward: vtimellm_arch.py:88-100 (position = tokens so far)
+ * + transformers Llama forward with past_key_values.
+ *   token_ids    [n_seq] int32 device: token to embed and append
+ *   seq_lens     [n_seq] int32 device, in/out: tokens already in the cache (= position of the new
+ *                token); incremented by one at the end of the step
+ *   logits_out   [n_seq, vocab] fp32 */
+RVL_API int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, int32_t n_seq,
+                    const int32_t* page_table, int32_t max_pages, float* logits_out, rvl_stream stream);
+
+/* Greedy sampling + per-step entropy + EOS bookkeeping on the device.
+ * Replaces vtimellm_llama.py:337-362 (argmax instead of multinomial; finished rows emit pad;
+ * a row finishes on EOS) and funs_get_feature_X.py:130-134 (H = -sum p*log(p+1e-10)).
+ *   logits        [n_seq, vocab] fp32
+ *   unfinished    [n_seq] int32 in/out (1 = still generating); may be NULL (no EOS handling)
+ *   next_tokens   [n_seq] int32 out
+ *   entropy_out   [n_seq] fp32 out (entropy of this step's distribution; may be NULL) */
+RVL_API int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq, int32_t vocab,
+                      int32_t* unfinished, int32_t eos_id, int32_t pad_id, int32_t* next_tokens,
+                      float* entropy_out, rvl_stream stream);
+
+/* CLIP text-to-frame cosine top-k score of each proposal.
+ * Replaces similarity.py:71-94 `_topk_pooling` + the caller arithmetic
+ * eval_nlq_negative.py:309-316 / eval_nlq_retrieval_e2e2.py:380-386:
+ * normalise frames (norm_axis 1 = per frame, 0 = across the frame axis, the stage-1 driver's
+ * quirk), sims = frames . cls, top-k frames (ties -> lowest index), score = dot(sum of the
+ * top-k normalised frames, cls) = sum of the top-k sims.
+ *   frames   [n_rows, dim] bf16;  seg_offsets [n_seg+1] int32 (rows of each proposal)
+ *   cls      [dim] bf16;  scores_out [n_seg] fp32;  topk_idx_out [n_seg, k] int32 (-1 padded, may be NULL)
+ *   max_seg_rows: upper bound on the rows of one proposal (<= 8192), k <= 16 */
+RVL_API int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, int32_t n_seg,
+                    int32_t dim, const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows,
+                    float* scores_out, int32_t* topk_idx_out, rvl_stream stream);
+
+/* Stage-2 segment selection: indices of the k largest fp32 scores, descending, ties -> lowest
+ * index (bit-exact given identical scores; BASELINE.json north_star). n <= 65536. */
+RVL_API int rvl_select_topk(rvl_handle* h, const float* scores, int32_t n, int32_t k, int32_t* idx_out,
+                    rvl_stream stream);
+
+/* ---- individual kernels (unit parity tests and host-side composition) ------------------------ */
+
+#define RVL_GEMM_OUT_BF16 0
+#define RVL_GEMM_OUT_F32 1
+#define RVL_GEMM_ADD_F32 2      /* out(fp32) += A.B^T, in place, non-atomic */
+#define RVL_GEMM_FLAG_RELU 1
+#define RVL_GEMM_FLAG_SWAP 2    /* stream the weight as the 128-row MMA operand (small-M / decode) */
+
+/* out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]); A, W, bias bf16; fp32 accumulation in TMEM.
+ * Replaces every nn.Linear on the path (cuBLAS via torch): q/k/v/o, gate/up/down, lm_head,
+ * mm_projector and the ClipEncoder linears.  K % 8 == 0, N % 8 == 0.
+ * rowmap (optional, int32 [M]) scatters output rows. split_k > 1 needs RVL_GEMM_ADD_F32. */
+RVL_API int rvl_gemm_bf16(rvl_handle* h, const void* A, const void* W, const void* bias, void* out,
+                  int64_t M, int64_t N, int64_t K, int64_t ldc, int32_t out_mode, int32_t flags,
+                  const int32_t* rowmap, int32_t split_k, rvl_stream stream);
+
+/* y(bf16) = x(fp32) * rsqrt(mean(x^2)+eps) * w(bf16); rows optional gather (int32 [n_rows]). */
+RVL_API int rvl_rmsnorm(rvl_handle* h, const float* x, const void* w, void* y, int64_t n_rows, int32_t dim,
+                float eps, const int32_t* rows, rvl_stream stream);
+
+/* RoPE (rotate-half) on q,k of qkv [n_tokens, 3*hidden] bf16 in place + KV page write.
+ * positions: explicit int32 [n_tokens] device array (decode: seq_lens), or NULL with tok_seq and
+ * cu_seqlens given (prefill: position = index inside the sequence).  tok_seq int32 [n_tokens] =
+ * sequence of each token (NULL: token i belongs to sequence i). */
+RVL_API int rvl_rope_kv(rvl_handle* h, void* qkv, int64_t n_tokens, const int32_t* positions,
+                const int32_t* tok_seq, const int32_t* cu_seqlens, const int32_t* page_table,
+                int32_t max_pages, int32_t layer, rvl_stream stream);
+
+/* act[n, I] = silu(gu[n, 0:I]) * gu[n, I:2I], bf16. */
+RVL_API int rvl_swiglu(rvl_handle* h, const void* gu, void* act, int64_t n_tokens, int32_t intermediate,
+               rvl_stream stream);
+
+/* Causal varlen attention over qkv [T, 3*hidden] (post-RoPE) -> out [T, hidden] bf16. */
+RVL_API int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const int32_t* cu_seqlens,
+                     int32_t n_seq, int32_t max_seqlen, rvl_stream stream);
+
+/* Paged-KV decode attention: q from qkv [n_seq, 3*hidden], keys 0..seq_lens[i] (inclusive of the
+ * token just appended) -> out [n_seq, hidden] bf16. */
+RVL_API int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int32_t* seq_lens, int32_t n_seq,
+                    const int32_t* page_table, int32_t max_pages, int32_t layer, rvl_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVISIONLLM_B200_H */

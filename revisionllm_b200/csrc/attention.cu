@@ -1,0 +1,345 @@
+// Attention kernels for head_dim = 128, no GQA.
+//
+//  * attn_prefill: causal varlen self-attention over the packed qkv stream (flash-style: K/V tiles of
+//    64 keys staged in shared memory with cp.async double buffering, QK^T and PV on the legacy
+//    mma.sync tensor path, online softmax in fp32 registers with warp-quad shuffles).  Prefill
+//    attention is 0.4 % of the prefill FLOPs at L=184 (8.9 of 2392 GFLOP per segment, BASELINE.md
+//    section 3), so it is kept on mma.sync in this round; the GEMMs carry the tcgen05 work.
+//  * attn_decode: one query row per (sequence, head) against the paged KV cache; HBM-bound
+//    (reads (L+t) * 512 B per (seq, head)), 16-byte coalesced loads of whole key/value rows.
+//
+// Replaces the eager `matmul -> softmax(fp32) -> matmul` attention of transformers' Llama
+// (modeling_llama.py eager_attention_forward) that the reference reaches from
+// revisionllm/model/vtimellm_llama.py:79-90, and its DynamicCache concat.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rvl_internal.h"
+#include "rvl_ptx.cuh"
+
+namespace rvl {
+
+constexpr int kD = 128;        // head_dim
+constexpr int kQT = 64;        // query rows per CTA
+constexpr int kKT = 64;        // keys per tile
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = smem_u32(smem);
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Tile in smem: [rows][128] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
+__device__ __forceinline__ uint32_t tile_off(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
+
+// Load a 64 x 128 tile; rows >= n_valid are zero-filled.
+__device__ __forceinline__ void load_tile(uint8_t* smem_tile, const __nv_bfloat16* g_row0, long long row_stride,
+                                          int n_valid, int tid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + i * 128;
+    const int r = idx >> 4, c = idx & 15;
+    const bool ok = r < n_valid;
+    const __nv_bfloat16* src = g_row0 + (ok ? r : 0) * row_stride + c * 8;
+    cp_async16(smem_tile + tile_off(r, c), src, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out,
+                                                            const int32_t* __restrict__ cu_seqlens, int n_heads,
+                                                            float scale_log2) {
+  const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int s0 = cu_seqlens[seq];
+  const int L = cu_seqlens[seq + 1] - s0;
+  const int q0 = qt * kQT;
+  if (q0 >= L) return;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;          // [2][64][128]
+  uint8_t* sV = smem + 16384 * 3;      // [2][64][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = n_heads * kD;
+  const long long stride = 3LL * H;
+  const __nv_bfloat16* qbase = qkv + (static_cast<long long>(s0) + q0) * stride + head * kD;
+  const __nv_bfloat16* kbase = qkv + static_cast<long long>(s0) * stride + H + head * kD;
+  const __nv_bfloat16* vbase = kbase + H;
+
+  const int n_tiles = min((L + kKT - 1) / kKT, qt + 1);  // causal: keys <= q0 + 63
+  load_tile(sQ, qbase, stride, min(kQT, L - q0), tid);
+  load_tile(sK, kbase, stride, min(kKT, L), tid);
+  load_tile(sV, vbase, stride, min(kKT, L), tid);
+  cp_async_commit();
+
+  uint32_t qf[8][4];
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int g = lane >> 2, t4 = lane & 3;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_tiles) {
+      const int k0n = (j + 1) * kKT;
+      load_tile(sK + (buf ^ 1) * 16384, kbase + k0n * stride, stride, min(kKT, L - k0n), tid);
+      load_tile(sV + (buf ^ 1) * 16384, vbase + k0n * stride, stride, min(kKT, L - k0n), tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (j == 0) {
+      // Q fragments (A operand, 16 rows of this warp x 16 dims per k-step)
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ) + tile_off(r, ks * 2 + (lane >> 4)));
+    }
+    const uint32_t kaddr = smem_u32(sK + buf * 16384);
+    const uint32_t vaddr = smem_u32(sV + buf * 16384);
+    // ---- S = Q K^T  (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        ldmatrix_x4(b, kaddr + tile_off(key, ks * 2 + ((lane >> 3) & 1)));
+        mma_bf16_16816(s[2 * np], qf[ks], b[0], b[1]);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], b[2], b[3]);
+      }
+    }
+    // ---- mask + online softmax (rows g and g+8 of this warp's 16)
+    const int k0 = j * kKT;
+    const int qrow0 = q0 + warp * 16 + g;  // local query index of c0/c1; c2/c3 are +8
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = k0 + nt * 8 + t4 * 2 + (e & 1);
+        const int qr = qrow0 + (e >> 1) * 8;
+        const bool ok = key <= qr && key < L;
+        s[nt][e] = ok ? s[nt][e] * scale_log2 : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      mnew[h] = fmaxf(m_run[h], mx[h]);
+      const float msafe = mnew[h] == -INFINITY ? 0.f : mnew[h];
+      corr[h] = exp2f(m_run[h] - msafe);  // m_run = -inf -> 0
+      m_run[h] = mnew[h];
+      mnew[h] = msafe;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = exp2f(s[nt][e] - mnew[e >> 1]);
+        s[nt][e] = p;
+        rs[e >> 1] += p;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * corr[h] + rs[h];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
+      pa[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
+      pa[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 8; ++dp) {
+        uint32_t b[4];
+        const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4_trans(b, vaddr + tile_off(key, dp * 2 + (lane >> 4)));
+        mma_bf16_16816(o[2 * dp], pa, b[0], b[1]);
+        mma_bf16_16816(o[2 * dp + 1], pa, b[2], b[3]);
+      }
+    }
+    __syncthreads();  // everyone done with buf before it is refilled (tile j+2)
+  }
+  // ---- normalise and store
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int qr = q0 + warp * 16 + g + h * 8;
+    if (qr < L) {
+      const float inv = 1.f / l_run[h];
+      __nv_bfloat16* dst = out + (static_cast<long long>(s0) + qr) * H + head * kD;
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        *reinterpret_cast<uint32_t*>(dst + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][2 * h] * inv, o[nt][2 * h + 1] * inv);
+      }
+    }
+  }
+}
+
+void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
+                         cudaStream_t st) {
+  if (n_seq <= 0 || max_seqlen <= 0) return;
+  static bool attr = false;
+  constexpr int smem = 16384 * 5;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  dim3 grid((max_seqlen + kQT - 1) / kQT, n_heads, n_seq);
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kD));
+  attn_prefill_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                               reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2);
+}
+
+// ------------------------------------------------------------------------------------------- decode
+// grid (n_heads, n_seq), 128 threads.  Phase 1: scores = q . k_j (8 threads per key, 16 dims each,
+// 16 keys per CTA iteration).  Phase 2: softmax over the row in shared memory.  Phase 3: out = sum p_j v_j
+// (16 threads per key cover 128 dims, 8 keys per iteration, cross-group reduction in shared memory).
+// Algorithmic bytes per (seq, head): n_keys * 128 * 2 * 2.
+__global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                           const int32_t* __restrict__ seq_lens,
+                                                           const int32_t* __restrict__ page_table, int max_pages,
+                                                           const __nv_bfloat16* __restrict__ k_pages,
+                                                           const __nv_bfloat16* __restrict__ v_pages, int n_heads,
+                                                           int page_size, float scale) {
+  extern __shared__ float s_scores[];          // [n_keys_max]
+  __shared__ float s_red[8][kD];
+  __shared__ float s_stat[8];
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_keys = seq_lens[seq] + 1;        // includes the token appended this step
+  const int H = n_heads * kD;
+  const int32_t* pt = page_table + static_cast<long long>(seq) * max_pages;
+
+  // ---- phase 1
+  {
+    const int dg = lane & 7;                   // dims [16 dg, 16 dg + 16)
+    const __nv_bfloat16* qp = qkv + static_cast<long long>(seq) * 3 * H + head * kD + dg * 16;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(qp);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(qp + 8);
+    const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float qf[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { qf[2 * e] = bf16_lo(qw[e]); qf[2 * e + 1] = bf16_hi(qw[e]); }
+    for (int kbase = 0; kbase < n_keys; kbase += 16) {
+      const int key = kbase + warp * 4 + (lane >> 3);
+      float acc = 0.f;
+      if (key < n_keys) {
+        const int page = pt[key / page_size];
+        const __nv_bfloat16* kp = k_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dg * 16;
+        const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(kp));
+        const uint4 k1 = __ldg(reinterpret_cast<const uint4*>(kp + 8));
+        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += qf[2 * e] * bf16_lo(kw[e]) + qf[2 * e + 1] * bf16_hi(kw[e]);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (dg == 0 && key < n_keys) s_scores[key] = acc * scale;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: softmax statistics
+  float mx = -INFINITY;
+  for (int i = tid; i < n_keys; i += 128) mx = fmaxf(mx, s_scores[i]);
+  mx = warp_max(mx);
+  if (lane == 0) s_stat[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3]));
+  float sum = 0.f;
+  for (int i = tid; i < n_keys; i += 128) {
+    const float p = __expf(s_scores[i] - mx);
+    s_scores[i] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_stat[4 + warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (s_stat[4] + s_stat[5] + s_stat[6] + s_stat[7]);
+  // ---- phase 3: PV
+  {
+    const int grp = tid >> 4;                  // 8 key groups
+    const int dv = (tid & 15) * 8;             // dims [dv, dv + 8)
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int key = grp; key < n_keys; key += 8) {
+      const int page = pt[key / page_size];
+      const __nv_bfloat16* vp = v_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dv;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(vp));
+      const float p = s_scores[key];
+      acc[0] += p * bf16_lo(v.x); acc[1] += p * bf16_hi(v.x);
+      acc[2] += p * bf16_lo(v.y); acc[3] += p * bf16_hi(v.y);
+      acc[4] += p * bf16_lo(v.z); acc[5] += p * bf16_hi(v.z);
+      acc[6] += p * bf16_lo(v.w); acc[7] += p * bf16_hi(v.w);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_red[grp][dv + e] = acc[e];
+  }
+  __syncthreads();
+  {
+    float r = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi) r += s_red[gi][tid];
+    out[static_cast<long long>(seq) * H + head * kD + tid] = __float2bfloat16(r * inv);
+  }
+}
+
+void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
+                        int max_pages, const void* k_pages, const void* v_pages, int n_heads, int page_size,
+                        cudaStream_t st) {
+  if (n_seq <= 0) return;
+  const int smem = max_pages * page_size * static_cast<int>(sizeof(float));
+  static int attr_smem = 0;
+  if (smem > 40000 && smem > attr_smem) {
+    cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_smem = smem;
+  }
+  dim3 grid(n_heads, n_seq);
+  attn_decode_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                              reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages,
+                                              reinterpret_cast<const __nv_bfloat16*>(k_pages),
+                                              reinterpret_cast<const __nv_bfloat16*>(v_pages), n_heads, page_size,
+                                              1.0f / sqrtf(static_cast<float>(kD)));
+}
+
+}  // namespace rvl

@@ -1,0 +1,242 @@
+// Bandwidth-bound kernels of the decoder stack: RMSNorm, embedding gather / splice scatter,
+// RoPE + KV page write, SwiGLU.  All are vectorised (16-byte accesses), coalesced along the
+// feature dimension and HBM-bound; grids are one CTA per token row (>> 148 SMs x resident CTAs).
+//
+// Replaces (reference runs unfused torch eager kernels through transformers' Llama):
+//   LlamaRMSNorm, rotate_half RoPE, DynamicCache append, SiLU*mul, nn.Embedding and the torch.cat
+//   splice of revisionllm/model/vtimellm_arch.py:165-238.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rvl_internal.h"
+#include "rvl_ptx.cuh"
+
+namespace rvl {
+
+// ------------------------------------------------------------------------------------ RMSNorm
+// y(bf16) = x(fp32) * rsqrt(mean(x^2) + eps) * w(bf16).  One CTA per row, the row is held in
+// registers between the reduction and the scaling pass (read once, write once).
+// Algorithmic bytes per row: dim*4 (read) + dim*2 (write) (+ dim*2 weight, L2 resident).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                           __nv_bfloat16* __restrict__ y, int dim, float eps,
+                                                           const int32_t* __restrict__ rows) {
+  constexpr int kMaxVec = 8;  // float4 per thread -> dim <= THREADS * 32
+  const long long src_row = rows ? rows[blockIdx.x] : blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + src_row * dim);
+  const int nvec = dim >> 2;
+  float4 c[kMaxVec];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = threadIdx.x + i * THREADS;
+    if (idx < nvec) {
+      c[i] = xr[idx];
+      ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
+    }
+  }
+  __shared__ float red[THREADS / 32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < THREADS / 32; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / static_cast<float>(dim) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(blockIdx.x) * dim);
+  const uint2* wr = reinterpret_cast<const uint2*>(w);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = threadIdx.x + i * THREADS;
+    if (idx < nvec) {
+      const uint2 wv = __ldg(wr + idx);
+      uint2 o;
+      o.x = pack_bf16x2(bf16_lo(wv.x) * (c[i].x * inv), bf16_hi(wv.x) * (c[i].y * inv));
+      o.y = pack_bf16x2(bf16_lo(wv.y) * (c[i].z * inv), bf16_hi(wv.y) * (c[i].w * inv));
+      yr[idx] = o;
+    }
+  }
+}
+
+void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int dim, float eps, const int32_t* rows,
+                    cudaStream_t st) {
+  if (n_rows <= 0) return;
+  if (dim <= 128 * 32)
+    rmsnorm_kernel<128><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
+        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows);
+  else
+    rmsnorm_kernel<256><<<static_cast<unsigned>(n_rows), 256, 0, st>>>(
+        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows);
+}
+
+// ------------------------------------------------------------------------------------ embedding / splice rows
+// out[dst_rows[i]] (fp32) = table[ids[i]] (bf16).  Text rows of the splice
+// (vtimellm_arch.py:194 `embed_tokens(cat(text chunks))`) and the decode-step token embedding.
+__global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ ids,
+                                  const int32_t* __restrict__ dst_rows, int dim, int vocab, float* __restrict__ out) {
+  const int i = blockIdx.x;
+  int id = ids[i];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const long long dst = dst_rows ? dst_rows[i] : i;
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<long long>(id) * dim);
+  float4* o = reinterpret_cast<float4*>(out + dst * dim);
+  for (int v = threadIdx.x; v < (dim >> 3); v += blockDim.x) {
+    const uint4 s = __ldg(src + v);
+    o[2 * v] = make_float4(bf16_lo(s.x), bf16_hi(s.x), bf16_lo(s.y), bf16_hi(s.y));
+    o[2 * v + 1] = make_float4(bf16_lo(s.z), bf16_hi(s.z), bf16_lo(s.w), bf16_hi(s.w));
+  }
+}
+void launch_embed_rows(const void* table, const int32_t* ids, const int32_t* dst_rows, int n, int dim, int vocab,
+                       float* out, cudaStream_t st) {
+  if (n <= 0) return;
+  embed_rows_kernel<<<n, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(table), ids, dst_rows, dim, vocab, out);
+}
+
+// out[dst_rows[i]] (fp32) = src[i] (bf16): already-projected visual rows (stage-2 CLS tokens).
+__global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ dst_rows, int dim,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x;
+  const long long dst = dst_rows ? dst_rows[i] : i;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * dim);
+  float4* o = reinterpret_cast<float4*>(out + dst * dim);
+  for (int v = threadIdx.x; v < (dim >> 3); v += blockDim.x) {
+    const uint4 s = __ldg(s4 + v);
+    o[2 * v] = make_float4(bf16_lo(s.x), bf16_hi(s.x), bf16_lo(s.y), bf16_hi(s.y));
+    o[2 * v + 1] = make_float4(bf16_lo(s.z), bf16_hi(s.z), bf16_lo(s.w), bf16_hi(s.w));
+  }
+}
+void launch_scatter_rows_bf16(const void* src, const int32_t* dst_rows, int n, int dim, float* out, cudaStream_t st) {
+  if (n <= 0) return;
+  scatter_rows_kernel<<<n, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst_rows, dim, out);
+}
+
+// ------------------------------------------------------------------------------------ token -> sequence map
+__global__ void token_seq_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict__ tok_seq,
+                                 int32_t* __restrict__ last_rows, long long total) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t < n_seq && last_rows) last_rows[t] = cu[t + 1] - 1;
+  if (t >= total) return;
+  int lo = 0, hi = n_seq;  // find s with cu[s] <= t < cu[s+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cu[mid] <= t) lo = mid; else hi = mid;
+  }
+  tok_seq[t] = lo;
+}
+void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, int32_t* last_rows, int64_t total,
+                      cudaStream_t st) {
+  const long long n = total > n_seq ? total : n_seq;
+  if (n <= 0) return;
+  token_seq_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(cu_seqlens, n_seq, tok_seq, last_rows, total);
+}
+
+// ------------------------------------------------------------------------------------ RoPE + KV write
+// In-place rotate-half RoPE on q and k of qkv [T, 3*H] (bf16) and write of the rotated k and of v into
+// the paged cache [page][head][slot][128].  One CTA per token; cos/sin computed once per token in fp32
+// (sincosf with full range reduction: positions reach 4096 rad) and shared by all heads.
+// Algorithmic bytes per token: read 3H*2, write 2H*2 (q,k in place) + 2H*2 (cache).
+__global__ void __launch_bounds__(128) rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ positions,
+                                                       const int32_t* __restrict__ tok_seq,
+                                                       const int32_t* __restrict__ cu_seqlens,
+                                                       const int32_t* __restrict__ page_table, int max_pages,
+                                                       __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
+                                                       int n_heads, int page_size, float theta) {
+  constexpr int D = 128;
+  __shared__ float s_cos[D / 2], s_sin[D / 2];
+  const long long tok = blockIdx.x;
+  const int seq = tok_seq ? tok_seq[tok] : static_cast<int>(tok);
+  const int pos = positions ? positions[tok] : static_cast<int>(tok - cu_seqlens[seq]);
+  if (threadIdx.x < D / 2) {
+    // inv_freq_i = theta^(-2i/D)  (LlamaRotaryEmbedding), angle in fp32 like the reference
+    const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * threadIdx.x) / static_cast<float>(D));
+    float s, c;
+    sincosf(static_cast<float>(pos) * inv_freq, &s, &c);
+    s_cos[threadIdx.x] = c;
+    s_sin[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int H = n_heads * D;
+  __nv_bfloat16* row = qkv + tok * 3LL * H;
+  const int page = page_table[static_cast<long long>(seq) * max_pages + pos / page_size];
+  const int slot = pos % page_size;
+  // q and k: (qk, head, j) with j in 0..7 covering dims [8j, 8j+8) and partner [64+8j, ...)
+  for (int it = threadIdx.x; it < 2 * n_heads * 8; it += blockDim.x) {
+    const int j = it & 7;
+    const int head = (it >> 3) % n_heads;
+    const int qk = it / (8 * n_heads);
+    __nv_bfloat16* base = row + qk * H + head * D;
+    uint4 lo = *reinterpret_cast<const uint4*>(base + 8 * j);
+    uint4 hi = *reinterpret_cast<const uint4*>(base + 64 + 8 * j);
+    uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+    uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d0 = 8 * j + 2 * e;
+      const float a0 = bf16_lo(l[e]), a1 = bf16_hi(l[e]);
+      const float b0 = bf16_lo(h[e]), b1 = bf16_hi(h[e]);
+      const float c0 = s_cos[d0], s0 = s_sin[d0], c1 = s_cos[d0 + 1], s1 = s_sin[d0 + 1];
+      l[e] = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
+      h[e] = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
+    }
+    *reinterpret_cast<uint4*>(base + 8 * j) = lo;
+    *reinterpret_cast<uint4*>(base + 64 + 8 * j) = hi;
+    if (qk == 1) {
+      __nv_bfloat16* kc = k_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + slot) * D;
+      *reinterpret_cast<uint4*>(kc + 8 * j) = lo;
+      *reinterpret_cast<uint4*>(kc + 64 + 8 * j) = hi;
+    }
+  }
+  // v: straight copy into the cache
+  for (int it = threadIdx.x; it < n_heads * 16; it += blockDim.x) {
+    const int j = it & 15;
+    const int head = it >> 4;
+    const uint4 val = *reinterpret_cast<const uint4*>(row + 2 * H + head * D + 8 * j);
+    __nv_bfloat16* vc = v_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + slot) * D;
+    *reinterpret_cast<uint4*>(vc + 8 * j) = val;
+  }
+}
+void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const int32_t* tok_seq,
+                    const int32_t* cu_seqlens, const int32_t* page_table, int max_pages, void* k_pages, void* v_pages,
+                    int n_heads, int page_size, float theta, cudaStream_t st) {
+  if (n_tokens <= 0) return;
+  rope_kv_kernel<<<static_cast<unsigned>(n_tokens), 128, 0, st>>>(
+      reinterpret_cast<__nv_bfloat16*>(qkv), positions, tok_seq, cu_seqlens, page_table, max_pages,
+      reinterpret_cast<__nv_bfloat16*>(k_pages), reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, theta);
+}
+
+// ------------------------------------------------------------------------------------ SwiGLU
+// act[t, i] = silu(gu[t, i]) * gu[t, I + i], bf16 in/out, fp32 math, 8 elements (16 B) per thread.
+// Algorithmic bytes per token: 2I*2 read + I*2 write.
+__global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ act, long long n_vec,
+                              int inter) {
+  const int vec_per_row = inter >> 3;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = v / vec_per_row;
+    const int i = static_cast<int>(v - t * vec_per_row) << 3;
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gu + t * 2LL * inter + i));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(gu + t * 2LL * inter + inter + i));
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float g0 = bf16_lo(gw[e]), g1 = bf16_hi(gw[e]);
+      const float r0 = g0 / (1.f + __expf(-g0)) * bf16_lo(uw[e]);
+      const float r1 = g1 / (1.f + __expf(-g1)) * bf16_hi(uw[e]);
+      o[e] = pack_bf16x2(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(act + t * static_cast<long long>(inter) + i) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaStream_t st) {
+  const long long n_vec = n_tokens * (inter >> 3);
+  if (n_vec <= 0) return;
+  long long blocks = (n_vec + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;  // grid-stride: a multiple of the SM count
+  swiglu_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gu),
+                                                               reinterpret_cast<__nv_bfloat16*>(act), n_vec, inter);
+}
+
+}  // namespace rvl

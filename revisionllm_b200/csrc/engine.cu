@@ -1,0 +1,377 @@
+// C ABI + host-side orchestration of the decoder stack (layer loop, workspace carving, KV pages).
+// Everything here only enqueues kernels on the caller's stream: no allocation, no synchronisation.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "rvl_internal.h"
+
+using namespace rvl;
+
+struct rvl_handle {
+  rvl_config cfg{};
+  int num_sms = 0;
+  bool weights_bound = false;
+  rvl_weights w{};
+  std::vector<rvl_layer_weights> layers;
+  // workspace
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t max_tokens = 0;
+  int32_t max_seqs = 0;
+  void *xnorm = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr;
+  float* dec_hidden = nullptr;
+  int32_t *tok_seq = nullptr, *last_rows = nullptr;
+  // kv
+  uint8_t* kv = nullptr;
+  int32_t n_pages = 0;
+  mutable std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(const rvl_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+static int check_cuda(const rvl_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, RVL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return RVL_OK;
+}
+static inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t xnorm, qkv, attn, gu, act, xlast, dec_hidden, tok_seq, last_rows, total;
+};
+static WsLayout ws_layout(const rvl_config& c, int64_t T, int32_t S) {
+  WsLayout l{};
+  const size_t H = c.hidden, I = c.intermediate;
+  const size_t rows = static_cast<size_t>(T > S ? T : S);
+  size_t off = 0;
+  l.xnorm = off; off += align_up(rows * H * 2);
+  l.qkv = off; off += align_up(rows * 3 * H * 2);
+  l.attn = off; off += align_up(rows * H * 2);
+  l.gu = off; off += align_up(rows * 2 * I * 2);
+  l.act = off; off += align_up(rows * I * 2);
+  l.xlast = off; off += align_up(static_cast<size_t>(S) * H * 2);
+  l.dec_hidden = off; off += align_up(static_cast<size_t>(S) * H * 4);
+  l.tok_seq = off; off += align_up(rows * 4);
+  l.last_rows = off; off += align_up(static_cast<size_t>(S) * 4);
+  l.total = off;
+  return l;
+}
+
+extern "C" {
+
+int rvl_abi_version(void) { return RVL_ABI_VERSION; }
+
+const char* rvl_last_error(const rvl_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int rvl_create(const rvl_config* cfg, rvl_handle** out) {
+  if (!cfg || !out) return fail(nullptr, RVL_ERR_INVALID, "rvl_create: null argument");
+  if (cfg->head_dim != 128) return fail(nullptr, RVL_ERR_INVALID, "rvl_create: head_dim must be 128");
+  if (cfg->hidden != cfg->n_heads * cfg->head_dim) return fail(nullptr, RVL_ERR_INVALID, "rvl_create: hidden != n_heads*head_dim");
+  if (cfg->hidden % 64 || cfg->intermediate % 64 || cfg->vocab % 8 || cfg->adapter_dim % 8 || cfg->hidden > 8192)
+    return fail(nullptr, RVL_ERR_INVALID, "rvl_create: unsupported dimensions");
+  if (cfg->kv_page_size <= 0 || cfg->kv_page_size > 256) return fail(nullptr, RVL_ERR_INVALID, "rvl_create: bad kv_page_size");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, RVL_ERR_CUDA, std::string("rvl_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, RVL_ERR_INVALID, "rvl_create: bad device ordinal");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, RVL_ERR_CUDA, "rvl_create: cudaGetDeviceProperties failed");
+  if (prop.major != 10) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "rvl_create: device is sm_%d%d; these kernels are sm_100a only", prop.major, prop.minor);
+    return fail(nullptr, RVL_ERR_UNSUPPORTED, buf);
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, RVL_ERR_CUDA, "rvl_create: cudaSetDevice failed");
+  rvl_handle* h = new rvl_handle();
+  h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return RVL_OK;
+}
+
+void rvl_destroy(rvl_handle* h) { delete h; }
+
+int rvl_bind_weights(rvl_handle* h, const rvl_weights* w) {
+  if (!h || !w || !w->layers) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: null argument");
+  if (!w->embed_tokens || !w->final_norm || !w->lm_head) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: missing tensor");
+  h->layers.assign(w->layers, w->layers + h->cfg.n_layers);
+  for (auto& l : h->layers)
+    if (!l.wqkv || !l.wo || !l.wgu || !l.wdown || !l.ln1 || !l.ln2) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: missing layer tensor");
+  h->w = *w;
+  h->w.layers = h->layers.data();
+  h->weights_bound = true;
+  return RVL_OK;
+}
+
+size_t rvl_workspace_bytes(const rvl_handle* h, int64_t max_tokens, int32_t max_seqs) {
+  if (!h || max_tokens <= 0 || max_seqs <= 0) return 0;
+  return ws_layout(h->cfg, max_tokens, max_seqs).total;
+}
+
+int rvl_set_workspace(rvl_handle* h, void* ws, size_t bytes, int64_t max_tokens, int32_t max_seqs) {
+  if (!h || !ws) return fail(h, RVL_ERR_INVALID, "rvl_set_workspace: null argument");
+  const WsLayout l = ws_layout(h->cfg, max_tokens, max_seqs);
+  if (bytes < l.total) return fail(h, RVL_ERR_INVALID, "rvl_set_workspace: buffer too small");
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(h, RVL_ERR_INVALID, "rvl_set_workspace: buffer must be 256-byte aligned");
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  h->ws = b; h->ws_bytes = bytes; h->max_tokens = max_tokens; h->max_seqs = max_seqs;
+  h->xnorm = b + l.xnorm; h->qkv = b + l.qkv; h->attn = b + l.attn; h->gu = b + l.gu; h->act = b + l.act;
+  h->xlast = b + l.xlast; h->dec_hidden = reinterpret_cast<float*>(b + l.dec_hidden);
+  h->tok_seq = reinterpret_cast<int32_t*>(b + l.tok_seq); h->last_rows = reinterpret_cast<int32_t*>(b + l.last_rows);
+  return RVL_OK;
+}
+
+static size_t kv_layer_half_bytes(const rvl_config& c, int32_t n_pages) {
+  return static_cast<size_t>(n_pages) * c.n_heads * c.kv_page_size * c.head_dim * 2;
+}
+size_t rvl_kv_bytes(const rvl_handle* h, int32_t n_pages) {
+  if (!h || n_pages <= 0) return 0;
+  return kv_layer_half_bytes(h->cfg, n_pages) * 2 * h->cfg.n_layers;
+}
+int rvl_set_kv(rvl_handle* h, void* kv, int32_t n_pages) {
+  if (!h || !kv || n_pages <= 0) return fail(h, RVL_ERR_INVALID, "rvl_set_kv: bad argument");
+  h->kv = static_cast<uint8_t*>(kv);
+  h->n_pages = n_pages;
+  return RVL_OK;
+}
+static void* k_pages(const rvl_handle* h, int layer) { return h->kv + kv_layer_half_bytes(h->cfg, h->n_pages) * (2 * layer); }
+static void* v_pages(const rvl_handle* h, int layer) { return h->kv + kv_layer_half_bytes(h->cfg, h->n_pages) * (2 * layer + 1); }
+
+// ------------------------------------------------------------------------------------------ GEMM helper
+static int linear(const rvl_handle* h, const void* x, const void* w, const void* bias, void* out, int64_t tokens,
+                  int64_t features, int64_t K, int64_t ldc, int mode, int flags, const int32_t* rowmap, cudaStream_t st) {
+  GemmCall c;
+  c.A = x; c.W = w; c.bias = bias; c.out = out; c.M = tokens; c.N = features; c.K = K; c.ldc = ldc;
+  c.out_mode = mode; c.flags = flags; c.rowmap = rowmap; c.split_k = 1;
+  if (tokens <= 256) {
+    // few tokens (decode, lm_head on last rows): stream the weight through the 128-row MMA slot once
+    c.flags |= RVL_GEMM_FLAG_SWAP;
+    if (mode == RVL_GEMM_ADD_F32) {
+      const int tiles = static_cast<int>((features + 127) / 128);
+      int sk = (h->num_sms + tiles - 1) / tiles;
+      const int kb = static_cast<int>((K + 63) / 64);
+      if (sk > kb / 8) sk = kb / 8;   // keep >= 8 k-blocks (512 of K) per split
+      if (sk < 1) sk = 1;
+      c.split_k = sk;
+    }
+  }
+  std::string err;
+  int rc = gemm_bf16(c, h->num_sms, st, &err);
+  if (rc) return fail(h, rc, err);
+  return RVL_OK;
+}
+
+int rvl_gemm_bf16(rvl_handle* h, const void* A, const void* W, const void* bias, void* out, int64_t M, int64_t N,
+                  int64_t K, int64_t ldc, int32_t out_mode, int32_t flags, const int32_t* rowmap, int32_t split_k,
+                  rvl_stream stream) {
+  if (!h || !A || !W || !out) return fail(h, RVL_ERR_INVALID, "rvl_gemm_bf16: null argument");
+  GemmCall c;
+  c.A = A; c.W = W; c.bias = bias; c.out = out; c.M = M; c.N = N; c.K = K; c.ldc = ldc;
+  c.out_mode = out_mode; c.flags = flags; c.rowmap = rowmap; c.split_k = split_k < 1 ? 1 : split_k;
+  std::string err;
+  int rc = gemm_bf16(c, h->num_sms, static_cast<cudaStream_t>(stream), &err);
+  if (rc) return fail(h, rc, err);
+  return check_cuda(h, "rvl_gemm_bf16");
+}
+
+// ------------------------------------------------------------------------------------------ splice
+int rvl_project_splice(rvl_handle* h, const void* feats, const int32_t* feat_dst, int32_t n_feat_rows,
+                       const int32_t* text_ids, const int32_t* text_dst, int32_t n_text, float* hidden_out,
+                       int64_t total_tokens, rvl_stream stream) {
+  if (!h || !hidden_out) return fail(h, RVL_ERR_INVALID, "rvl_project_splice: null argument");
+  if (!h->weights_bound || !h->w.proj_w || !h->w.proj_b) return fail(h, RVL_ERR_STATE, "rvl_project_splice: projector weights not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  (void)total_tokens;
+  if (n_text > 0) launch_embed_rows(h->w.embed_tokens, text_ids, text_dst, n_text, h->cfg.hidden, h->cfg.vocab, hidden_out, st);
+  if (n_feat_rows > 0) {
+    // the epilogue adds the bias and writes each projected frame straight to its spliced row
+    GemmCall c;
+    c.A = feats; c.W = h->w.proj_w; c.bias = h->w.proj_b; c.out = hidden_out;
+    c.M = n_feat_rows; c.N = h->cfg.hidden; c.K = h->cfg.adapter_dim; c.ldc = h->cfg.hidden;
+    c.out_mode = RVL_GEMM_OUT_F32; c.rowmap = feat_dst;
+    if (n_feat_rows <= 256) c.flags |= RVL_GEMM_FLAG_SWAP;
+    std::string err;
+    int rc = gemm_bf16(c, h->num_sms, st, &err);
+    if (rc) return fail(h, rc, err);
+  }
+  return check_cuda(h, "rvl_project_splice");
+}
+
+int rvl_splice_rows(rvl_handle* h, const void* vis, const int32_t* vis_dst, int32_t n_vis, const int32_t* text_ids,
+                    const int32_t* text_dst, int32_t n_text, float* hidden_out, int64_t total_tokens, rvl_stream stream) {
+  if (!h || !hidden_out) return fail(h, RVL_ERR_INVALID, "rvl_splice_rows: null argument");
+  if (!h->weights_bound) return fail(h, RVL_ERR_STATE, "rvl_splice_rows: weights not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  (void)total_tokens;
+  if (n_text > 0) launch_embed_rows(h->w.embed_tokens, text_ids, text_dst, n_text, h->cfg.hidden, h->cfg.vocab, hidden_out, st);
+  if (n_vis > 0) launch_scatter_rows_bf16(vis, vis_dst, n_vis, h->cfg.hidden, hidden_out, st);
+  return check_cuda(h, "rvl_splice_rows");
+}
+
+// ------------------------------------------------------------------------------------------ decoder stack
+static int ready(const rvl_handle* h, const char* who) {
+  if (!h) return fail(h, RVL_ERR_INVALID, std::string(who) + ": null handle");
+  if (!h->weights_bound) return fail(h, RVL_ERR_STATE, std::string(who) + ": weights not bound");
+  if (!h->ws) return fail(h, RVL_ERR_STATE, std::string(who) + ": workspace not set");
+  if (!h->kv) return fail(h, RVL_ERR_STATE, std::string(who) + ": kv pages not set");
+  return RVL_OK;
+}
+
+int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t n_seq, int64_t total_tokens,
+                int32_t max_seqlen, const int32_t* page_table, int32_t max_pages, float* logits_out, int32_t all_logits,
+                rvl_stream stream) {
+  int rc = ready(h, "rvl_prefill");
+  if (rc) return rc;
+  if (!hidden || !cu_seqlens || !page_table || !logits_out) return fail(h, RVL_ERR_INVALID, "rvl_prefill: null argument");
+  if (total_tokens > h->max_tokens || n_seq > h->max_seqs || n_seq <= 0 || total_tokens <= 0)
+    return fail(h, RVL_ERR_INVALID, "rvl_prefill: batch exceeds the workspace");
+  if (max_seqlen > max_pages * h->cfg.kv_page_size) return fail(h, RVL_ERR_INVALID, "rvl_prefill: page table too small for max_seqlen");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const rvl_config& c = h->cfg;
+  const int64_t T = total_tokens;
+  const int H = c.hidden, I = c.intermediate;
+  launch_token_seq(cu_seqlens, n_seq, h->tok_seq, h->last_rows, T, st);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const rvl_layer_weights& w = h->layers[l];
+    launch_rmsnorm(hidden, w.ln1, h->xnorm, T, H, c.rms_eps, nullptr, st);
+    if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, T, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
+    launch_rope_kv(h->qkv, T, nullptr, h->tok_seq, cu_seqlens, page_table, max_pages, k_pages(h, l), v_pages(h, l),
+                   c.n_heads, c.kv_page_size, c.rope_theta, st);
+    launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st);
+    if ((rc = linear(h, h->attn, w.wo, nullptr, hidden, T, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
+    launch_rmsnorm(hidden, w.ln2, h->xnorm, T, H, c.rms_eps, nullptr, st);
+    if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, T, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
+    launch_swiglu(h->gu, h->act, T, I, st);
+    if ((rc = linear(h, h->act, w.wdown, nullptr, hidden, T, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
+  }
+  if (all_logits) {
+    // LlamaForCausalLM.forward semantics: logits for every position (fp32)
+    launch_rmsnorm(hidden, h->w.final_norm, h->xnorm, T, H, c.rms_eps, nullptr, st);
+    if ((rc = linear(h, h->xnorm, h->w.lm_head, nullptr, logits_out, T, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;
+  } else {
+    // generation only needs the last row of each sequence: gather -> norm -> lm_head
+    launch_rmsnorm(hidden, h->w.final_norm, h->xlast, n_seq, H, c.rms_eps, h->last_rows, st);
+    if ((rc = linear(h, h->xlast, h->w.lm_head, nullptr, logits_out, n_seq, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;
+  }
+  return check_cuda(h, "rvl_prefill");
+}
+
+__global__ void inc_kernel(int32_t* v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += 1;
+}
+
+int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, int32_t n_seq,
+                    const int32_t* page_table, int32_t max_pages, float* logits_out, rvl_stream stream) {
+  int rc = ready(h, "rvl_decode_step");
+  if (rc) return rc;
+  if (!token_ids || !seq_lens || !page_table || !logits_out) return fail(h, RVL_ERR_INVALID, "rvl_decode_step: null argument");
+  if (n_seq <= 0 || n_seq > h->max_seqs) return fail(h, RVL_ERR_INVALID, "rvl_decode_step: n_seq exceeds the workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const rvl_config& c = h->cfg;
+  const int H = c.hidden, I = c.intermediate;
+  const int64_t n = n_seq;
+  float* hid = h->dec_hidden;
+  launch_embed_rows(h->w.embed_tokens, token_ids, nullptr, n_seq, H, c.vocab, hid, st);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const rvl_layer_weights& w = h->layers[l];
+    launch_rmsnorm(hid, w.ln1, h->xnorm, n, H, c.rms_eps, nullptr, st);
+    if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, n, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
+    launch_rope_kv(h->qkv, n, seq_lens, nullptr, nullptr, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
+                   c.kv_page_size, c.rope_theta, st);
+    launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
+                       c.kv_page_size, st);
+    if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
+    launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st);
+    if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, n, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
+    launch_swiglu(h->gu, h->act, n, I, st);
+    if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
+  }
+  launch_rmsnorm(hid, h->w.final_norm, h->xlast, n, H, c.rms_eps, nullptr, st);
+  if ((rc = linear(h, h->xlast, h->w.lm_head, nullptr, logits_out, n, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;
+  inc_kernel<<<(n_seq + 127) / 128, 128, 0, st>>>(seq_lens, n_seq);
+  return check_cuda(h, "rvl_decode_step");
+}
+
+int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq, int32_t vocab, int32_t* unfinished,
+                      int32_t eos_id, int32_t pad_id, int32_t* next_tokens, float* entropy_out, rvl_stream stream) {
+  if (!h || !logits || !next_tokens) return fail(h, RVL_ERR_INVALID, "rvl_sample_greedy: null argument");
+  launch_sample_greedy(logits, n_seq, vocab, unfinished, eos_id, pad_id, next_tokens, entropy_out, nullptr, nullptr,
+                       static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_sample_greedy");
+}
+
+int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, int32_t n_seg, int32_t dim,
+                    const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows, float* scores_out,
+                    int32_t* topk_idx_out, rvl_stream stream) {
+  if (!h || !frames || !seg_offsets || !cls || !scores_out) return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: null argument");
+  if (dim % 8 || k < 1 || k > 16 || (norm_axis != 0 && norm_axis != 1) || max_seg_rows < 1 || max_seg_rows > 8192)
+    return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: need dim % 8 == 0, 1 <= k <= 16, norm_axis in {0,1}, max_seg_rows <= 8192");
+  launch_cosine_topk(frames, seg_offsets, n_seg, dim, cls, k, norm_axis, max_seg_rows, scores_out, topk_idx_out,
+                     static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_cosine_topk");
+}
+
+int rvl_select_topk(rvl_handle* h, const float* scores, int32_t n, int32_t k, int32_t* idx_out, rvl_stream stream) {
+  if (!h || !scores || !idx_out) return fail(h, RVL_ERR_INVALID, "rvl_select_topk: null argument");
+  if (n > 65536 || k > n) return fail(h, RVL_ERR_INVALID, "rvl_select_topk: need k <= n <= 65536");
+  launch_select_topk(scores, n, k, idx_out, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_select_topk");
+}
+
+// ------------------------------------------------------------------------------------------ single kernels
+int rvl_rmsnorm(rvl_handle* h, const float* x, const void* w, void* y, int64_t n_rows, int32_t dim, float eps,
+                const int32_t* rows, rvl_stream stream) {
+  if (!h || !x || !w || !y) return fail(h, RVL_ERR_INVALID, "rvl_rmsnorm: null argument");
+  if (dim % 4 || dim > 8192) return fail(h, RVL_ERR_INVALID, "rvl_rmsnorm: dim must be a multiple of 4 and <= 8192");
+  launch_rmsnorm(x, w, y, n_rows, dim, eps, rows, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_rmsnorm");
+}
+
+int rvl_rope_kv(rvl_handle* h, void* qkv, int64_t n_tokens, const int32_t* positions, const int32_t* tok_seq,
+                const int32_t* cu_seqlens, const int32_t* page_table, int32_t max_pages, int32_t layer, rvl_stream stream) {
+  if (!h || !qkv || !page_table) return fail(h, RVL_ERR_INVALID, "rvl_rope_kv: null argument");
+  if (!h->kv) return fail(h, RVL_ERR_STATE, "rvl_rope_kv: kv pages not set");
+  if (!positions && !(tok_seq && cu_seqlens)) return fail(h, RVL_ERR_INVALID, "rvl_rope_kv: need positions or (tok_seq, cu_seqlens)");
+  if (layer < 0 || layer >= h->cfg.n_layers) return fail(h, RVL_ERR_INVALID, "rvl_rope_kv: bad layer");
+  launch_rope_kv(qkv, n_tokens, positions, tok_seq, cu_seqlens, page_table, max_pages, k_pages(h, layer), v_pages(h, layer),
+                 h->cfg.n_heads, h->cfg.kv_page_size, h->cfg.rope_theta, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_rope_kv");
+}
+
+int rvl_swiglu(rvl_handle* h, const void* gu, void* act, int64_t n_tokens, int32_t intermediate, rvl_stream stream) {
+  if (!h || !gu || !act) return fail(h, RVL_ERR_INVALID, "rvl_swiglu: null argument");
+  if (intermediate % 8) return fail(h, RVL_ERR_INVALID, "rvl_swiglu: intermediate must be a multiple of 8");
+  launch_swiglu(gu, act, n_tokens, intermediate, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_swiglu");
+}
+
+int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const int32_t* cu_seqlens, int32_t n_seq,
+                     int32_t max_seqlen, rvl_stream stream) {
+  if (!h || !qkv || !out || !cu_seqlens) return fail(h, RVL_ERR_INVALID, "rvl_attn_prefill: null argument");
+  launch_attn_prefill(qkv, out, cu_seqlens, n_seq, max_seqlen, h->cfg.n_heads, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_attn_prefill");
+}
+
+int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int32_t* seq_lens, int32_t n_seq,
+                    const int32_t* page_table, int32_t max_pages, int32_t layer, rvl_stream stream) {
+  if (!h || !qkv || !out || !seq_lens || !page_table) return fail(h, RVL_ERR_INVALID, "rvl_attn_decode: null argument");
+  if (!h->kv) return fail(h, RVL_ERR_STATE, "rvl_attn_decode: kv pages not set");
+  if (layer < 0 || layer >= h->cfg.n_layers) return fail(h, RVL_ERR_INVALID, "rvl_attn_decode: bad layer");
+  launch_attn_decode(qkv, out, seq_lens, n_seq, page_table, max_pages, k_pages(h, layer), v_pages(h, layer), h->cfg.n_heads,
+                     h->cfg.kv_page_size, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_attn_decode");
+}
+
+}  // extern "C"

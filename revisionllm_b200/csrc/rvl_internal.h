@@ -1,0 +1,52 @@
+// Internal declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/revisionllm_b200.h"
+
+namespace rvl {
+
+struct GemmCall {
+  const void* A = nullptr;     // [M, K] bf16 activations (tokens)
+  const void* W = nullptr;     // [N, K] bf16 weights (features)
+  const void* bias = nullptr;  // [N] bf16 or null
+  void* out = nullptr;         // [M(rowmap), ldc] bf16 / fp32
+  int64_t M = 0, N = 0, K = 0, ldc = 0;
+  int out_mode = RVL_GEMM_OUT_BF16;
+  int flags = 0;
+  const int32_t* rowmap = nullptr;
+  int split_k = 1;
+};
+int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err);
+
+// elementwise.cu
+void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int dim, float eps, const int32_t* rows,
+                    cudaStream_t st);
+void launch_embed_rows(const void* table, const int32_t* ids, const int32_t* dst_rows, int n, int dim, int vocab,
+                       float* out, cudaStream_t st);
+void launch_scatter_rows_bf16(const void* src, const int32_t* dst_rows, int n, int dim, float* out, cudaStream_t st);
+void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const int32_t* tok_seq,
+                    const int32_t* cu_seqlens, const int32_t* page_table, int max_pages, void* k_pages, void* v_pages,
+                    int n_heads, int page_size, float theta, cudaStream_t st);
+void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaStream_t st);
+void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, int32_t* last_rows, int64_t total,
+                      cudaStream_t st);
+// attention.cu
+void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
+                         cudaStream_t st);
+void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
+                        int max_pages, const void* k_pages, const void* v_pages, int n_heads, int page_size,
+                        cudaStream_t st);
+// sampling.cu
+void launch_sample_greedy(const float* logits, int n_seq, int vocab, int32_t* unfinished, int eos_id, int pad_id,
+                          int32_t* next_tokens, float* entropy_out, int32_t* seq_lens, int32_t* n_unfinished,
+                          cudaStream_t st);
+// scoring.cu
+void launch_cosine_topk(const void* frames, const int32_t* seg_offsets, int n_seg, int dim, const void* cls, int k,
+                        int norm_axis, int max_seg_rows, float* scores_out, int32_t* topk_idx_out, cudaStream_t st);
+void launch_select_topk(const float* scores, int n, int k, int32_t* idx_out, cudaStream_t st);
+
+}  // namespace rvl
