@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the stage-1 dense sweep (BASELINE.json metric: segments/sec, Vicuna-7B shape,
+100-frame segments) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                         # the reference's CPU fp32 path (oracle port)
+
+A step = one pass of the hot path over one synthetic 1-hour MAD-shaped movie-query: 180 segments x 100
+CLIP frames (768-d), 85 prompt ids (one <video> placeholder) -> L = 184, projector + splice + varlen
+prefill + 16 greedy KV-cached decode steps + per-step entropy + CLIP cosine top-3 score per segment
+(BASELINE.json configs[1]).  With N > 1 each rank sweeps its own movie-query (the reference shards its
+eval by query, eval_nlq_negative.py:179-180) and one all-gather of the fixed-size per-segment records
+closes the step: weak scaling.  `--scaling strong` shards ONE movie's segments round-robin instead
+(BASELINE.json configs[2]).
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the
+public sweep API with pinned host features and a device->host read of the records every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "segments/sec (Vicuna-7B, 100-frame segs)"
+N_SEG, N_FRAMES, NEW_TOKENS = 180, 100, 16
+# algorithmic work per unit (BASELINE.md section 3 / SURVEY.md section 8d)
+FLOP_PER_TOKEN = 12.952e9
+WEIGHT_BYTES_PER_STEP = 13.214e9
+KV_BYTES_PER_TOKEN = 0.524288e6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        load = [c for c in sm if c >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_segment(weights_f32, cfg, feats_1, ids, new_tokens):
+    """The reference's CPU fp32 path restated (oracle/): projector + splice + prefill + greedy decode of ONE segment."""
+    from oracle import llama_ref, splice_ref
+    shape = llama_ref.LlamaShape(cfg.hidden, cfg.n_layers, cfg.n_heads, cfg.head_dim, cfg.intermediate, cfg.vocab,
+                                 cfg.rms_eps, cfg.rope_theta, cfg.adapter_dim)
+    t0 = time.perf_counter()
+    x = torch.stack(splice_ref.splice(weights_f32, ids[None], splice_ref.mm_projector_linear(weights_f32, feats_1)))
+    toks, scores = llama_ref.greedy_decode(weights_f32, shape, x, new_tokens, stop_on_eos=False)
+    return toks[0], torch.stack(scores)[:, 0], time.perf_counter() - t0
+
+
+def host_weights_f32(sd_bf16):
+    return {k: v.detach().to("cpu").float() for k, v in sd_bf16.items()}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  /root/reference does not exist on
+    the GPU box and the decoder arithmetic lives in `transformers` (not vendored), so this is the oracle port
+    (kind 'port'), fp32, all host threads, one segment per step."""
+    if rank != 0:
+        return
+    from revisionllm_b200 import synthetic as syn
+    cfg = syn.VICUNA_7B
+    torch.set_num_threads(os.cpu_count() or 1)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sd = syn.make_llama_weights(cfg, seed=0, device=dev)
+    w = host_weights_f32(sd)
+    del sd
+    if dev == "cuda":
+        torch.cuda.empty_cache()
+    feats = syn.make_features(N_SEG, N_FRAMES, cfg.adapter_dim, seed=1)
+    ids = syn.make_prompt_ids(cfg, seed=2)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, _, dt = oracle_segment(w, cfg, feats[i % N_SEG: i % N_SEG + 1].float(), ids, NEW_TOKENS)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = len(times) / total
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "stage1_sweep_1h_movie", "segments": N_SEG, "frames": N_FRAMES, "seq_len": 184,
+                       "new_tokens": NEW_TOKENS, "sample": "1 segment per step"},
+            "cpu_baseline": {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
+                             "sample": f"1 segment (L=184, {NEW_TOKENS} greedy tokens) per step, fp32, torch {torch.__version__}"},
+            "e2e": {"value": val, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--segments", type=int, default=N_SEG)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from revisionllm_b200 import _cabi, scoring, sweep, synthetic as syn
+    from revisionllm_b200.model import RevisionConfig, RevisionLlamaForCausalLM
+    cfg = syn.VICUNA_7B
+    n_seg = args.segments
+    sd = syn.make_llama_weights(cfg, seed=0, device="cuda")
+    keep_for_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    sd_cpu_src = dict(sd) if keep_for_cpu else None
+    model = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg), sd).bfloat16().cuda(local_rank)
+    eng = model.engine
+    dev = model.device
+    # every rank: its own movie-query (weak) or the same movie (strong)
+    movie_seed = 1 + (rank if args.scaling == "weak" else 0)
+    feats_host = syn.make_features(n_seg, N_FRAMES, cfg.adapter_dim, seed=movie_seed).pin_memory()
+    ids = syn.make_prompt_ids(cfg, seed=2)
+    g = torch.Generator().manual_seed(3)
+    cls_host = torch.randn(cfg.adapter_dim, generator=g).to(torch.bfloat16).pin_memory()
+    feats_dev, cls_dev, ids_dev = feats_host.to(dev), cls_host.to(dev), ids.to(dev)
+    seq_len = ids.shape[0] - 1 + N_FRAMES
+
+    def resident_step():
+        if args.scaling == "strong":
+            mine = torch.from_numpy(sweep.shard_indices(n_seg, rank, world)).to(dev)
+            local = sweep.score_segments(model, feats_dev.index_select(0, mine), ids_dev, cls_dev, NEW_TOKENS, eos_token_id=None)
+            return sweep.allgather_records(local, n_seg, rank, world)
+        local = sweep.score_segments(model, feats_dev, ids_dev, cls_dev, NEW_TOKENS, eos_token_id=None)
+        if world > 1:
+            out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=dev)
+            dist.all_gather_into_tensor(out, local)
+            return out
+        return local
+
+    def e2e_step():
+        if args.scaling == "strong":
+            res = sweep.stage1_sweep(model, feats_host, ids, cls_host, NEW_TOKENS, rank, world, eos_token_id=None)
+            return res.records.cpu()
+        local = sweep.score_segments(model, feats_host, ids, cls_host, NEW_TOKENS, eos_token_id=None)
+        if world > 1:
+            out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=dev)
+            dist.all_gather_into_tensor(out, local)
+            local = out
+        return local.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    units_per_step = n_seg * (world if args.scaling == "weak" else 1)
+    for _ in range(max(args.warmup, 3)):
+        rec = resident_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        rec = resident_step()
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launches - launches0
+    # ---- e2e: host features in, records out, every step
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rec_host = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- one extra profiled step: per-launch CUDA events on the launching stream (roofline numerators)
+    eng.profile(True)
+    resident_step()
+    torch.cuda.synchronize()
+    eng.profile(False)
+    pk = peaks()
+    gemm = eng.profile_read(0)
+    gemm_small = eng.profile_read(1)
+    attn_p = eng.profile_read(2)
+    attn_d = eng.profile_read(3)
+    n_local = n_seg if args.scaling == "weak" else len(sweep.shard_indices(n_seg, rank, world))
+    # decode step t reads K and V of (seq_len + t + 1) tokens per sequence, all layers
+    attn_d_bytes = sum(n_local * KV_BYTES_PER_TOKEN * (seq_len + t + 1) for t in range(NEW_TOKENS - 1))
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (prefill GEMMs: qkv, o, gate|up, down, projector)",
+        "achieved": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else None,
+        "peak": pk["tf_sust"], "unit": "TFLOP/s", "peak_source": pk["src"] + ", sustained bf16",
+        "frac": (gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / pk["tf_sust"]) if gemm["ms"] > 0 else None,
+        "traffic": None, "launches": gemm["launches"], "ms_in_step": gemm["ms"],
+        "decode_gemm": {"bound": "hbm", "achieved": gemm_small["bytes"] / (gemm_small["ms"] * 1e-3) / 1e9 if gemm_small["ms"] > 0 else None,
+                        "peak": pk["hbm"], "unit": "GB/s", "ms_in_step": gemm_small["ms"], "launches": gemm_small["launches"]},
+        "decode_attention": {"bound": "hbm", "achieved": attn_d_bytes / (attn_d["ms"] * 1e-3) / 1e9 if attn_d["ms"] > 0 else None,
+                             "peak": pk["hbm"], "unit": "GB/s", "ms_in_step": attn_d["ms"], "launches": attn_d["launches"]},
+        "prefill_attention_ms_in_step": attn_p["ms"],
+    }
+    if roofline["decode_gemm"]["achieved"]:
+        roofline["decode_gemm"]["frac"] = roofline["decode_gemm"]["achieved"] / pk["hbm"]
+    if roofline["decode_attention"]["achieved"]:
+        roofline["decode_attention"]["frac"] = roofline["decode_attention"]["achieved"] / pk["hbm"]
+
+    value = units_per_step * args.steps / (dev_ms * 1e-3)
+    e2e_val = units_per_step * args.steps / e2e_s
+    h2d = n_local * N_FRAMES * cfg.adapter_dim * 2 + ids.numel() * 8 + cfg.adapter_dim * 2
+    d2h = int(rec_host.numel() * 4)
+    line = {
+        "metric": METRIC, "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "stage1_sweep_1h_movie (BASELINE.json configs[1]): 180 segments x 100 frames, L=184, "
+                               "projector+splice+prefill+16 greedy decode steps+entropy+cosine top-3",
+                   "model": "Vicuna-7B shape (Llama-2-7B), random-init planted weights", "segments_per_rank_step": n_local,
+                   "seq_len": seq_len, "new_tokens": NEW_TOKENS, "parallelism": f"segment-parallel dp{world}",
+                   "l2": "inputs larger than L2: 13.2 GB of weights are streamed every prefill/decode pass"},
+        "prefill_tokens_per_s": units_per_step * seq_len * args.steps / (dev_ms * 1e-3),
+        "roofline": roofline,
+        "e2e": {"value": e2e_val, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    # ---- CPU baseline beside it (rank 0, N=1): the oracle port on ONE segment, and full-size parity of that segment
+    if keep_for_cpu:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 0
+        if avail > 48e9:
+            torch.set_num_threads(os.cpu_count() or 1)
+            w32 = host_weights_f32(sd_cpu_src)
+            sd_cpu_src = None
+            toks, sc, dt = oracle_segment(w32, cfg, feats_host[0:1].float(), ids, NEW_TOKENS)
+            out = model.generate(ids[None], images=feats_host[0:1], max_new_tokens=NEW_TOKENS, output_scores=True,
+                                 return_dict_in_generate=True, eos_token_id=None)
+            got = out["sequences"][0, ids.shape[0]:].cpu()
+            gsc = torch.stack(out["scores"])[:, 0].cpu()
+            rel = float((gsc.double() - sc.double()).abs().max() / sc.double().abs().max())
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "segments/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"1 of {n_seg} segments (L={seq_len}, {NEW_TOKENS} greedy tokens), fp32 oracle, {dt:.1f} s"}
+            line["parity_full_size"] = {"tokens_identical": bool(torch.equal(got.long(), toks.long())), "logit_max_rel_err": rel,
+                                        "segment": 0}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": "segments/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"skipped: only {avail / 1e9:.0f} GB host RAM available (fp32 7B needs 27 GB + headroom)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

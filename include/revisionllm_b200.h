@@ -163,7 +163,7 @@ RVL_API int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq,
  * Replaces similarity.py:71-94 `_topk_pooling` + the caller arithmetic
  * eval_nlq_negative.py:309-316 / eval_nlq_retrieval_e2e2.py:380-386:
  * normalise frames (norm_axis 1 = per frame, 0 = across the frame axis, the stage-1 driver's
- * quirk), sims = frames . cls, top-k frames (ties -> lowest index), score = dot(sum of the
+ * quirk, 2 = none: raw dot products as in _topk_pooling itself), sims = frames . cls, top-k frames (ties -> lowest index), score = dot(sum of the
  * top-k normalised frames, cls) = sum of the top-k sims.
  *   frames   [n_rows, dim] bf16;  seg_offsets [n_seg+1] int32 (rows of each proposal)
  *   cls      [dim] bf16;  scores_out [n_seg] fp32;  topk_idx_out [n_seg, k] int32 (-1 padded, may be NULL)
@@ -176,6 +176,18 @@ RVL_API int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* se
  * index (bit-exact given identical scores; BASELINE.json north_star). n <= 65536. */
 RVL_API int rvl_select_topk(rvl_handle* h, const float* scores, int32_t n, int32_t k, int32_t* idx_out,
                     rvl_stream stream);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+#define RVL_PROF_GEMM 0          /* tcgen05 GEMM, token-major (prefill) */
+#define RVL_PROF_GEMM_SMALL_M 1  /* tcgen05 GEMM, weight-streaming orientation (decode / last rows) */
+#define RVL_PROF_ATTN_PREFILL 2
+#define RVL_PROF_ATTN_DECODE 3
+/* Per-launch CUDA-event timing of the kernels rvl_prefill / rvl_decode_step enqueue, on the launching
+ * stream (bench.py's roofline numbers).  Off by default; enabling it (re)starts the recording. */
+RVL_API int rvl_profile_enable(rvl_handle* h, int32_t on, int32_t capacity);
+/* Sums over the recorded launches of one category: device ms, algorithmic FLOPs and bytes. Synchronises. */
+RVL_API int rvl_profile_read(rvl_handle* h, int32_t category, double* total_ms, double* total_flops,
+                     double* total_bytes, int64_t* launches);
 
 /* ---- individual kernels (unit parity tests and host-side composition) ------------------------ */
 

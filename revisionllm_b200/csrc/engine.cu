@@ -29,8 +29,29 @@ struct rvl_handle {
   // kv
   uint8_t* kv = nullptr;
   int32_t n_pages = 0;
+  // optional per-launch timing (bench.py roofline): CUDA event pairs on the launching stream
+  bool prof_on = false;
+  struct ProfRec { int cat; double flops, bytes; };
+  std::vector<cudaEvent_t> prof_ev;      // 2 per record
+  std::vector<ProfRec> prof_rec;
+  size_t prof_cap = 0;
   mutable std::string err;
 };
+
+namespace {
+struct ProfScope {
+  rvl_handle* h; cudaStream_t st; size_t idx; bool on;
+  ProfScope(const rvl_handle* hc, cudaStream_t s, int cat, double flops, double bytes)
+      : h(const_cast<rvl_handle*>(hc)), st(s), idx(0), on(false) {
+    if (!h->prof_on || h->prof_rec.size() >= h->prof_cap) return;
+    on = true;
+    idx = h->prof_rec.size();
+    h->prof_rec.push_back({cat, flops, bytes});
+    cudaEventRecord(h->prof_ev[2 * idx], st);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(h->prof_ev[2 * idx + 1], st); }
+};
+}  // namespace
 
 static thread_local std::string g_err;
 
@@ -167,6 +188,9 @@ static int linear(const rvl_handle* h, const void* x, const void* w, const void*
     }
   }
   std::string err;
+  const double out_b = (mode == RVL_GEMM_OUT_BF16 ? 2.0 : (mode == RVL_GEMM_ADD_F32 ? 8.0 : 4.0)) * tokens * features;
+  ProfScope ps(h, st, tokens <= 256 ? RVL_PROF_GEMM_SMALL_M : RVL_PROF_GEMM, 2.0 * tokens * features * K,
+               2.0 * features * K + 2.0 * tokens * K + out_b);
   int rc = gemm_bf16(c, h->num_sms, st, &err);
   if (rc) return fail(h, rc, err);
   return RVL_OK;
@@ -248,7 +272,11 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
     if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, T, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_rope_kv(h->qkv, T, nullptr, h->tok_seq, cu_seqlens, page_table, max_pages, k_pages(h, l), v_pages(h, l),
                    c.n_heads, c.kv_page_size, c.rope_theta, st);
-    launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st);
+    {
+      // causal FLOPs need the per-sequence lengths (device side); use the uniform-length bound T*max_seqlen
+      ProfScope ps(h, st, RVL_PROF_ATTN_PREFILL, 2.0 * T * max_seqlen * H, 2.0 * T * 4 * H);
+      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st);
+    }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hidden, T, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
     launch_rmsnorm(hidden, w.ln2, h->xnorm, T, H, c.rms_eps, nullptr, st);
     if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, T, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
@@ -290,8 +318,11 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
     if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, n, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_rope_kv(h->qkv, n, seq_lens, nullptr, nullptr, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
                    c.kv_page_size, c.rope_theta, st);
-    launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
-                       c.kv_page_size, st);
+    {
+      ProfScope ps(h, st, RVL_PROF_ATTN_DECODE, 0.0, 0.0);   // bytes depend on seq_lens: the caller supplies them
+      launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
+                         c.kv_page_size, st);
+    }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
     launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st);
     if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, n, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
@@ -316,8 +347,8 @@ int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offset
                     const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows, float* scores_out,
                     int32_t* topk_idx_out, rvl_stream stream) {
   if (!h || !frames || !seg_offsets || !cls || !scores_out) return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: null argument");
-  if (dim % 8 || k < 1 || k > 16 || (norm_axis != 0 && norm_axis != 1) || max_seg_rows < 1 || max_seg_rows > 8192)
-    return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: need dim % 8 == 0, 1 <= k <= 16, norm_axis in {0,1}, max_seg_rows <= 8192");
+  if (dim % 8 || k < 1 || k > 16 || (norm_axis < 0 || norm_axis > 2) || max_seg_rows < 1 || max_seg_rows > 8192)
+    return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: need dim % 8 == 0, 1 <= k <= 16, norm_axis in {0,1,2}, max_seg_rows <= 8192");
   launch_cosine_topk(frames, seg_offsets, n_seg, dim, cls, k, norm_axis, max_seg_rows, scores_out, topk_idx_out,
                      static_cast<cudaStream_t>(stream));
   return check_cuda(h, "rvl_cosine_topk");
@@ -328,6 +359,40 @@ int rvl_select_topk(rvl_handle* h, const float* scores, int32_t n, int32_t k, in
   if (n > 65536 || k > n) return fail(h, RVL_ERR_INVALID, "rvl_select_topk: need k <= n <= 65536");
   launch_select_topk(scores, n, k, idx_out, static_cast<cudaStream_t>(stream));
   return check_cuda(h, "rvl_select_topk");
+}
+
+// ------------------------------------------------------------------------------------------ profiling
+int rvl_profile_enable(rvl_handle* h, int32_t on, int32_t capacity) {
+  if (!h) return fail(h, RVL_ERR_INVALID, "rvl_profile_enable: null handle");
+  if (on) {
+    const size_t cap = capacity > 0 ? capacity : 16384;
+    while (h->prof_ev.size() < 2 * cap) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(h, RVL_ERR_CUDA, "rvl_profile_enable: cudaEventCreate failed");
+      h->prof_ev.push_back(e);
+    }
+    h->prof_cap = cap;
+    h->prof_rec.clear();
+    h->prof_rec.reserve(cap);
+  }
+  h->prof_on = on != 0;
+  return RVL_OK;
+}
+
+int rvl_profile_read(rvl_handle* h, int32_t category, double* total_ms, double* total_flops, double* total_bytes,
+                     int64_t* launches) {
+  if (!h || !total_ms || !total_flops || !total_bytes || !launches) return fail(h, RVL_ERR_INVALID, "rvl_profile_read: null argument");
+  double ms = 0, fl = 0, by = 0;
+  int64_t n = 0;
+  for (size_t i = 0; i < h->prof_rec.size(); ++i) {
+    if (h->prof_rec[i].cat != category) continue;
+    if (cudaEventSynchronize(h->prof_ev[2 * i + 1]) != cudaSuccess) return fail(h, RVL_ERR_CUDA, "rvl_profile_read: event sync failed");
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) != cudaSuccess) return fail(h, RVL_ERR_CUDA, "rvl_profile_read: elapsed failed");
+    ms += t; fl += h->prof_rec[i].flops; by += h->prof_rec[i].bytes; ++n;
+  }
+  *total_ms = ms; *total_flops = fl; *total_bytes = by; *launches = n;
+  return RVL_OK;
 }
 
 // ------------------------------------------------------------------------------------------ single kernels

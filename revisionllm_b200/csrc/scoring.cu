@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kScoreThreads) cosine_topk_kernel(const __nv_b
     }
     dot = warp_sum(dot);
     ss = warp_sum(ss);
-    if (lane == 0) sims[f] = norm_axis == 1 ? dot / sqrtf(ss) : dot;
+    if (lane == 0) sims[f] = norm_axis == 1 ? dot / sqrtf(ss) : dot;  // axis 0 is folded into s_w; 2 = raw dot
   }
   __syncthreads();
   // top-k by repeated arg-max over the (short) sims row; ties -> lowest index. Warp 0 only.

@@ -1,0 +1,339 @@
+"""Thin Python owner of one `rvl_handle`: device buffers (torch tensors) + calls into the C ABI.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only - every FLOP of
+the hot path runs in the kernels of `csrc/` behind `include/revisionllm_b200.h`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import GEMM_ADD_F32, GEMM_FLAG_RELU, GEMM_FLAG_SWAP, GEMM_OUT_BF16, GEMM_OUT_F32, RvlError
+
+
+@dataclass
+class EngineConfig:
+    hidden: int = 4096
+    n_layers: int = 32
+    n_heads: int = 32
+    head_dim: int = 128
+    intermediate: int = 11008
+    vocab: int = 32000
+    adapter_dim: int = 768
+    max_pos: int = 4096
+    kv_page_size: int = 32
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+
+    @classmethod
+    def from_synth(cls, s) -> "EngineConfig":
+        return cls(hidden=s.hidden, n_layers=s.n_layers, n_heads=s.n_heads, head_dim=s.head_dim,
+                   intermediate=s.intermediate, vocab=s.vocab, adapter_dim=s.adapter_dim, max_pos=s.max_pos,
+                   rms_eps=s.rms_eps, rope_theta=s.rope_theta)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise RvlError(f"{name}: expected a contiguous CUDA tensor of {dtype}, got {t.dtype} on {t.device}")
+    return t
+
+
+class Engine:
+    """One per (process, GPU).  Not thread-safe."""
+
+    def __init__(self, cfg: EngineConfig, device: Optional[int] = None):
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise RvlError("revisionllm_b200 needs an sm_100 GPU: torch.cuda.is_available() is False (no CPU fallback)")
+        self.cfg = cfg
+        self.device_index = torch.cuda.current_device() if device is None else device
+        self.device = torch.device("cuda", self.device_index)
+        c = _cabi.rvl_config(cfg.hidden, cfg.n_layers, cfg.n_heads, cfg.head_dim, cfg.intermediate, cfg.vocab,
+                             cfg.adapter_dim, cfg.max_pos, cfg.kv_page_size, self.device_index, cfg.rms_eps,
+                             cfg.rope_theta)
+        h = C.c_void_p()
+        _cabi.check(self.lib.rvl_create(C.byref(c), C.byref(h)), None, "rvl_create")
+        self.h = h
+        self._keep: List[torch.Tensor] = []      # bound weights stay alive as long as the engine
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_cap = (0, 0)
+        self._kv: Optional[torch.Tensor] = None
+        self.n_pages = 0
+        self.launches = 0                         # kernels enqueued through this engine (bench's gpu_launches)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rvl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        _cabi.check(rc, self.h, what)
+
+    # ------------------------------------------------------------------ weights
+    def bind_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """HF-named bf16 state dict -> fused per-layer tensors on this GPU, bound by pointer.
+        q/k/v and gate/up are concatenated once here (the 'one-time repack' of SURVEY.md section 8b)."""
+        cfg = self.cfg
+        dev = self.device
+
+        def g(name):
+            return sd[name].to(device=dev, dtype=torch.bfloat16).contiguous()
+
+        layers = (_cabi.rvl_layer_weights * cfg.n_layers)()
+        keep: List[torch.Tensor] = []
+        for i in range(cfg.n_layers):
+            p = f"model.layers.{i}."
+            wqkv = torch.cat([g(p + f"self_attn.{n}_proj.weight") for n in ("q", "k", "v")], dim=0).contiguous()
+            wgu = torch.cat([g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")], dim=0).contiguous()
+            wo, wd = g(p + "self_attn.o_proj.weight"), g(p + "mlp.down_proj.weight")
+            ln1, ln2 = g(p + "input_layernorm.weight"), g(p + "post_attention_layernorm.weight")
+            keep += [wqkv, wgu, wo, wd, ln1, ln2]
+            layers[i] = _cabi.rvl_layer_weights(wqkv.data_ptr(), wo.data_ptr(), wgu.data_ptr(), wd.data_ptr(),
+                                                ln1.data_ptr(), ln2.data_ptr())
+        emb, fn, head = g("model.embed_tokens.weight"), g("model.norm.weight"), g("lm_head.weight")
+        keep += [emb, fn, head]
+        pw = pb = None
+        if "model.mm_projector.weight" in sd:
+            pw, pb = g("model.mm_projector.weight"), g("model.mm_projector.bias")
+            keep += [pw, pb]
+        w = _cabi.rvl_weights(emb.data_ptr(), fn.data_ptr(), head.data_ptr(), _ptr(pw), _ptr(pb), layers)
+        self._check(self.lib.rvl_bind_weights(self.h, C.byref(w)), "rvl_bind_weights")
+        self._keep = keep
+        self.embed_tokens, self.lm_head_w, self.proj_w, self.proj_b = emb, head, pw, pb
+
+    # ------------------------------------------------------------------ buffers
+    def ensure_workspace(self, max_tokens: int, max_seqs: int):
+        if self._ws is not None and self._ws_cap[0] >= max_tokens and self._ws_cap[1] >= max_seqs:
+            return
+        max_tokens = max(max_tokens, self._ws_cap[0])
+        max_seqs = max(max_seqs, self._ws_cap[1])
+        nbytes = self.lib.rvl_workspace_bytes(self.h, max_tokens, max_seqs)
+        self._ws = None
+        self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.rvl_set_workspace(self.h, self._ws.data_ptr(), nbytes, max_tokens, max_seqs), "rvl_set_workspace")
+        self._ws_cap = (max_tokens, max_seqs)
+
+    def ensure_kv(self, n_pages: int):
+        if self._kv is not None and self.n_pages >= n_pages:
+            return
+        nbytes = self.lib.rvl_kv_bytes(self.h, n_pages)
+        self._kv = None
+        self._kv = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.rvl_set_kv(self.h, self._kv.data_ptr(), n_pages), "rvl_set_kv")
+        self.n_pages = n_pages
+
+    def kv_bytes(self, n_pages: int) -> int:
+        return self.lib.rvl_kv_bytes(self.h, n_pages)
+
+    # ------------------------------------------------------------------ hot path
+    def project_splice(self, feats, feat_dst, text_ids, text_dst, hidden_out):
+        n_feat = 0 if feats is None else feats.shape[0]
+        n_text = 0 if text_ids is None else text_ids.shape[0]
+        if n_feat:
+            _req(feats, torch.bfloat16, "feats"); _req(feat_dst, torch.int32, "feat_dst")
+        if n_text:
+            _req(text_ids, torch.int32, "text_ids"); _req(text_dst, torch.int32, "text_dst")
+        _req(hidden_out, torch.float32, "hidden_out")
+        self._check(self.lib.rvl_project_splice(self.h, _ptr(feats), _ptr(feat_dst), n_feat, _ptr(text_ids),
+                                                _ptr(text_dst), n_text, hidden_out.data_ptr(), hidden_out.shape[0],
+                                                _stream()), "rvl_project_splice")
+        self.launches += (1 if n_feat else 0) + (1 if n_text else 0)
+
+    def splice_rows(self, vis, vis_dst, text_ids, text_dst, hidden_out):
+        n_vis = 0 if vis is None else vis.shape[0]
+        n_text = 0 if text_ids is None else text_ids.shape[0]
+        if n_vis:
+            _req(vis, torch.bfloat16, "vis"); _req(vis_dst, torch.int32, "vis_dst")
+        _req(hidden_out, torch.float32, "hidden_out")
+        self._check(self.lib.rvl_splice_rows(self.h, _ptr(vis), _ptr(vis_dst), n_vis, _ptr(text_ids), _ptr(text_dst),
+                                             n_text, hidden_out.data_ptr(), hidden_out.shape[0], _stream()),
+                    "rvl_splice_rows")
+        self.launches += (1 if n_vis else 0) + (1 if n_text else 0)
+
+    def prefill(self, hidden, cu_seqlens, n_seq, max_seqlen, page_table, logits_out, all_logits=False):
+        _req(hidden, torch.float32, "hidden"); _req(cu_seqlens, torch.int32, "cu_seqlens")
+        _req(page_table, torch.int32, "page_table"); _req(logits_out, torch.float32, "logits_out")
+        T = hidden.shape[0]
+        self.ensure_workspace(T, n_seq)
+        self._check(self.lib.rvl_prefill(self.h, hidden.data_ptr(), cu_seqlens.data_ptr(), n_seq, T, max_seqlen,
+                                         page_table.data_ptr(), page_table.shape[1], logits_out.data_ptr(),
+                                         1 if all_logits else 0, _stream()), "rvl_prefill")
+        self.launches += 1 + 9 * self.cfg.n_layers + 2
+
+    def decode_step(self, token_ids, seq_lens, page_table, logits_out):
+        _req(token_ids, torch.int32, "token_ids"); _req(seq_lens, torch.int32, "seq_lens")
+        _req(page_table, torch.int32, "page_table"); _req(logits_out, torch.float32, "logits_out")
+        n = token_ids.shape[0]
+        self.ensure_workspace(n, n)
+        self._check(self.lib.rvl_decode_step(self.h, token_ids.data_ptr(), seq_lens.data_ptr(), n, page_table.data_ptr(),
+                                             page_table.shape[1], logits_out.data_ptr(), _stream()), "rvl_decode_step")
+        self.launches += 1 + 9 * self.cfg.n_layers + 3
+
+    def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
+        _req(logits, torch.float32, "logits"); _req(next_tokens, torch.int32, "next_tokens")
+        n, v = logits.shape
+        self._check(self.lib.rvl_sample_greedy(self.h, logits.data_ptr(), n, v, _ptr(unfinished), eos_id, pad_id,
+                                               next_tokens.data_ptr(), _ptr(entropy), _stream()), "rvl_sample_greedy")
+        self.launches += 1
+
+    def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True):
+        _req(frames, torch.bfloat16, "frames"); _req(seg_offsets, torch.int32, "seg_offsets"); _req(cls, torch.bfloat16, "cls")
+        n_seg = seg_offsets.shape[0] - 1
+        if max_seg_rows is None:
+            max_seg_rows = int(frames.shape[0])
+        scores = torch.empty(n_seg, dtype=torch.float32, device=frames.device)
+        idx = torch.empty((n_seg, k), dtype=torch.int32, device=frames.device) if want_idx else None
+        self._check(self.lib.rvl_cosine_topk(self.h, frames.data_ptr(), seg_offsets.data_ptr(), n_seg, frames.shape[1],
+                                             cls.data_ptr(), k, norm_axis, min(max_seg_rows, 8192), scores.data_ptr(),
+                                             _ptr(idx), _stream()), "rvl_cosine_topk")
+        self.launches += 1
+        return scores, idx
+
+    def select_topk(self, scores, k):
+        _req(scores, torch.float32, "scores")
+        idx = torch.empty(k, dtype=torch.int32, device=scores.device)
+        self._check(self.lib.rvl_select_topk(self.h, scores.data_ptr(), scores.shape[0], k, idx.data_ptr(), _stream()),
+                    "rvl_select_topk")
+        self.launches += 1
+        return idx
+
+    # ------------------------------------------------------------------ measurement
+    def profile(self, on: bool, capacity: int = 16384):
+        self._check(self.lib.rvl_profile_enable(self.h, 1 if on else 0, capacity), "rvl_profile_enable")
+
+    def profile_read(self, category: int):
+        ms, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        self._check(self.lib.rvl_profile_read(self.h, category, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)), "rvl_profile_read")
+        return dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
+
+    # ------------------------------------------------------------------ single kernels
+    def gemm(self, A, W, bias=None, out=None, out_mode=GEMM_OUT_BF16, flags=0, rowmap=None, split_k=1, ldc=None):
+        _req(A, torch.bfloat16, "A"); _req(W, torch.bfloat16, "W")
+        M, K = A.shape
+        N = W.shape[0]
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16 if out_mode == GEMM_OUT_BF16 else torch.float32, device=A.device)
+        ldc = out.shape[1] if ldc is None else ldc
+        self._check(self.lib.rvl_gemm_bf16(self.h, A.data_ptr(), W.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, ldc,
+                                           out_mode, flags, _ptr(rowmap), split_k, _stream()), "rvl_gemm_bf16")
+        self.launches += 1
+        return out
+
+    def rmsnorm(self, x, w, eps=None, rows=None):
+        _req(x, torch.float32, "x"); _req(w, torch.bfloat16, "w")
+        n = x.shape[0] if rows is None else rows.shape[0]
+        y = torch.empty((n, x.shape[1]), dtype=torch.bfloat16, device=x.device)
+        self._check(self.lib.rvl_rmsnorm(self.h, x.data_ptr(), w.data_ptr(), y.data_ptr(), n, x.shape[1],
+                                         self.cfg.rms_eps if eps is None else eps, _ptr(rows), _stream()), "rvl_rmsnorm")
+        self.launches += 1
+        return y
+
+    def rope_kv(self, qkv, page_table, layer, positions=None, tok_seq=None, cu_seqlens=None):
+        _req(qkv, torch.bfloat16, "qkv")
+        self._check(self.lib.rvl_rope_kv(self.h, qkv.data_ptr(), qkv.shape[0], _ptr(positions), _ptr(tok_seq),
+                                         _ptr(cu_seqlens), page_table.data_ptr(), page_table.shape[1], layer, _stream()),
+                    "rvl_rope_kv")
+        self.launches += 1
+
+    def swiglu(self, gu):
+        _req(gu, torch.bfloat16, "gu")
+        inter = gu.shape[1] // 2
+        act = torch.empty((gu.shape[0], inter), dtype=torch.bfloat16, device=gu.device)
+        self._check(self.lib.rvl_swiglu(self.h, gu.data_ptr(), act.data_ptr(), gu.shape[0], inter, _stream()), "rvl_swiglu")
+        self.launches += 1
+        return act
+
+    def attn_prefill(self, qkv, cu_seqlens, n_seq, max_seqlen):
+        _req(qkv, torch.bfloat16, "qkv")
+        out = torch.empty((qkv.shape[0], self.cfg.hidden), dtype=torch.bfloat16, device=qkv.device)
+        self._check(self.lib.rvl_attn_prefill(self.h, qkv.data_ptr(), out.data_ptr(), cu_seqlens.data_ptr(), n_seq,
+                                              max_seqlen, _stream()), "rvl_attn_prefill")
+        self.launches += 1
+        return out
+
+    def attn_decode(self, qkv, seq_lens, page_table, layer):
+        _req(qkv, torch.bfloat16, "qkv")
+        out = torch.empty((qkv.shape[0], self.cfg.hidden), dtype=torch.bfloat16, device=qkv.device)
+        self._check(self.lib.rvl_attn_decode(self.h, qkv.data_ptr(), out.data_ptr(), seq_lens.data_ptr(), qkv.shape[0],
+                                             page_table.data_ptr(), page_table.shape[1], layer, _stream()), "rvl_attn_decode")
+        self.launches += 1
+        return out
+
+    def kv_view(self, layer: int):
+        """(k, v) views [n_pages, n_heads, page, 128] bf16 of one layer's cache (tests only)."""
+        c = self.cfg
+        per = self.n_pages * c.n_heads * c.kv_page_size * c.head_dim
+        flat = self._kv.view(torch.bfloat16)
+        k = flat[(2 * layer) * per:(2 * layer + 1) * per].view(self.n_pages, c.n_heads, c.kv_page_size, c.head_dim)
+        v = flat[(2 * layer + 1) * per:(2 * layer + 2) * per].view(self.n_pages, c.n_heads, c.kv_page_size, c.head_dim)
+        return k, v
+
+
+# ---------------------------------------------------------------------- host-side splice planning
+def plan_splice(input_ids: np.ndarray, n_visual: Sequence[int], attention_mask: Optional[np.ndarray] = None,
+                max_length: Optional[int] = None, image_token: int = -200):
+    """Index math of `prepare_inputs_labels_for_multimodal`
+    (/root/reference/revisionllm/model/vtimellm_arch.py:149-244) without touching embeddings:
+    for each row drop masked ids, replace every placeholder by that row's next visual block, truncate to
+    `max_length`, and pack all rows back to back.
+
+    input_ids [B, Ltxt] int64; n_visual[i] = rows of the i-th visual block (blocks are consumed in
+    order, one per placeholder; a row without placeholder consumes one block and uses none of it).
+    Returns dict(cu_seqlens [B+1], text_ids, text_dst, vis_src, vis_dst, lengths) as int32 numpy arrays;
+    vis_src indexes rows of the concatenated visual blocks."""
+    B = input_ids.shape[0]
+    vis_start = np.concatenate([[0], np.cumsum(np.asarray(n_visual, dtype=np.int64))])
+    text_ids: List[int] = []
+    text_dst: List[int] = []
+    vis_src: List[int] = []
+    vis_dst: List[int] = []
+    cu = [0]
+    blk = 0
+    for b in range(B):
+        ids = input_ids[b]
+        if attention_mask is not None:
+            ids = ids[attention_mask[b].astype(bool)]
+        base = cu[-1]
+        pos = 0
+        limit = max_length if max_length is not None else 1 << 60
+        n_img = int((ids == image_token).sum())
+        if n_img == 0:
+            blk += 1                       # vtimellm_arch.py:168-176
+        for t in ids.tolist():
+            if t == image_token:
+                n = int(vis_start[blk + 1] - vis_start[blk])
+                for r in range(n):
+                    if pos < limit:
+                        vis_src.append(int(vis_start[blk]) + r)
+                        vis_dst.append(base + pos)
+                        pos += 1
+                blk += 1
+            else:
+                if pos < limit:
+                    text_ids.append(int(t))
+                    text_dst.append(base + pos)
+                    pos += 1
+        cu.append(base + pos)
+    i32 = lambda a: np.asarray(a, dtype=np.int32)
+    lengths = np.diff(np.asarray(cu, dtype=np.int64)).astype(np.int32)
+    return dict(cu_seqlens=i32(cu), text_ids=i32(text_ids), text_dst=i32(text_dst), vis_src=i32(vis_src),
+                vis_dst=i32(vis_dst), lengths=lengths)

@@ -1,0 +1,43 @@
+"""`inference()` - the call the eval drivers make per batch of windows.
+
+Mirrors /root/reference/revisionllm/inference.py:28-75: Vicuna-v1 prompt -> ids with the -200
+placeholder -> `model.generate(images=..., query_feats=...)` -> decoded, stripped strings plus the
+generate output (`['sequences']`, `['scores']`).  Callers: eval_nlq_negative.py:287,
+eval_nlq_retrieval_e2e2.py:353.
+"""
+from __future__ import annotations
+
+import torch
+
+from .constants import IMAGE_TOKEN_INDEX
+from .conversation import SeparatorStyle, conv_templates
+from .mm_utils import tokenizer_image_token
+
+
+def inference(model, image, query_feats, query, tokenizer, visual_memory=None, prefix_memory=None, return_list=False,
+              max_new_tokens: int = 1024, output_scores: bool = True):
+    if visual_memory is not None:
+        query = query + "<memory>"
+    conv = conv_templates["v1"].copy()
+    conv.append_message(conv.roles[0], query)
+    conv.append_message(conv.roles[1], None)
+    prompt = conv.get_prompt()
+    input_ids = tokenizer_image_token(prompt, tokenizer, IMAGE_TOKEN_INDEX, return_tensors="pt").unsqueeze(0)
+    input_ids = input_ids.repeat(image.shape[0], 1)
+    stop_str = conv.sep if conv.sep_style != SeparatorStyle.TWO else conv.sep2
+    with torch.inference_mode():
+        model_output = model.generate(
+            input_ids, images=image, query_feats=query_feats, do_sample=False, num_beams=1,
+            max_new_tokens=max_new_tokens, use_cache=True, visual_memory=visual_memory, prefix_memory=prefix_memory,
+            output_scores=output_scores, return_dict_in_generate=True, output_hidden_states=False)
+    output_ids = model_output["sequences"]
+    input_token_len = input_ids.shape[1]
+    outputs = tokenizer.batch_decode(output_ids[:, input_token_len:].cpu(), skip_special_tokens=True)
+    for i in range(len(outputs)):
+        outputs[i] = outputs[i].strip()
+        if outputs[i].endswith(stop_str):
+            outputs[i] = outputs[i][: -len(stop_str)]
+        outputs[i] = outputs[i].strip()
+    if len(outputs) == 1 and not return_list:
+        outputs = outputs[0]
+    return outputs, model_output

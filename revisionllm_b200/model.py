@@ -1,0 +1,367 @@
+"""Host-side mirror of the reference model surface, backed by the sm_100a kernels.
+
+Mirrors `VTimeLLMLlamaForCausalLM` (/root/reference/revisionllm/model/vtimellm_llama.py:23-110):
+`forward(...)` with the reference's keyword list (:38-56), `generate(input_ids, images=, query_feats=, ...)`
+as called by `inference()` (/root/reference/revisionllm/inference.py:45-59), `get_model()`,
+`get_input_embeddings()`, `.config`, `.bfloat16().cuda()`.  The splice index math follows
+`prepare_inputs_labels_for_multimodal` (/root/reference/revisionllm/model/vtimellm_arch.py:81-299).
+
+Differences, all deliberate and documented in DESIGN.md:
+  * decoding is greedy (BASELINE.json north_star) - `do_sample` / `temperature` are accepted and ignored;
+  * ragged batches are packed (cu_seqlens) instead of right-padded; outputs are re-padded on return;
+  * there is no CPU path: `.float()` / CPU placement raise.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import constants
+from ._cabi import RvlError
+from .engine import Engine, EngineConfig, plan_splice
+
+
+@dataclass
+class RevisionConfig:
+    """Subset of the HF/VTimeLLM config the reference touches (vtimellm_arch.py:106,172,241,257,291)."""
+    hidden_size: int = 4096
+    intermediate_size: int = 11008
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 32
+    vocab_size: int = 32000
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    max_position_embeddings: int = 4096
+    adapter_input_dim: int = 768
+    model_type: str = "VTimeLLM"
+    tokenizer_model_max_length: Optional[int] = None
+    tokenizer_padding_side: str = "right"
+    bos_token_id: int = 1
+    eos_token_id: int = 2
+    pad_token_id: Optional[int] = None
+    # stage-2 adapter switches (vtimellm_arch.py:12-31)
+    clip_adapter: bool = False
+    clip_adapter_text: bool = False
+    hierarchy: bool = False
+
+    @classmethod
+    def from_synth(cls, s, **kw) -> "RevisionConfig":
+        return cls(hidden_size=s.hidden, intermediate_size=s.intermediate, num_hidden_layers=s.n_layers,
+                   num_attention_heads=s.n_heads, vocab_size=s.vocab, rms_norm_eps=s.rms_eps, rope_theta=s.rope_theta,
+                   max_position_embeddings=s.max_pos, adapter_input_dim=s.adapter_dim, **kw)
+
+    def engine_config(self) -> EngineConfig:
+        return EngineConfig(hidden=self.hidden_size, n_layers=self.num_hidden_layers, n_heads=self.num_attention_heads,
+                            head_dim=self.hidden_size // self.num_attention_heads, intermediate=self.intermediate_size,
+                            vocab=self.vocab_size, adapter_dim=self.adapter_input_dim, max_pos=self.max_position_embeddings,
+                            rms_eps=self.rms_norm_eps, rope_theta=self.rope_theta)
+
+
+class KVState:
+    """What `past_key_values` is here: the paged-cache bookkeeping of one live batch."""
+
+    def __init__(self, page_table: torch.Tensor, seq_lens: torch.Tensor, reserve: int, lengths: np.ndarray):
+        self.page_table, self.seq_lens = page_table, seq_lens
+        self.reserve = reserve             # new tokens every sequence has pages for
+        self.lengths = lengths.copy()      # host copy of the prompt lengths
+        self.steps = 0                     # tokens appended since the prefill
+
+    def get_seq_length(self) -> int:
+        return int(self.lengths.max()) + self.steps
+
+
+class CausalLMOutput(dict):
+    """dict with attribute access (`out.logits`, `out['logits']`)."""
+    __getattr__ = dict.get
+
+
+class _Linear:
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class _Core:
+    """What `model.get_model()` returns: `.mm_projector`, `.embed_tokens`, `.config` and the adapter
+    flags the reference's splice consults."""
+
+    def __init__(self, outer):
+        self._outer = outer
+        self.config = outer.config
+        self.clip_adapter = outer.config.clip_adapter
+        self.hierarchy = outer.config.hierarchy
+
+    @property
+    def mm_projector(self):
+        e = self._outer.engine
+        return _Linear(e.proj_w, e.proj_b)
+
+    @property
+    def embed_tokens(self):
+        return self._outer.engine.embed_tokens
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+
+class RevisionLlamaForCausalLM:
+    def __init__(self, config: RevisionConfig, state_dict: Dict[str, torch.Tensor],
+                 clip_encoder_state: Optional[Dict[str, torch.Tensor]] = None):
+        self.config = config
+        self._sd = state_dict
+        self._clip_sd = clip_encoder_state
+        self.engine: Optional[Engine] = None
+        self.device = torch.device("cpu")
+        self.dtype = torch.bfloat16
+        self._warned_sampling = False
+        self.clip_encoder = None
+
+    # ---- placement (eval_nlq_negative.py:144-148 does `model.bfloat16().cuda()`)
+    def bfloat16(self):
+        return self
+
+    def eval(self):
+        return self
+
+    def float(self):
+        raise RvlError("fp32 execution is the CPU oracle's job (oracle/); this model only runs bf16 on sm_100")
+
+    def to(self, *args, **kw):
+        for a in list(args) + list(kw.values()):
+            if a == torch.float32:
+                return self.float()
+            if isinstance(a, (str, torch.device)) and torch.device(a).type == "cuda":
+                return self.cuda(torch.device(a).index)
+        return self
+
+    def cuda(self, device: Optional[int] = None):
+        if self.engine is None:
+            self.engine = Engine(self.config.engine_config(), device)
+            self.engine.bind_state_dict(self._sd)
+            self.device = self.engine.device
+            self._sd = None        # the engine keeps the device copies alive
+            if self._clip_sd is not None:
+                from .clip_encoder import ClipEncoder
+                self.clip_encoder = ClipEncoder(self.engine, self._clip_sd)
+                self._clip_sd = None
+        return self
+
+    def get_model(self):
+        return _Core(self)
+
+    def get_input_embeddings(self):
+        return self.engine.embed_tokens
+
+    def _need_engine(self):
+        if self.engine is None:
+            raise RvlError("call .cuda() first: the model only runs on an sm_100 GPU (no CPU fallback)")
+
+    # ---- visual adapter + splice ----------------------------------------------------------------
+    def _visual_blocks(self, images, query_feats):
+        """Returns (rows [n, 768 or hidden] bf16, n_visual per block, projected?)."""
+        dev = self.device
+        if isinstance(images, (list, tuple)):           # vtimellm_arch.py:102-109: list of [F_i, 768]
+            n_vis = [int(im.shape[0]) for im in images]
+            rows = torch.cat([im.reshape(-1, im.shape[-1]) for im in images], dim=0)
+            return rows.to(dev, torch.bfloat16).contiguous(), n_vis, False
+        if images.dim() == 4:                            # hierarchy: [b, v, t, d] -> one CLS row per segment (:114-121)
+            if self.clip_encoder is None:
+                raise RvlError("4-D `images` need the stage-2 ClipEncoder adapter (pass clip_encoder_state)")
+            b, v, t, d = images.shape
+            q_tok, q_mask = query_feats
+            feats = images.to(dev, torch.bfloat16).reshape(b * v, t, d).contiguous()
+            qt = q_tok.to(dev, torch.bfloat16)[:, None].expand(b, v, *q_tok.shape[1:]).reshape(b * v, *q_tok.shape[1:]).contiguous()
+            qm = q_mask.to(dev)[:, None].expand(b, v, q_mask.shape[1]).reshape(b * v, q_mask.shape[1]).contiguous()
+            cls_rows = self.clip_encoder(feats, qt, qm)          # [b*v, hidden] bf16
+            return cls_rows, [v] * b, True
+        B, F, D = images.shape                           # stage 1: [B, F, 768] through the Linear projector (:125)
+        return images.to(dev, torch.bfloat16).reshape(B * F, D).contiguous(), [F] * B, False
+
+    def _splice(self, input_ids, attention_mask, images, query_feats):
+        """Projector + splice into a packed fp32 residual stream.  Returns (hidden [T, H], plan)."""
+        eng = self.engine
+        rows, n_vis, projected = self._visual_blocks(images, query_feats)
+        ids_np = input_ids.detach().cpu().numpy().astype(np.int64)
+        am_np = None if attention_mask is None else attention_mask.detach().cpu().numpy().astype(bool)
+        plan = plan_splice(ids_np, n_vis, am_np, self.config.tokenizer_model_max_length, constants.IMAGE_TOKEN_INDEX)
+        dev = self.device
+        T = int(plan["cu_seqlens"][-1])
+        hidden = torch.empty((T, self.config.hidden_size), dtype=torch.float32, device=dev)
+        h2d = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)
+        text_ids, text_dst = h2d(plan["text_ids"]), h2d(plan["text_dst"])
+        vis_dst = h2d(plan["vis_dst"])
+        if plan["vis_src"].shape[0] != rows.shape[0] or not np.array_equal(plan["vis_src"], np.arange(rows.shape[0])):
+            rows = rows.index_select(0, h2d(plan["vis_src"]).long()).contiguous()   # truncation dropped some rows
+        if projected:
+            eng.splice_rows(rows, vis_dst, text_ids, text_dst, hidden)
+        else:
+            eng.project_splice(rows, vis_dst, text_ids, text_dst, hidden)
+        return hidden, plan
+
+    def _alloc_kv(self, lengths: np.ndarray, extra: int) -> KVState:
+        eng = self.engine
+        ps = eng.cfg.kv_page_size
+        pages_per = [int(math.ceil((int(l) + extra) / ps)) for l in lengths]
+        max_pages = max(pages_per)
+        total = sum(pages_per)
+        eng.ensure_kv(total)
+        table = np.zeros((len(lengths), max_pages), dtype=np.int32)
+        nxt = 0
+        for i, n in enumerate(pages_per):
+            table[i, :n] = np.arange(nxt, nxt + n, dtype=np.int32)
+            nxt += n
+        dev = self.device
+        return KVState(torch.from_numpy(table).to(dev), torch.from_numpy(lengths.astype(np.int32)).to(dev), extra, lengths)
+
+    # ---- forward (vtimellm_llama.py:38-90) ---------------------------------------------------------
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, images=None,
+                visual_memory=None, prefix_memory=None, query_feats=None, return_dict=None, start_end_frame=None,
+                iteration_step=None, logits_to_keep: int = 0, reserve_new_tokens: int = 64):
+        self._need_engine()
+        if visual_memory is not None or prefix_memory is not None:
+            raise NotImplementedError("the <memory> streaming branch (vtimellm_arch.py:208-232) is listed as 'next' in SURVEY.md section 8f")
+        if labels is not None or output_attentions:
+            raise NotImplementedError("training-time outputs are out of scope (inference path only)")
+        eng, cfg = self.engine, self.config
+        dev = self.device
+        with torch.cuda.device(dev):
+            if past_key_values is not None and input_ids is not None and input_ids.shape[1] == 1:
+                # decode step: position = tokens so far (vtimellm_arch.py:88-100)
+                kv: KVState = past_key_values
+                if kv.steps + 1 > kv.reserve:
+                    raise RvlError("KV pages exhausted: pass a larger reserve_new_tokens to the prefill forward()")
+                B = input_ids.shape[0]
+                logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.decode_step(input_ids.reshape(B).to(dev, torch.int32).contiguous(), kv.seq_lens, kv.page_table, logits)
+                kv.steps += 1
+                return CausalLMOutput(logits=logits[:, None, :], past_key_values=kv)
+            if inputs_embeds is not None:
+                B, L, H = inputs_embeds.shape
+                am = torch.ones((B, L), dtype=torch.bool) if attention_mask is None else attention_mask.bool().cpu()
+                lengths = am.sum(1).numpy().astype(np.int32)
+                hidden = inputs_embeds.to(dev)[am.to(dev)].float().contiguous()
+                cu = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+            else:
+                if images is None:
+                    raise RvlError("forward() without `images` or `inputs_embeds` is not part of the scoring path")
+                hidden, plan = self._splice(input_ids, attention_mask, images, query_feats)
+                lengths, cu = plan["lengths"], plan["cu_seqlens"]
+            B = len(lengths)
+            kv = self._alloc_kv(lengths, reserve_new_tokens)
+            cu_d = torch.from_numpy(cu).to(dev)
+            Lmax, T = int(lengths.max()), int(cu[-1])
+            if logits_to_keep == 1:
+                last = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.prefill(hidden, cu_d, B, Lmax, kv.page_table, last, all_logits=False)
+                return CausalLMOutput(logits=last[:, None, :], past_key_values=kv)
+            flat = torch.empty((T, cfg.vocab_size), dtype=torch.float32, device=dev)
+            eng.prefill(hidden, cu_d, B, Lmax, kv.page_table, flat, all_logits=True)
+            logits = torch.zeros((B, Lmax, cfg.vocab_size), dtype=torch.float32, device=dev)   # right padded
+            for b in range(B):
+                logits[b, : lengths[b]] = flat[cu[b]: cu[b + 1]]
+            return CausalLMOutput(logits=logits, past_key_values=kv)
+
+    __call__ = forward
+
+    # ---- generate (inference.py:45-59) ---------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids, images=None, query_feats=None, do_sample=False, temperature=1.0, num_beams=1,
+                 max_new_tokens=1024, use_cache=True, visual_memory=None, prefix_memory=None, output_scores=False,
+                 return_dict_in_generate=False, output_hidden_states=False, attention_mask=None,
+                 eos_token_id="config", pad_token_id=None, stopping_criteria=None, **unused):
+        self._need_engine()
+        if num_beams != 1:
+            raise NotImplementedError("beam search is not part of the reference path (num_beams=1, inference.py:49)")
+        if visual_memory is not None or prefix_memory is not None:
+            raise NotImplementedError("the <memory> streaming branch is listed as 'next' in SURVEY.md section 8f")
+        if images is None:
+            raise RvlError("generate() needs `images` (pre-extracted CLIP features)")
+        if do_sample and not self._warned_sampling:
+            warnings.warn("revisionllm_b200 decodes greedily (BASELINE.json north_star); do_sample/temperature are ignored")
+            self._warned_sampling = True
+        eng, cfg = self.engine, self.config
+        dev = self.device
+        eos = cfg.eos_token_id if eos_token_id == "config" else eos_token_id
+        pad = pad_token_id if pad_token_id is not None else (cfg.pad_token_id if cfg.pad_token_id is not None else (eos if eos is not None else 0))
+        with torch.cuda.device(dev):
+            hidden, plan = self._splice(input_ids, attention_mask, images, query_feats)
+            lengths, cu = plan["lengths"], plan["cu_seqlens"]
+            B = len(lengths)
+            room = cfg.max_position_embeddings - int(lengths.max())
+            if room <= 0:
+                raise RvlError(f"prompt of {int(lengths.max())} tokens exceeds max_position_embeddings={cfg.max_position_embeddings}")
+            max_new = min(int(max_new_tokens), room)
+            # KV pages: everything up front when small, else grow in chunks of 64 tokens as decoding proceeds
+            chunk = max_new if max_new <= 64 else 64
+            kv = self._alloc_kv(lengths, chunk)
+            cu_d = torch.from_numpy(cu).to(dev)
+            logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+            eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
+            del hidden
+            tokens = torch.empty((max_new, B), dtype=torch.int32, device=dev)
+            entropies = torch.empty((max_new, B), dtype=torch.float32, device=dev)
+            unfinished = torch.ones(B, dtype=torch.int32, device=dev) if eos is not None else None
+            scores: List[torch.Tensor] = []
+            n_steps = 0
+            for t in range(max_new):
+                eng.sample_greedy(logits, tokens[t], entropies[t], unfinished, -1 if eos is None else eos, pad)
+                if output_scores:
+                    scores.append(logits)
+                n_steps = t + 1
+                if unfinished is not None and int(unfinished.sum().item()) == 0:     # vtimellm_llama.py:359-362
+                    break
+                if t == max_new - 1:
+                    break
+                if t + 1 > kv.reserve:
+                    kv = self._grow_kv(kv, lengths, t + 1 + chunk)
+                if output_scores:
+                    logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.decode_step(tokens[t], kv.seq_lens, kv.page_table, logits)
+                kv.steps += 1
+            new_tokens = tokens[:n_steps].t().contiguous()
+            ids_dev = input_ids.to(dev)
+            sequences = torch.cat([ids_dev, new_tokens.to(ids_dev.dtype)], dim=1)     # prompt ids (placeholder echoed) + new
+            out = CausalLMOutput(sequences=sequences, scores=tuple(scores) if output_scores else None,
+                                 entropies=entropies[:n_steps].t().contiguous(), prompt_lengths=torch.from_numpy(lengths.copy()),
+                                 past_key_values=kv)
+        if return_dict_in_generate:
+            return out
+        return sequences
+
+    def _grow_kv(self, kv: KVState, lengths: np.ndarray, extra: int) -> KVState:
+        """Re-page with more room, copying the live cache (rare: only for > 64 new tokens)."""
+        eng = self.engine
+        old_table, old_kv, old_pages = kv.page_table, eng._kv, eng.n_pages
+        c = eng.cfg
+        eng._kv = None
+        eng.n_pages = 0
+        new = self._alloc_kv(lengths, extra)
+        per_old = old_pages * c.n_heads * c.kv_page_size * c.head_dim
+        per_new = eng.n_pages * c.n_heads * c.kv_page_size * c.head_dim
+        src, dst = old_kv.view(torch.bfloat16), eng._kv.view(torch.bfloat16)
+        page_elems = c.n_heads * c.kv_page_size * c.head_dim
+        n_old = old_table.shape[1]
+        o_idx = old_table.long().reshape(-1)
+        n_idx = new.page_table[:, :n_old].long().reshape(-1)
+        for half in range(2 * c.n_layers):
+            s = src[half * per_old:(half + 1) * per_old].view(old_pages, page_elems)
+            d = dst[half * per_new:(half + 1) * per_new].view(eng.n_pages, page_elems)
+            d[n_idx] = s[o_idx]
+        new.seq_lens = kv.seq_lens
+        new.steps = kv.steps
+        return new
+
+    # ---- construction helpers ----------------------------------------------------------------------
+    @classmethod
+    def from_synthetic(cls, synth_cfg, seed: int = 0, device: str = "cuda", clip_encoder: bool = False, **cfg_kw):
+        from . import synthetic as syn
+        sd = syn.make_llama_weights(synth_cfg, seed=seed, device=device)
+        clip_sd = syn.make_clip_encoder_weights(synth_cfg.hidden, seed=seed, device=device) if clip_encoder else None
+        cfg = RevisionConfig.from_synth(synth_cfg, clip_adapter=clip_encoder, clip_adapter_text=clip_encoder,
+                                        hierarchy=clip_encoder, **cfg_kw)
+        return cls(cfg, sd, clip_sd)

@@ -1,0 +1,122 @@
+"""Stage-1 dense sweep of a movie and the stage-2 pass, sharded segment-parallel across ranks.
+
+What the reference does with independent 1-GPU jobs that append JSONL files merged later by file
+reads (/root/reference/revisionllm/eval/eval_nlq_negative.py:138,179-180,281-298,337;
+/root/reference/revisionllm/eval/metric_retrieval_forward.py:59-79) is done here inside one
+torchrun job: segment i of a movie goes to rank i mod R, every rank runs projector + splice +
+prefill + greedy decode + cosine scoring on its shard, and ONE small all-gather of a fixed-size
+per-segment record puts all results on every rank before stage-2 selection.  There is no other
+data-path collective: weights are replicated, segments are independent.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import scoring
+
+REC_TOKENS = 16
+# int32 words: 16 tokens | n_tokens | span_start | span_end | H_mean | H_max | cos   (floats stored as raw bits)
+REC_WORDS = REC_TOKENS + 6
+
+
+def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
+    """Round-robin: segment i -> rank i mod world."""
+    return np.arange(rank, n, world, dtype=np.int64)
+
+
+def pack_records(tokens: torch.Tensor, spans: torch.Tensor, h_mean: torch.Tensor, h_max: torch.Tensor,
+                 cos: torch.Tensor) -> torch.Tensor:
+    """tokens [n, T'<=16] int32, spans [n, 2] int32 (-1 = 'Not Present'), h_mean/h_max/cos [n] fp32 ->
+    [n, REC_WORDS] int32."""
+    n, t = tokens.shape
+    rec = torch.full((n, REC_WORDS), -1, dtype=torch.int32, device=tokens.device)
+    tt = min(t, REC_TOKENS)
+    rec[:, :tt] = tokens[:, :tt].to(torch.int32)
+    rec[:, REC_TOKENS] = tt
+    rec[:, REC_TOKENS + 1: REC_TOKENS + 3] = spans.to(torch.int32)
+    rec[:, REC_TOKENS + 3] = h_mean.to(torch.float32).contiguous().view(torch.int32)
+    rec[:, REC_TOKENS + 4] = h_max.to(torch.float32).contiguous().view(torch.int32)
+    rec[:, REC_TOKENS + 5] = cos.to(torch.float32).contiguous().view(torch.int32)
+    return rec
+
+
+def unpack_records(rec: torch.Tensor) -> Dict[str, torch.Tensor]:
+    f = lambda c: rec[:, c].contiguous().view(torch.float32)
+    return dict(tokens=rec[:, :REC_TOKENS], n_tokens=rec[:, REC_TOKENS], spans=rec[:, REC_TOKENS + 1: REC_TOKENS + 3],
+                h_mean=f(REC_TOKENS + 3), h_max=f(REC_TOKENS + 4), cos=f(REC_TOKENS + 5))
+
+
+def allgather_records(local: torch.Tensor, n_total: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """The single exchange step: every rank contributes its round-robin shard, every rank receives all
+    `n_total` records in global segment order.  A pure copy, so downstream selection is bit-exact."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    per = (n_total + world - 1) // world
+    buf = torch.full((per, REC_WORDS), -1, dtype=torch.int32, device=local.device)
+    buf[: local.shape[0]] = local
+    out = torch.empty((world * per, REC_WORDS), dtype=torch.int32, device=local.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    # rank r, slot j  ->  global segment j * world + r
+    out = out.view(world, per, REC_WORDS).transpose(0, 1).reshape(world * per, REC_WORDS)
+    return out[:n_total].contiguous()
+
+
+@dataclass
+class SweepResult:
+    records: torch.Tensor          # [n_segments, REC_WORDS] int32, global order, on every rank
+    local_indices: np.ndarray      # segments this rank scored
+    stage2_indices: Optional[torch.Tensor] = None
+
+
+def score_segments(model, seg_feats: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor],
+                   max_new_tokens: int = 16, decode_spans: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                   batch: Optional[int] = None, eos_token_id="config", norm_axis: int = scoring.NORM_PER_FRAME,
+                   ) -> torch.Tensor:
+    """Score `seg_feats` [n, F, 768] (host or device): generate up to `max_new_tokens` greedy tokens per
+    segment, entropy statistics from the device-side per-step entropies, CLIP cosine top-3 score of each
+    segment against `cls` [768].  Returns packed records [n, REC_WORDS] on the model's device."""
+    eng = model.engine
+    dev = model.device
+    n, F, D = seg_feats.shape
+    batch = n if batch is None else batch
+    recs = []
+    for s in range(0, n, batch):
+        feats = seg_feats[s: s + batch].to(dev, torch.bfloat16, non_blocking=True)
+        b = feats.shape[0]
+        ids = input_ids[None].expand(b, -1) if input_ids.dim() == 1 else input_ids[s: s + b]
+        out = model.generate(ids, images=feats, max_new_tokens=max_new_tokens, output_scores=False,
+                             return_dict_in_generate=True, eos_token_id=eos_token_id)
+        new_tok = out["sequences"][:, ids.shape[1]:].to(torch.int32)
+        ent = out["entropies"]
+        stats = scoring.entropy_stats_from_steps(ent)
+        if cls is not None:
+            offs = torch.arange(0, (b + 1) * F, F, dtype=torch.int32, device=dev)
+            cos, _ = eng.cosine_topk(feats.reshape(b * F, D), offs, cls.to(dev, torch.bfloat16).contiguous(), k=3,
+                                     norm_axis=norm_axis, max_seg_rows=F)
+        else:
+            cos = torch.zeros(b, dtype=torch.float32, device=dev)
+        spans = decode_spans(new_tok) if decode_spans is not None else torch.full((b, 2), -1, dtype=torch.int32, device=dev)
+        recs.append(pack_records(new_tok, spans.to(dev), stats[:, 2], stats[:, 0], cos))
+    return torch.cat(recs, dim=0)
+
+
+def stage1_sweep(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor],
+                 max_new_tokens: int = 16, rank: int = 0, world: int = 1, group=None, batch: Optional[int] = None,
+                 decode_spans=None, eos_token_id="config", stage2_topk: Optional[int] = None) -> SweepResult:
+    """`segments` [W, F, 768]: all windows of the movie (every rank holds the same host tensor; only the
+    local shard is copied to the GPU)."""
+    W = segments.shape[0]
+    mine = shard_indices(W, rank, world)
+    local = score_segments(model, segments[torch.from_numpy(mine)], input_ids, cls, max_new_tokens, decode_spans, batch,
+                           eos_token_id)
+    allrec = allgather_records(local, W, rank, world, group)
+    res = SweepResult(allrec, mine)
+    if stage2_topk is not None:
+        cos = unpack_records(allrec)["cos"]
+        res.stage2_indices = scoring.select_topk_segments(model.engine, cos, stage2_topk)
+    return res

@@ -1,0 +1,142 @@
+"""CPU tests of the host-side mirror (no GPU): prompt/tokenisation, splice planning, windows,
+selection rules, record packing, C-ABI surface."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scoring_ref, splice_ref
+from revisionllm_b200 import _cabi, conversation, mm_utils, scoring, sweep, synthetic as syn
+from revisionllm_b200.engine import plan_splice
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_prompt_and_tokenizer_match_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "prompt.npz"), allow_pickle=True)
+    tok = syn.StubTokenizer(32000)
+    for key, q in (("stage1", "<video>\nDuring which frames can we see a man opens the door?"),
+                   ("stage2", "<video>\nDuring which video can we see she picks up 2 cups?"),
+                   ("memory", "<video>\nWhere is the cat?<memory>")):
+        conv = conversation.conv_templates["v1"].copy()
+        conv.append_message(conv.roles[0], q)
+        conv.append_message(conv.roles[1], None)
+        prompt = conv.get_prompt()
+        assert prompt == str(g[key + "_prompt"])
+        ids = mm_utils.tokenizer_image_token(prompt, tok, -200, return_tensors="pt")
+        assert ids.tolist() == g[key + "_ids"].tolist()
+    # the template object must not leak messages between copies
+    assert conversation.conv_templates["v1"].messages == []
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_plan_splice_matches_oracle_splice(ragged):
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    B, F = 4, 7
+    ids = syn.make_prompt_ids(cfg, 5, 9, seed=3)[None].repeat(B, 1)
+    attn = None
+    if ragged:
+        attn = torch.ones_like(ids, dtype=torch.bool)
+        for b in range(B):
+            cut = (2 * b) % 5
+            if cut:
+                attn[b, -cut:] = False
+    feats = syn.make_features(B, F, cfg.adapter_dim, seed=4)
+    img = splice_ref.mm_projector_linear(w, feats)
+    ref = splice_ref.splice(w, ids, img, attention_mask=attn, max_length=18 if ragged else None)
+    plan = plan_splice(ids.numpy(), [F] * B, None if attn is None else attn.numpy(), 18 if ragged else None)
+    assert plan["lengths"].tolist() == [e.shape[0] for e in ref]
+    # rebuild the packed stream from the plan with the oracle's embeddings and compare
+    T = int(plan["cu_seqlens"][-1])
+    packed = torch.zeros(T, cfg.hidden)
+    emb = w["model.embed_tokens.weight"].float()
+    packed[torch.from_numpy(plan["text_dst"]).long()] = emb[torch.from_numpy(plan["text_ids"]).long()]
+    packed[torch.from_numpy(plan["vis_dst"]).long()] = img.reshape(B * F, -1)[torch.from_numpy(plan["vis_src"]).long()]
+    np.testing.assert_array_equal(packed.numpy(), torch.cat(ref).numpy())
+
+
+def test_plan_splice_row_without_placeholder_consumes_a_block():
+    ids = np.array([[1, 5, 6, 7], [1, -200, 8, 9]], dtype=np.int64)
+    plan = plan_splice(ids, [3, 3])
+    assert plan["lengths"].tolist() == [4, 6]
+    assert plan["vis_src"].tolist() == [3, 4, 5]          # row 1 uses the SECOND block (vtimellm_arch.py:168-176)
+    assert plan["vis_dst"].tolist() == [5, 6, 7]
+
+
+def test_windows_selection_and_merge_match_oracle():
+    for ctx, clip, nf in ((18000, 625, 250), (7200, 1000, 100), (700, 625, 250)):
+        np.testing.assert_array_equal(scoring.stage1_windows(ctx, clip, nf), scoring_ref.stage1_windows(ctx, clip, nf))
+        a, ta = scoring.stage2_windows(ctx, clip, nf, 5)
+        b, tb = scoring_ref.stage2_windows(ctx, clip, nf, 5)
+        np.testing.assert_array_equal(a, b)
+        assert ta == tb
+    assert scoring.nonoverlap_segments(18000, 100).shape == (180, 100)
+    answers = ["Not Present", "From 3 to 9.", "Not Present", "From 1 to 2.", "Not Present"] * 3
+    for batch in (4, 10, 33):
+        assert scoring.stage2_select_windows(answers, 40, batch) == scoring_ref.stage2_select_windows(answers, 40, batch)
+    assert scoring.parse_span("From 34 to 12.") == (12, 34) == scoring_ref.parse_span("From 34 to 12.")
+    assert scoring.parse_span("Not Present") is None
+    assert scoring.parse_first_int("video 17 and 3") == 17
+    cos, ent = [0.2, 0.5, 0.4], [1.0, 4.0, 2.0]
+    for mode in ("add", "multiply", "neg"):
+        assert scoring.merge_scores(cos, ent, mode) == scoring_ref.merge_scores(cos, ent, mode)
+
+
+def test_entropy_stats_from_steps_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(3, 5, 97, generator=g) * 2
+    ent = torch.stack([scoring_ref.step_entropy(logits[:, t]) for t in range(5)], dim=1)
+    np.testing.assert_allclose(scoring.entropy_stats_from_steps(ent).numpy(),
+                               scoring_ref.get_entropy_statistics(logits).numpy(), rtol=1e-6, atol=1e-6)
+    one = scoring.entropy_stats_from_steps(ent[:, :1])
+    assert one[:, 3].abs().max() == 0
+
+
+def test_record_pack_roundtrip_and_shards():
+    n = 7
+    tok = torch.arange(n * 5, dtype=torch.int32).view(n, 5)
+    spans = torch.tensor([[i, i + 3] for i in range(n)], dtype=torch.int32)
+    hm, hx, cs = torch.rand(n), torch.rand(n) + 1, torch.rand(n) - 0.5
+    rec = sweep.pack_records(tok, spans, hm, hx, cs)
+    un = sweep.unpack_records(rec)
+    assert rec.shape == (n, sweep.REC_WORDS) and rec.dtype == torch.int32
+    assert torch.equal(un["tokens"][:, :5], tok) and (un["tokens"][:, 5:] == -1).all()
+    assert torch.equal(un["spans"], spans) and torch.equal(un["h_mean"], hm) and torch.equal(un["cos"], cs)
+    all_idx = np.sort(np.concatenate([sweep.shard_indices(n, r, 3) for r in range(3)]))
+    assert all_idx.tolist() == list(range(n))
+
+
+def test_cabi_exports_every_symbol_the_header_declares():
+    header = open(os.path.join(ROOT, "include", "revisionllm_b200.h")).read()
+    declared = sorted(set(re.findall(r"RVL_API[^;(]*?\b(rvl_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_cabi.PROTOTYPES) == declared, "ctypes prototypes and header are out of sync"
+    assert lib.rvl_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert [e for e in exported if e.startswith("rvl_")] == declared
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the loud failure on a box without a GPU")
+def test_product_path_fails_loudly_without_gpu():
+    lib = _cabi.load()
+    h = ctypes.c_void_p()
+    cfg = _cabi.rvl_config(256, 2, 2, 128, 512, 512, 768, 1024, 32, 0, 1e-5, 10000.0)
+    rc = lib.rvl_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc != 0 and "no CPU fallback" in _cabi.last_error()
+    from revisionllm_b200.model import RevisionConfig, RevisionLlamaForCausalLM
+    model = RevisionLlamaForCausalLM(RevisionConfig.from_synth(syn.TINY), {})
+    with pytest.raises(_cabi.RvlError):
+        model.cuda()
+    with pytest.raises(_cabi.RvlError):
+        model.generate(torch.zeros(1, 4, dtype=torch.long), images=torch.zeros(1, 2, 768))
+    with pytest.raises(_cabi.RvlError):
+        model.float()
