@@ -230,6 +230,26 @@ RVL_API int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const in
 RVL_API int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int32_t* seq_lens, int32_t n_seq,
                     const int32_t* page_table, int32_t max_pages, int32_t layer, rvl_stream stream);
 
+/* ---- stage-2 adapter (ClipEncoder) kernels; the host composes them with rvl_gemm_bf16 ------------ */
+
+/* LayerNorm over the last dim (<= 1024, biased variance, like nn.LayerNorm; transformer.py:199-200):
+ * y = (x - mean) * rsqrt(var + eps) * w + b, or y = x when w == b == NULL.  Any of the outputs may be
+ * NULL: y_f32 (may alias x), y_bf16, y_pos_bf16 = bf16(y + pos[row % period]) (`with_pos_embed`,
+ * transformer.py:207-208).  x fp32 [rows, dim]; w, b bf16 [dim]; pos fp32 [period, dim]. */
+RVL_API int rvl_layernorm(rvl_handle* h, const float* x, const void* w, const void* b, float* y_f32, void* y_bf16,
+                  const float* pos, void* y_pos_bf16, int64_t rows, int32_t dim, int32_t period, float eps,
+                  rvl_stream stream);
+
+/* Multi-head attention with head_dim 96 and optional key padding (nn.MultiheadAttention core of
+ * transformer.py:216-217 and :288-289): for sequence s and head a,
+ *   out[s*Tq + t, a*96:(a+1)*96] = softmax_j(q[s*Tq + t] . k[kv(s)*Tk + j] / sqrt(96) + mask) v[kv(s)*Tk + j]
+ * q/k/v/out are bf16 with explicit row strides (elements), so they can be column slices of fused
+ * projections.  kv_seq_idx int32 [n_seq] (NULL: kv(s) = s) lets many query sequences share one key/value
+ * sequence (the text of a query is shared by all its segments).  key_mask fp32 [n_kv_seq, Tk], 0 = padded. */
+RVL_API int rvl_mha96(rvl_handle* h, const void* q, int64_t q_stride, const void* k, int64_t k_stride, const void* v,
+              int64_t v_stride, void* out, int64_t out_stride, int32_t n_seq, int32_t n_heads, int32_t Tq,
+              int32_t Tk, const int32_t* kv_seq_idx, const float* key_mask, rvl_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,6 +278,23 @@ class Engine:
         self.launches += 1
         return out
 
+    def layernorm(self, x, w=None, b=None, y_f32=None, y_bf16=None, pos=None, y_pos_bf16=None, period=0, eps=1e-5):
+        _req(x, torch.float32, "x")
+        rows, dim = x.shape
+        self._check(self.lib.rvl_layernorm(self.h, x.data_ptr(), _ptr(w), _ptr(b), _ptr(y_f32), _ptr(y_bf16), _ptr(pos),
+                                           _ptr(y_pos_bf16), rows, dim, period, eps, _stream()), "rvl_layernorm")
+        self.launches += 1
+
+    def mha96(self, q, k, v, out, n_seq, n_heads, Tq, Tk, kv_seq_idx=None, key_mask=None):
+        """q/k/v/out: 2-D bf16 views whose rows are `stride(0)` apart (column slices of fused projections are fine)."""
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+            if t.dtype != torch.bfloat16 or not t.is_cuda or t.stride(1) != 1:
+                raise RvlError(f"mha96: {n} must be a CUDA bf16 matrix with unit column stride")
+        self._check(self.lib.rvl_mha96(self.h, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                       out.data_ptr(), out.stride(0), n_seq, n_heads, Tq, Tk, _ptr(kv_seq_idx),
+                                       _ptr(key_mask), _stream()), "rvl_mha96")
+        self.launches += 1
+
     def kv_view(self, layer: int):
         """(k, v) views [n_pages, n_heads, page, 128] bf16 of one layer's cache (tests only)."""
         c = self.cfg

@@ -174,9 +174,10 @@ class RevisionLlamaForCausalLM:
             b, v, t, d = images.shape
             q_tok, q_mask = query_feats
             feats = images.to(dev, torch.bfloat16).reshape(b * v, t, d).contiguous()
-            qt = q_tok.to(dev, torch.bfloat16)[:, None].expand(b, v, *q_tok.shape[1:]).reshape(b * v, *q_tok.shape[1:]).contiguous()
-            qm = q_mask.to(dev)[:, None].expand(b, v, q_mask.shape[1]).reshape(b * v, q_mask.shape[1]).contiguous()
-            cls_rows = self.clip_encoder(feats, qt, qm)          # [b*v, hidden] bf16
+            # the reference repeats the query tokens/mask once per segment (vtimellm_arch.py:116-119); here every
+            # segment of batch row i just points at text i
+            seg_text = torch.arange(b, dtype=torch.int32, device=dev).repeat_interleave(v).contiguous()
+            cls_rows = self.clip_encoder(feats, q_tok.to(dev, torch.bfloat16), q_mask.to(dev), seg_text)   # [b*v, hidden] bf16
             return cls_rows, [v] * b, True
         B, F, D = images.shape                           # stage 1: [B, F, 768] through the Linear projector (:125)
         return images.to(dev, torch.bfloat16).reshape(B * F, D).contiguous(), [F] * B, False

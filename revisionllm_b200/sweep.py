@@ -120,3 +120,49 @@ def stage1_sweep(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Op
         cos = unpack_records(allrec)["cos"]
         res.stage2_indices = scoring.select_topk_segments(model.engine, cos, stage2_topk)
     return res
+
+
+def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tensor, grounding_windows: Sequence[int],
+                batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16, perm_seed: Optional[int] = 0,
+                answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config") -> List[Dict]:
+    """Stage-2 hierarchical pass (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:337-386).
+
+    `windows` [N, T, 768]: the selected stage-2 windows (already restricted to `grounding_windows`).  For each
+    zoom in (4, 2, 1): chunks of batch // zoom windows, permuted, each repeated `zoom` times, go through ONE
+    generate() call as a [1, batch, T, 768] hierarchy input (one ClipEncoder CLS token per window); the first
+    integer of the answer // zoom indexes the permuted chunk and is mapped back to a window id.
+    The reference permutes with an unseeded torch.randperm (:348); here the permutation comes from
+    `perm_seed` (None = identity) so runs are reproducible.
+    Returns one dict per generate() call: tokens, entropy stats (1/max, 1/mean as in :356-359), picked window."""
+    N = windows.shape[0]
+    gen = torch.Generator().manual_seed(perm_seed) if perm_seed is not None else None
+    out: List[Dict] = []
+    for zoom in zooms:
+        b = max(1, batch // zoom)
+        n_chunks = (N + b - 1) // b
+        for i in range(n_chunks):
+            start = i * b
+            end = min(start + b, N)
+            if end - start < b:
+                start = max(0, end - b)
+            feat = windows[start:end]
+            n = feat.shape[0]
+            idx = torch.randperm(n, generator=gen) if gen is not None else torch.arange(n)
+            feat = feat[idx]
+            if zoom > 1:
+                feat = feat.repeat_interleave(zoom, dim=0)
+            res = model.generate(input_ids[None], images=feat[None], query_feats=query_feats, max_new_tokens=max_new_tokens,
+                                 output_scores=False, return_dict_in_generate=True, eos_token_id=eos_token_id)
+            new_tok = res["sequences"][0, input_ids.shape[0]:]
+            stats = scoring.entropy_stats_from_steps(res["entropies"])[0]
+            number = answer_number(new_tok) if answer_number is not None else None
+            picked = None
+            if number is not None:
+                j = number // zoom
+                if j < n:
+                    j = int(idx[j])
+                j = min(max(start + j, 0), len(grounding_windows) - 1)
+                picked = int(grounding_windows[j])
+            out.append(dict(zoom=zoom, start=start, perm=idx.tolist(), tokens=new_tok.tolist(), inv_max_entropy=1.0 / float(stats[0]),
+                            inv_mean_entropy=1.0 / float(stats[2]), window=picked))
+    return out
