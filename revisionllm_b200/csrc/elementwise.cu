@@ -18,10 +18,14 @@ namespace rvl {
 // y(bf16) = x(fp32) * rsqrt(mean(x^2) + eps) * w(bf16).  One CTA per row, the row is held in
 // registers between the reduction and the scaling pass (read once, write once).
 // Algorithmic bytes per row: dim*4 (read) + dim*2 (write) (+ dim*2 weight, L2 resident).
+// Optional fused split-k reduction (decode): the row is first completed with the partial sums the preceding
+// weight-streaming GEMM left in `partials` ([n_partials][rows][dim] fp32) and written back as the new residual.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+__global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const __nv_bfloat16* __restrict__ w,
                                                            __nv_bfloat16* __restrict__ y, int dim, float eps,
-                                                           const int32_t* __restrict__ rows) {
+                                                           const int32_t* __restrict__ rows,
+                                                           const float* __restrict__ partials, int n_partials,
+                                                           long long partial_stride, float* x_out) {
   constexpr int kMaxVec = 8;  // float4 per thread -> dim <= THREADS * 32
   const long long src_row = rows ? rows[blockIdx.x] : blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + src_row * dim);
@@ -33,6 +37,11 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* __restric
     const int idx = threadIdx.x + i * THREADS;
     if (idx < nvec) {
       c[i] = xr[idx];
+      for (int p = 0; p < n_partials; ++p) {
+        const float4 q = reinterpret_cast<const float4*>(partials + p * partial_stride + src_row * dim)[idx];
+        c[i].x += q.x; c[i].y += q.y; c[i].z += q.z; c[i].w += q.w;
+      }
+      if (x_out) reinterpret_cast<float4*>(x_out + src_row * dim)[idx] = c[i];
       ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
     }
   }
@@ -60,14 +69,16 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* __restric
 }
 
 void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int dim, float eps, const int32_t* rows,
-                    cudaStream_t st) {
+                    cudaStream_t st, const float* partials, int n_partials, int64_t partial_stride, float* x_out) {
   if (n_rows <= 0) return;
   if (dim <= 128 * 32)
     rmsnorm_kernel<128><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
-        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows);
+        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows, partials,
+        n_partials, partial_stride, x_out);
   else
     rmsnorm_kernel<256><<<static_cast<unsigned>(n_rows), 256, 0, st>>>(
-        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows);
+        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows, partials,
+        n_partials, partial_stride, x_out);
 }
 
 // ------------------------------------------------------------------------------------ embedding / splice rows

@@ -25,6 +25,7 @@ struct rvl_handle {
   int32_t max_seqs = 0;
   void *xnorm = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr;
   float* dec_hidden = nullptr;
+  float* partials = nullptr;   // [kMaxSplit][max_seqs][hidden] fp32 split-k partial sums of the decode o/down GEMMs
   int32_t *tok_seq = nullptr, *last_rows = nullptr;
   // kv
   uint8_t* kv = nullptr;
@@ -67,8 +68,9 @@ static int check_cuda(const rvl_handle* h, const char* what) {
 }
 static inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
+constexpr int kMaxSplit = 8;
 struct WsLayout {
-  size_t xnorm, qkv, attn, gu, act, xlast, dec_hidden, tok_seq, last_rows, total;
+  size_t xnorm, qkv, attn, gu, act, xlast, dec_hidden, partials, tok_seq, last_rows, total;
 };
 static WsLayout ws_layout(const rvl_config& c, int64_t T, int32_t S) {
   WsLayout l{};
@@ -82,6 +84,7 @@ static WsLayout ws_layout(const rvl_config& c, int64_t T, int32_t S) {
   l.act = off; off += align_up(rows * I * 2);
   l.xlast = off; off += align_up(static_cast<size_t>(S) * H * 2);
   l.dec_hidden = off; off += align_up(static_cast<size_t>(S) * H * 4);
+  l.partials = off; off += align_up(static_cast<size_t>(kMaxSplit) * S * H * 4);
   l.tok_seq = off; off += align_up(rows * 4);
   l.last_rows = off; off += align_up(static_cast<size_t>(S) * 4);
   l.total = off;
@@ -149,6 +152,7 @@ int rvl_set_workspace(rvl_handle* h, void* ws, size_t bytes, int64_t max_tokens,
   h->ws = b; h->ws_bytes = bytes; h->max_tokens = max_tokens; h->max_seqs = max_seqs;
   h->xnorm = b + l.xnorm; h->qkv = b + l.qkv; h->attn = b + l.attn; h->gu = b + l.gu; h->act = b + l.act;
   h->xlast = b + l.xlast; h->dec_hidden = reinterpret_cast<float*>(b + l.dec_hidden);
+  h->partials = reinterpret_cast<float*>(b + l.partials);
   h->tok_seq = reinterpret_cast<int32_t*>(b + l.tok_seq); h->last_rows = reinterpret_cast<int32_t*>(b + l.last_rows);
   return RVL_OK;
 }
@@ -171,20 +175,22 @@ static void* v_pages(const rvl_handle* h, int layer) { return h->kv + kv_layer_h
 
 // ------------------------------------------------------------------------------------------ GEMM helper
 static int linear(const rvl_handle* h, const void* x, const void* w, const void* bias, void* out, int64_t tokens,
-                  int64_t features, int64_t K, int64_t ldc, int mode, int flags, const int32_t* rowmap, cudaStream_t st) {
+                  int64_t features, int64_t K, int64_t ldc, int mode, int flags, const int32_t* rowmap, cudaStream_t st,
+                  float* partial_buf = nullptr, int64_t partial_stride = 0, int* split_used = nullptr) {
   GemmCall c;
   c.A = x; c.W = w; c.bias = bias; c.out = out; c.M = tokens; c.N = features; c.K = K; c.ldc = ldc;
   c.out_mode = mode; c.flags = flags; c.rowmap = rowmap; c.split_k = 1;
   if (tokens <= 256) {
-    // few tokens (decode, lm_head on last rows): stream the weight through the 128-row MMA slot once
+    // few tokens (decode, lm_head on last rows): stream the weight through the 128-row MMA slot once; rows per tile
+    // and split-k are planned so the tiles fill all SMs in whole waves
     c.flags |= RVL_GEMM_FLAG_SWAP;
-    if (mode == RVL_GEMM_ADD_F32) {
-      const int tiles = static_cast<int>((features + 127) / 128);
-      int sk = (h->num_sms + tiles - 1) / tiles;
-      const int kb = static_cast<int>((K + 63) / 64);
-      if (sk > kb / 8) sk = kb / 8;   // keep >= 8 k-blocks (512 of K) per split
-      if (sk < 1) sk = 1;
-      c.split_k = sk;
+    c.auto_plan = true;
+    if (partial_buf) {
+      // residual GEMM (o_proj / down_proj): split-k partial sums, reduced by the RMSNorm that follows
+      c.out = partial_buf; c.out_mode = RVL_GEMM_OUT_F32; c.split_stride = partial_stride; c.max_split = kMaxSplit;
+      c.split_used = split_used;
+    } else if (mode == RVL_GEMM_ADD_F32) {
+      c.max_split = 1;
     }
   }
   std::string err;
@@ -312,9 +318,12 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
   const int64_t n = n_seq;
   float* hid = h->dec_hidden;
   launch_embed_rows(h->w.embed_tokens, token_ids, nullptr, n_seq, H, c.vocab, hid, st);
+  // o_proj / down_proj leave split-k partial sums in h->partials; the next RMSNorm adds them to the residual
+  const int64_t pstride = n * H;
+  int pending = 0;
   for (int l = 0; l < c.n_layers; ++l) {
     const rvl_layer_weights& w = h->layers[l];
-    launch_rmsnorm(hid, w.ln1, h->xnorm, n, H, c.rms_eps, nullptr, st);
+    launch_rmsnorm(hid, w.ln1, h->xnorm, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, pending ? hid : nullptr);
     if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, n, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_rope_kv(h->qkv, n, seq_lens, nullptr, nullptr, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
                    c.kv_page_size, c.rope_theta, st);
@@ -323,13 +332,13 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
       launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
                          c.kv_page_size, st);
     }
-    if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
-    launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st);
+    if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, pstride, &pending))) return rc;
+    launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
     if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, n, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_swiglu(h->gu, h->act, n, I, st);
-    if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
+    if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, pstride, &pending))) return rc;
   }
-  launch_rmsnorm(hid, h->w.final_norm, h->xlast, n, H, c.rms_eps, nullptr, st);
+  launch_rmsnorm(hid, h->w.final_norm, h->xlast, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
   if ((rc = linear(h, h->xlast, h->w.lm_head, nullptr, logits_out, n, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;
   inc_kernel<<<(n_seq + 127) / 128, 128, 0, st>>>(seq_lens, n_seq);
   return check_cuda(h, "rvl_decode_step");

@@ -18,13 +18,19 @@ struct GemmCall {
   int out_mode = RVL_GEMM_OUT_BF16;
   int flags = 0;
   const int32_t* rowmap = nullptr;
-  int split_k = 1;
+  int split_k = 1;             // explicit split (ignored when auto_plan picks one)
+  bool auto_plan = false;      // weight-streaming orientation: choose rows-per-tile and split-k from the SM count
+  int max_split = 0;           // cap for the planned split (capacity of the partial buffer)
+  int64_t split_stride = 0;    // > 0: split-k partials written to out + s * split_stride (fp32, no atomics)
+  int* split_used = nullptr;   // out: the split actually launched
 };
 int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err);
 
 // elementwise.cu
+// y = rmsnorm(x + sum_p partials[p]) ; when x_out != null the summed row is written back (residual update)
 void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int dim, float eps, const int32_t* rows,
-                    cudaStream_t st);
+                    cudaStream_t st, const float* partials = nullptr, int n_partials = 0, int64_t partial_stride = 0,
+                    float* x_out = nullptr);
 void launch_embed_rows(const void* table, const int32_t* ids, const int32_t* dst_rows, int n, int dim, int vocab,
                        float* out, cudaStream_t st);
 void launch_scatter_rows_bf16(const void* src, const int32_t* dst_rows, int n, int dim, float* out, cudaStream_t st);

@@ -51,13 +51,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug turns into a trap (reported as a CUDA error) instead of a hang
 // that would wedge the GPU.  try_wait itself suspends for a HW time slice, so the bound is seconds.
+static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  printf("rvl: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;   // fast path: already complete
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("rvl: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 24)) mbar_timeout(bar, parity);
   }
 }
 
@@ -79,6 +81,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
       "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+// Fire-and-forget prefetch of a 2D tile into L2 (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
