@@ -196,6 +196,8 @@ RVL_API int rvl_profile_read(rvl_handle* h, int32_t category, double* total_ms, 
 #define RVL_GEMM_ADD_F32 2      /* out(fp32) += A.B^T, in place, non-atomic */
 #define RVL_GEMM_FLAG_RELU 1
 #define RVL_GEMM_FLAG_SWAP 2    /* stream the weight as the 128-row MMA operand (small-M / decode) */
+#define RVL_GEMM_FLAG_STREAMK 4 /* with SWAP and a bound workspace: always deal the k-blocks evenly to the SMs (stream-K);
+                                   by default the library does so only when plain tiles leave a ragged last wave */
 
 /* out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]); A, W, bias bf16; fp32 accumulation in TMEM.
  * Replaces every nn.Linear on the path (cuBLAS via torch): q/k/v/o, gate/up/down, lm_head,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librevisionllm_b200.so")
 
 RVL_OK = 0
 GEMM_OUT_BF16, GEMM_OUT_F32, GEMM_ADD_F32 = 0, 1, 2
-GEMM_FLAG_RELU, GEMM_FLAG_SWAP = 1, 2
+GEMM_FLAG_RELU, GEMM_FLAG_SWAP, GEMM_FLAG_STREAMK = 1, 2, 4
 
 
 class RvlError(RuntimeError):

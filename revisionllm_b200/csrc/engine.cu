@@ -25,7 +25,11 @@ struct rvl_handle {
   int32_t max_seqs = 0;
   void *xnorm = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr;
   float* dec_hidden = nullptr;
-  float* partials = nullptr;   // [kMaxSplit][max_seqs][hidden] fp32 split-k partial sums of the decode o/down GEMMs
+  float* stream_ws = nullptr;        // stream-K partial tiles of the weight-streaming GEMMs: [num_sms][256][256] fp32
+  size_t stream_ws_bytes = 0;
+  unsigned int* stream_flags = nullptr;  // [num_sms] epoch flags
+  mutable unsigned int stream_epoch = 0;
+  float* partials = nullptr;             // [kMaxSplit][max_seqs][hidden] fp32 split-k partials of the decode o/down GEMMs
   int32_t *tok_seq = nullptr, *last_rows = nullptr;
   // kv
   uint8_t* kv = nullptr;
@@ -68,9 +72,10 @@ static int check_cuda(const rvl_handle* h, const char* what) {
 }
 static inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
+constexpr size_t kStreamWsBytes = 160ull * 2 * 8 * 8 * 128 * 16;   // up to 160 SMs x 2 A tiles x 128 KB of fp32 partial
 constexpr int kMaxSplit = 8;
 struct WsLayout {
-  size_t xnorm, qkv, attn, gu, act, xlast, dec_hidden, partials, tok_seq, last_rows, total;
+  size_t xnorm, qkv, attn, gu, act, xlast, dec_hidden, stream_ws, stream_flags, partials, tok_seq, last_rows, total;
 };
 static WsLayout ws_layout(const rvl_config& c, int64_t T, int32_t S) {
   WsLayout l{};
@@ -84,6 +89,8 @@ static WsLayout ws_layout(const rvl_config& c, int64_t T, int32_t S) {
   l.act = off; off += align_up(rows * I * 2);
   l.xlast = off; off += align_up(static_cast<size_t>(S) * H * 2);
   l.dec_hidden = off; off += align_up(static_cast<size_t>(S) * H * 4);
+  l.stream_ws = off; off += align_up(kStreamWsBytes);
+  l.stream_flags = off; off += align_up(1024);
   l.partials = off; off += align_up(static_cast<size_t>(kMaxSplit) * S * H * 4);
   l.tok_seq = off; off += align_up(rows * 4);
   l.last_rows = off; off += align_up(static_cast<size_t>(S) * 4);
@@ -152,7 +159,12 @@ int rvl_set_workspace(rvl_handle* h, void* ws, size_t bytes, int64_t max_tokens,
   h->ws = b; h->ws_bytes = bytes; h->max_tokens = max_tokens; h->max_seqs = max_seqs;
   h->xnorm = b + l.xnorm; h->qkv = b + l.qkv; h->attn = b + l.attn; h->gu = b + l.gu; h->act = b + l.act;
   h->xlast = b + l.xlast; h->dec_hidden = reinterpret_cast<float*>(b + l.dec_hidden);
+  h->stream_ws = reinterpret_cast<float*>(b + l.stream_ws);
+  h->stream_ws_bytes = kStreamWsBytes;
+  h->stream_flags = reinterpret_cast<unsigned int*>(b + l.stream_flags);
   h->partials = reinterpret_cast<float*>(b + l.partials);
+  h->stream_epoch = 0;
+  if (cudaMemset(h->stream_flags, 0, 1024) != cudaSuccess) return fail(h, RVL_ERR_CUDA, "rvl_set_workspace: cudaMemset failed");
   h->tok_seq = reinterpret_cast<int32_t*>(b + l.tok_seq); h->last_rows = reinterpret_cast<int32_t*>(b + l.last_rows);
   return RVL_OK;
 }
@@ -174,23 +186,30 @@ static void* k_pages(const rvl_handle* h, int layer) { return h->kv + kv_layer_h
 static void* v_pages(const rvl_handle* h, int layer) { return h->kv + kv_layer_half_bytes(h->cfg, h->n_pages) * (2 * layer + 1); }
 
 // ------------------------------------------------------------------------------------------ GEMM helper
+// partial_buf != null (decode o_proj / down_proj): the GEMM leaves `*split_used` fp32 partial sums
+// [split][tokens][features] there and the RMSNorm that follows adds them to the residual stream.
 static int linear(const rvl_handle* h, const void* x, const void* w, const void* bias, void* out, int64_t tokens,
                   int64_t features, int64_t K, int64_t ldc, int mode, int flags, const int32_t* rowmap, cudaStream_t st,
-                  float* partial_buf = nullptr, int64_t partial_stride = 0, int* split_used = nullptr) {
+                  float* partial_buf = nullptr, int* split_used = nullptr) {
   GemmCall c;
   c.A = x; c.W = w; c.bias = bias; c.out = out; c.M = tokens; c.N = features; c.K = K; c.ldc = ldc;
   c.out_mode = mode; c.flags = flags; c.rowmap = rowmap; c.split_k = 1;
   if (tokens <= 256) {
-    // few tokens (decode, lm_head on last rows): stream the weight through the 128-row MMA slot once; rows per tile
-    // and split-k are planned so the tiles fill all SMs in whole waves
+    // few tokens (decode, lm_head on last rows): stream the weight through the 128-row MMA slot once
     c.flags |= RVL_GEMM_FLAG_SWAP;
-    c.auto_plan = true;
     if (partial_buf) {
-      // residual GEMM (o_proj / down_proj): split-k partial sums, reduced by the RMSNorm that follows
-      c.out = partial_buf; c.out_mode = RVL_GEMM_OUT_F32; c.split_stride = partial_stride; c.max_split = kMaxSplit;
+      const int tiles = static_cast<int>((features + 127) / 128);
+      const int kb = static_cast<int>((K + 63) / 64);
+      int sk = h->num_sms / tiles;                       // fill the SMs once: 32 tiles x 4 splits
+      if (sk > kMaxSplit) sk = kMaxSplit;
+      while (sk > 1 && kb / sk < 8) --sk;
+      if (sk < 1) sk = 1;
+      c.split_k = sk;
+      c.out = partial_buf; c.out_mode = RVL_GEMM_OUT_F32; c.ldc = features; c.split_stride = tokens * features;
       c.split_used = split_used;
-    } else if (mode == RVL_GEMM_ADD_F32) {
-      c.max_split = 1;
+    } else if (h->stream_ws) {
+      c.stream_ws = h->stream_ws; c.stream_ws_bytes = h->stream_ws_bytes; c.stream_flags = h->stream_flags;
+      c.stream_epoch = ++h->stream_epoch;
     }
   }
   std::string err;
@@ -209,6 +228,10 @@ int rvl_gemm_bf16(rvl_handle* h, const void* A, const void* W, const void* bias,
   GemmCall c;
   c.A = A; c.W = W; c.bias = bias; c.out = out; c.M = M; c.N = N; c.K = K; c.ldc = ldc;
   c.out_mode = out_mode; c.flags = flags; c.rowmap = rowmap; c.split_k = split_k < 1 ? 1 : split_k;
+  if ((flags & RVL_GEMM_FLAG_SWAP) && c.split_k == 1 && h->stream_ws) {
+    c.stream_ws = h->stream_ws; c.stream_ws_bytes = h->stream_ws_bytes; c.stream_flags = h->stream_flags;
+    c.stream_epoch = ++h->stream_epoch;
+  }
   std::string err;
   int rc = gemm_bf16(c, h->num_sms, static_cast<cudaStream_t>(stream), &err);
   if (rc) return fail(h, rc, err);
@@ -332,11 +355,11 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
       launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
                          c.kv_page_size, st);
     }
-    if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, pstride, &pending))) return rc;
+    if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, &pending))) return rc;
     launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
     if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, n, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_swiglu(h->gu, h->act, n, I, st);
-    if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, pstride, &pending))) return rc;
+    if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, &pending))) return rc;
   }
   launch_rmsnorm(hid, h->w.final_norm, h->xlast, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
   if ((rc = linear(h, h->xlast, h->w.lm_head, nullptr, logits_out, n, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;

@@ -5,18 +5,25 @@
 // revisionllm/model/vtimellm_llama.py:79-90), mm_projector (revisionllm/model/vtimellm_arch.py:42,125)
 // and the ClipEncoder linears (revisionllm/model/adapter/transformer.py).
 //
-// Design (one CTA per SM, persistent over output tiles, warp-specialised):
-//   warp 0 / one lane : TMA producer  - cp.async.bulk.tensor 2D loads of a 128 x 64 A tile and a
-//                                      BN x 64 B tile per pipeline stage (128-byte swizzle)
-//   warp 1 / one lane : MMA issuer    - tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 x 4 per stage,
-//                                      fp32 accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2..5        : epilogue      - tcgen05.ld 32x32b.x32 -> registers -> bias / ReLU / residual /
-//                                      row scatter -> global
+// Design (one CTA per SM, persistent, warp-specialised, 192 threads):
+//   warp 0 : TMA producer  - per pipeline stage one cp.async.bulk.tensor 2D load of an (a_tiles x 128) x 64 A box
+//                            and one of a BN x 64 B box (128-byte swizzle), mbarrier complete_tx
+//   warp 1 : MMA issuer    - tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, four K=16 steps per stage and A tile,
+//                            fp32 accumulators in TMEM
+//   warps 2..5 : epilogue  - tcgen05.ld 32x32b.x32 -> registers -> bias / ReLU / residual / row scatter -> global
 //   smem ring full/empty mbarriers (TMA <-> MMA) and tmem full/empty mbarriers (MMA <-> epilogue).
-// The A operand always supplies the 128-row MMA dimension.  For token-major outputs with many tokens
-// the activations are A and the weights B; for small token counts (decode, lm_head on last rows) the
-// host swaps the roles so the weight streams through the 128-row slot once and the tokens sit in N
-// (epilogue then stores transposed).
+// Whole warps run the role loops and one elected lane issues the TMA / MMA instructions, so the loop state stays
+// in uniform registers (an `if (lane == 0)` role body makes ptxas serialise every uniform-datapath instruction).
+//
+// Measured on B200 (tools/probes/tma_probe.cu, profiles/): one SM's TMA path delivers ~55-72 B/clk from L2 and
+// ~25 B/clk from HBM whatever the pipeline depth, so
+//   * a 128x256 tile (48 KB per k-block) is TMA-bound (620 clk per k-block against 512 clk of MMA).  With
+//     a_tiles = 2 the CTA owns a 256 x 256 tile: two A tiles share each B tile, 64 KB feed 1024 clk of MMA;
+//   * weight streaming (few tokens: decode, last-row lm_head) only reaches HBM speed when every SM streams full
+//     128-row boxes all the time.  The host swaps operand roles so the weight is the A operand, and the k-blocks of
+//     all tiles are dealt out evenly to the CTAs (stream-K); a CTA that starts in the middle of a tile leaves an
+//     fp32 partial in a workspace and the CTA that owns the head of that tile adds it in a fixed order
+//     (deterministic, no atomics).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,18 +40,29 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 192;
 constexpr int kGroupM = 16;  // tile rasterisation: 16 m-tiles share each n-tile sweep (L2 reuse)
+constexpr int kMaxStages = 12;
+constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB per 128-row A tile and k-block
+constexpr int kEpiScratchBytes = 4 * 32 * 33 * 4;   // per epilogue warp a 32 x 33 fp32 transpose tile
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - kEpiScratchBytes;
 
 struct GemmArgs {
   int M, N, K;          // A rows, B rows, reduction
-  int tiles_m, tiles_n;
+  int tiles_m, tiles_n; // tiles_m counts (a_tiles x 128)-row tiles
   int k_blocks;         // ceil(K / 64)
-  int split_k;
-  int bm;               // A rows per tile (TMA box rows, <= 128; the MMA always spans 128 smem rows)
+  int split_k;          // tile mode: k-range split (atomics into fp32 out, or partial buffers via split_stride)
+  int a_tiles;          // 1 or 2: 128-row A tiles per CTA tile (they share the B tile)
   int bn;               // B rows per tile = MMA N (multiple of 16, <= 256)
   int stages;           // smem ring depth
-  int tmem_cols;        // power of two >= 2 * bn
+  int acc_stages;       // TMEM accumulator stages (2 = epilogue overlaps the next tile's MMAs)
+  int sub_stride;       // TMEM columns per A tile accumulator
+  int tmem_cols;        // power of two >= acc_stages * a_tiles * sub_stride
   int stream_a;         // A is a weight streamed once from HBM: L2 evict-first for A, evict-last for B
-  int prefetch;         // stream_a: k-blocks of A prefetched into L2 ahead of the TMA loads
+  int stream_k;         // deal k-blocks of all tiles evenly to the CTAs (weight streaming)
+  int units_per_cta;    // stream-K: k-blocks per CTA
+  float* ws;            // stream-K: per-CTA fp32 partial [a_tiles*128][ws_ld]
+  unsigned int* flags;  // stream-K: per-CTA "partial written" epoch
+  unsigned int epoch;
+  int ws_ld;
   long long split_stride;  // > 0: split-k partial s goes to out + s * split_stride (plain stores, no atomics)
   long long ldc;
   void* out;
@@ -56,9 +74,13 @@ struct GemmArgs {
   int atomic;                 // split-k partial sums: atomicAdd into fp32 out
 };
 
-constexpr int kMaxStages = 12;
-constexpr int kATileBytes = kBM * kBK * 2;           // 16 KB slot; TMA fills bm rows of it
-constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
+// One unit of work of a CTA: k-blocks [kb0, kb1) of tile (m_blk, n_blk).
+struct WorkItem {
+  int m_blk, n_blk, kb0, kb1, ks;
+  int kind;  // 0 = whole k-range handled here (normal epilogue); 1 = stream-K tail piece: write the partial;
+             // 2 = stream-K head piece: add `followers` partials, then normal epilogue
+  int followers;
+};
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m_blk, int& n_blk) {
   const int group = kGroupM * tiles_n;
@@ -70,24 +92,89 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   n_blk = r / gsz;
 }
 
+// idx-th work item of this CTA; false when there is none.  All three roles call it with the same arguments.
+template <bool kStreamK>
+__device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w) {
+  const int tiles_mn = a.tiles_m * a.tiles_n;
+  if (!kStreamK) {
+    const int tile = blockIdx.x + idx * gridDim.x;
+    if (tile >= tiles_mn * a.split_k) return false;
+    const int kb_per_split = (a.k_blocks + a.split_k - 1) / a.split_k;
+    w.ks = tile / tiles_mn;
+    tile_coords(tile - w.ks * tiles_mn, a.tiles_m, a.tiles_n, w.m_blk, w.n_blk);
+    w.kb0 = w.ks * kb_per_split;
+    w.kb1 = min(a.k_blocks, w.kb0 + kb_per_split);
+    w.kind = 0;
+    w.followers = 0;
+    return true;
+  }
+  // stream-K: units are (tile, k-block) in tile-major order; this CTA owns [u0, u1)
+  const long long total = static_cast<long long>(tiles_mn) * a.k_blocks;
+  const long long u0 = static_cast<long long>(blockIdx.x) * a.units_per_cta;
+  const long long u1 = min(total, u0 + a.units_per_cta);
+  if (u0 >= u1) return false;
+  const int t_first = static_cast<int>(u0 / a.k_blocks);
+  const int tile = t_first + idx;
+  const long long t_begin = static_cast<long long>(tile) * a.k_blocks;
+  if (t_begin >= u1) return false;
+  w.ks = 0;
+  tile_coords(tile, a.tiles_m, a.tiles_n, w.m_blk, w.n_blk);
+  w.kb0 = static_cast<int>(max(u0, t_begin) - t_begin);
+  w.kb1 = static_cast<int>(min(u1, t_begin + a.k_blocks) - t_begin);
+  w.followers = 0;
+  if (w.kb0 > 0) {
+    w.kind = 1;  // the head of this tile belongs to an earlier CTA
+  } else if (w.kb1 < a.k_blocks) {
+    w.kind = 2;  // later CTAs hold the rest: CTAs blockIdx.x+1 .. whose ranges start inside this tile
+    const long long t_end = t_begin + a.k_blocks;
+    int f = 0;
+    while ((static_cast<long long>(blockIdx.x) + f + 1) * a.units_per_cta < t_end) ++f;
+    w.followers = f;
+  } else {
+    w.kind = 0;
+  }
+  return true;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Optional per-CTA timestamps (clock64) for tools/: [start, producer done, mma done, first accumulator ready,
+// follower flags seen, epilogue done, partial published, -]
+__device__ unsigned long long g_gemm_dbg[160 * 8];
+__device__ int g_gemm_dbg_on = 0;
+#define DBG_T(slot) do { if (g_gemm_dbg_on && lane == 0) g_gemm_dbg[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+
+// kATiles: 128-row A tiles per CTA tile (compile time so the MMA / epilogue loops specialise);
+// kStreamK: k-blocks dealt evenly to the CTAs with in-kernel fix-up of the partial tiles.
+template <int kATiles, bool kStreamK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmArgs args) {
   const int kStages = args.stages;
   const int BN = args.bn;
+  constexpr int a_tiles = kATiles;
+  const int a_slot_bytes = a_tiles * kATileBytes;
   const int b_tile_bytes = BN * kBK * 2;
-  const uint32_t stage_tx_bytes = static_cast<uint32_t>((args.bm + BN) * kBK * 2);
-  const int acc_stride = args.tmem_cols >> 1;              // TMEM columns between the two accumulator stages
+  const uint32_t stage_tx_bytes = static_cast<uint32_t>(a_slot_bytes + b_tile_bytes);
+  const int acc_cols = a_tiles * args.sub_stride;          // TMEM columns of one accumulator stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                  // [kStages][128 x 64] bf16
-  uint8_t* smem_b = smem + kStages * kATileBytes;          // [kStages][BN x 64] bf16 (BN * 128 B is a multiple of 1024)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kATileBytes + b_tile_bytes));
+  uint8_t* smem_a = smem;                                  // [kStages][a_tiles][128 x 64] bf16
+  uint8_t* smem_b = smem + kStages * a_slot_bytes;         // [kStages][BN x 64] bf16 (BN * 128 B is a multiple of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (a_slot_bytes + b_tile_bytes));
   uint64_t* full_bar = bars;                       // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* epi_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [4 warps][32][33]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,34 +200,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-
-  const int tiles_mn = args.tiles_m * args.tiles_n;
-  const int total_tiles = tiles_mn * args.split_k;
-  const int kb_per_split = (args.k_blocks + args.split_k - 1) / args.split_k;
+  if (warp == 0) DBG_T(0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    // The whole warp runs the loop (warp-convergent control flow keeps descriptors/addresses in uniform
-    // registers); one elected lane issues the TMA instructions.
     int stage = 0;
     uint32_t phase = 0;
     const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ks = tile / tiles_mn;
-      int m_blk, n_blk;
-      tile_coords(tile - ks * tiles_mn, args.tiles_m, args.tiles_n, m_blk, n_blk);
-      const int kb0 = ks * kb_per_split;
-      const int kb1 = min(args.k_blocks, kb0 + kb_per_split);
-      const int m0 = m_blk * args.bm, n0 = n_blk * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
+    WorkItem w;
+    for (int it = 0; get_work<kStreamK>(args, it, w); ++it) {
+      const int m0 = w.m_blk * a_tiles * kBM, n0 = w.n_blk * BN;
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
           if (args.stream_a) {
-            tma_load_2d_hint(smem_a + stage * kATileBytes, &tmap_a, &full_bar[stage], kb * kBK, m0, pol_a);
+            tma_load_2d_hint(smem_a + stage * a_slot_bytes, &tmap_a, &full_bar[stage], kb * kBK, m0, pol_a);
             tma_load_2d_hint(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0, pol_b);
           } else {
-            tma_load_2d(smem_a + stage * kATileBytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d(smem_a + stage * a_slot_bytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
             tma_load_2d(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0);
           }
         }
@@ -148,164 +226,278 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+    DBG_T(1);
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN));
     const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem_a));
     const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem_b));
-    const uint64_t a_step = static_cast<uint64_t>(kATileBytes >> 4), b_step = static_cast<uint64_t>(b_tile_bytes >> 4);
+    const uint64_t a_step = static_cast<uint64_t>(a_slot_bytes >> 4), b_step = static_cast<uint64_t>(b_tile_bytes >> 4);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ks = tile / tiles_mn;
-      const int kb0 = ks * kb_per_split;
-      const int kb1 = min(args.k_blocks, kb0 + kb_per_split);
+    WorkItem w;
+    for (int it = 0; get_work<kStreamK>(args, it, w); ++it) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * acc_stride;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const uint32_t d_tmem = tmem_base + acc * acc_cols;
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_desc = a_desc0 + a_step * stage;
           const uint64_t b_desc = b_desc0 + b_step * stage;
+          const uint32_t accum = kb > w.kb0 ? 1u : 0u;
+          for (int at = 0; at < a_tiles; ++at) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 elements = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 elements = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem + at * args.sub_stride, a_desc + at * (kATileBytes >> 4) + 2 * k, b_desc + 2 * k, idesc,
+                        (accum | (k > 0)) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          if (kb == w.kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
+    DBG_T(2);
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int m_local = quarter * 32 + lane;
+    const int n_chunks = (BN + 31) >> 5;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ks = tile / tiles_mn;
-      int m_blk, n_blk;
-      tile_coords(tile - ks * tiles_mn, args.tiles_m, args.tiles_n, m_blk, n_blk);
+    WorkItem w;
+    for (int it = 0; get_work<kStreamK>(args, it, w); ++it) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m_local = quarter * 32 + lane;
-      const int m = m_blk * args.bm + m_local;  // A-row owned by this thread
-      const uint32_t taddr = tmem_base + acc * acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
-      const bool m_ok = m_local < args.bm && m < args.M;
-      const int n_chunks = (BN + 31) >> 5;
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (c == n_chunks - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (warp == 2 && it == 0) DBG_T(3);
+      if (kStreamK && w.kind == 2) {
+        // head piece of a stream-K tile: the CTAs after this one computed the rest of the k-range early in their
+        // own ranges; wait for their flags (they never wait on anything before publishing, and all CTAs are
+        // co-resident, so this cannot deadlock)
+        for (int f = 1; f <= w.followers; ++f) {
+          const unsigned int* fl = args.flags + blockIdx.x + f;
+          unsigned int spins = 0;
+          while (ld_acquire(fl) != args.epoch) {
+            if (++spins > (1u << 26)) mbar_timeout(nullptr, 0xdead);
+          }
         }
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= args.N || c * 32 >= BN) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int nvalid = min(min(32, args.N - n0), BN - c * 32);
-        if (!args.transposed) {
-          // thread = token row m, 32 consecutive features n0..n0+31
-          if (!m_ok) continue;
-          if (args.bias != nullptr && ks == 0) {
-            if (nvalid == 32) {
-              const uint4* bp = reinterpret_cast<const uint4*>(args.bias + n0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 b = __ldg(bp + q);
-                v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
-                v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
-                v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
-                v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += __bfloat162float(args.bias[n0 + j]);
-            }
+        if (warp == 2) DBG_T(4);
+      }
+      const int ks = w.ks;
+      for (int at = 0; at < a_tiles; ++at) {
+        const int m = (w.m_blk * a_tiles + at) * kBM + m_local;  // A-row owned by this thread
+        const uint32_t taddr = tmem_base + acc * acc_cols + at * args.sub_stride + (static_cast<uint32_t>(quarter * 32) << 16);
+        const bool m_ok = m < args.M;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (at == a_tiles - 1 && c == n_chunks - 1) {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
-          if (args.relu) {
+          const int n0 = w.n_blk * BN + c * 32;
+          if (n0 >= args.N || c * 32 >= BN) continue;
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int nvalid = min(min(32, args.N - n0), BN - c * 32);
+          // stream-K partial tiles live in the workspace in "register order": [cta][a tile][chunk][q][thread][4 floats],
+          // so every warp-level 16-byte access is one contiguous 512-byte run
+          if (kStreamK && w.kind == 1) {
+            float4* dst = reinterpret_cast<float4*>(args.ws) +
+                          ((static_cast<long long>(blockIdx.x) * a_tiles + at) * 8 + c) * (8 * 128) + m_local;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q * 128] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            continue;
           }
-          const long long row = args.rowmap ? args.rowmap[m] : m;
-          if (args.mode == RVL_GEMM_OUT_BF16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + n0;
-            if (nvalid == 32) {
+          if (kStreamK && w.kind == 2) {
+            for (int f = 1; f <= w.followers; ++f) {
+              const float4* src = reinterpret_cast<const float4*>(args.ws) +
+                                  ((static_cast<long long>(blockIdx.x + f) * a_tiles + at) * 8 + c) * (8 * 128) + m_local;
+              float4 p[8];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 o;
-                o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                reinterpret_cast<uint4*>(dst)[q] = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
-            }
-          } else {
-            float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + n0;
-            if (args.atomic) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) atomicAdd(dst + j, v[j]);
-            } else if (nvalid == 32) {
+              for (int q = 0; q < 8; ++q) p[q] = __ldcg(src + q * 128);
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                if (args.mode == RVL_GEMM_ADD_F32) {
-                  const float4 p = reinterpret_cast<const float4*>(dst)[q];
-                  o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-                }
-                reinterpret_cast<float4*>(dst)[q] = o;
+                v[q * 4] += p[q].x; v[q * 4 + 1] += p[q].y; v[q * 4 + 2] += p[q].z; v[q * 4 + 3] += p[q].w;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dst[j] = (args.mode == RVL_GEMM_ADD_F32 ? dst[j] : 0.f) + v[j];
             }
           }
-        } else {
-          // thread = feature m, its 32 values are tokens n0..n0+31: out[token][feature], lanes -> consecutive
-          // features (coalesced along the feature dimension)
-          if (!m_ok) continue;
-          const float b = (args.bias != nullptr && ks == 0) ? __bfloat162float(args.bias[m]) : 0.f;
+          // ---- fast paths (full 32-column chunk, no bias / ReLU / row map): few instructions per element, because
+          // the four epilogue warps run one per scheduler and every instruction's latency is exposed
+          const bool plain = nvalid == 32 && args.bias == nullptr && !args.relu && args.rowmap == nullptr && !args.atomic;
+          if (plain && !args.transposed) {
+            if (!m_ok) continue;
+            if (args.mode == RVL_GEMM_OUT_BF16) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(m) * args.ldc + n0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < nvalid) {
-              float x = v[j] + b;
-              if (args.relu) x = fmaxf(x, 0.f);
-              const long long row = args.rowmap ? args.rowmap[n0 + j] : (n0 + j);
-              if (args.mode == RVL_GEMM_OUT_BF16) {
-                reinterpret_cast<__nv_bfloat16*>(args.out)[row * args.ldc + m] = __float2bfloat16(x);
+              for (int q = 0; q < 4; ++q)
+                dst[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                    pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+            } else {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + ks * args.split_stride + static_cast<long long>(m) * args.ldc + n0);
+              if (args.mode == RVL_GEMM_ADD_F32) {
+                float4 p[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[q] = dst[q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  dst[q] = make_float4(v[q * 4] + p[q].x, v[q * 4 + 1] + p[q].y, v[q * 4 + 2] + p[q].z, v[q * 4 + 3] + p[q].w);
               } else {
-                float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + m;
-                if (args.atomic) atomicAdd(dst, x);
-                else if (args.mode == RVL_GEMM_ADD_F32) *dst += x;
-                else *dst = x;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              }
+            }
+            continue;
+          }
+          if (plain && args.transposed && (w.m_blk * a_tiles + at) * kBM + quarter * 32 + 32 <= args.M) {
+            // out[token][feature]: transpose the warp's 32 features x 32 tokens through shared memory so that each
+            // lane stores 16 contiguous bytes of one token row
+            float* sc = epi_scratch + (warp - 2) * (32 * 33);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = v[j];
+            __syncwarp();
+            const int f_base = (w.m_blk * a_tiles + at) * kBM + quarter * 32;   // first feature of this warp
+            if (args.mode == RVL_GEMM_OUT_BF16) {
+              const int f0 = (lane & 3) * 8, t0 = lane >> 2;
+              __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(n0 + t0) * args.ldc + f_base + f0;
+#pragma unroll
+              for (int pass = 0; pass < 4; ++pass) {
+                const int t = t0 + pass * 8;
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = sc[(f0 + i) * 33 + t];
+                *reinterpret_cast<uint4*>(base + static_cast<long long>(pass) * 8 * args.ldc) =
+                    make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+              }
+            } else {
+              const int f0 = (lane & 7) * 4, t0 = lane >> 3;
+              float* base = reinterpret_cast<float*>(args.out) + ks * args.split_stride + static_cast<long long>(n0 + t0) * args.ldc + f_base + f0;
+#pragma unroll
+              for (int pass = 0; pass < 8; ++pass) {
+                const int t = t0 + pass * 4;
+                float4 x = make_float4(sc[(f0 + 0) * 33 + t], sc[(f0 + 1) * 33 + t], sc[(f0 + 2) * 33 + t], sc[(f0 + 3) * 33 + t]);
+                float4* dst = reinterpret_cast<float4*>(base + static_cast<long long>(pass) * 4 * args.ldc);
+                if (args.mode == RVL_GEMM_ADD_F32) {
+                  const float4 p = *dst;
+                  x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+                }
+                *dst = x;
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+          if (!args.transposed) {
+            // thread = token row m, 32 consecutive features n0..n0+31
+            if (!m_ok) continue;
+            if (args.bias != nullptr && ks == 0) {
+              if (nvalid == 32) {
+                const uint4* bp = reinterpret_cast<const uint4*>(args.bias + n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 b = __ldg(bp + q);
+                  v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
+                  v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
+                  v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
+                  v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) v[j] += __bfloat162float(args.bias[n0 + j]);
+              }
+            }
+            if (args.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            const long long row = args.rowmap ? args.rowmap[m] : m;
+            if (args.mode == RVL_GEMM_OUT_BF16) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + n0;
+              if (nvalid == 32) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 o;
+                  o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                  o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                  o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                  o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                  reinterpret_cast<uint4*>(dst)[q] = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + n0;
+              if (args.atomic) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) atomicAdd(dst + j, v[j]);
+              } else if (nvalid == 32) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                  if (args.mode == RVL_GEMM_ADD_F32) {
+                    const float4 p = reinterpret_cast<const float4*>(dst)[q];
+                    o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                  }
+                  reinterpret_cast<float4*>(dst)[q] = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) dst[j] = (args.mode == RVL_GEMM_ADD_F32 ? dst[j] : 0.f) + v[j];
+              }
+            }
+          } else {
+            // thread = feature m, its 32 values are tokens n0..n0+31: out[token][feature], lanes -> consecutive
+            // features (coalesced along the feature dimension)
+            if (!m_ok) continue;
+            const float b = (args.bias != nullptr && ks == 0) ? __bfloat162float(args.bias[m]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                float x = v[j] + b;
+                if (args.relu) x = fmaxf(x, 0.f);
+                const long long row = args.rowmap ? args.rowmap[n0 + j] : (n0 + j);
+                if (args.mode == RVL_GEMM_OUT_BF16) {
+                  reinterpret_cast<__nv_bfloat16*>(args.out)[row * args.ldc + m] = __float2bfloat16(x);
+                } else {
+                  float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + m;
+                  if (args.atomic) atomicAdd(dst, x);
+                  else if (args.mode == RVL_GEMM_ADD_F32) *dst += x;
+                  else *dst = x;
+                }
               }
             }
           }
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (kStreamK && w.kind == 1) {
+        // publish the partial: every epilogue thread fences its own stores, then one thread raises the flag
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) st_release(args.flags + blockIdx.x, args.epoch);
+        if (warp == 2) DBG_T(6);
+      }
+      if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
+    if (warp == 2) DBG_T(5);
   }
 
   tc_fence_before();
@@ -359,61 +551,10 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
   return RVL_OK;
 }
 
-// Smallest power of two >= 2 * bn (two accumulator stages), at least 32 columns.
-static int tmem_cols_for(int bn) {
+static int pow2_at_least(int x) {
   int c = 32;
-  while (c < 2 * bn) c <<= 1;
+  while (c < x) c <<= 1;
   return c;
-}
-
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int num_sms, cudaStream_t st, std::string* err) {
-  const int stage_bytes = kATileBytes + a.bn * kBK * 2;
-  a.stages = kSmemBudget / stage_bytes;
-  if (a.stages > kMaxStages) a.stages = kMaxStages;
-  if (a.stages < 2) { *err = "gemm: tile does not fit in shared memory"; return RVL_ERR_INVALID; }
-  a.tmem_cols = tmem_cols_for(a.bn);
-
-  const int smem = a.stages * stage_bytes + 1024 + 512;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return RVL_ERR_CUDA; }
-    attr_smem = 227 * 1024;
-  }
-  const int total = a.tiles_m * a.tiles_n * a.split_k;
-  const int grid = total < num_sms ? total : num_sms;
-  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { *err = std::string("gemm launch: ") + cudaGetErrorString(e); return RVL_ERR_CUDA; }
-  return RVL_OK;
-}
-
-// Weight-streaming plan (few tokens): rows of W per tile (bm) and split-k chosen so that the tiles fill the SMs in
-// whole waves.  Measured on B200 (tools/decode_gemm_sweep.py): one CTA streams ~38 GB/s from HBM whatever the
-// pipeline depth, so the only way to approach the 6.5 TB/s peak is to keep all 148 SMs streaming equal shares.
-static void plan_stream(int64_t features, int64_t K, int bn, int num_sms, bool allow_split, int fixed_sk, int* bm_out,
-                        int* sk_out) {
-  const double sm_bw = 38e9, fixed = 3.0e-6, clk = 1.8e9;
-  const int k_blocks = static_cast<int>((K + kBK - 1) / kBK);
-  double best = 1e30;
-  int best_bm = 128, best_sk = 1;
-  const int sks[6] = {1, 2, 3, 4, 6, 8};
-  for (int bm = 128; bm >= 64; bm -= 8) {
-    for (int si = 0; si < (fixed_sk > 0 ? 1 : (allow_split ? 6 : 1)); ++si) {
-      const int sk = fixed_sk > 0 ? fixed_sk : sks[si];
-      if (fixed_sk <= 0 && sk > 1 && k_blocks / sk < 8) continue;
-      const int tiles = static_cast<int>((features + bm - 1) / bm) * sk;
-      const int waves = (tiles + num_sms - 1) / num_sms;
-      const double kb = static_cast<double>((k_blocks + sk - 1) / sk);
-      const double t_mem = kb * (bm + 0.25 * bn) * kBK * 2 / sm_bw;          // activations come from L2: cheaper
-      const double t_mma = kb * 4.0 * (bn * 0.5) / clk;                         // 128 x bn x 16 MMA ~ bn/2 cycles
-      double t = waves * ((t_mem > t_mma ? t_mem : t_mma) + fixed);
-      t += sk > 1 ? 1.0e-6 * sk : 0.0;                                           // partial-sum traffic
-      if (t < best) { best = t; best_bm = bm; best_sk = sk; }
-    }
-  }
-  *bm_out = best_bm;
-  *sk_out = best_sk;
 }
 
 // out[tokens, features] = act(X[tokens,K] . W[features,K]^T + bias)
@@ -424,6 +565,9 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   if (c.split_k > 1 && !partials && c.out_mode != RVL_GEMM_ADD_F32) { *err = "gemm: split_k needs RVL_GEMM_ADD_F32 or a partial buffer"; return RVL_ERR_INVALID; }
   if (partials && c.out_mode != RVL_GEMM_OUT_F32) { *err = "gemm: split-k partials are fp32 (RVL_GEMM_OUT_F32)"; return RVL_ERR_INVALID; }
   const bool swap = (c.flags & RVL_GEMM_FLAG_SWAP) != 0;
+  static const char* env_at = getenv("RVL_A_TILES");      // experiment hooks
+  static const char* env_sk = getenv("RVL_STREAM_K");
+  static const char* env_dbg = getenv("RVL_PLAN_DEBUG");
   GemmArgs a{};
   a.K = static_cast<int>(c.K);
   a.k_blocks = static_cast<int>((c.K + kBK - 1) / kBK);
@@ -434,44 +578,97 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   a.mode = c.out_mode;
   a.relu = (c.flags & RVL_GEMM_FLAG_RELU) ? 1 : 0;
   a.transposed = swap ? 1 : 0;
-  const void* pa = swap ? c.W : c.A;   // operand that supplies the (up to) 128-row MMA dimension
+  const void* pa = swap ? c.W : c.A;   // operand that supplies the 128-row MMA dimension
   const void* pb = swap ? c.A : c.W;   // operand that supplies MMA N
   a.M = static_cast<int>(swap ? c.N : c.M);
   a.N = static_cast<int>(swap ? c.M : c.N);
-  a.bm = kBM;
+  a.bn = a.N >= 256 ? 256 : ((a.N + 15) / 16) * 16;
+  a.stream_a = swap ? 1 : 0;
+  a.sub_stride = ((a.bn + 31) / 32) * 32;
   int sk = c.split_k < 1 ? 1 : c.split_k;
-  if (swap) {
-    a.bn = a.N >= 256 ? 256 : ((a.N + 15) / 16) * 16;
-    a.stream_a = 1;
-    const bool may_split = c.auto_plan && (partials || c.out_mode == RVL_GEMM_ADD_F32);
-    plan_stream(a.M, c.K, a.bn, num_sms, may_split, c.auto_plan ? 0 : sk, &a.bm, &sk);
-    if (c.max_split > 0 && sk > c.max_split) sk = c.max_split;
-    // experiment hooks (tools/decode_gemm_sweep.py): RVL_BM / RVL_SK override the plan, RVL_PLAN_DEBUG prints it
-    static const char* env_bm = getenv("RVL_BM");
-    static const char* env_sk = getenv("RVL_SK");
-    static const char* env_dbg = getenv("RVL_PLAN_DEBUG");
-    static const char* env_pf = getenv("RVL_PREFETCH");
-    a.prefetch = env_pf ? atoi(env_pf) : 16;
-    if (env_bm && atoi(env_bm) >= 8) a.bm = atoi(env_bm);
-    if (env_sk && atoi(env_sk) >= 1 && (partials || c.out_mode == RVL_GEMM_ADD_F32)) sk = atoi(env_sk);
-    if (env_dbg) fprintf(stderr, "rvl plan: features=%d tokens=%d K=%lld bn=%d bm=%d sk=%d\n", a.M, a.N, (long long)c.K, a.bn, a.bm, sk);
-  } else {
-    a.bn = a.N >= 256 ? 256 : ((a.N + 15) / 16) * 16;
-    a.stream_a = 0;
+  // two A tiles per CTA tile (256 x 256) for big token-major GEMMs: the B tile is fetched once per two A tiles.
+  // Weight streaming keeps 128-row tiles: more, smaller units balance better and the partial tiles stay small.
+  // (measured on B200: 1-4 % faster in isolation, no gain inside the power-capped sweep, so it stays opt-in)
+  a.a_tiles = 1;
+  if (env_at && atoi(env_at) == 2 && !swap && a.M >= 4 * kBM && a.N >= 256) a.a_tiles = 2;
+  a.tiles_m = (a.M + a.a_tiles * kBM - 1) / (a.a_tiles * kBM);
+  a.tiles_n = (a.N + a.bn - 1) / a.bn;
+  // stream-K for the weight-streaming orientation: needs the workspace, a single n-tile and no explicit split
+  a.stream_k = 0;
+  // Worth it when plain tiles would leave a ragged last wave (e.g. gate|up: 172 tiles on 148 SMs, measured 58 -> 48 us);
+  // for less than one wave of tiles the fix-up traffic eats the gain (qkv: 34.3 vs 35.0 us).
+  const int waves = (a.tiles_m + num_sms - 1) / num_sms;
+  const bool ragged = a.tiles_m > num_sms && a.tiles_m < 0.7 * waves * num_sms;
+  const bool force_sk = (env_sk && atoi(env_sk) == 2) || (c.flags & RVL_GEMM_FLAG_STREAMK);
+  if (swap && c.stream_ws && c.stream_flags && sk == 1 && a.tiles_n == 1 && !a.rowmap && !partials && a.a_tiles == 1 &&
+      (ragged || force_sk)) {
+    const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
+    const int ctas = static_cast<int>(total < num_sms ? total : num_sms);
+    int upc = static_cast<int>((total + ctas - 1) / ctas);
+    if (upc < 8 && total >= 8) upc = 8;                                   // keep pipelines worth starting
+    const size_t need = static_cast<size_t>(num_sms) * a.a_tiles * 8 * 8 * 128 * 16;
+    if (need <= c.stream_ws_bytes && (!env_sk || atoi(env_sk) != 0)) {
+      a.stream_k = 1;
+      a.units_per_cta = upc;
+      a.ws = c.stream_ws;
+      a.flags = c.stream_flags;
+      a.epoch = c.stream_epoch;
+      a.ws_ld = a.sub_stride;
+    }
   }
-  a.split_k = sk > a.k_blocks ? a.k_blocks : sk;
+  a.split_k = a.stream_k ? 1 : (sk > a.k_blocks ? a.k_blocks : sk);
   while (a.split_k > 1 && ((a.k_blocks + a.split_k - 1) / a.split_k) * (a.split_k - 1) >= a.k_blocks) --a.split_k;  // no empty split
   a.split_stride = partials ? c.split_stride : 0;
   a.atomic = (a.split_k > 1 && !partials) ? 1 : 0;
-  a.tiles_m = (a.M + a.bm - 1) / a.bm;
-  a.tiles_n = (a.N + a.bn - 1) / a.bn;
   if (c.split_used) *c.split_used = a.split_k;
+  // TMEM: two accumulator stages when they fit in 512 columns
+  a.acc_stages = (2 * a.a_tiles * a.sub_stride <= 512) ? 2 : 1;
+  a.tmem_cols = pow2_at_least(a.acc_stages * a.a_tiles * a.sub_stride);
+  const int stage_bytes = a.a_tiles * kATileBytes + a.bn * kBK * 2;
+  a.stages = kSmemBudget / stage_bytes;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  if (a.stages < 2) { *err = "gemm: tile does not fit in shared memory"; return RVL_ERR_INVALID; }
+  if (env_dbg)
+    fprintf(stderr, "rvl gemm: A rows=%d B rows=%d K=%d bn=%d a_tiles=%d stages=%d acc_stages=%d tmem=%d split_k=%d stream_k=%d upc=%d\n",
+            a.M, a.N, a.K, a.bn, a.a_tiles, a.stages, a.acc_stages, a.tmem_cols, a.split_k, a.stream_k, a.units_per_cta);
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, pa, a.M, c.K, a.bm, err);
+  int rc = make_tmap(&ta, pa, a.M, c.K, a.a_tiles * kBM, err);
   if (rc) return rc;
   rc = make_tmap(&tb, pb, a.N, c.K, a.bn, err);
   if (rc) return rc;
-  return launch(ta, tb, a, num_sms, st, err);
+  const int smem = a.stages * stage_bytes + 1024 + 512 + kEpiScratchBytes;
+  int grid;
+  if (a.stream_k) {
+    const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
+    grid = static_cast<int>((total + a.units_per_cta - 1) / a.units_per_cta);
+  } else {
+    const int total = a.tiles_m * a.tiles_n * a.split_k;
+    grid = total < num_sms ? total : num_sms;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e3 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { *err = "cudaFuncSetAttribute(max dynamic smem) failed"; return RVL_ERR_CUDA; }
+    attr_set = true;
+  }
+  if (a.stream_k) gemm_bf16_tcgen05_kernel<1, true><<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
+  else if (a.a_tiles == 2) gemm_bf16_tcgen05_kernel<2, false><<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
+  else gemm_bf16_tcgen05_kernel<1, false><<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("gemm launch: ") + cudaGetErrorString(e); return RVL_ERR_CUDA; }
+  return RVL_OK;
 }
 
+// tools/ only: switch the per-CTA timestamps on/off and read them back
+void gemm_debug_enable(int on) { cudaMemcpyToSymbol(g_gemm_dbg_on, &on, sizeof(int)); }
+void gemm_debug_read(unsigned long long* out, int n) { cudaMemcpyFromSymbol(out, g_gemm_dbg, sizeof(unsigned long long) * n); }
+
 }  // namespace rvl
+
+extern "C" __attribute__((visibility("default"))) void rvl_debug_gemm_timestamps(int enable, unsigned long long* out, int n) {
+  if (out && n > 0) rvl::gemm_debug_read(out, n);
+  rvl::gemm_debug_enable(enable);
+}

@@ -18,11 +18,14 @@ struct GemmCall {
   int out_mode = RVL_GEMM_OUT_BF16;
   int flags = 0;
   const int32_t* rowmap = nullptr;
-  int split_k = 1;             // explicit split (ignored when auto_plan picks one)
-  bool auto_plan = false;      // weight-streaming orientation: choose rows-per-tile and split-k from the SM count
-  int max_split = 0;           // cap for the planned split (capacity of the partial buffer)
+  int split_k = 1;             // explicit k split (tile mode); > 1 needs RVL_GEMM_ADD_F32 (atomics) or split_stride
   int64_t split_stride = 0;    // > 0: split-k partials written to out + s * split_stride (fp32, no atomics)
   int* split_used = nullptr;   // out: the split actually launched
+  // stream-K workspace (weight-streaming orientation only): fp32 partial tiles and per-CTA flags
+  float* stream_ws = nullptr;
+  size_t stream_ws_bytes = 0;
+  unsigned int* stream_flags = nullptr;
+  unsigned int stream_epoch = 0;
 };
 int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err);
 

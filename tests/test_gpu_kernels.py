@@ -24,6 +24,16 @@ def eng():
     e.close()
 
 
+@pytest.fixture(scope="module")
+def eng_ws():
+    """Engine with a workspace bound: weight-streaming (SWAP) GEMMs then run stream-K."""
+    from revisionllm_b200.engine import Engine, EngineConfig
+    e = Engine(EngineConfig.from_synth(syn.TINY))
+    e.ensure_workspace(512, 256)
+    yield e
+    e.close()
+
+
 def _rand(shape, seed, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
@@ -87,6 +97,49 @@ def test_gemm_fp32_modes(eng, M, N, K):
     exp = torch.zeros(M, N)
     exp[perm.long()] = ref.clamp(min=0)
     assert _relerr(out.cpu(), exp) < 2e-5
+
+
+STREAM_SHAPES = [
+    # tokens, features, K : weight-streaming orientation with the k-blocks of all tiles dealt evenly to the SMs
+    (180, 4096, 4096),     # 16 super tiles x 64 k-blocks over 128 CTAs: every tile is cut into 8 pieces
+    (180, 12288, 4096),    # qkv decode shape
+    (23, 22016, 4096),     # gate|up at 8-GPU batch
+    (7, 4096, 11008),      # down proj, tiny batch
+    (200, 1280, 512),      # features not a multiple of 256, few k-blocks
+    (16, 256, 64),         # one tile, one k-block
+]
+
+
+@pytest.mark.parametrize("M,N,K", STREAM_SHAPES)
+def test_gemm_stream_k_exact_and_modes(eng_ws, M, N, K):
+    from revisionllm_b200 import _cabi
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randint(-3, 4, (M, K), generator=g).to(torch.bfloat16)
+    W = torch.randint(-3, 4, (N, K), generator=g).to(torch.bfloat16)
+    bias = torch.randint(-3, 4, (N,), generator=g).to(torch.bfloat16)
+    ref = F.linear(A.float(), W.float(), bias.float())
+    Ad, Wd, bd = A.cuda(), W.cuda(), bias.cuda()
+    SK = _cabi.GEMM_FLAG_SWAP | _cabi.GEMM_FLAG_STREAMK
+    for rep in range(3):                                   # the per-CTA flags are re-used with a new epoch
+        out = eng_ws.gemm(Ad, Wd, bias=bd, out_mode=_cabi.GEMM_OUT_F32, flags=SK)
+        assert torch.equal(out.cpu(), ref), f"stream-K fp32 {M}x{N}x{K} rep {rep}: max diff {(out.cpu() - ref).abs().max()}"
+    res = torch.randint(-5, 6, (M, N), generator=g).float()
+    acc = res.cuda().clone()
+    eng_ws.gemm(Ad, Wd, bias=bd, out=acc, out_mode=_cabi.GEMM_ADD_F32, flags=SK)
+    assert torch.equal(acc.cpu(), ref + res)
+    outb = eng_ws.gemm(Ad, Wd, bias=bd, flags=SK)
+    assert _relerr(outb.float().cpu(), ref) < 1e-2
+
+
+def test_gemm_large_exact(eng):
+    """Multi-wave persistent loop with exact integer inputs (bit-exact fp32 accumulation)."""
+    from revisionllm_b200 import _cabi
+    for (M, N, K) in ((1024, 512, 256), (777, 264, 192), (4224, 1024, 1024)):
+        g = torch.Generator().manual_seed(M)
+        A = torch.randint(-3, 4, (M, K), generator=g).to(torch.bfloat16).cuda()
+        W = torch.randint(-3, 4, (N, K), generator=g).to(torch.bfloat16).cuda()
+        out = eng.gemm(A, W, out_mode=_cabi.GEMM_OUT_F32)
+        assert torch.equal(out, A.float() @ W.float().t()), f"{M}x{N}x{K}"
 
 
 def test_gemm_linearity_full_size(eng):

@@ -5,6 +5,7 @@ import torch
 from revisionllm_b200 import _cabi, synthetic as syn
 from revisionllm_b200.engine import Engine, EngineConfig
 eng = Engine(EngineConfig.from_synth(syn.TINY))
+eng.ensure_workspace(512, 256)
 def bench(M, N, K, reps=20):
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     Ws = [torch.randn(N, K, device="cuda").to(torch.bfloat16) for _ in range(4)]

@@ -6,6 +6,7 @@ from revisionllm_b200 import _cabi, synthetic as syn
 from revisionllm_b200.engine import Engine, EngineConfig
 
 eng = Engine(EngineConfig.from_synth(syn.TINY))
+eng.ensure_workspace(512, 256)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def bench(M, N, K, mode=_cabi.GEMM_OUT_BF16, split_k=1, reps=20):
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)

@@ -16,6 +16,7 @@ from revisionllm_b200.engine import Engine, EngineConfig  # noqa: E402
 def main():
     print("device", torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
     eng = Engine(EngineConfig.from_synth(syn.TINY))
+    eng.ensure_workspace(512, 256)
     g = torch.Generator(device="cuda").manual_seed(0)
 
     def run(M, N, K, mode=_cabi.GEMM_OUT_F32, flags=0, tag="", a_mask=None):
