@@ -189,6 +189,10 @@ RVL_API int rvl_profile_enable(rvl_handle* h, int32_t on, int32_t capacity);
 RVL_API int rvl_profile_read(rvl_handle* h, int32_t category, double* total_ms, double* total_flops,
                      double* total_bytes, int64_t* launches);
 
+/* tools/gemm_timeline.py only: per-CTA clock64 timestamps of the GEMM roles (8 x uint64 per CTA, up to 160 CTAs).
+ * Reads the previous launch's stamps into `out` (n entries) when out != NULL, then switches stamping on/off. */
+RVL_API void rvl_debug_gemm_timestamps(int enable, unsigned long long* out, int n);
+
 /* ---- individual kernels (unit parity tests and host-side composition) ------------------------ */
 
 #define RVL_GEMM_OUT_BF16 0

@@ -668,7 +668,7 @@ void gemm_debug_read(unsigned long long* out, int n) { cudaMemcpyFromSymbol(out,
 
 }  // namespace rvl
 
-extern "C" __attribute__((visibility("default"))) void rvl_debug_gemm_timestamps(int enable, unsigned long long* out, int n) {
+extern "C" void rvl_debug_gemm_timestamps(int enable, unsigned long long* out, int n) {
   if (out && n > 0) rvl::gemm_debug_read(out, n);
   rvl::gemm_debug_enable(enable);
 }

@@ -319,6 +319,30 @@ def plan_splice(input_ids: np.ndarray, n_visual: Sequence[int], attention_mask: 
     vis_src indexes rows of the concatenated visual blocks."""
     B = input_ids.shape[0]
     vis_start = np.concatenate([[0], np.cumsum(np.asarray(n_visual, dtype=np.int64))])
+    valid = np.ones(input_ids.shape, dtype=bool) if attention_mask is None else attention_mask.astype(bool)
+    is_img = (input_ids == image_token) & valid
+    if (is_img.sum(axis=1) == 1).all() and len(n_visual) == B:
+        # common case (one placeholder per row, block i belongs to row i): pure numpy, no per-token Python loop
+        nv = (vis_start[1:] - vis_start[:-1]).astype(np.int64)                      # [B]
+        tok_len = np.where(is_img, nv[:, None], valid.astype(np.int64))             # rows each id expands to
+        start = np.cumsum(tok_len, axis=1) - tok_len                                 # position inside the row
+        limit = max_length if max_length is not None else np.iinfo(np.int64).max
+        row_len = np.minimum(tok_len.sum(axis=1), limit)
+        cu64 = np.concatenate([[0], np.cumsum(row_len)])
+        txt = valid & ~is_img & (start < limit)
+        rows_t, cols_t = np.nonzero(txt)
+        text_ids = input_ids[rows_t, cols_t]
+        text_dst = cu64[rows_t] + start[rows_t, cols_t]
+        img_col = np.argmax(is_img, axis=1)
+        img_start = start[np.arange(B), img_col]
+        n_keep = np.clip(np.minimum(nv, limit - img_start), 0, None)                 # visual rows surviving truncation
+        rep = np.repeat(np.arange(B), n_keep)
+        within = np.arange(int(n_keep.sum())) - np.repeat(np.cumsum(n_keep) - n_keep, n_keep)
+        vis_src = vis_start[rep] + within
+        vis_dst = cu64[rep] + img_start[rep] + within
+        i32v = lambda a: np.asarray(a, dtype=np.int32)
+        return dict(cu_seqlens=i32v(cu64), text_ids=i32v(text_ids), text_dst=i32v(text_dst), vis_src=i32v(vis_src),
+                    vis_dst=i32v(vis_dst), lengths=i32v(row_len))
     text_ids: List[int] = []
     text_dst: List[int] = []
     vis_src: List[int] = []
