@@ -151,6 +151,162 @@ __device__ unsigned long long g_gemm_dbg[160 * 8];
 __device__ int g_gemm_dbg_on = 0;
 #define DBG_T(slot) do { if (g_gemm_dbg_on && lane == 0) g_gemm_dbg[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
+// Store one 32-column chunk of the accumulator row(s) this thread owns.  v: the 32 fp32 values; m: A-row index of the
+// thread; n0: first B-row index of the chunk; f_base: first A-row of this warp (transposed mode); sc: the warp's 32x33
+// fp32 shared-memory transpose scratch.
+__device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32], int m, bool m_ok, int n0, int nvalid, int ks,
+                                            int f_base, float* sc, int lane) {
+  // ---- fast paths (full 32-column chunk, no bias / ReLU / row map): few instructions per element, because
+  // the four epilogue warps run one per scheduler and every instruction's latency is exposed
+  const bool plain = nvalid == 32 && args.bias == nullptr && !args.relu && args.rowmap == nullptr && !args.atomic;
+  if (plain && !args.transposed) {
+    if (!m_ok) return;
+    if (args.mode == RVL_GEMM_OUT_BF16) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(m) * args.ldc + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        dst[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                            pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+    } else {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + ks * args.split_stride + static_cast<long long>(m) * args.ldc + n0);
+      if (args.mode == RVL_GEMM_ADD_F32) {
+        float4 p[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) p[q] = dst[q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          dst[q] = make_float4(v[q * 4] + p[q].x, v[q * 4 + 1] + p[q].y, v[q * 4 + 2] + p[q].z, v[q * 4 + 3] + p[q].w);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+    return;
+  }
+  if (plain && args.transposed && f_base + 32 <= args.M) {
+    // out[token][feature]: transpose the warp's 32 features x 32 tokens through shared memory so that each
+    // lane stores 16 contiguous bytes of one token row
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = v[j];
+    __syncwarp();
+    if (args.mode == RVL_GEMM_OUT_BF16) {
+      const int f0 = (lane & 3) * 8, t0 = lane >> 2;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(n0 + t0) * args.ldc + f_base + f0;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int t = t0 + pass * 8;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = sc[(f0 + i) * 33 + t];
+        *reinterpret_cast<uint4*>(base + static_cast<long long>(pass) * 8 * args.ldc) =
+            make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+      }
+    } else {
+      const int f0 = (lane & 7) * 4, t0 = lane >> 3;
+      float* base = reinterpret_cast<float*>(args.out) + ks * args.split_stride + static_cast<long long>(n0 + t0) * args.ldc + f_base + f0;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int t = t0 + pass * 4;
+        float4 x = make_float4(sc[(f0 + 0) * 33 + t], sc[(f0 + 1) * 33 + t], sc[(f0 + 2) * 33 + t], sc[(f0 + 3) * 33 + t]);
+        float4* dst = reinterpret_cast<float4*>(base + static_cast<long long>(pass) * 4 * args.ldc);
+        if (args.mode == RVL_GEMM_ADD_F32) {
+          const float4 p = *dst;
+          x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+        }
+        *dst = x;
+      }
+    }
+    __syncwarp();
+    return;
+  }
+  if (!args.transposed) {
+    // thread = token row m, 32 consecutive features n0..n0+31
+    if (!m_ok) return;
+    if (args.bias != nullptr && ks == 0) {
+      if (nvalid == 32) {
+        const uint4* bp = reinterpret_cast<const uint4*>(args.bias + n0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 b = __ldg(bp + q);
+          v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
+          v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
+          v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
+          v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __bfloat162float(args.bias[n0 + j]);
+      }
+    }
+    if (args.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    const long long row = args.rowmap ? args.rowmap[m] : m;
+    if (args.mode == RVL_GEMM_OUT_BF16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + n0;
+      if (nvalid == 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+          o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+          o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+          o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+          reinterpret_cast<uint4*>(dst)[q] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+      }
+    } else {
+      float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + n0;
+      if (args.atomic) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) atomicAdd(dst + j, v[j]);
+      } else if (nvalid == 32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          if (args.mode == RVL_GEMM_ADD_F32) {
+            const float4 p = reinterpret_cast<const float4*>(dst)[q];
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          reinterpret_cast<float4*>(dst)[q] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = (args.mode == RVL_GEMM_ADD_F32 ? dst[j] : 0.f) + v[j];
+      }
+    }
+  } else {
+    // thread = feature m, its 32 values are tokens n0..n0+31: out[token][feature], lanes -> consecutive
+    // features (coalesced along the feature dimension)
+    if (!m_ok) return;
+    const float b = (args.bias != nullptr && ks == 0) ? __bfloat162float(args.bias[m]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < nvalid) {
+        float x = v[j] + b;
+        if (args.relu) x = fmaxf(x, 0.f);
+        const long long row = args.rowmap ? args.rowmap[n0 + j] : (n0 + j);
+        if (args.mode == RVL_GEMM_OUT_BF16) {
+          reinterpret_cast<__nv_bfloat16*>(args.out)[row * args.ldc + m] = __float2bfloat16(x);
+        } else {
+          float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + m;
+          if (args.atomic) atomicAdd(dst, x);
+          else if (args.mode == RVL_GEMM_ADD_F32) *dst += x;
+          else *dst = x;
+        }
+      }
+    }
+  }
+}
+
 // kATiles: 128-row A tiles per CTA tile (compile time so the MMA / epilogue loops specialise);
 // kStreamK: k-blocks dealt evenly to the CTAs with in-kernel fix-up of the partial tiles.
 template <int kATiles, bool kStreamK>
@@ -335,157 +491,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
           }
-          // ---- fast paths (full 32-column chunk, no bias / ReLU / row map): few instructions per element, because
-          // the four epilogue warps run one per scheduler and every instruction's latency is exposed
-          const bool plain = nvalid == 32 && args.bias == nullptr && !args.relu && args.rowmap == nullptr && !args.atomic;
-          if (plain && !args.transposed) {
-            if (!m_ok) continue;
-            if (args.mode == RVL_GEMM_OUT_BF16) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(m) * args.ldc + n0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                dst[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                                    pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-            } else {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + ks * args.split_stride + static_cast<long long>(m) * args.ldc + n0);
-              if (args.mode == RVL_GEMM_ADD_F32) {
-                float4 p[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) p[q] = dst[q];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  dst[q] = make_float4(v[q * 4] + p[q].x, v[q * 4 + 1] + p[q].y, v[q * 4 + 2] + p[q].z, v[q * 4 + 3] + p[q].w);
-              } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              }
-            }
-            continue;
-          }
-          if (plain && args.transposed && (w.m_blk * a_tiles + at) * kBM + quarter * 32 + 32 <= args.M) {
-            // out[token][feature]: transpose the warp's 32 features x 32 tokens through shared memory so that each
-            // lane stores 16 contiguous bytes of one token row
-            float* sc = epi_scratch + (warp - 2) * (32 * 33);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = v[j];
-            __syncwarp();
-            const int f_base = (w.m_blk * a_tiles + at) * kBM + quarter * 32;   // first feature of this warp
-            if (args.mode == RVL_GEMM_OUT_BF16) {
-              const int f0 = (lane & 3) * 8, t0 = lane >> 2;
-              __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(n0 + t0) * args.ldc + f_base + f0;
-#pragma unroll
-              for (int pass = 0; pass < 4; ++pass) {
-                const int t = t0 + pass * 8;
-                float x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = sc[(f0 + i) * 33 + t];
-                *reinterpret_cast<uint4*>(base + static_cast<long long>(pass) * 8 * args.ldc) =
-                    make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-              }
-            } else {
-              const int f0 = (lane & 7) * 4, t0 = lane >> 3;
-              float* base = reinterpret_cast<float*>(args.out) + ks * args.split_stride + static_cast<long long>(n0 + t0) * args.ldc + f_base + f0;
-#pragma unroll
-              for (int pass = 0; pass < 8; ++pass) {
-                const int t = t0 + pass * 4;
-                float4 x = make_float4(sc[(f0 + 0) * 33 + t], sc[(f0 + 1) * 33 + t], sc[(f0 + 2) * 33 + t], sc[(f0 + 3) * 33 + t]);
-                float4* dst = reinterpret_cast<float4*>(base + static_cast<long long>(pass) * 4 * args.ldc);
-                if (args.mode == RVL_GEMM_ADD_F32) {
-                  const float4 p = *dst;
-                  x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
-                }
-                *dst = x;
-              }
-            }
-            __syncwarp();
-            continue;
-          }
-          if (!args.transposed) {
-            // thread = token row m, 32 consecutive features n0..n0+31
-            if (!m_ok) continue;
-            if (args.bias != nullptr && ks == 0) {
-              if (nvalid == 32) {
-                const uint4* bp = reinterpret_cast<const uint4*>(args.bias + n0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint4 b = __ldg(bp + q);
-                  v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
-                  v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
-                  v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
-                  v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) v[j] += __bfloat162float(args.bias[n0 + j]);
-              }
-            }
-            if (args.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            const long long row = args.rowmap ? args.rowmap[m] : m;
-            if (args.mode == RVL_GEMM_OUT_BF16) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + row * args.ldc + n0;
-              if (nvalid == 32) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint4 o;
-                  o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                  o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                  o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                  o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                  reinterpret_cast<uint4*>(dst)[q] = o;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
-              }
-            } else {
-              float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + n0;
-              if (args.atomic) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) atomicAdd(dst + j, v[j]);
-              } else if (nvalid == 32) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                  if (args.mode == RVL_GEMM_ADD_F32) {
-                    const float4 p = reinterpret_cast<const float4*>(dst)[q];
-                    o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-                  }
-                  reinterpret_cast<float4*>(dst)[q] = o;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) dst[j] = (args.mode == RVL_GEMM_ADD_F32 ? dst[j] : 0.f) + v[j];
-              }
-            }
-          } else {
-            // thread = feature m, its 32 values are tokens n0..n0+31: out[token][feature], lanes -> consecutive
-            // features (coalesced along the feature dimension)
-            if (!m_ok) continue;
-            const float b = (args.bias != nullptr && ks == 0) ? __bfloat162float(args.bias[m]) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nvalid) {
-                float x = v[j] + b;
-                if (args.relu) x = fmaxf(x, 0.f);
-                const long long row = args.rowmap ? args.rowmap[n0 + j] : (n0 + j);
-                if (args.mode == RVL_GEMM_OUT_BF16) {
-                  reinterpret_cast<__nv_bfloat16*>(args.out)[row * args.ldc + m] = __float2bfloat16(x);
-                } else {
-                  float* dst = reinterpret_cast<float*>(args.out) + ks * args.split_stride + row * args.ldc + m;
-                  if (args.atomic) atomicAdd(dst, x);
-                  else if (args.mode == RVL_GEMM_ADD_F32) *dst += x;
-                  else *dst = x;
-                }
-              }
-            }
-          }
+          store_chunk(args, v, m, m_ok, n0, nvalid, ks, (w.m_blk * a_tiles + at) * kBM + quarter * 32,
+                      epi_scratch + (warp - 2) * (32 * 33), lane);
         }
       }
       if (kStreamK && w.kind == 1) {
@@ -505,6 +512,164 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------- CTA-pair variant
+// Token-major GEMMs with many rows (prefill): two CTAs of a cluster share one 256 x 256 output tile through
+// tcgen05.mma.cta_group::2.  Each CTA loads its own 128 A rows and HALF of the B tile (128 of the 256 rows), so a
+// k-block costs 32 KB of TMA traffic per SM instead of 48 KB - the single-CTA tile is bound by the ~55-72 B/clk one
+// SM's TMA path delivers, not by the tensor pipe.  The even CTA issues the MMAs for both; accumulators (128 rows x
+// 256 columns per CTA, two stages) sit in each CTA's own TMEM and each CTA's epilogue warps store its 128 rows.
+// Barriers: full[s] lives in the leader and counts the bytes of both CTAs' loads; empty[s] and tmem_full[a] exist in
+// both CTAs and are signalled by multicast tcgen05.commit; tmem_empty[a] lives in the leader and is arrived on by the
+// 8 epilogue warps of the pair.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const GemmArgs args) {
+  constexpr int BN = 256, kHalfN = 128;
+  constexpr int kStageBytesP = kATileBytes + kHalfN * kBK * 2;   // 32 KB
+  const int kStages = args.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kATileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytesP);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* epi_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);     // leader's instance is the one used: one arrive.expect_tx for the bytes of both CTAs
+      mbar_init(&empty_bar[i], 1);    // multicast commit from the leader's MMA warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);    // multicast commit
+      mbar_init(&tmem_empty[i], 8);   // leader's instance: 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer's barriers must exist before anything is signalled remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int total_tiles = args.tiles_m * args.tiles_n;     // tiles_m counts 256-row pair tiles
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      int m_blk, n_blk;
+      tile_coords(tile, args.tiles_m, args.tiles_n, m_blk, n_blk);
+      const int m0 = (m_blk * 2 + rank) * kBM, n0 = n_blk * BN + rank * kHalfN;
+      for (int kb = 0; kb < args.k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytesP);
+          tma_load_2d_pair(smem_a + stage * kATileBytes, &tmap_a, full_leader, kb * kBK, m0);
+          tma_load_2d_pair(smem_b + stage * (kHalfN * kBK * 2), &tmap_b, full_leader, kb * kBK, n0);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------------------------------------------------- MMA issuer (leader CTA only)
+      const uint32_t idesc = umma_idesc_bf16(256, BN);
+      const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem_a));
+      const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem_b));
+      const uint64_t a_step = static_cast<uint64_t>(kATileBytes >> 4), b_step = static_cast<uint64_t>((kHalfN * kBK * 2) >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < args.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + a_step * stage;
+            const uint64_t b_desc = b_desc0 + b_step * stage;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);                          // frees the slot in both CTAs
+            if (kb == args.k_blocks - 1) umma_commit_pair(&tmem_full[acc], 3);  // accumulators ready in both CTAs
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
+    const int quarter = warp & 3;
+    const int m_local = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      int m_blk, n_blk;
+      tile_coords(tile, args.tiles_m, args.tiles_n, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = (m_blk * 2 + rank) * kBM + m_local;
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const bool m_ok = m < args.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        }
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= args.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        store_chunk(args, v, m, m_ok, n0, min(32, args.N - n0), 0, (m_blk * 2 + rank) * kBM + quarter * 32,
+                    epi_scratch + (warp - 2) * (32 * 33), lane);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // nobody frees TMEM or exits while the peer may still signal / be read
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -568,6 +733,7 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   static const char* env_at = getenv("RVL_A_TILES");      // experiment hooks
   static const char* env_sk = getenv("RVL_STREAM_K");
   static const char* env_dbg = getenv("RVL_PLAN_DEBUG");
+  static const char* env_pair = getenv("RVL_PAIR");
   GemmArgs a{};
   a.K = static_cast<int>(c.K);
   a.k_blocks = static_cast<int>((c.K + kBK - 1) / kBK);
@@ -631,6 +797,36 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   if (env_dbg)
     fprintf(stderr, "rvl gemm: A rows=%d B rows=%d K=%d bn=%d a_tiles=%d stages=%d acc_stages=%d tmem=%d split_k=%d stream_k=%d upc=%d\n",
             a.M, a.N, a.K, a.bn, a.a_tiles, a.stages, a.acc_stages, a.tmem_cols, a.split_k, a.stream_k, a.units_per_cta);
+  // CTA-pair kernel (tcgen05 cta_group::2): token-major GEMMs with >= one wave of 256 x 256 tiles
+  const bool pair_ok = !swap && a.split_k == 1 && !a.stream_k && a.N >= 256 && a.M >= 1024 && (num_sms % 2 == 0);
+  if (pair_ok && !(env_pair && atoi(env_pair) == 0)) {   // RVL_PAIR=0 falls back to the single-CTA kernel
+    a.a_tiles = 1;
+    a.bn = 256;
+    a.tiles_m = (a.M + 255) / 256;
+    a.tiles_n = (a.N + 255) / 256;
+    a.stages = kSmemBudget / (kATileBytes + 128 * kBK * 2);
+    if (a.stages > kMaxStages) a.stages = kMaxStages;
+    CUtensorMap ta2, tb2;
+    int rc2 = make_tmap(&ta2, pa, a.M, c.K, kBM, err);
+    if (rc2) return rc2;
+    rc2 = make_tmap(&tb2, pb, a.N, c.K, 128, err);
+    if (rc2) return rc2;
+    static bool pair_attr = false;
+    if (!pair_attr) {
+      if (cudaFuncSetAttribute(gemm_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        *err = "cudaFuncSetAttribute(pair kernel) failed"; return RVL_ERR_CUDA;
+      }
+      pair_attr = true;
+    }
+    const int smem2 = a.stages * (kATileBytes + 128 * kBK * 2) + 1024 + 512 + kEpiScratchBytes;
+    const int total2 = a.tiles_m * a.tiles_n;
+    int grid2 = 2 * (total2 < num_sms / 2 ? total2 : num_sms / 2);
+    if (env_dbg) fprintf(stderr, "rvl gemm pair: M=%d N=%d K=%d stages=%d grid=%d\n", a.M, a.N, a.K, a.stages, grid2);
+    gemm_bf16_pair_kernel<<<grid2, kGemmThreads, smem2, st>>>(ta2, tb2, a);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { *err = std::string("gemm pair launch: ") + cudaGetErrorString(e2); return RVL_ERR_CUDA; }
+    return RVL_OK;
+  }
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, pa, a.M, c.K, a.a_tiles * kBM, err);
   if (rc) return rc;
