@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RVL_ABI_VERSION 1
+#define RVL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RVL_API __attribute__((visibility("default")))
@@ -70,7 +70,9 @@ typedef struct rvl_config {
  * once at load time:
  *   wqkv  = cat(self_attn.{q,k,v}_proj.weight)        [3*hidden, hidden]
  *   wo    = self_attn.o_proj.weight                   [hidden, hidden]
- *   wgu   = cat(mlp.gate_proj.weight, up_proj.weight) [2*intermediate, hidden]
+ *   wgu   = cat(mlp.gate_proj.weight, up_proj.weight) [2*intermediate, hidden]  (rvl_weights.wgu_layout 0), or the same
+ *           rows interleaved in blocks of 32 = [gate 16b..16b+15 | up 16b..16b+15] (wgu_layout 1, intermediate % 16 == 0):
+ *           SwiGLU is then fused into the gate/up GEMM epilogue and the [tokens, 2*intermediate] tensor is never written
  *   wdown = mlp.down_proj.weight                      [hidden, intermediate]
  *   ln1   = input_layernorm.weight, ln2 = post_attention_layernorm.weight  [hidden] */
 typedef struct rvl_layer_weights {
@@ -89,6 +91,7 @@ typedef struct rvl_weights {
   const void* proj_w;              /* model.mm_projector.weight [hidden, adapter_dim] bf16 (stage 1) */
   const void* proj_b;              /* model.mm_projector.bias [hidden] bf16 */
   const rvl_layer_weights* layers; /* n_layers entries (host array, copied) */
+  int32_t wgu_layout;              /* 0: cat(gate, up); 1: 16-row interleave (see rvl_layer_weights) */
 } rvl_weights;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
@@ -202,6 +205,12 @@ RVL_API void rvl_debug_gemm_timestamps(int enable, unsigned long long* out, int 
 #define RVL_GEMM_FLAG_SWAP 2    /* stream the weight as the 128-row MMA operand (small-M / decode) */
 #define RVL_GEMM_FLAG_STREAMK 4 /* with SWAP and a bound workspace: always deal the k-blocks evenly to the SMs (stream-K);
                                    by default the library does so only when plain tiles leave a ragged last wave */
+#define RVL_GEMM_FLAG_SWIGLU 16 /* W rows are interleaved in blocks of 32 = [16 gate rows | 16 up rows] (rvl_weights.wgu_layout 1):
+                                   the epilogue stores silu(gate) * up as bf16 [M, N / 2] (ldc counts act columns); needs
+                                   N % 32 == 0, RVL_GEMM_OUT_BF16, no bias / ReLU / rowmap / split_k */
+#define RVL_GEMM_FLAG_W_CONST 8 /* W is a bound weight that no work queued earlier on the stream writes: with SWAP the kernel
+                                   (launched with programmatic stream serialization) may prefetch W into shared memory
+                                   while the kernel that produces A is still running */
 
 /* out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]); A, W, bias bf16; fp32 accumulation in TMEM.
  * Replaces every nn.Linear on the path (cuBLAS via torch): q/k/v/o, gate/up/down, lm_head,

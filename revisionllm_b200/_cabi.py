@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librevisionllm_b200.so")
 
 RVL_OK = 0
 GEMM_OUT_BF16, GEMM_OUT_F32, GEMM_ADD_F32 = 0, 1, 2
-GEMM_FLAG_RELU, GEMM_FLAG_SWAP, GEMM_FLAG_STREAMK = 1, 2, 4
+GEMM_FLAG_RELU, GEMM_FLAG_SWAP, GEMM_FLAG_STREAMK, GEMM_FLAG_W_CONST, GEMM_FLAG_SWIGLU = 1, 2, 4, 8, 16
 
 
 class RvlError(RuntimeError):
@@ -33,7 +33,8 @@ class rvl_layer_weights(C.Structure):
 
 class rvl_weights(C.Structure):
     _fields_ = [("embed_tokens", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p),
-                ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("layers", C.POINTER(rvl_layer_weights))]
+                ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("layers", C.POINTER(rvl_layer_weights)),
+                ("wgu_layout", C.c_int32)]
 
 
 _P, _I32, _I64, _SZ, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
                                                             __nv_bfloat16* __restrict__ out,
                                                             const int32_t* __restrict__ cu_seqlens, int n_heads,
                                                             float scale_log2) {
+  pdl_trigger();
+  pdl_wait();
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int s0 = cu_seqlens[seq];
   const int L = cu_seqlens[seq + 1] - s0;
@@ -226,8 +228,8 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
   }
   dim3 grid((max_seqlen + kQT - 1) / kQT, n_heads, n_seq);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kD));
-  attn_prefill_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                               reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2);
+  launch_k(attn_prefill_kernel, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+           reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2);
 }
 
 // ------------------------------------------------------------------------------------------- decode
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
   extern __shared__ float s_scores[];          // [n_keys_max]
   __shared__ float s_red[8][kD];
   __shared__ float s_stat[8];
+  pdl_trigger();
+  pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_keys = seq_lens[seq] + 1;        // includes the token appended this step
@@ -335,11 +339,10 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
     attr_smem = smem;
   }
   dim3 grid(n_heads, n_seq);
-  attn_decode_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                              reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages,
-                                              reinterpret_cast<const __nv_bfloat16*>(k_pages),
-                                              reinterpret_cast<const __nv_bfloat16*>(v_pages), n_heads, page_size,
-                                              1.0f / sqrtf(static_cast<float>(kD)));
+  launch_k(attn_decode_kernel, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+           reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages,
+           reinterpret_cast<const __nv_bfloat16*>(k_pages), reinterpret_cast<const __nv_bfloat16*>(v_pages), n_heads, page_size,
+           1.0f / sqrtf(static_cast<float>(kD)));
 }
 
 }  // namespace rvl

@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
                                                            const int32_t* __restrict__ rows,
                                                            const float* __restrict__ partials, int n_partials,
                                                            long long partial_stride, float* x_out) {
-  constexpr int kMaxVec = 8;  // float4 per thread -> dim <= THREADS * 32
+  constexpr int kMaxVec = 8192 / 4 / THREADS;  // float4 per thread, dim <= 8192
+  constexpr int kMaxPartials = 8;
+  pdl_trigger();
+  pdl_wait();
   const long long src_row = rows ? rows[blockIdx.x] : blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + src_row * dim);
   const int nvec = dim >> 2;
@@ -37,9 +40,15 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
     const int idx = threadIdx.x + i * THREADS;
     if (idx < nvec) {
       c[i] = xr[idx];
-      for (int p = 0; p < n_partials; ++p) {
-        const float4 q = reinterpret_cast<const float4*>(partials + p * partial_stride + src_row * dim)[idx];
-        c[i].x += q.x; c[i].y += q.y; c[i].z += q.z; c[i].w += q.w;
+      if (n_partials > 0) {
+        // all partial loads are issued before the first add: one round trip instead of n_partials
+        float4 q[kMaxPartials];
+#pragma unroll
+        for (int p = 0; p < kMaxPartials; ++p)
+          if (p < n_partials) q[p] = __ldcg(reinterpret_cast<const float4*>(partials + p * partial_stride + src_row * dim) + idx);
+#pragma unroll
+        for (int p = 0; p < kMaxPartials; ++p)
+          if (p < n_partials) { c[i].x += q[p].x; c[i].y += q[p].y; c[i].z += q[p].z; c[i].w += q[p].w; }
       }
       if (x_out) reinterpret_cast<float4*>(x_out + src_row * dim)[idx] = c[i];
       ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
@@ -71,14 +80,17 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
 void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int dim, float eps, const int32_t* rows,
                     cudaStream_t st, const float* partials, int n_partials, int64_t partial_stride, float* x_out) {
   if (n_rows <= 0) return;
-  if (dim <= 128 * 32)
-    rmsnorm_kernel<128><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
-        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows, partials,
-        n_partials, partial_stride, x_out);
+  const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const long long ps = partial_stride;
+  // few rows (decode): one float4 per thread so that a row's loads are all in flight at once (the 128-thread
+  // variant took 9.7 us for 180 rows with 4 split-k partials - latency, not bandwidth)
+  if (n_rows <= 1024 && dim >= 2048)
+    launch_k(rmsnorm_kernel<1024>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+  else if (dim <= 256 * 8)
+    launch_k(rmsnorm_kernel<256>, dim3(static_cast<unsigned>(n_rows)), dim3(256), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
   else
-    rmsnorm_kernel<256><<<static_cast<unsigned>(n_rows), 256, 0, st>>>(
-        x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(y), dim, eps, rows, partials,
-        n_partials, partial_stride, x_out);
+    launch_k(rmsnorm_kernel<512>, dim3(static_cast<unsigned>(n_rows)), dim3(512), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
 }
 
 // ------------------------------------------------------------------------------------ embedding / splice rows
@@ -86,6 +98,8 @@ void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int 
 // (vtimellm_arch.py:194 `embed_tokens(cat(text chunks))`) and the decode-step token embedding.
 __global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ ids,
                                   const int32_t* __restrict__ dst_rows, int dim, int vocab, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x;
   int id = ids[i];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -101,12 +115,14 @@ __global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, const
 void launch_embed_rows(const void* table, const int32_t* ids, const int32_t* dst_rows, int n, int dim, int vocab,
                        float* out, cudaStream_t st) {
   if (n <= 0) return;
-  embed_rows_kernel<<<n, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(table), ids, dst_rows, dim, vocab, out);
+  launch_k(embed_rows_kernel, dim3(n), dim3(128), 0, st, reinterpret_cast<const __nv_bfloat16*>(table), ids, dst_rows, dim, vocab, out);
 }
 
 // out[dst_rows[i]] (fp32) = src[i] (bf16): already-projected visual rows (stage-2 CLS tokens).
 __global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ dst_rows, int dim,
                                     float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x;
   const long long dst = dst_rows ? dst_rows[i] : i;
   const uint4* s4 = reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * dim);
@@ -119,12 +135,14 @@ __global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const
 }
 void launch_scatter_rows_bf16(const void* src, const int32_t* dst_rows, int n, int dim, float* out, cudaStream_t st) {
   if (n <= 0) return;
-  scatter_rows_kernel<<<n, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst_rows, dim, out);
+  launch_k(scatter_rows_kernel, dim3(n), dim3(128), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), dst_rows, dim, out);
 }
 
 // ------------------------------------------------------------------------------------ token -> sequence map
 __global__ void token_seq_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict__ tok_seq,
                                  int32_t* __restrict__ last_rows, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (t < n_seq && last_rows) last_rows[t] = cu[t + 1] - 1;
   if (t >= total) return;
@@ -139,7 +157,8 @@ void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, in
                       cudaStream_t st) {
   const long long n = total > n_seq ? total : n_seq;
   if (n <= 0) return;
-  token_seq_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(cu_seqlens, n_seq, tok_seq, last_rows, total);
+  launch_k(token_seq_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, cu_seqlens, n_seq, tok_seq, last_rows,
+           static_cast<long long>(total));
 }
 
 // ------------------------------------------------------------------------------------ RoPE + KV write
@@ -155,6 +174,8 @@ __global__ void __launch_bounds__(128) rope_kv_kernel(__nv_bfloat16* __restrict_
                                                        int n_heads, int page_size, float theta) {
   constexpr int D = 128;
   __shared__ float s_cos[D / 2], s_sin[D / 2];
+  pdl_trigger();
+  pdl_wait();
   const long long tok = blockIdx.x;
   const int seq = tok_seq ? tok_seq[tok] : static_cast<int>(tok);
   const int pos = positions ? positions[tok] : static_cast<int>(tok - cu_seqlens[seq]);
@@ -211,9 +232,9 @@ void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const
                     const int32_t* cu_seqlens, const int32_t* page_table, int max_pages, void* k_pages, void* v_pages,
                     int n_heads, int page_size, float theta, cudaStream_t st) {
   if (n_tokens <= 0) return;
-  rope_kv_kernel<<<static_cast<unsigned>(n_tokens), 128, 0, st>>>(
-      reinterpret_cast<__nv_bfloat16*>(qkv), positions, tok_seq, cu_seqlens, page_table, max_pages,
-      reinterpret_cast<__nv_bfloat16*>(k_pages), reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, theta);
+  launch_k(rope_kv_kernel, dim3(static_cast<unsigned>(n_tokens)), dim3(128), 0, st, reinterpret_cast<__nv_bfloat16*>(qkv), positions,
+           tok_seq, cu_seqlens, page_table, max_pages, reinterpret_cast<__nv_bfloat16*>(k_pages),
+           reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, theta);
 }
 
 // ------------------------------------------------------------------------------------ SwiGLU
@@ -221,6 +242,8 @@ void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const
 // Algorithmic bytes per token: 2I*2 read + I*2 write.
 __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ act, long long n_vec,
                               int inter) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = inter >> 3;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -246,8 +269,8 @@ void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaS
   if (n_vec <= 0) return;
   long long blocks = (n_vec + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;  // grid-stride: a multiple of the SM count
-  swiglu_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gu),
-                                                               reinterpret_cast<__nv_bfloat16*>(act), n_vec, inter);
+  launch_k(swiglu_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(gu),
+           reinterpret_cast<__nv_bfloat16*>(act), n_vec, inter);
 }
 
 }  // namespace rvl

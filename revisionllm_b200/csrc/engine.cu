@@ -136,6 +136,8 @@ void rvl_destroy(rvl_handle* h) { delete h; }
 int rvl_bind_weights(rvl_handle* h, const rvl_weights* w) {
   if (!h || !w || !w->layers) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: null argument");
   if (!w->embed_tokens || !w->final_norm || !w->lm_head) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: missing tensor");
+  if (w->wgu_layout != 0 && w->wgu_layout != 1) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: wgu_layout must be 0 or 1");
+  if (w->wgu_layout == 1 && h->cfg.intermediate % 16) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: wgu_layout 1 needs intermediate % 16 == 0");
   h->layers.assign(w->layers, w->layers + h->cfg.n_layers);
   for (auto& l : h->layers)
     if (!l.wqkv || !l.wo || !l.wgu || !l.wdown || !l.ln1 || !l.ln2) return fail(h, RVL_ERR_INVALID, "rvl_bind_weights: missing layer tensor");
@@ -196,7 +198,7 @@ static int linear(const rvl_handle* h, const void* x, const void* w, const void*
   c.out_mode = mode; c.flags = flags; c.rowmap = rowmap; c.split_k = 1;
   if (tokens <= 256) {
     // few tokens (decode, lm_head on last rows): stream the weight through the 128-row MMA slot once
-    c.flags |= RVL_GEMM_FLAG_SWAP;
+    c.flags |= RVL_GEMM_FLAG_SWAP | RVL_GEMM_FLAG_W_CONST;   // w is a bound weight: prefetchable before the producer of x ends
     if (partial_buf) {
       const int tiles = static_cast<int>((features + 127) / 128);
       const int kb = static_cast<int>((K + 63) / 64);
@@ -218,6 +220,18 @@ static int linear(const rvl_handle* h, const void* x, const void* w, const void*
                2.0 * features * K + 2.0 * tokens * K + out_b);
   int rc = gemm_bf16(c, h->num_sms, st, &err);
   if (rc) return fail(h, rc, err);
+  return RVL_OK;
+}
+
+// act = silu(x . Wgate^T) * (x . Wup^T): one GEMM with the SwiGLU in its epilogue when the weight is interleaved
+// (wgu_layout 1), else GEMM -> [tokens, 2I] -> swiglu kernel.
+static int gate_up(const rvl_handle* h, const rvl_layer_weights& w, int64_t tokens, cudaStream_t st) {
+  const int H = h->cfg.hidden, I = h->cfg.intermediate;
+  if (h->w.wgu_layout == 1)
+    return linear(h, h->xnorm, w.wgu, nullptr, h->act, tokens, 2 * I, H, I, RVL_GEMM_OUT_BF16, RVL_GEMM_FLAG_SWIGLU, nullptr, st);
+  int rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, tokens, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st);
+  if (rc) return rc;
+  launch_swiglu(h->gu, h->act, tokens, I, st);
   return RVL_OK;
 }
 
@@ -308,8 +322,7 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
     }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hidden, T, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
     launch_rmsnorm(hidden, w.ln2, h->xnorm, T, H, c.rms_eps, nullptr, st);
-    if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, T, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
-    launch_swiglu(h->gu, h->act, T, I, st);
+    if ((rc = gate_up(h, w, T, st))) return rc;
     if ((rc = linear(h, h->act, w.wdown, nullptr, hidden, T, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
   }
   if (all_logits) {
@@ -325,6 +338,8 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
 }
 
 __global__ void inc_kernel(int32_t* v, int n) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] += 1;
 }
@@ -357,13 +372,12 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
     }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, &pending))) return rc;
     launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
-    if ((rc = linear(h, h->xnorm, w.wgu, nullptr, h->gu, n, 2 * I, H, 2 * I, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
-    launch_swiglu(h->gu, h->act, n, I, st);
+    if ((rc = gate_up(h, w, n, st))) return rc;
     if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, &pending))) return rc;
   }
   launch_rmsnorm(hid, h->w.final_norm, h->xlast, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
   if ((rc = linear(h, h->xlast, h->w.lm_head, nullptr, logits_out, n, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;
-  inc_kernel<<<(n_seq + 127) / 128, 128, 0, st>>>(seq_lens, n_seq);
+  launch_k(inc_kernel, dim3((n_seq + 127) / 128), dim3(128), 0, st, seq_lens, static_cast<int>(n_seq));
   return check_cuda(h, "rvl_decode_step");
 }
 

@@ -58,6 +58,7 @@ struct GemmArgs {
   int tmem_cols;        // power of two >= acc_stages * a_tiles * sub_stride
   int stream_a;         // A is a weight streamed once from HBM: L2 evict-first for A, evict-last for B
   int stream_k;         // deal k-blocks of all tiles evenly to the CTAs (weight streaming)
+  int prefetch_a;       // A is a bound weight no earlier kernel writes: fill the smem ring with A before pdl_wait()
   int units_per_cta;    // stream-K: k-blocks per CTA
   float* ws;            // stream-K: per-CTA fp32 partial [a_tiles*128][ws_ld]
   unsigned int* flags;  // stream-K: per-CTA "partial written" epoch
@@ -72,6 +73,7 @@ struct GemmArgs {
   int relu;
   int transposed;             // 0: tokens = A rows (m), features = B rows (n); 1: the other way round
   int atomic;                 // split-k partial sums: atomicAdd into fp32 out
+  int swiglu;                 // feature rows come in blocks of [16 gate | 16 up]: store silu(gate) * up, bf16, [tokens][features / 2]
 };
 
 // One unit of work of a CTA: k-blocks [kb0, kb1) of tile (m_blk, n_blk).
@@ -156,6 +158,38 @@ __device__ int g_gemm_dbg_on = 0;
 // fp32 shared-memory transpose scratch.
 __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32], int m, bool m_ok, int n0, int nvalid, int ks,
                                             int f_base, float* sc, int lane) {
+  if (args.swiglu) {
+    // Fused SwiGLU (replaces `act_fn(gate_proj(x)) * up_proj(x)` of LlamaMLP): the weight's rows are interleaved at bind
+    // time in blocks of 32 = [gate i0..i0+15 | up i0..i0+15], so gate and up of one act element meet in one chunk.
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out);
+    if (!args.transposed) {
+      // thread = token m, v[0..15] = gate, v[16..31] = up of act columns n0/2 .. n0/2+15 (host guarantees N % 32 == 0)
+      if (!m_ok) return;
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g0 = v[2 * j], g1 = v[2 * j + 1];
+        o[j] = pack_bf16x2(g0 / (1.f + __expf(-g0)) * v[16 + 2 * j], g1 / (1.f + __expf(-g1)) * v[17 + 2 * j]);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + static_cast<long long>(m) * args.ldc + (n0 >> 1));
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+      // thread = weight row m: lanes 0-15 hold gate, lanes 16-31 up of act columns f_base/2 + (lane & 15); v[j] = token
+      // n0 + j.  Lower lanes finish the even tokens, upper lanes the odd ones: one shuffle per token pair.
+      const bool lower = lane < 16;
+      __nv_bfloat16* col = out + (f_base >> 1) + (lane & 15);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float got = __shfl_xor_sync(0xffffffffu, lower ? v[j + 1] : v[j], 16);
+        const float g = lower ? v[j] : got;
+        const float u = lower ? got : v[j + 1];
+        const int jj = j + (lower ? 0 : 1);
+        if (jj < nvalid && m_ok) col[static_cast<long long>(n0 + jj) * args.ldc] = __float2bfloat16(g / (1.f + __expf(-g)) * u);
+      }
+    }
+    return;
+  }
   // ---- fast paths (full 32-column chunk, no bias / ReLU / row map): few instructions per element, because
   // the four epilogue warps run one per scheduler and every instruction's latency is exposed
   const bool plain = nvalid == 32 && args.bias == nullptr && !args.relu && args.rowmap == nullptr && !args.atomic;
@@ -183,7 +217,8 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32]
     }
     return;
   }
-  if (plain && args.transposed && f_base + 32 <= args.M) {
+  const bool plain_any = args.bias == nullptr && !args.relu && args.rowmap == nullptr && !args.atomic;
+  if (plain_any && args.transposed && f_base + 32 <= args.M) {
     // out[token][feature]: transpose the warp's 32 features x 32 tokens through shared memory so that each
     // lane stores 16 contiguous bytes of one token row
 #pragma unroll
@@ -198,8 +233,9 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32]
         float x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = sc[(f0 + i) * 33 + t];
-        *reinterpret_cast<uint4*>(base + static_cast<long long>(pass) * 8 * args.ldc) =
-            make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+        if (t < nvalid)   // ragged last chunk of the token dimension
+          *reinterpret_cast<uint4*>(base + static_cast<long long>(pass) * 8 * args.ldc) =
+              make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
       }
     } else {
       const int f0 = (lane & 7) * 4, t0 = lane >> 3;
@@ -209,11 +245,13 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32]
         const int t = t0 + pass * 4;
         float4 x = make_float4(sc[(f0 + 0) * 33 + t], sc[(f0 + 1) * 33 + t], sc[(f0 + 2) * 33 + t], sc[(f0 + 3) * 33 + t]);
         float4* dst = reinterpret_cast<float4*>(base + static_cast<long long>(pass) * 4 * args.ldc);
-        if (args.mode == RVL_GEMM_ADD_F32) {
-          const float4 p = *dst;
-          x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+        if (t < nvalid) {
+          if (args.mode == RVL_GEMM_ADD_F32) {
+            const float4 p = *dst;
+            x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+          }
+          *dst = x;
         }
-        *dst = x;
       }
     }
     __syncwarp();
@@ -357,6 +395,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (warp == 0) DBG_T(0);
+  // Programmatic dependent launch: this CTA may have started while the previous kernel of the stream (the one that
+  // produces the activations) is still running.  Everything above touched only kernel parameters and shared memory.
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -364,18 +405,40 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t phase = 0;
     const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
     WorkItem w;
+    // Weight prefetch: A (a bound weight in the weight-streaming orientation) depends on no earlier kernel, so the first
+    // kStages k-blocks of it are already on their way into the ring while the producer of the activations finishes.
+    int prefetched = 0;
+    if (args.prefetch_a) {
+      for (int it = 0; prefetched < kStages && get_work<kStreamK>(args, it, w); ++it) {
+        const int m0 = w.m_blk * a_tiles * kBM;
+        for (int kb = w.kb0; kb < w.kb1 && prefetched < kStages; ++kb, ++prefetched) {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[prefetched], stage_tx_bytes);   // B's bytes are issued after pdl_wait()
+            tma_load_2d_hint(smem_a + prefetched * a_slot_bytes, &tmap_a, &full_bar[prefetched], kb * kBK, m0, pol_a);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    pdl_wait();
+    int n_iter = 0;
     for (int it = 0; get_work<kStreamK>(args, it, w); ++it) {
       const int m0 = w.m_blk * a_tiles * kBM, n0 = w.n_blk * BN;
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
-          if (args.stream_a) {
-            tma_load_2d_hint(smem_a + stage * a_slot_bytes, &tmap_a, &full_bar[stage], kb * kBK, m0, pol_a);
-            tma_load_2d_hint(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0, pol_b);
-          } else {
-            tma_load_2d(smem_a + stage * a_slot_bytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0);
+      for (int kb = w.kb0; kb < w.kb1; ++kb, ++n_iter) {
+        if (n_iter < prefetched) {
+          // slot's first use: A is in flight already, the barrier already expects B's bytes
+          if (elect_one()) tma_load_2d_hint(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0, pol_b);
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
+            if (args.stream_a) {
+              tma_load_2d_hint(smem_a + stage * a_slot_bytes, &tmap_a, &full_bar[stage], kb * kBK, m0, pol_a);
+              tma_load_2d_hint(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0, pol_b);
+            } else {
+              tma_load_2d(smem_a + stage * a_slot_bytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
+              tma_load_2d(smem_b + stage * b_tile_bytes, &tmap_b, &full_bar[stage], kb * kBK, n0);
+            }
           }
         }
         __syncwarp();
@@ -424,6 +487,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     DBG_T(2);
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
+    pdl_wait();                    // residual / partial / flag reads and every store come after the earlier kernels
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int m_local = quarter * 32 + lane;
     const int n_chunks = (BN + 31) >> 5;
@@ -457,6 +521,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (!kStreamK && warp == 2 && c == 0) DBG_T(4);
+          if (!kStreamK && warp == 2 && c == 1) DBG_T(6);
           if (at == a_tiles - 1 && c == n_chunks - 1) {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
             tc_fence_before();
@@ -509,6 +575,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) DBG_T(7);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
@@ -570,6 +637,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   cluster_sync_all();                 // the peer's barriers must exist before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();                      // the set-up above overlapped the previous kernel's tail (programmatic dependent launch)
+  pdl_wait();
 
   const int n_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
@@ -744,12 +813,18 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   a.mode = c.out_mode;
   a.relu = (c.flags & RVL_GEMM_FLAG_RELU) ? 1 : 0;
   a.transposed = swap ? 1 : 0;
+  a.swiglu = (c.flags & RVL_GEMM_FLAG_SWIGLU) ? 1 : 0;
+  if (a.swiglu && (c.N % 32 || c.out_mode != RVL_GEMM_OUT_BF16 || c.bias || c.rowmap || (c.flags & RVL_GEMM_FLAG_RELU) || c.split_k > 1 || partials)) {
+    *err = "gemm: RVL_GEMM_FLAG_SWIGLU needs N % 32 == 0, bf16 output, no bias / ReLU / rowmap / split-k";
+    return RVL_ERR_INVALID;
+  }
   const void* pa = swap ? c.W : c.A;   // operand that supplies the 128-row MMA dimension
   const void* pb = swap ? c.A : c.W;   // operand that supplies MMA N
   a.M = static_cast<int>(swap ? c.N : c.M);
   a.N = static_cast<int>(swap ? c.M : c.N);
   a.bn = a.N >= 256 ? 256 : ((a.N + 15) / 16) * 16;
   a.stream_a = swap ? 1 : 0;
+  a.prefetch_a = (swap && (c.flags & RVL_GEMM_FLAG_W_CONST)) ? 1 : 0;
   a.sub_stride = ((a.bn + 31) / 32) * 32;
   int sk = c.split_k < 1 ? 1 : c.split_k;
   // two A tiles per CTA tile (256 x 256) for big token-major GEMMs: the B tile is fetched once per two A tiles.
@@ -822,8 +897,8 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     const int total2 = a.tiles_m * a.tiles_n;
     int grid2 = 2 * (total2 < num_sms / 2 ? total2 : num_sms / 2);
     if (env_dbg) fprintf(stderr, "rvl gemm pair: M=%d N=%d K=%d stages=%d grid=%d\n", a.M, a.N, a.K, a.stages, grid2);
-    gemm_bf16_pair_kernel<<<grid2, kGemmThreads, smem2, st>>>(ta2, tb2, a);
-    cudaError_t e2 = cudaGetLastError();
+    cudaError_t e2 = launch_gemm_k(gemm_bf16_pair_kernel, dim3(grid2), dim3(kGemmThreads), smem2, st, ta2, tb2, a);
+    if (e2 == cudaSuccess) e2 = cudaGetLastError();
     if (e2 != cudaSuccess) { *err = std::string("gemm pair launch: ") + cudaGetErrorString(e2); return RVL_ERR_CUDA; }
     return RVL_OK;
   }
@@ -849,11 +924,11 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { *err = "cudaFuncSetAttribute(max dynamic smem) failed"; return RVL_ERR_CUDA; }
     attr_set = true;
   }
-  if (a.stream_k) gemm_bf16_tcgen05_kernel<1, true><<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
-  else if (a.a_tiles == 2) gemm_bf16_tcgen05_kernel<2, false><<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
-  else gemm_bf16_tcgen05_kernel<1, false><<<grid, kGemmThreads, smem, st>>>(ta, tb, a);
-  if (rc) return rc;
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (a.stream_k) e = launch_gemm_k(gemm_bf16_tcgen05_kernel<1, true>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, a);
+  else if (a.a_tiles == 2) e = launch_gemm_k(gemm_bf16_tcgen05_kernel<2, false>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, a);
+  else e = launch_gemm_k(gemm_bf16_tcgen05_kernel<1, false>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("gemm launch: ") + cudaGetErrorString(e); return RVL_ERR_CUDA; }
   return RVL_OK;
 }

@@ -217,6 +217,17 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the path is launched with cudaLaunchAttributeProgrammaticStreamSerialization (rvl_internal.h
+// launch_k): its CTAs may become resident while the previous kernel of the stream is still running.
+//   pdl_trigger(): this CTA no longer objects to the NEXT kernel's CTAs being scheduled (they still block in their
+//                  own pdl_wait until this grid has completed);
+//   pdl_wait():    returns once every earlier grid of the stream has completed and its writes are visible.
+// Anything executed before pdl_wait() may only touch memory no earlier kernel writes (weights, kernel parameters).
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

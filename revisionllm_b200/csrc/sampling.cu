@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_greedy_kernel(const flo
   __shared__ float s_val[kSampleThreads / 32];
   __shared__ int s_idx[kSampleThreads / 32];
   __shared__ float s_sum[kSampleThreads / 32];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const float* x = logits + static_cast<long long>(row) * vocab;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -88,8 +90,8 @@ void launch_sample_greedy(const float* logits, int n_seq, int vocab, int32_t* un
                           int32_t* next_tokens, float* entropy_out, int32_t* /*seq_lens*/, int32_t* /*n_unfinished*/,
                           cudaStream_t st) {
   if (n_seq <= 0) return;
-  sample_greedy_kernel<<<n_seq, kSampleThreads, 0, st>>>(logits, vocab, unfinished, eos_id, pad_id, next_tokens,
-                                                         entropy_out);
+  launch_k(sample_greedy_kernel, dim3(n_seq), dim3(kSampleThreads), 0, st, logits, vocab, unfinished, eos_id, pad_id, next_tokens,
+           entropy_out);
 }
 
 }  // namespace rvl

@@ -6,6 +6,7 @@ the hot path runs in the kernels of `csrc/` behind `include/revisionllm_b200.h`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -100,10 +101,18 @@ class Engine:
 
         layers = (_cabi.rvl_layer_weights * cfg.n_layers)()
         keep: List[torch.Tensor] = []
+        # gate/up rows interleaved in blocks of 16 so the GEMM epilogue can apply SwiGLU (rvl_weights.wgu_layout 1)
+        I = cfg.intermediate
+        interleave = I % 16 == 0 and os.environ.get("RVL_WGU_LAYOUT", "1") != "0"
         for i in range(cfg.n_layers):
             p = f"model.layers.{i}."
             wqkv = torch.cat([g(p + f"self_attn.{n}_proj.weight") for n in ("q", "k", "v")], dim=0).contiguous()
-            wgu = torch.cat([g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")], dim=0).contiguous()
+            gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
+            if interleave:
+                wgu = torch.stack([gate.view(I // 16, 16, -1), up.view(I // 16, 16, -1)], dim=1).reshape(2 * I, -1).contiguous()
+            else:
+                wgu = torch.cat([gate, up], dim=0).contiguous()
+            del gate, up
             wo, wd = g(p + "self_attn.o_proj.weight"), g(p + "mlp.down_proj.weight")
             ln1, ln2 = g(p + "input_layernorm.weight"), g(p + "post_attention_layernorm.weight")
             keep += [wqkv, wgu, wo, wd, ln1, ln2]
@@ -115,7 +124,7 @@ class Engine:
         if "model.mm_projector.weight" in sd:
             pw, pb = g("model.mm_projector.weight"), g("model.mm_projector.bias")
             keep += [pw, pb]
-        w = _cabi.rvl_weights(emb.data_ptr(), fn.data_ptr(), head.data_ptr(), _ptr(pw), _ptr(pb), layers)
+        w = _cabi.rvl_weights(emb.data_ptr(), fn.data_ptr(), head.data_ptr(), _ptr(pw), _ptr(pb), layers, 1 if interleave else 0)
         self._check(self.lib.rvl_bind_weights(self.h, C.byref(w)), "rvl_bind_weights")
         self._keep = keep
         self.embed_tokens, self.lm_head_w, self.proj_w, self.proj_b = emb, head, pw, pb

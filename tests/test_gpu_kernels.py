@@ -131,6 +131,31 @@ def test_gemm_stream_k_exact_and_modes(eng_ws, M, N, K):
     assert _relerr(outb.float().cpu(), ref) < 1e-2
 
 
+def _interleave_gate_up(gate, up):
+    """rvl_weights.wgu_layout 1: blocks of 32 rows = [16 gate rows | 16 up rows]."""
+    I = gate.shape[0]
+    return torch.stack([gate.view(I // 16, 16, -1), up.view(I // 16, 16, -1)], dim=1).reshape(2 * I, -1).contiguous()
+
+
+@pytest.mark.parametrize("M,I,K", [(180, 1024, 512), (37, 2752, 256), (1, 512, 256), (1500, 512, 256), (4224, 1024, 512)])
+def test_gemm_fused_swiglu_epilogue(eng_ws, M, I, K):
+    """gate/up GEMM with SwiGLU in the epilogue == silu(x Wg^T) * (x Wu^T) (transformers LlamaMLP), token-major
+    (pair / single-CTA kernels), weight-streaming and stream-K orientations, ragged token chunks."""
+    from revisionllm_b200 import _cabi
+    A = _rand((M, K), 11)
+    gate, up = _rand((I, K), 12, 1.0 / math.sqrt(K)), _rand((I, K), 13, 1.0 / math.sqrt(K))
+    ref = F.silu(F.linear(A.float(), gate.float())) * F.linear(A.float(), up.float())
+    Wd = _interleave_gate_up(gate, up).cuda()
+    Ad = A.cuda()
+    modes = [_cabi.GEMM_FLAG_SWIGLU]
+    if M <= 256:
+        modes += [_cabi.GEMM_FLAG_SWIGLU | _cabi.GEMM_FLAG_SWAP, _cabi.GEMM_FLAG_SWIGLU | _cabi.GEMM_FLAG_SWAP | _cabi.GEMM_FLAG_STREAMK]
+    for flags in modes:
+        out = torch.full((M, I), float("nan"), dtype=torch.bfloat16, device="cuda")
+        eng_ws.gemm(Ad, Wd, out=out, flags=flags, ldc=I)
+        assert _relerr(out.float().cpu(), ref) < 1e-2, (flags, M, I, K)      # one bf16 rounding of the product
+
+
 def test_gemm_large_exact(eng):
     """Multi-wave persistent loop with exact integer inputs (bit-exact fp32 accumulation)."""
     from revisionllm_b200 import _cabi
@@ -160,8 +185,9 @@ def test_gemm_linearity_full_size(eng):
 
 # ------------------------------------------------------------------------------------------- elementwise
 @pytest.mark.parametrize("dim", [256, 4096])
-def test_rmsnorm(eng, dim):
-    x = torch.randn(77, dim, generator=torch.Generator().manual_seed(1)) * 3
+@pytest.mark.parametrize("rows", [77, 2000])
+def test_rmsnorm(eng, dim, rows):
+    x = torch.randn(rows, dim, generator=torch.Generator().manual_seed(1)) * 3
     w = (1 + 0.1 * torch.randn(dim, generator=torch.Generator().manual_seed(2))).to(torch.bfloat16)
     ref = llama_ref.rmsnorm(x, w, 1e-5)
     got = eng.rmsnorm(x.cuda(), w.cuda(), eps=1e-5)

@@ -17,8 +17,8 @@ eng.gemm(A, W, out=out, flags=_cabi.GEMM_FLAG_SWAP); torch.cuda.synchronize()
 buf = np.zeros(160 * 8, dtype=np.uint64)
 lib.rvl_debug_gemm_timestamps(0, buf.ctypes.data, buf.size)
 t = buf.reshape(160, 8).astype(np.int64)
-names = ["start", "prod_done", "mma_done", "acc_ready", "flags_seen", "epi_done", "published"]
-print(f"M={M} N={N} K={K}  (cycles relative to each CTA's start; 0 = not reached)")
-for c in list(range(0, 12)) + [50, 100, 140, 147]:
+names = ["start", "prod_done", "mma_done", "acc_ready", "flags_seen|ld0", "epi_done", "published|ld1", "all_done"]
+print(os.environ.get("RVL_EPI"), f"M={M} N={N} K={K}  (cycles relative to each CTA's start; 0 = not reached)")
+for c in list(range(0, 3)) + [50, 100, 147]:
     if t[c, 0] == 0: continue
     print(f"cta {c:3d}: " + "  ".join(f"{n}={int(t[c, i] - t[c, 0]) if t[c, i] else 0:7d}" for i, n in enumerate(names) if i))
