@@ -240,10 +240,15 @@ RVL_API int rvl_swiglu(rvl_handle* h, const void* gu, void* act, int64_t n_token
 RVL_API int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const int32_t* cu_seqlens,
                      int32_t n_seq, int32_t max_seqlen, rvl_stream stream);
 
-/* Paged-KV decode attention: q from qkv [n_seq, 3*hidden], keys 0..seq_lens[i] (inclusive of the
- * token just appended) -> out [n_seq, hidden] bf16. */
+/* Paged-KV decode attention: q from qkv [n_seq, 3*hidden], keys 0..seq_lens[i] (inclusive of this
+ * step's token) -> out [n_seq, hidden] bf16.
+ *   fused_rope == 0: qkv is post-RoPE and the cache already holds this step's token (after rvl_rope_kv);
+ *   fused_rope != 0: qkv holds the un-rotated q, k of this step; the kernel applies RoPE at position
+ *                    seq_lens[i] and appends k', v to the cache page itself (what rvl_decode_step does - the
+ *                    separate apply_rotary_pos_emb + DynamicCache.update kernels of the reference disappear). */
 RVL_API int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int32_t* seq_lens, int32_t n_seq,
-                    const int32_t* page_table, int32_t max_pages, int32_t layer, rvl_stream stream);
+                    const int32_t* page_table, int32_t max_pages, int32_t layer, int32_t fused_rope,
+                    rvl_stream stream);
 
 /* ---- stage-2 adapter (ClipEncoder) kernels; the host composes them with rvl_gemm_bf16 ------------ */
 

@@ -233,53 +233,103 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
 }
 
 // ------------------------------------------------------------------------------------------- decode
-// grid (n_heads, n_seq), 128 threads.  Phase 1: scores = q . k_j (8 threads per key, 16 dims each,
-// 16 keys per CTA iteration).  Phase 2: softmax over the row in shared memory.  Phase 3: out = sum p_j v_j
-// (16 threads per key cover 128 dims, 8 keys per iteration, cross-group reduction in shared memory).
-// Algorithmic bytes per (seq, head): n_keys * 128 * 2 * 2.
+// grid (n_heads, n_seq), 128 threads: one query row per (sequence, head) against the paged KV cache.
+//   phase 0 (kFused): RoPE of this step's q and k (rotate-half, fp32 sincosf like LlamaRotaryEmbedding, results rounded
+//            to bf16 exactly as rope_kv_kernel does) and append of k', v to the cache page - the separate RoPE / KV
+//            kernel and its launch disappear from the decode step;
+//   phase 1: scores = q . k_j, 8 threads per key (16 dims each), 16 keys per CTA iteration, four iterations' loads
+//            in flight before the first FMA;
+//   phase 2: softmax over the row in shared memory;
+//   phase 3: out = sum p_j v_j, 16 threads per key cover 128 dims, 8 keys per iteration (eight loads in flight),
+//            cross-group reduction in shared memory.
+// Algorithmic bytes per (seq, head): n_keys * 128 * 2 * 2.  HBM-bound: reads whole 256-byte K / V rows.
+template <bool kFused>
 __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ seq_lens,
                                                            const int32_t* __restrict__ page_table, int max_pages,
-                                                           const __nv_bfloat16* __restrict__ k_pages,
-                                                           const __nv_bfloat16* __restrict__ v_pages, int n_heads,
-                                                           int page_size, float scale) {
+                                                           __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, int n_heads,
+                                                           int page_size, float scale, float theta) {
   extern __shared__ float s_scores[];          // [n_keys_max]
   __shared__ float s_red[8][kD];
   __shared__ float s_stat[8];
+  __shared__ __align__(16) float s_q[kD];               // this step's (rotated) query, bf16-rounded values
+  __shared__ __align__(16) __nv_bfloat16 s_knew[kD];    // this step's rotated key
   pdl_trigger();
   pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_keys = seq_lens[seq] + 1;        // includes the token appended this step
+  const int pos = seq_lens[seq];               // tokens already cached = position of this step's token
+  const int n_keys = pos + 1;                  // includes the token appended this step
   const int H = n_heads * kD;
   const int32_t* pt = page_table + static_cast<long long>(seq) * max_pages;
+  const __nv_bfloat16* row = qkv + static_cast<long long>(seq) * 3 * H + head * kD;
+
+  // ---- phase 0
+  if (kFused) {
+    if (tid < kD / 2) {
+      const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * tid) / static_cast<float>(kD));
+      float sn, cs;
+      sincosf(static_cast<float>(pos) * inv_freq, &sn, &cs);
+      const float q0 = __bfloat162float(row[tid]), q1 = __bfloat162float(row[tid + 64]);
+      const float k0 = __bfloat162float(row[H + tid]), k1 = __bfloat162float(row[H + tid + 64]);
+      s_q[tid] = __bfloat162float(__float2bfloat16(q0 * cs - q1 * sn));
+      s_q[tid + 64] = __bfloat162float(__float2bfloat16(q1 * cs + q0 * sn));
+      s_knew[tid] = __float2bfloat16(k0 * cs - k1 * sn);
+      s_knew[tid + 64] = __float2bfloat16(k1 * cs + k0 * sn);
+    }
+    __syncthreads();
+    const int page = pt[pos / page_size];
+    const long long slot = ((static_cast<long long>(page) * n_heads + head) * page_size + pos % page_size) * kD;
+    if (tid < 16) {
+      reinterpret_cast<uint4*>(k_pages + slot)[tid] = reinterpret_cast<const uint4*>(s_knew)[tid];
+    } else if (tid < 32) {
+      reinterpret_cast<uint4*>(v_pages + slot)[tid - 16] = reinterpret_cast<const uint4*>(row + 2 * H)[tid - 16];
+    }
+  } else {
+    s_q[tid] = __bfloat162float(row[tid]);
+    __syncthreads();
+  }
 
   // ---- phase 1
   {
     const int dg = lane & 7;                   // dims [16 dg, 16 dg + 16)
-    const __nv_bfloat16* qp = qkv + static_cast<long long>(seq) * 3 * H + head * kD + dg * 16;
-    const uint4 q0 = *reinterpret_cast<const uint4*>(qp);
-    const uint4 q1 = *reinterpret_cast<const uint4*>(qp + 8);
-    const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     float qf[16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { qf[2 * e] = bf16_lo(qw[e]); qf[2 * e + 1] = bf16_hi(qw[e]); }
-    for (int kbase = 0; kbase < n_keys; kbase += 16) {
-      const int key = kbase + warp * 4 + (lane >> 3);
-      float acc = 0.f;
-      if (key < n_keys) {
-        const int page = pt[key / page_size];
-        const __nv_bfloat16* kp = k_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dg * 16;
-        const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(kp));
-        const uint4 k1 = __ldg(reinterpret_cast<const uint4*>(kp + 8));
-        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    for (int e = 0; e < 4; ++e) {
+      const float4 t = reinterpret_cast<const float4*>(s_q)[dg * 4 + e];
+      qf[4 * e] = t.x; qf[4 * e + 1] = t.y; qf[4 * e + 2] = t.z; qf[4 * e + 3] = t.w;
+    }
+    const int ksub = warp * 4 + (lane >> 3);   // key inside a 16-key iteration
+    for (int kbase = 0; kbase < n_keys; kbase += 64) {
+      uint4 kv[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int key = kbase + u * 16 + ksub;
+        kv[u][0] = kv[u][1] = make_uint4(0u, 0u, 0u, 0u);
+        if (key < n_keys) {
+          const uint4* kp;
+          if (kFused && key == pos) {
+            kp = reinterpret_cast<const uint4*>(s_knew) + dg * 2;        // not yet visible through the read-only path
+            kv[u][0] = kp[0]; kv[u][1] = kp[1];
+          } else {
+            const int page = pt[key / page_size];
+            kp = reinterpret_cast<const uint4*>(k_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dg * 16);
+            kv[u][0] = __ldg(kp); kv[u][1] = __ldg(kp + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int key = kbase + u * 16 + ksub;
+        const uint32_t kw[8] = {kv[u][0].x, kv[u][0].y, kv[u][0].z, kv[u][0].w, kv[u][1].x, kv[u][1].y, kv[u][1].z, kv[u][1].w};
+        float acc = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc += qf[2 * e] * bf16_lo(kw[e]) + qf[2 * e + 1] * bf16_hi(kw[e]);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (dg == 0 && key < n_keys) s_scores[key] = acc * scale;
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if (dg == 0 && key < n_keys) s_scores[key] = acc * scale;
     }
   }
   __syncthreads();
@@ -305,16 +355,32 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
     const int grp = tid >> 4;                  // 8 key groups
     const int dv = (tid & 15) * 8;             // dims [dv, dv + 8)
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int key = grp; key < n_keys; key += 8) {
-      const int page = pt[key / page_size];
-      const __nv_bfloat16* vp = v_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dv;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(vp));
-      const float p = s_scores[key];
-      acc[0] += p * bf16_lo(v.x); acc[1] += p * bf16_hi(v.x);
-      acc[2] += p * bf16_lo(v.y); acc[3] += p * bf16_hi(v.y);
-      acc[4] += p * bf16_lo(v.z); acc[5] += p * bf16_hi(v.z);
-      acc[6] += p * bf16_lo(v.w); acc[7] += p * bf16_hi(v.w);
+    for (int kbase = 0; kbase < n_keys; kbase += 64) {
+      uint4 vv[8];
+      float pp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int key = kbase + u * 8 + grp;
+        vv[u] = make_uint4(0u, 0u, 0u, 0u);
+        pp[u] = 0.f;
+        if (key < n_keys) {
+          if (kFused && key == pos) {
+            vv[u] = *reinterpret_cast<const uint4*>(row + 2 * H + dv);
+          } else {
+            const int page = pt[key / page_size];
+            vv[u] = __ldg(reinterpret_cast<const uint4*>(v_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dv));
+          }
+          pp[u] = s_scores[key];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float p = pp[u];
+        acc[0] += p * bf16_lo(vv[u].x); acc[1] += p * bf16_hi(vv[u].x);
+        acc[2] += p * bf16_lo(vv[u].y); acc[3] += p * bf16_hi(vv[u].y);
+        acc[4] += p * bf16_lo(vv[u].z); acc[5] += p * bf16_hi(vv[u].z);
+        acc[6] += p * bf16_lo(vv[u].w); acc[7] += p * bf16_hi(vv[u].w);
+      }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_red[grp][dv + e] = acc[e];
@@ -328,21 +394,30 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
   }
 }
 
+// fused != 0: qkv holds the un-rotated q, k of this step; the kernel applies RoPE at position seq_lens[i] and appends
+// k', v to the cache itself (the decode step of the engine).  fused == 0: qkv is post-RoPE and the cache already
+// holds this step's token (after rvl_rope_kv).
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
-                        int max_pages, const void* k_pages, const void* v_pages, int n_heads, int page_size,
-                        cudaStream_t st) {
+                        int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused,
+                        float theta, cudaStream_t st) {
   if (n_seq <= 0) return;
   const int smem = max_pages * page_size * static_cast<int>(sizeof(float));
   static int attr_smem = 0;
   if (smem > 40000 && smem > attr_smem) {
-    cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem = smem;
   }
   dim3 grid(n_heads, n_seq);
-  launch_k(attn_decode_kernel, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
-           reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages,
-           reinterpret_cast<const __nv_bfloat16*>(k_pages), reinterpret_cast<const __nv_bfloat16*>(v_pages), n_heads, page_size,
-           1.0f / sqrtf(static_cast<float>(kD)));
+  const float scale = 1.0f / sqrtf(static_cast<float>(kD));
+  if (fused)
+    launch_k(attn_decode_kernel<true>, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+             reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages, reinterpret_cast<__nv_bfloat16*>(k_pages),
+             reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, scale, theta);
+  else
+    launch_k(attn_decode_kernel<false>, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+             reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages, reinterpret_cast<__nv_bfloat16*>(k_pages),
+             reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, scale, theta);
 }
 
 }  // namespace rvl

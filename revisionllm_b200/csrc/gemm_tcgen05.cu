@@ -44,6 +44,10 @@ constexpr int kMaxStages = 12;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB per 128-row A tile and k-block
 constexpr int kEpiScratchBytes = 4 * 32 * 33 * 4;   // per epilogue warp a 32 x 33 fp32 transpose tile
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - kEpiScratchBytes;
+// Weight-streaming (transposed) epilogue: output tiles are staged in shared memory as [token][feature] and written with
+// TMA stores, one 32-token box per accumulator chunk; the staging buffer replaces the transpose scratch.
+constexpr int kStageOutBytes = 48 * 1024;
+constexpr int kSmemBudgetStaged = 227 * 1024 - 1024 - 512 - kStageOutBytes;
 
 struct GemmArgs {
   int M, N, K;          // A rows, B rows, reduction
@@ -73,6 +77,7 @@ struct GemmArgs {
   int relu;
   int transposed;             // 0: tokens = A rows (m), features = B rows (n); 1: the other way round
   int atomic;                 // split-k partial sums: atomicAdd into fp32 out
+  int staged;                 // transposed epilogue through shared-memory staging + TMA stores (tmap_out); chunks per group
   int swiglu;                 // feature rows come in blocks of [16 gate | 16 up]: store silu(gate) * up, bf16, [tokens][features / 2]
 };
 
@@ -350,7 +355,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32]
 template <int kATiles, bool kStreamK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmArgs args) {
+                         const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
   const int kStages = args.stages;
   const int BN = args.bn;
   constexpr int a_tiles = kATiles;
@@ -376,6 +381,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (args.staged) tma_prefetch_desc(&tmap_out);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -512,6 +518,89 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (warp == 2) DBG_T(4);
       }
       const int ks = w.ks;
+      if (args.staged && !(kStreamK && w.kind == 1)) {
+        // ---- staged epilogue (weight-streaming orientation, a_tiles == 1): thread = feature row, registers = tokens.
+        // Each chunk's 32 tokens x 128 features land in shared memory as [token][feature] (every st.shared of a warp
+        // writes 32 consecutive features of one token: conflict-free, one instruction per value with an immediate
+        // offset) and leave through one TMA store per chunk, which also clips the ragged token / feature edges.
+        // Measured before this path: ~1050 cycles per chunk for the register transpose + 16-byte global stores with one
+        // epilogue warp per scheduler (every instruction's latency exposed), ~4900 for a ragged chunk.
+        const uint32_t stg = smem_u32(epi_scratch);
+        const uint32_t taddr = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int cpg = args.staged;                       // chunks per staging group
+        const int feat0 = w.m_blk * kBM;                   // first weight row of the tile
+        for (int c0 = 0; c0 < n_chunks; c0 += cpg) {
+          // the staging buffer may still be read by the previous group's stores
+          if (threadIdx.x == 64) bulk_wait_read_all();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int c1 = min(c0 + cpg, n_chunks);
+          for (int c = c0; c < c1; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if (c == n_chunks - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (kStreamK && w.kind == 2) {
+              for (int f = 1; f <= w.followers; ++f) {
+                const float4* src = reinterpret_cast<const float4*>(args.ws) +
+                                    (static_cast<long long>(blockIdx.x + f) * 8 + c) * (8 * 128) + m_local;
+                float4 p[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[q] = __ldcg(src + q * 128);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  v[q * 4] += p[q].x; v[q * 4 + 1] += p[q].y; v[q * 4 + 2] += p[q].z; v[q * 4 + 3] += p[q].w;
+                }
+              }
+            }
+            const int lc = c - c0;
+            if (args.swiglu) {
+              // lanes 0-15 hold gate, lanes 16-31 up of act columns quarter*16 + (lane & 15); lower lanes finish the even
+              // tokens, upper lanes the odd ones (one shuffle per token pair); staging row = 64 act columns = 128 B
+              const bool lower = lane < 16;
+              const uint32_t base = stg + lc * (32 * 128) + (quarter * 16 + (lane & 15)) * 2 + (lower ? 0 : 128);
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float got = __shfl_xor_sync(0xffffffffu, lower ? v[j + 1] : v[j], 16);
+                const float g = lower ? v[j] : got;
+                const float u = lower ? got : v[j + 1];
+                const __nv_bfloat16 a = __float2bfloat16(g / (1.f + __expf(-g)) * u);
+                st_shared_u16(base + j * 128, *reinterpret_cast<const uint16_t*>(&a));
+              }
+            } else if (args.mode == RVL_GEMM_OUT_BF16) {
+              const uint32_t base = stg + lc * (32 * 256) + m_local * 2;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const __nv_bfloat16 a = __float2bfloat16(v[j]);
+                st_shared_u16(base + j * 256, *reinterpret_cast<const uint16_t*>(&a));
+              }
+            } else {
+              const uint32_t base = stg + lc * (32 * 512) + m_local * 4;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) st_shared_f32(base + j * 512, v[j]);
+            }
+          }
+          fence_proxy_async();                             // generic-proxy writes -> visible to the TMA engine
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            const int chunk_bytes = args.swiglu ? 32 * 128 : (args.mode == RVL_GEMM_OUT_BF16 ? 32 * 256 : 32 * 512);
+            for (int c = c0; c < c1; ++c) {
+              const int tok0 = w.n_blk * BN + c * 32;
+              if (tok0 < args.N && c * 32 < BN)
+                tma_store_3d(&tmap_out, epi_scratch + (c - c0) * (chunk_bytes / 4), args.swiglu ? (feat0 >> 1) : feat0, tok0, ks);
+            }
+            bulk_commit_group();
+          }
+        }
+        if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int at = 0; at < a_tiles; ++at) {
         const int m = (w.m_blk * a_tiles + at) * kBM + m_local;  // A-row owned by this thread
         const uint32_t taddr = tmem_base + acc * acc_cols + at * args.sub_stride + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -570,6 +659,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
+    if (args.staged && threadIdx.x == 64) bulk_wait_all();   // the staging buffer must outlive the stores that read it
     if (warp == 2) DBG_T(5);
   }
 
@@ -785,6 +875,31 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
   return RVL_OK;
 }
 
+// Output tensor map for the staged epilogue: [splits][tokens][features] (features contiguous), box = 32 tokens x box_feat
+// features, no swizzle (the staging buffer is a dense [token][feature] tile).
+static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t n_feat, int64_t n_tok, int64_t n_split, int64_t ld_elems,
+                         int64_t split_stride_elems, int box_feat, bool f32, std::string* err) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { *err = "cuTensorMapEncodeTiled entry point not available"; return RVL_ERR_CUDA; }
+  const int es = f32 ? 4 : 2;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(n_feat), static_cast<cuuint64_t>(n_tok), static_cast<cuuint64_t>(n_split)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld_elems) * es,
+                        static_cast<cuuint64_t>(n_split > 1 ? split_stride_elems : ld_elems * n_tok) * es};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_feat), 32u, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(out) failed (%d) feat=%lld tok=%lld ld=%lld", (int)r, (long long)n_feat,
+             (long long)n_tok, (long long)ld_elems);
+    *err = buf;
+    return RVL_ERR_CUDA;
+  }
+  return RVL_OK;
+}
+
 static int pow2_at_least(int x) {
   int c = 32;
   while (c < x) c <<= 1;
@@ -866,7 +981,16 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   a.acc_stages = (2 * a.a_tiles * a.sub_stride <= 512) ? 2 : 1;
   a.tmem_cols = pow2_at_least(a.acc_stages * a.a_tiles * a.sub_stride);
   const int stage_bytes = a.a_tiles * kATileBytes + a.bn * kBK * 2;
-  a.stages = kSmemBudget / stage_bytes;
+  // staged TMA-store epilogue for the weight-streaming orientation (plain bf16 / fp32 / SwiGLU outputs)
+  static const char* env_staged = getenv("RVL_STAGED");
+  const bool out_f32 = c.out_mode != RVL_GEMM_OUT_BF16;
+  const int out_es = out_f32 ? 4 : 2;
+  a.staged = 0;
+  if (swap && a.a_tiles == 1 && !c.bias && !c.rowmap && !a.relu && !a.atomic && c.out_mode != RVL_GEMM_ADD_F32 &&
+      (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && (c.ldc * out_es) % 16 == 0 && (a.split_stride * out_es) % 16 == 0 &&
+      !(env_staged && atoi(env_staged) == 0))
+    a.staged = a.swiglu ? 12 : (out_f32 ? 3 : 6);
+  a.stages = (a.staged ? kSmemBudgetStaged : kSmemBudget) / stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   if (a.stages < 2) { *err = "gemm: tile does not fit in shared memory"; return RVL_ERR_INVALID; }
   if (env_dbg)
@@ -902,12 +1026,19 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     if (e2 != cudaSuccess) { *err = std::string("gemm pair launch: ") + cudaGetErrorString(e2); return RVL_ERR_CUDA; }
     return RVL_OK;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tout;
   int rc = make_tmap(&ta, pa, a.M, c.K, a.a_tiles * kBM, err);
   if (rc) return rc;
   rc = make_tmap(&tb, pb, a.N, c.K, a.bn, err);
   if (rc) return rc;
-  const int smem = a.stages * stage_bytes + 1024 + 512 + kEpiScratchBytes;
+  tout = ta;
+  if (a.staged) {
+    // features = weight rows (a.M; halved by SwiGLU), tokens = a.N
+    rc = make_tmap_out(&tout, c.out, a.swiglu ? a.M / 2 : a.M, a.N, a.split_stride > 0 ? a.split_k : 1, c.ldc, a.split_stride,
+                       a.swiglu ? 64 : 128, out_f32, err);
+    if (rc) return rc;
+  }
+  const int smem = a.stages * stage_bytes + 1024 + 512 + (a.staged ? kStageOutBytes : kEpiScratchBytes);
   int grid;
   if (a.stream_k) {
     const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
@@ -925,9 +1056,9 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     attr_set = true;
   }
   cudaError_t e;
-  if (a.stream_k) e = launch_gemm_k(gemm_bf16_tcgen05_kernel<1, true>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, a);
-  else if (a.a_tiles == 2) e = launch_gemm_k(gemm_bf16_tcgen05_kernel<2, false>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, a);
-  else e = launch_gemm_k(gemm_bf16_tcgen05_kernel<1, false>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, a);
+  if (a.stream_k) e = launch_gemm_k(gemm_bf16_tcgen05_kernel<1, true>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, tout, a);
+  else if (a.a_tiles == 2) e = launch_gemm_k(gemm_bf16_tcgen05_kernel<2, false>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, tout, a);
+  else e = launch_gemm_k(gemm_bf16_tcgen05_kernel<1, false>, dim3(grid), dim3(kGemmThreads), smem, st, ta, tb, tout, a);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("gemm launch: ") + cudaGetErrorString(e); return RVL_ERR_CUDA; }
   return RVL_OK;

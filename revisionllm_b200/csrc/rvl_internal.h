@@ -83,7 +83,7 @@ void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, in
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
                          cudaStream_t st);
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
-                        int max_pages, const void* k_pages, const void* v_pages, int n_heads, int page_size,
+                        int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused, float theta,
                         cudaStream_t st);
 // sampling.cu
 void launch_sample_greedy(const float* logits, int n_seq, int vocab, int32_t* unfinished, int eos_id, int pad_id,

@@ -128,6 +128,7 @@ class Engine:
         self._check(self.lib.rvl_bind_weights(self.h, C.byref(w)), "rvl_bind_weights")
         self._keep = keep
         self.embed_tokens, self.lm_head_w, self.proj_w, self.proj_b = emb, head, pw, pb
+        self.wgu_interleaved = interleave
 
     # ------------------------------------------------------------------ buffers
     def ensure_workspace(self, max_tokens: int, max_seqs: int):
@@ -186,7 +187,7 @@ class Engine:
         self._check(self.lib.rvl_prefill(self.h, hidden.data_ptr(), cu_seqlens.data_ptr(), n_seq, T, max_seqlen,
                                          page_table.data_ptr(), page_table.shape[1], logits_out.data_ptr(),
                                          1 if all_logits else 0, _stream()), "rvl_prefill")
-        self.launches += 1 + 9 * self.cfg.n_layers + 2
+        self.launches += 1 + (8 if self.wgu_interleaved else 9) * self.cfg.n_layers + 2
 
     def decode_step(self, token_ids, seq_lens, page_table, logits_out):
         _req(token_ids, torch.int32, "token_ids"); _req(seq_lens, torch.int32, "seq_lens")
@@ -195,7 +196,7 @@ class Engine:
         self.ensure_workspace(n, n)
         self._check(self.lib.rvl_decode_step(self.h, token_ids.data_ptr(), seq_lens.data_ptr(), n, page_table.data_ptr(),
                                              page_table.shape[1], logits_out.data_ptr(), _stream()), "rvl_decode_step")
-        self.launches += 1 + 9 * self.cfg.n_layers + 3
+        self.launches += 1 + (7 if self.wgu_interleaved else 8) * self.cfg.n_layers + 3
 
     def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
         _req(logits, torch.float32, "logits"); _req(next_tokens, torch.int32, "next_tokens")
@@ -279,11 +280,12 @@ class Engine:
         self.launches += 1
         return out
 
-    def attn_decode(self, qkv, seq_lens, page_table, layer):
+    def attn_decode(self, qkv, seq_lens, page_table, layer, fused_rope=False):
         _req(qkv, torch.bfloat16, "qkv")
         out = torch.empty((qkv.shape[0], self.cfg.hidden), dtype=torch.bfloat16, device=qkv.device)
         self._check(self.lib.rvl_attn_decode(self.h, qkv.data_ptr(), out.data_ptr(), seq_lens.data_ptr(), qkv.shape[0],
-                                             page_table.data_ptr(), page_table.shape[1], layer, _stream()), "rvl_attn_decode")
+                                             page_table.data_ptr(), page_table.shape[1], layer, 1 if fused_rope else 0, _stream()),
+                    "rvl_attn_decode")
         self.launches += 1
         return out
 

@@ -269,6 +269,16 @@ def test_rope_kv_and_attention_prefill_and_decode(eng):
         ref = torch.einsum("hl,lhd->hd", torch.softmax(att, -1), vals).reshape(H)
         err = _relerr(dec[s].float().cpu(), ref)
         assert err < 1e-2, f"decode attention seq {s}: rel err {err}"
+    # ---- the same step through the fused kernel (RoPE + KV append inside the attention kernel, as rvl_decode_step runs
+    # it): identical cache contents and identical output bits, because both paths round q', k' to bf16 the same way
+    k_ref, v_ref = kc.clone(), vc.clone()
+    for s, L in enumerate(lengths):                                                   # wipe the appended slot
+        kc[table[s, L // ps], :, L % ps] = 0
+        vc[table[s, L // ps], :, L % ps] = 0
+    dec2 = eng.attn_decode(new.cuda(), seq_lens, table_d, layer=1, fused_rope=True)
+    torch.cuda.synchronize()
+    assert torch.equal(kc, k_ref) and torch.equal(vc, v_ref)
+    assert torch.equal(dec2, dec)
 
 
 # ------------------------------------------------------------------------------------------- sampling / scoring

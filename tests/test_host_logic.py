@@ -119,7 +119,8 @@ def test_cabi_exports_every_symbol_the_header_declares():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_cabi.PROTOTYPES) == declared, "ctypes prototypes and header are out of sync"
-    assert lib.rvl_abi_version() == 1
+    m = re.search(r"#define RVL_ABI_VERSION (\d+)", header)
+    assert lib.rvl_abi_version() == int(m.group(1))
     out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
     assert [e for e in exported if e.startswith("rvl_")] == declared
