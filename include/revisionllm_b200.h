@@ -147,9 +147,12 @@ RVL_API int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens,
  *   token_ids    [n_seq] int32 device: token to embed and append
  *   seq_lens     [n_seq] int32 device, in/out: tokens already in the cache (= position of the new
  *                token); incremented by one at the end of the step
+ *   max_kv_len   host-side upper bound of seq_lens[i] + 1 over the batch (sizes the attention kernel's
+ *                shared-memory K/V staging; 0 = unknown: max_pages * kv_page_size is assumed)
  *   logits_out   [n_seq, vocab] fp32 */
 RVL_API int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, int32_t n_seq,
-                    const int32_t* page_table, int32_t max_pages, float* logits_out, rvl_stream stream);
+                    const int32_t* page_table, int32_t max_pages, int32_t max_kv_len, float* logits_out,
+                    rvl_stream stream);
 
 /* Greedy sampling + per-step entropy + EOS bookkeeping on the device.
  * Replaces vtimellm_llama.py:337-362 (argmax instead of multinomial; finished rows emit pad;
@@ -248,7 +251,7 @@ RVL_API int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const in
  *                    separate apply_rotary_pos_emb + DynamicCache.update kernels of the reference disappear). */
 RVL_API int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int32_t* seq_lens, int32_t n_seq,
                     const int32_t* page_table, int32_t max_pages, int32_t layer, int32_t fused_rope,
-                    rvl_stream stream);
+                    int32_t max_kv_len /* as in rvl_decode_step */, rvl_stream stream);
 
 /* ---- stage-2 adapter (ClipEncoder) kernels; the host composes them with rvl_gemm_bf16 ------------ */
 

@@ -53,7 +53,7 @@ PROTOTYPES = {
     "rvl_project_splice": (C.c_int, [_P, _P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
     "rvl_splice_rows": (C.c_int, [_P, _P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
     "rvl_prefill": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _P, _I32, _P, _I32, _P]),
-    "rvl_decode_step": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _P, _P]),
+    "rvl_decode_step": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "rvl_sample_greedy": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),
     "rvl_cosine_topk": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P]),
     "rvl_select_topk": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
@@ -65,7 +65,7 @@ PROTOTYPES = {
     "rvl_rope_kv": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I32, _I32, _P]),
     "rvl_swiglu": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "rvl_attn_prefill": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),
-    "rvl_attn_decode": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _P]),
+    "rvl_attn_decode": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P]),
     "rvl_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P]),
     "rvl_mha96": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
 }

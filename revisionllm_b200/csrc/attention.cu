@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rvl_internal.h"
 #include "rvl_ptx.cuh"
@@ -243,8 +244,11 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
 //   phase 3: out = sum p_j v_j, 16 threads per key cover 128 dims, 8 keys per iteration (eight loads in flight),
 //            cross-group reduction in shared memory.
 // Algorithmic bytes per (seq, head): n_keys * 128 * 2 * 2.  HBM-bound: reads whole 256-byte K / V rows.
-template <bool kFused>
-__global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+// kU: 16-key groups whose K loads are in flight together (phase 1) - and 2 kU 8-key groups of V (phase 3).  kU = 4 (64 registers,
+// 8 CTAs per SM) is the measured optimum on B200: kU = 12 (one round trip per context, 128 registers, 4 CTAs per SM) ran
+// the 7B decode step at 10.7 ms against 9.3 ms.
+template <bool kFused, int kU = 4>
+__global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ seq_lens,
                                                            const int32_t* __restrict__ page_table, int max_pages,
                                                            __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, int n_heads,
@@ -300,10 +304,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
       qf[4 * e] = t.x; qf[4 * e + 1] = t.y; qf[4 * e + 2] = t.z; qf[4 * e + 3] = t.w;
     }
     const int ksub = warp * 4 + (lane >> 3);   // key inside a 16-key iteration
-    for (int kbase = 0; kbase < n_keys; kbase += 64) {
-      uint4 kv[4][2];
+    for (int kbase = 0; kbase < n_keys; kbase += 16 * kU) {
+      uint4 kv[kU][2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const int key = kbase + u * 16 + ksub;
         kv[u][0] = kv[u][1] = make_uint4(0u, 0u, 0u, 0u);
         if (key < n_keys) {
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const int key = kbase + u * 16 + ksub;
         const uint32_t kw[8] = {kv[u][0].x, kv[u][0].y, kv[u][0].z, kv[u][0].w, kv[u][1].x, kv[u][1].y, kv[u][1].z, kv[u][1].w};
         float acc = 0.f;
@@ -355,11 +359,11 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
     const int grp = tid >> 4;                  // 8 key groups
     const int dv = (tid & 15) * 8;             // dims [dv, dv + 8)
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int kbase = 0; kbase < n_keys; kbase += 64) {
-      uint4 vv[8];
-      float pp[8];
+    for (int kbase = 0; kbase < n_keys; kbase += 16 * kU) {
+      uint4 vv[2 * kU];
+      float pp[2 * kU];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 2 * kU; ++u) {
         const int key = kbase + u * 8 + grp;
         vv[u] = make_uint4(0u, 0u, 0u, 0u);
         pp[u] = 0.f;
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 2 * kU; ++u) {
         const float p = pp[u];
         acc[0] += p * bf16_lo(vv[u].x); acc[1] += p * bf16_hi(vv[u].x);
         acc[2] += p * bf16_lo(vv[u].y); acc[3] += p * bf16_hi(vv[u].y);
@@ -394,30 +398,245 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------------------------------- decode, staged
+// Same arithmetic, different data movement: the cached K and V rows of the (sequence, head) are fetched with bulk async
+// copies (one per page and per K / V: a (page, head) chunk is 8 KB contiguous) into shared memory, everything in flight
+// at once and without occupying registers; QK^T starts when K has landed while V is still arriving.  The register-
+// staged kernel above makes six dependent HBM round trips per CTA (three 64-key rounds for K, three for V) and was
+// measured at 108 us per layer for 180 x 32 rows of ~190 keys (0.69 of HBM peak, latency- not bandwidth-bound: mapping
+// 1/6 of the reads to L2-resident shared pages changed nothing).  Contexts longer than the buffer are processed in
+// chunks with an online softmax.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool kFused>
+__global__ void __launch_bounds__(128) attn_decode_staged_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                                  const int32_t* __restrict__ seq_lens,
+                                                                  const int32_t* __restrict__ page_table, int max_pages,
+                                                                  __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, int n_heads,
+                                                                  int page_size, float scale, float theta, int cap_keys) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(dsm);            // [cap_keys][128]
+  __nv_bfloat16* sV = sK + static_cast<size_t>(cap_keys) * kD;           // [cap_keys][128]
+  float* s_scores = reinterpret_cast<float*>(sV + static_cast<size_t>(cap_keys) * kD);   // [cap_keys]
+  __shared__ float s_red[8][kD];
+  __shared__ float s_stat[8];
+  __shared__ __align__(16) float s_q[kD];
+  __shared__ __align__(16) __nv_bfloat16 s_knew[kD];
+  __shared__ __align__(8) uint64_t bars[2];
+  pdl_trigger();
+  pdl_wait();
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pos = seq_lens[seq];
+  const int n_keys = pos + 1;
+  const int n_cached = kFused ? pos : n_keys;     // rows to fetch from the cache (the fused kernel produces row `pos` itself)
+  const int H = n_heads * kD;
+  const int32_t* pt = page_table + static_cast<long long>(seq) * max_pages;
+  const __nv_bfloat16* row = qkv + static_cast<long long>(seq) * 3 * H + head * kD;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int grp = tid >> 4;                  // phase 3: 8 key groups
+  const int dv = (tid & 15) * 8;             //          dims [dv, dv + 8)
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float m_run = -INFINITY, l_run = 0.f;
+  uint32_t phase = 0;
+  for (int k0 = 0; k0 < n_keys; k0 += cap_keys) {
+    const int nk = min(cap_keys, n_keys - k0);
+    const int nk_cached = max(0, min(nk, n_cached - k0));
+    if (tid == 0) {
+      fence_proxy_async();                   // earlier generic reads of the buffers precede the async writes
+      mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(nk_cached) * 256u);
+      mbar_arrive_expect_tx(&bars[1], static_cast<uint32_t>(nk_cached) * 256u);
+    }
+    {
+      // one thread per (K | V, page piece) issues its copy, so the page-table reads run in parallel (a single issuing
+      // thread spent ~500 cycles per copy waiting for its page id).  A copy may complete before thread 0's expect_tx:
+      // the phase cannot end early because thread 0's arrival is still pending.
+      const int first_slot = k0 % page_size;
+      const int n_pieces = nk_cached > 0 ? (first_slot + nk_cached + page_size - 1) / page_size : 0;
+      for (int i = tid; i < 2 * n_pieces; i += 128) {
+        const int pass = i >= n_pieces ? 1 : 0;
+        const int piece = i - pass * n_pieces;
+        const int kk = piece == 0 ? 0 : piece * page_size - first_slot;      // first key (chunk-relative) of the piece
+        const int key = k0 + kk;
+        const int slot = key % page_size;
+        const int n = min(page_size - slot, nk_cached - kk);
+        const int page = pt[key / page_size];
+        const __nv_bfloat16* pages = pass ? v_pages : k_pages;
+        bulk_copy_g2s((pass ? sV : sK) + static_cast<size_t>(kk) * kD,
+                      pages + ((static_cast<long long>(page) * n_heads + head) * page_size + slot) * kD,
+                      static_cast<uint32_t>(n) * 256u, &bars[pass]);
+      }
+    }
+    if (k0 == 0) {
+      // ---- phase 0: this step's query (and, fused, RoPE + KV append)
+      if (kFused) {
+        if (tid < kD / 2) {
+          const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * tid) / static_cast<float>(kD));
+          float sn, cs;
+          sincosf(static_cast<float>(pos) * inv_freq, &sn, &cs);
+          const float q0 = __bfloat162float(row[tid]), q1 = __bfloat162float(row[tid + 64]);
+          const float kx = __bfloat162float(row[H + tid]), ky = __bfloat162float(row[H + tid + 64]);
+          s_q[tid] = __bfloat162float(__float2bfloat16(q0 * cs - q1 * sn));
+          s_q[tid + 64] = __bfloat162float(__float2bfloat16(q1 * cs + q0 * sn));
+          s_knew[tid] = __float2bfloat16(kx * cs - ky * sn);
+          s_knew[tid + 64] = __float2bfloat16(ky * cs + kx * sn);
+        }
+      } else {
+        s_q[tid] = __bfloat162float(row[tid]);
+      }
+      __syncthreads();
+      if (kFused) {
+        const int page = pt[pos / page_size];
+        const long long slot = ((static_cast<long long>(page) * n_heads + head) * page_size + pos % page_size) * kD;
+        if (tid < 16) reinterpret_cast<uint4*>(k_pages + slot)[tid] = reinterpret_cast<const uint4*>(s_knew)[tid];
+        else if (tid < 32) reinterpret_cast<uint4*>(v_pages + slot)[tid - 16] = reinterpret_cast<const uint4*>(row + 2 * H)[tid - 16];
+      }
+    }
+    if (kFused && pos >= k0 && pos < k0 + nk) {
+      // the new token's row of this chunk comes from registers / qkv, not from the cache
+      if (tid < 16) reinterpret_cast<uint4*>(sK + static_cast<size_t>(pos - k0) * kD)[tid] = reinterpret_cast<const uint4*>(s_knew)[tid];
+      else if (tid < 32) reinterpret_cast<uint4*>(sV + static_cast<size_t>(pos - k0) * kD)[tid - 16] = reinterpret_cast<const uint4*>(row + 2 * H)[tid - 16];
+    }
+    __syncthreads();
+    // ---- phase 1: scores (8 threads per key, each dims [8 dg, 8 dg + 8) and [64 + 8 dg, ...): conflict-free 128 B runs)
+    mbar_wait(&bars[0], phase);
+    {
+      const int dg = lane & 7;
+      float qf[16];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float4 t0 = reinterpret_cast<const float4*>(s_q)[e * 16 + dg * 2];
+        const float4 t1 = reinterpret_cast<const float4*>(s_q)[e * 16 + dg * 2 + 1];
+        qf[8 * e] = t0.x; qf[8 * e + 1] = t0.y; qf[8 * e + 2] = t0.z; qf[8 * e + 3] = t0.w;
+        qf[8 * e + 4] = t1.x; qf[8 * e + 5] = t1.y; qf[8 * e + 6] = t1.z; qf[8 * e + 7] = t1.w;
+      }
+      const int ksub = warp * 4 + (lane >> 3);
+      for (int kb = 0; kb < nk; kb += 16) {
+        const int key = kb + ksub;
+        float a = 0.f;
+        if (key < nk) {
+          const uint4* kp = reinterpret_cast<const uint4*>(sK + static_cast<size_t>(key) * kD);
+          const uint4 ka = kp[dg], kb2 = kp[8 + dg];
+          const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb2.x, kb2.y, kb2.z, kb2.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a += qf[2 * e] * bf16_lo(kw[e]) + qf[2 * e + 1] * bf16_hi(kw[e]);
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (dg == 0 && key < nk) s_scores[key] = a * scale;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: (online) softmax statistics of the chunk
+    float mx = -INFINITY;
+    for (int i = tid; i < nk; i += 128) mx = fmaxf(mx, s_scores[i]);
+    mx = warp_max(mx);
+    if (lane == 0) s_stat[warp] = mx;
+    __syncthreads();
+    const float m_new = fmaxf(m_run, fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3])));
+    float sum = 0.f;
+    for (int i = tid; i < nk; i += 128) {
+      const float p = __expf(s_scores[i] - m_new);
+      s_scores[i] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_stat[4 + warp] = sum;
+    __syncthreads();
+    const float corr = __expf(m_run - m_new);      // first chunk: exp(-inf) = 0
+    l_run = l_run * corr + (s_stat[4] + s_stat[5] + s_stat[6] + s_stat[7]);
+    m_run = m_new;
+    // ---- phase 3: PV
+    mbar_wait(&bars[1], phase);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll 4
+    for (int key = grp; key < nk; key += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sV + static_cast<size_t>(key) * kD + dv);
+      const float p = s_scores[key];
+      acc[0] += p * bf16_lo(v.x); acc[1] += p * bf16_hi(v.x);
+      acc[2] += p * bf16_lo(v.y); acc[3] += p * bf16_hi(v.y);
+      acc[4] += p * bf16_lo(v.z); acc[5] += p * bf16_hi(v.z);
+      acc[6] += p * bf16_lo(v.w); acc[7] += p * bf16_hi(v.w);
+    }
+    phase ^= 1;
+    __syncthreads();                             // buffers and scores are free for the next chunk
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_red[grp][dv + e] = acc[e];
+  __syncthreads();
+  {
+    float r = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi) r += s_red[gi][tid];
+    out[static_cast<long long>(seq) * H + head * kD + tid] = __float2bfloat16(r / l_run);
+  }
+}
+
 // fused != 0: qkv holds the un-rotated q, k of this step; the kernel applies RoPE at position seq_lens[i] and appends
 // k', v to the cache itself (the decode step of the engine).  fused == 0: qkv is post-RoPE and the cache already
 // holds this step's token (after rvl_rope_kv).
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
                         int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused,
-                        float theta, cudaStream_t st) {
+                        float theta, int max_kv_len, cudaStream_t st) {
   if (n_seq <= 0) return;
-  const int smem = max_pages * page_size * static_cast<int>(sizeof(float));
-  static int attr_smem = 0;
-  if (smem > 40000 && smem > attr_smem) {
-    cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_smem = smem;
-  }
   dim3 grid(n_heads, n_seq);
   const float scale = 1.0f / sqrtf(static_cast<float>(kD));
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  __nv_bfloat16* kp = reinterpret_cast<__nv_bfloat16*>(k_pages);
+  __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(v_pages);
+  // Few (sequence, head) rows (stage 2 runs one query at a time): latency matters, the staged kernel wins (B = 1: 3.25 vs
+  // 3.50 ms per 7B decode step); many rows: 8 register-staged CTAs per SM overlap better than 2 staged ones (B = 180: 9.4
+  // vs 9.9 ms).  RVL_ATTN_DECODE = "regs" / "staged" forces one of them.
+  static const char* env = getenv("RVL_ATTN_DECODE");
+  const char mode = env ? env[0] : (n_seq * n_heads >= 1024 ? 'r' : 's');
+  if (mode == 's') {
+    // staged kernel: K and V rows of the whole context (or of a 432-key chunk) in shared memory.  Up to 220 keys two
+    // CTAs share an SM (one computes while the other's copies are in flight).
+    int keys = max_pages * page_size;
+    if (max_kv_len > 0 && max_kv_len < keys) keys = max_kv_len;
+    int cap = (keys + 7) / 8 * 8;
+    if (cap > 432) cap = 432;
+    const int smem = cap * (2 * kD * 2 + 4);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaFuncSetAttribute(attn_decode_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 432 * (2 * kD * 2 + 4));
+      cudaFuncSetAttribute(attn_decode_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 432 * (2 * kD * 2 + 4));
+      attr_smem = 432 * (2 * kD * 2 + 4);
+    }
+    if (fused)
+      launch_k(attn_decode_staged_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads,
+               page_size, scale, theta, cap);
+    else
+      launch_k(attn_decode_staged_kernel<false>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads,
+               page_size, scale, theta, cap);
+    return;
+  }
+  const int smem = max_pages * page_size * static_cast<int>(sizeof(float));
+  static int attr_smem_r = 0;
+  if (smem > 40000 && smem > attr_smem_r) {
+    cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_smem_r = smem;
+  }
   if (fused)
-    launch_k(attn_decode_kernel<true>, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
-             reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages, reinterpret_cast<__nv_bfloat16*>(k_pages),
-             reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, scale, theta);
+    launch_k(attn_decode_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+             scale, theta);
   else
-    launch_k(attn_decode_kernel<false>, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
-             reinterpret_cast<__nv_bfloat16*>(out), seq_lens, page_table, max_pages, reinterpret_cast<__nv_bfloat16*>(k_pages),
-             reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, scale, theta);
+    launch_k(attn_decode_kernel<false>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+             scale, theta);
 }
 
 }  // namespace rvl

@@ -345,7 +345,7 @@ __global__ void inc_kernel(int32_t* v, int n) {
 }
 
 int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, int32_t n_seq,
-                    const int32_t* page_table, int32_t max_pages, float* logits_out, rvl_stream stream) {
+                    const int32_t* page_table, int32_t max_pages, int32_t max_kv_len, float* logits_out, rvl_stream stream) {
   int rc = ready(h, "rvl_decode_step");
   if (rc) return rc;
   if (!token_ids || !seq_lens || !page_table || !logits_out) return fail(h, RVL_ERR_INVALID, "rvl_decode_step: null argument");
@@ -367,7 +367,7 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
       // RoPE of this step's q / k and the KV append happen inside the attention kernel
       ProfScope ps(h, st, RVL_PROF_ATTN_DECODE, 0.0, 0.0);   // bytes depend on seq_lens: the caller supplies them
       launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
-                         c.kv_page_size, 1, c.rope_theta, st);
+                         c.kv_page_size, 1, c.rope_theta, max_kv_len, st);
     }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st, h->partials, &pending))) return rc;
     launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st, h->partials, pending, pstride, hid);
@@ -475,12 +475,13 @@ int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const int32_t* c
 }
 
 int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int32_t* seq_lens, int32_t n_seq,
-                    const int32_t* page_table, int32_t max_pages, int32_t layer, int32_t fused_rope, rvl_stream stream) {
+                    const int32_t* page_table, int32_t max_pages, int32_t layer, int32_t fused_rope, int32_t max_kv_len,
+                    rvl_stream stream) {
   if (!h || !qkv || !out || !seq_lens || !page_table) return fail(h, RVL_ERR_INVALID, "rvl_attn_decode: null argument");
   if (!h->kv) return fail(h, RVL_ERR_STATE, "rvl_attn_decode: kv pages not set");
   if (layer < 0 || layer >= h->cfg.n_layers) return fail(h, RVL_ERR_INVALID, "rvl_attn_decode: bad layer");
   launch_attn_decode(qkv, out, seq_lens, n_seq, page_table, max_pages, k_pages(h, layer), v_pages(h, layer), h->cfg.n_heads,
-                     h->cfg.kv_page_size, fused_rope, h->cfg.rope_theta, static_cast<cudaStream_t>(stream));
+                     h->cfg.kv_page_size, fused_rope, h->cfg.rope_theta, max_kv_len, static_cast<cudaStream_t>(stream));
   return check_cuda(h, "rvl_attn_decode");
 }
 

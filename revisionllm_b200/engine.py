@@ -189,13 +189,13 @@ class Engine:
                                          1 if all_logits else 0, _stream()), "rvl_prefill")
         self.launches += 1 + (8 if self.wgu_interleaved else 9) * self.cfg.n_layers + 2
 
-    def decode_step(self, token_ids, seq_lens, page_table, logits_out):
+    def decode_step(self, token_ids, seq_lens, page_table, logits_out, max_kv_len: int = 0):
         _req(token_ids, torch.int32, "token_ids"); _req(seq_lens, torch.int32, "seq_lens")
         _req(page_table, torch.int32, "page_table"); _req(logits_out, torch.float32, "logits_out")
         n = token_ids.shape[0]
         self.ensure_workspace(n, n)
         self._check(self.lib.rvl_decode_step(self.h, token_ids.data_ptr(), seq_lens.data_ptr(), n, page_table.data_ptr(),
-                                             page_table.shape[1], logits_out.data_ptr(), _stream()), "rvl_decode_step")
+                                             page_table.shape[1], max_kv_len, logits_out.data_ptr(), _stream()), "rvl_decode_step")
         self.launches += 1 + (7 if self.wgu_interleaved else 8) * self.cfg.n_layers + 3
 
     def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
@@ -280,11 +280,11 @@ class Engine:
         self.launches += 1
         return out
 
-    def attn_decode(self, qkv, seq_lens, page_table, layer, fused_rope=False):
+    def attn_decode(self, qkv, seq_lens, page_table, layer, fused_rope=False, max_kv_len: int = 0):
         _req(qkv, torch.bfloat16, "qkv")
         out = torch.empty((qkv.shape[0], self.cfg.hidden), dtype=torch.bfloat16, device=qkv.device)
         self._check(self.lib.rvl_attn_decode(self.h, qkv.data_ptr(), out.data_ptr(), seq_lens.data_ptr(), qkv.shape[0],
-                                             page_table.data_ptr(), page_table.shape[1], layer, 1 if fused_rope else 0, _stream()),
+                                             page_table.data_ptr(), page_table.shape[1], layer, 1 if fused_rope else 0, max_kv_len, _stream()),
                     "rvl_attn_decode")
         self.launches += 1
         return out

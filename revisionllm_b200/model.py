@@ -119,6 +119,7 @@ class RevisionLlamaForCausalLM:
         self.dtype = torch.bfloat16
         self._warned_sampling = False
         self.clip_encoder = None
+        self.share_prefix_pages = True     # map the KV pages of a prompt prefix common to the whole batch once (see _alloc_kv)
 
     # ---- placement (eval_nlq_negative.py:144-148 does `model.bfloat16().cuda()`)
     def bfloat16(self):
@@ -189,6 +190,7 @@ class RevisionLlamaForCausalLM:
         ids_np = input_ids.detach().cpu().numpy().astype(np.int64)
         am_np = None if attention_mask is None else attention_mask.detach().cpu().numpy().astype(bool)
         plan = plan_splice(ids_np, n_vis, am_np, self.config.tokenizer_model_max_length, constants.IMAGE_TOKEN_INDEX)
+        plan["shared_prefix"] = min(self._common_text_prefix(ids_np, am_np), int(plan["lengths"].min()))
         dev = self.device
         T = int(plan["cu_seqlens"][-1])
         hidden = torch.empty((T, self.config.hidden_size), dtype=torch.float32, device=dev)
@@ -203,20 +205,42 @@ class RevisionLlamaForCausalLM:
             eng.project_splice(rows, vis_dst, text_ids, text_dst, hidden)
         return hidden, plan
 
-    def _alloc_kv(self, lengths: np.ndarray, extra: int) -> KVState:
+    def _alloc_kv(self, lengths: np.ndarray, extra: int, shared_prefix: int = 0) -> KVState:
+        """Page table of one live batch.  `shared_prefix` = number of leading prompt positions whose tokens are identical
+        in every sequence (the system prompt in front of <video>): causal attention makes their K/V identical too, so
+        the whole pages they fill are mapped to the SAME physical pages for all sequences.  Every sequence still
+        computes and writes them at prefill (identical bits); what changes is that the 180 x 32 decode-attention CTAs
+        of a step read one copy that stays in the 126 MB L2 instead of 180 copies from HBM."""
         eng = self.engine
         ps = eng.cfg.kv_page_size
+        n_shared = (shared_prefix // ps) if (self.share_prefix_pages and len(lengths) > 1) else 0
         pages_per = [int(math.ceil((int(l) + extra) / ps)) for l in lengths]
+        n_shared = min([n_shared] + [int(l) // ps for l in lengths])
         max_pages = max(pages_per)
-        total = sum(pages_per)
+        total = n_shared + sum(n - n_shared for n in pages_per)
         eng.ensure_kv(total)
         table = np.zeros((len(lengths), max_pages), dtype=np.int32)
-        nxt = 0
+        nxt = n_shared
         for i, n in enumerate(pages_per):
-            table[i, :n] = np.arange(nxt, nxt + n, dtype=np.int32)
-            nxt += n
+            table[i, :n_shared] = np.arange(n_shared, dtype=np.int32)
+            table[i, n_shared:n] = np.arange(nxt, nxt + n - n_shared, dtype=np.int32)
+            nxt += n - n_shared
         dev = self.device
-        return KVState(torch.from_numpy(table).to(dev), torch.from_numpy(lengths.astype(np.int32)).to(dev), extra, lengths)
+        kv = KVState(torch.from_numpy(table).to(dev), torch.from_numpy(lengths.astype(np.int32)).to(dev), extra, lengths)
+        kv.shared_prefix = shared_prefix
+        return kv
+
+    @staticmethod
+    def _common_text_prefix(ids: np.ndarray, mask: Optional[np.ndarray]) -> int:
+        """Leading positions that hold the same text token in every row (stops at the first placeholder / masked id)."""
+        if ids.shape[0] < 2:
+            return 0
+        special = ids < 0
+        if mask is not None:
+            special = special | ~mask
+        upto = int(np.where(special.any(axis=1), special.argmax(axis=1), ids.shape[1]).min())
+        same = (ids[:, :upto] == ids[:1, :upto]).all(axis=0)
+        return int(upto if same.all() else same.argmin())
 
     # ---- forward (vtimellm_llama.py:38-90) ---------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
@@ -238,7 +262,8 @@ class RevisionLlamaForCausalLM:
                     raise RvlError("KV pages exhausted: pass a larger reserve_new_tokens to the prefill forward()")
                 B = input_ids.shape[0]
                 logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
-                eng.decode_step(input_ids.reshape(B).to(dev, torch.int32).contiguous(), kv.seq_lens, kv.page_table, logits)
+                eng.decode_step(input_ids.reshape(B).to(dev, torch.int32).contiguous(), kv.seq_lens, kv.page_table, logits,
+                                max_kv_len=kv.get_seq_length() + 1)
                 kv.steps += 1
                 return CausalLMOutput(logits=logits[:, None, :], past_key_values=kv)
             if inputs_embeds is not None:
@@ -253,7 +278,7 @@ class RevisionLlamaForCausalLM:
                 hidden, plan = self._splice(input_ids, attention_mask, images, query_feats)
                 lengths, cu = plan["lengths"], plan["cu_seqlens"]
             B = len(lengths)
-            kv = self._alloc_kv(lengths, reserve_new_tokens)
+            kv = self._alloc_kv(lengths, reserve_new_tokens, plan["shared_prefix"] if inputs_embeds is None else 0)
             cu_d = torch.from_numpy(cu).to(dev)
             Lmax, T = int(lengths.max()), int(cu[-1])
             if logits_to_keep == 1:
@@ -299,7 +324,7 @@ class RevisionLlamaForCausalLM:
             max_new = min(int(max_new_tokens), room)
             # KV pages: everything up front when small, else grow in chunks of 64 tokens as decoding proceeds
             chunk = max_new if max_new <= 64 else 64
-            kv = self._alloc_kv(lengths, chunk)
+            kv = self._alloc_kv(lengths, chunk, plan["shared_prefix"])
             cu_d = torch.from_numpy(cu).to(dev)
             logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
             eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
@@ -322,7 +347,7 @@ class RevisionLlamaForCausalLM:
                     kv = self._grow_kv(kv, lengths, t + 1 + chunk)
                 if output_scores:
                     logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
-                eng.decode_step(tokens[t], kv.seq_lens, kv.page_table, logits)
+                eng.decode_step(tokens[t], kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
                 kv.steps += 1
             new_tokens = tokens[:n_steps].t().contiguous()
             ids_dev = input_ids.to(dev)
@@ -341,7 +366,7 @@ class RevisionLlamaForCausalLM:
         c = eng.cfg
         eng._kv = None
         eng.n_pages = 0
-        new = self._alloc_kv(lengths, extra)
+        new = self._alloc_kv(lengths, extra, getattr(kv, "shared_prefix", 0))
         per_old = old_pages * c.n_heads * c.kv_page_size * c.head_dim
         per_new = eng.n_pages * c.n_heads * c.kv_page_size * c.head_dim
         src, dst = old_kv.view(torch.bfloat16), eng._kv.view(torch.bfloat16)

@@ -33,7 +33,7 @@ for B in [int(b) for b in args.batches.split(",")]:
         e[0].record()
         for t in range(args.steps):
             eng.sample_greedy(logits, tok, ent, None, -1, 0)
-            eng.decode_step(tok, kv.seq_lens, kv.page_table, logits)
+            eng.decode_step(tok, kv.seq_lens, kv.page_table, logits, max_kv_len=int(kv.lengths.max()) + t + 1)
         e[1].record()
         torch.cuda.synchronize()
         ms = e[0].elapsed_time(e[1]) / args.steps
