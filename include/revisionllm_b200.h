@@ -165,6 +165,16 @@ RVL_API int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq,
                       int32_t* unfinished, int32_t eos_id, int32_t pad_id, int32_t* next_tokens,
                       float* entropy_out, rvl_stream stream);
 
+/* The reference's own sampling rule: next token ~ softmax(logits / temperature) (vtimellm_llama.py:312-338 with
+ * inference.py:47-48: do_sample=True, temperature=0.05), same EOS / pad bookkeeping and entropy output as
+ * rvl_sample_greedy.  The uniform variate of (seed, step, row) comes from Philox4x32-10 with key = seed and counter =
+ * (row, step, 0, 0), u = (x0 >> 8) / 2^24, and the draw is the inverse CDF of exp((x - max) / T) in index order, so a
+ * run is reproducible and independent of batch composition (torch.multinomial's stream is not reproduced - no two
+ * torch versions agree on it either).  philox_out (optional, [n_seq, 4] uint32) returns the raw Philox words (tests). */
+RVL_API int rvl_sample_multinomial(rvl_handle* h, const float* logits, int32_t n_seq, int32_t vocab, float temperature,
+                           uint64_t seed, uint32_t step, int32_t* unfinished, int32_t eos_id, int32_t pad_id,
+                           int32_t* next_tokens, float* entropy_out, uint32_t* philox_out, rvl_stream stream);
+
 /* CLIP text-to-frame cosine top-k score of each proposal.
  * Replaces similarity.py:71-94 `_topk_pooling` + the caller arithmetic
  * eval_nlq_negative.py:309-316 / eval_nlq_retrieval_e2e2.py:380-386:
@@ -182,6 +192,22 @@ RVL_API int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* se
  * index (bit-exact given identical scores; BASELINE.json north_star). n <= 65536. */
 RVL_API int rvl_select_topk(rvl_handle* h, const float* scores, int32_t n, int32_t k, int32_t* idx_out,
                     rvl_stream stream);
+
+/* Per-query scoring tail: normalise, merge, min-max, stage-2 cover filter and ranking of the stage-1 proposals.
+ * Replaces eval_nlq_negative.py:317-336 (max-normalisation + `cos - entropy` / `cos / entropy` merge),
+ * metric_retrieval_forward.py:119-152 (cover filter, min-max normalisation) and the descending stable sort of
+ * grounding_metrics_stream (:38), in double precision like the Python floats of the reference.
+ *   cos, ent     [n] fp32 device (either may be NULL when `mode` does not read it)
+ *   keep         [n] int32: proposal parsed to a span (not "Not Present", not the 249-249 sentinel)
+ *   cover1       [n] int32 or NULL: proposal lies in the windows kept by the first stage-2 log
+ *   cover_all    [n] int32 or NULL (= cover1): ... by either stage-2 log
+ *   mode         0: cos - ent, 1: cos / ent, 2: -ent, 3: cos;  normalize / minmax: 0 or 1
+ *   scores_out   [n] fp64 merged scores (NaN where keep == 0)
+ *   order_out    [n] int32: the first *n_out entries are the surviving proposals, best first (ties: lower index)
+ * n <= 8192. */
+RVL_API int rvl_merge_rank(rvl_handle* h, const float* cos, const float* ent, const int32_t* keep,
+                   const int32_t* cover1, const int32_t* cover_all, int32_t n, int32_t mode, int32_t normalize,
+                   int32_t minmax, double* scores_out, int32_t* order_out, int32_t* n_out, rvl_stream stream);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 #define RVL_PROF_GEMM 0          /* tcgen05 GEMM, token-major (prefill) */

@@ -85,6 +85,8 @@ def splice(
     image_features: torch.Tensor,          # [B, F, hidden] already projected
     attention_mask: Optional[torch.Tensor] = None,
     max_length: Optional[int] = None,
+    visual_memory: Optional[torch.Tensor] = None,    # [B, M, 768] (or [B, 768]) raw CLIP rows of the streaming memory
+    prefix_memory: Optional[torch.Tensor] = None,    # [B, P] int64 text ids in front of the memory rows
 ) -> List[torch.Tensor]:
     """vtimellm_arch.py:149-244 (visual_memory=None branch): per row, drop
     padded ids, split at the placeholder(s), embed the text chunks, interleave
@@ -94,6 +96,18 @@ def splice(
     emb = w["model.embed_tokens.weight"].float()
     out = []
     cur_image = 0
+    if visual_memory is not None:
+        # vtimellm_arch.py:208-232: [text ; video ; text ; embed(prefix_memory) ; mm_projector(visual_memory) ; text]
+        vm = visual_memory[:, None] if visual_memory.dim() == 2 else visual_memory
+        mem = torch.cat([emb[prefix_memory], mm_projector_linear(w, vm)], dim=1)          # [B, P + M, hidden]
+        for b in range(input_ids.shape[0]):
+            ids = input_ids[b]
+            cut = [-1] + torch.where(ids == IMAGE_TOKEN_INDEX)[0].tolist() + torch.where(ids == MEMORY_TOKEN_INDEX)[0].tolist() + [ids.shape[0]]
+            chunks = [emb[ids[cut[i] + 1: cut[i + 1]]] for i in range(len(cut) - 1)]
+            parts = [chunks[0], image_features[b].float(), chunks[1], mem[b]] + ([chunks[2]] if len(chunks) == 3 else [])
+            e = torch.cat(parts, dim=0)
+            out.append(e[:max_length] if max_length is not None else e)
+        return out
     for b in range(input_ids.shape[0]):
         ids = input_ids[b]
         if attention_mask is not None:

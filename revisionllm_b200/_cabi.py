@@ -55,8 +55,10 @@ PROTOTYPES = {
     "rvl_prefill": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _P, _I32, _P, _I32, _P]),
     "rvl_decode_step": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "rvl_sample_greedy": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),
+    "rvl_sample_multinomial": (C.c_int, [_P, _P, _I32, _I32, _F, C.c_uint64, C.c_uint32, _P, _I32, _I32, _P, _P, _P, _P]),
     "rvl_cosine_topk": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P]),
     "rvl_select_topk": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "rvl_merge_rank": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "rvl_profile_enable": (C.c_int, [_P, _I32, _I32]),
     "rvl_profile_read": (C.c_int, [_P, _I32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "rvl_debug_gemm_timestamps": (None, [C.c_int, _P, C.c_int]),

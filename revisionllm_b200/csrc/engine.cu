@@ -388,6 +388,16 @@ int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq, int32_t
   return check_cuda(h, "rvl_sample_greedy");
 }
 
+int rvl_sample_multinomial(rvl_handle* h, const float* logits, int32_t n_seq, int32_t vocab, float temperature, uint64_t seed,
+                            uint32_t step, int32_t* unfinished, int32_t eos_id, int32_t pad_id, int32_t* next_tokens,
+                            float* entropy_out, uint32_t* philox_out, rvl_stream stream) {
+  if (!h || !logits || !next_tokens) return fail(h, RVL_ERR_INVALID, "rvl_sample_multinomial: null argument");
+  if (!(temperature > 0.f)) return fail(h, RVL_ERR_INVALID, "rvl_sample_multinomial: temperature must be > 0 (use rvl_sample_greedy for argmax)");
+  launch_sample_multinomial(logits, n_seq, vocab, temperature, seed, step, unfinished, eos_id, pad_id, next_tokens, entropy_out,
+                            philox_out, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_sample_multinomial");
+}
+
 int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, int32_t n_seg, int32_t dim,
                     const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows, float* scores_out,
                     int32_t* topk_idx_out, rvl_stream stream) {
@@ -404,6 +414,18 @@ int rvl_select_topk(rvl_handle* h, const float* scores, int32_t n, int32_t k, in
   if (n > 65536 || k > n) return fail(h, RVL_ERR_INVALID, "rvl_select_topk: need k <= n <= 65536");
   launch_select_topk(scores, n, k, idx_out, static_cast<cudaStream_t>(stream));
   return check_cuda(h, "rvl_select_topk");
+}
+
+int rvl_merge_rank(rvl_handle* h, const float* cos, const float* ent, const int32_t* keep, const int32_t* cover1,
+                   const int32_t* cover_all, int32_t n, int32_t mode, int32_t normalize, int32_t minmax, double* scores_out,
+                   int32_t* order_out, int32_t* n_out, rvl_stream stream) {
+  if (!h || !keep || !scores_out || !order_out || !n_out) return fail(h, RVL_ERR_INVALID, "rvl_merge_rank: null argument");
+  if (n <= 0 || n > 8192 || mode < 0 || mode > 3) return fail(h, RVL_ERR_INVALID, "rvl_merge_rank: need 0 < n <= 8192 and mode in 0..3");
+  if ((mode <= 1 && (!cos || !ent)) || (mode == 2 && !ent) || (mode == 3 && !cos))
+    return fail(h, RVL_ERR_INVALID, "rvl_merge_rank: the score arrays the mode reads are missing");
+  launch_merge_rank(cos, ent, keep, cover1, cover_all, n, mode, normalize, minmax, scores_out, order_out, n_out,
+                    static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_merge_rank");
 }
 
 // ------------------------------------------------------------------------------------------ profiling

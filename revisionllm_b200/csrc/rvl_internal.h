@@ -89,9 +89,15 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
 void launch_sample_greedy(const float* logits, int n_seq, int vocab, int32_t* unfinished, int eos_id, int pad_id,
                           int32_t* next_tokens, float* entropy_out, int32_t* seq_lens, int32_t* n_unfinished,
                           cudaStream_t st);
+void launch_sample_multinomial(const float* logits, int n_seq, int vocab, float temperature, unsigned long long seed,
+                               uint32_t step, int32_t* unfinished, int eos_id, int pad_id, int32_t* next_tokens,
+                               float* entropy_out, uint32_t* philox_out, cudaStream_t st);
 // scoring.cu
 void launch_cosine_topk(const void* frames, const int32_t* seg_offsets, int n_seg, int dim, const void* cls, int k,
                         int norm_axis, int max_seg_rows, float* scores_out, int32_t* topk_idx_out, cudaStream_t st);
 void launch_select_topk(const float* scores, int n, int k, int32_t* idx_out, cudaStream_t st);
+void launch_merge_rank(const float* cos, const float* ent, const int32_t* keep, const int32_t* cover1, const int32_t* cover_all,
+                       int n, int mode, int normalize, int minmax, double* scores_out, int32_t* order_out, int32_t* n_out,
+                       cudaStream_t st);
 
 }  // namespace rvl

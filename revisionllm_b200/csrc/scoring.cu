@@ -120,4 +120,106 @@ void launch_select_topk(const float* scores, int n, int k, int32_t* idx_out, cud
   select_topk_kernel<<<(n + 127) / 128, 128, 0, st>>>(scores, n, k, idx_out);
 }
 
+// ------------------------------------------------------------------------------------------- merge + rank
+// The per-query scoring tail of the reference, on the device and in double precision like the Python floats it
+// restates (so the ranking is bit-identical to a float64 numpy restatement):
+//   1. over the kept proposals (keep != 0: the answer parsed to a span): cos /= max(cos), ent /= max(ent) when
+//      `normalize` (revisionllm/eval/eval_nlq_negative.py:321-327);
+//   2. merged = cos - ent (mode 0, --score_merge add) | cos / ent (1, multiply) | -ent (2) | cos (3)   (:328-336);
+//   3. min-max normalisation of the merged scores when `minmax` and min != max
+//      (revisionllm/eval/metric_retrieval_forward.py:146-152);
+//   4. stage-2 cover filter (:119-141): if any kept proposal lies in cover1, only kept proposals inside cover_all
+//      survive; otherwise all kept proposals do;
+//   5. order = surviving proposals by descending score, ties in index order (Python's stable sorted(..., reverse=True) of
+//      grounding_metrics_stream, :38).
+// One CTA; n <= 8192 proposals per query (MAD: 57 - 143 windows).  scores_out[i] is NaN for proposals that are not kept.
+constexpr int kRankThreads = 1024;
+
+__device__ __forceinline__ double block_reduce_max(double v, double* red, bool want_min) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double x = __shfl_xor_sync(0xffffffffu, v, o);
+    v = want_min ? fmin(v, x) : fmax(v, x);
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double r = red[0];
+  for (int w = 1; w < kRankThreads / 32; ++w) r = want_min ? fmin(r, red[w]) : fmax(r, red[w]);
+  return r;
+}
+
+__global__ void __launch_bounds__(kRankThreads) merge_rank_kernel(const float* __restrict__ cos, const float* __restrict__ ent,
+                                                                   const int32_t* __restrict__ keep,
+                                                                   const int32_t* __restrict__ cover1,
+                                                                   const int32_t* __restrict__ cover_all, int n, int mode,
+                                                                   int normalize, int minmax, double* __restrict__ scores_out,
+                                                                   int32_t* __restrict__ order_out, int32_t* __restrict__ n_out) {
+  __shared__ double red[kRankThreads / 32];
+  __shared__ int s_any;
+  const int tid = threadIdx.x;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  if (tid == 0) s_any = 0;
+  double mc = -inf, me = -inf;
+  for (int i = tid; i < n; i += kRankThreads)
+    if (keep[i]) {
+      if (cos) mc = fmax(mc, static_cast<double>(cos[i]));
+      if (ent) me = fmax(me, static_cast<double>(ent[i]));
+    }
+  mc = block_reduce_max(mc, red, false);
+  me = block_reduce_max(me, red, false);
+  double lo = inf, hi = -inf;
+  for (int i = tid; i < n; i += kRankThreads) {
+    double sc = __longlong_as_double(0x7ff8000000000000LL);
+    if (keep[i]) {
+      double c = cos ? static_cast<double>(cos[i]) : 0.0, e = ent ? static_cast<double>(ent[i]) : 0.0;
+      if (normalize) { c = c / mc; e = e / me; }
+      sc = mode == 0 ? c - e : (mode == 1 ? c / e : (mode == 2 ? -e : c));
+      lo = fmin(lo, sc);
+      hi = fmax(hi, sc);
+      if (cover1 && cover1[i]) s_any = 1;
+    }
+    scores_out[i] = sc;
+  }
+  lo = block_reduce_max(lo, red, true);
+  hi = block_reduce_max(hi, red, false);
+  __syncthreads();
+  // the reference min-max normalises only inside the branch that applies the stage-2 filter (metric_retrieval_forward.py:137)
+  if (minmax && lo != hi && (cover1 == nullptr || s_any != 0)) {
+    for (int i = tid; i < n; i += kRankThreads)
+      if (keep[i]) scores_out[i] = (scores_out[i] - lo) / (hi - lo);
+  }
+  __syncthreads();
+  const bool filter = cover1 != nullptr && s_any != 0;
+  const int32_t* cov = cover_all ? cover_all : cover1;
+  int alive_local = 0;
+  for (int i = tid; i < n; i += kRankThreads) {
+    const bool alive = keep[i] && (!filter || cov[i]);
+    if (!alive) continue;
+    ++alive_local;
+    const double si = scores_out[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      if (!(keep[j] && (!filter || cov[j]))) continue;
+      const double sj = scores_out[j];
+      rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    }
+    order_out[rank] = i;
+  }
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  atomicAdd(&s_cnt, alive_local);
+  __syncthreads();
+  if (tid == 0) *n_out = s_cnt;
+}
+
+void launch_merge_rank(const float* cos, const float* ent, const int32_t* keep, const int32_t* cover1, const int32_t* cover_all,
+                       int n, int mode, int normalize, int minmax, double* scores_out, int32_t* order_out, int32_t* n_out,
+                       cudaStream_t st) {
+  merge_rank_kernel<<<1, kRankThreads, 0, st>>>(cos, ent, keep, cover1, cover_all, n, mode, normalize, minmax, scores_out,
+                                                order_out, n_out);
+}
+
 }  // namespace rvl

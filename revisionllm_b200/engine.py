@@ -205,6 +205,15 @@ class Engine:
                                                next_tokens.data_ptr(), _ptr(entropy), _stream()), "rvl_sample_greedy")
         self.launches += 1
 
+    def sample_multinomial(self, logits, next_tokens, temperature, seed, step, entropy=None, unfinished=None, eos_id=2, pad_id=2,
+                           philox_out=None):
+        _req(logits, torch.float32, "logits"); _req(next_tokens, torch.int32, "next_tokens")
+        n, v = logits.shape
+        self._check(self.lib.rvl_sample_multinomial(self.h, logits.data_ptr(), n, v, float(temperature), int(seed) & (2 ** 64 - 1),
+                                                    int(step), _ptr(unfinished), eos_id, pad_id, next_tokens.data_ptr(),
+                                                    _ptr(entropy), _ptr(philox_out), _stream()), "rvl_sample_multinomial")
+        self.launches += 1
+
     def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True):
         _req(frames, torch.bfloat16, "frames"); _req(seg_offsets, torch.int32, "seg_offsets"); _req(cls, torch.bfloat16, "cls")
         n_seg = seg_offsets.shape[0] - 1
@@ -225,6 +234,24 @@ class Engine:
                     "rvl_select_topk")
         self.launches += 1
         return idx
+
+    def merge_rank(self, cos, ent, keep, cover1=None, cover_all=None, mode=0, normalize=True, minmax=True):
+        """-> (scores fp64 [n], order int32 [n], n_out int32 [1]) on the device (see rvl_merge_rank)."""
+        n = keep.shape[0]
+        for t, name in ((cos, "cos"), (ent, "ent")):
+            if t is not None:
+                _req(t, torch.float32, name)
+        for t, name in ((keep, "keep"), (cover1, "cover1"), (cover_all, "cover_all")):
+            if t is not None:
+                _req(t, torch.int32, name)
+        scores = torch.empty(n, dtype=torch.float64, device=keep.device)
+        order = torch.full((n,), -1, dtype=torch.int32, device=keep.device)
+        n_out = torch.zeros(1, dtype=torch.int32, device=keep.device)
+        self._check(self.lib.rvl_merge_rank(self.h, _ptr(cos), _ptr(ent), keep.data_ptr(), _ptr(cover1), _ptr(cover_all), n, mode,
+                                            1 if normalize else 0, 1 if minmax else 0, scores.data_ptr(), order.data_ptr(),
+                                            n_out.data_ptr(), _stream()), "rvl_merge_rank")
+        self.launches += 1
+        return scores, order, n_out
 
     # ------------------------------------------------------------------ measurement
     def profile(self, on: bool, capacity: int = 16384):

@@ -15,7 +15,10 @@ from .mm_utils import tokenizer_image_token
 
 
 def inference(model, image, query_feats, query, tokenizer, visual_memory=None, prefix_memory=None, return_list=False,
-              max_new_tokens: int = 1024, output_scores: bool = True):
+              max_new_tokens: int = 1024, output_scores: bool = True, do_sample: bool = False, temperature: float = 0.05,
+              seed: int = 0):
+    """`do_sample=False` (default) decodes greedily (BASELINE.json north_star); `do_sample=True` is the reference's own rule
+    (inference.py:47-48: multinomial at temperature 0.05)."""
     if visual_memory is not None:
         query = query + "<memory>"
     conv = conv_templates["v1"].copy()
@@ -27,7 +30,7 @@ def inference(model, image, query_feats, query, tokenizer, visual_memory=None, p
     stop_str = conv.sep if conv.sep_style != SeparatorStyle.TWO else conv.sep2
     with torch.inference_mode():
         model_output = model.generate(
-            input_ids, images=image, query_feats=query_feats, do_sample=False, num_beams=1,
+            input_ids, images=image, query_feats=query_feats, do_sample=do_sample, temperature=temperature, seed=seed, num_beams=1,
             max_new_tokens=max_new_tokens, use_cache=True, visual_memory=visual_memory, prefix_memory=prefix_memory,
             output_scores=output_scores, return_dict_in_generate=True, output_hidden_states=False)
     output_ids = model_output["sequences"]

@@ -7,7 +7,9 @@ as called by `inference()` (/root/reference/revisionllm/inference.py:45-59), `ge
 `prepare_inputs_labels_for_multimodal` (/root/reference/revisionllm/model/vtimellm_arch.py:81-299).
 
 Differences, all deliberate and documented in DESIGN.md:
-  * decoding is greedy (BASELINE.json north_star) - `do_sample` / `temperature` are accepted and ignored;
+  * decoding is greedy by default (BASELINE.json north_star); `do_sample=True, temperature=T` draws from
+    softmax(logits / T) like the reference's `sample()` (vtimellm_llama.py:312-338), with a counter-based Philox stream
+    instead of torch.multinomial's;
   * ragged batches are packed (cu_seqlens) instead of right-padded; outputs are re-padded on return;
   * there is no CPU path: `.float()` / CPU placement raise.
 """
@@ -183,12 +185,36 @@ class RevisionLlamaForCausalLM:
         B, F, D = images.shape                           # stage 1: [B, F, 768] through the Linear projector (:125)
         return images.to(dev, torch.bfloat16).reshape(B * F, D).contiguous(), [F] * B, False
 
-    def _splice(self, input_ids, attention_mask, images, query_feats):
+    def _splice(self, input_ids, attention_mask, images, query_feats, visual_memory=None, prefix_memory=None):
         """Projector + splice into a packed fp32 residual stream.  Returns (hidden [T, H], plan)."""
         eng = self.engine
         rows, n_vis, projected = self._visual_blocks(images, query_feats)
         ids_np = input_ids.detach().cpu().numpy().astype(np.int64)
         am_np = None if attention_mask is None else attention_mask.detach().cpu().numpy().astype(bool)
+        if visual_memory is not None:
+            # <memory> streaming branch (vtimellm_arch.py:208-232): the -300 placeholder expands to
+            # [embed_tokens(prefix_memory[b]) ; mm_projector(visual_memory[b])].  Here the placeholder is rewritten as the
+            # prefix ids followed by one more visual placeholder, and the memory vectors join the projector GEMM as a second
+            # visual block of the row - one GEMM for frames and memory, no concatenations.
+            if projected or isinstance(images, (list, tuple)):
+                raise RvlError("visual_memory is only defined for the stage-1 Linear projector ([B, F, D] `images`)")
+            if attention_mask is not None:
+                raise RvlError("visual_memory with an attention_mask is not part of the reference path")
+            vm = visual_memory[:, None] if visual_memory.dim() == 2 else visual_memory       # [B, M, D]
+            B, F = len(n_vis), n_vis[0]
+            M = vm.shape[1]
+            pm = prefix_memory.detach().cpu().numpy().astype(np.int64)                         # [B, P]
+            new_ids = []
+            for b in range(B):
+                where = np.nonzero(ids_np[b] == constants.MEMORY_TOKEN_INDEX)[0]
+                if where.shape[0] != 1 or (ids_np[b] == constants.IMAGE_TOKEN_INDEX).sum() != 1 or \
+                        where[0] < np.argmax(ids_np[b] == constants.IMAGE_TOKEN_INDEX):
+                    raise RvlError("visual_memory needs exactly one <video> followed by one <memory> placeholder per row")
+                new_ids.append(np.concatenate([ids_np[b, :where[0]], pm[b], [constants.IMAGE_TOKEN_INDEX], ids_np[b, where[0] + 1:]]))
+            ids_np = np.stack(new_ids)
+            D = rows.shape[1]
+            rows = torch.cat([rows.view(B, F, D), vm.to(self.device, torch.bfloat16)], dim=1).reshape(B * (F + M), D).contiguous()
+            n_vis = [n for _ in range(B) for n in (F, M)]
         plan = plan_splice(ids_np, n_vis, am_np, self.config.tokenizer_model_max_length, constants.IMAGE_TOKEN_INDEX)
         plan["shared_prefix"] = min(self._common_text_prefix(ids_np, am_np), int(plan["lengths"].min()))
         dev = self.device
@@ -248,8 +274,8 @@ class RevisionLlamaForCausalLM:
                 visual_memory=None, prefix_memory=None, query_feats=None, return_dict=None, start_end_frame=None,
                 iteration_step=None, logits_to_keep: int = 0, reserve_new_tokens: int = 64):
         self._need_engine()
-        if visual_memory is not None or prefix_memory is not None:
-            raise NotImplementedError("the <memory> streaming branch (vtimellm_arch.py:208-232) is listed as 'next' in SURVEY.md section 8f")
+        if (visual_memory is None) != (prefix_memory is None):
+            raise RvlError("visual_memory and prefix_memory come together (vtimellm_arch.py:226-228)")
         if labels is not None or output_attentions:
             raise NotImplementedError("training-time outputs are out of scope (inference path only)")
         eng, cfg = self.engine, self.config
@@ -275,7 +301,7 @@ class RevisionLlamaForCausalLM:
             else:
                 if images is None:
                     raise RvlError("forward() without `images` or `inputs_embeds` is not part of the scoring path")
-                hidden, plan = self._splice(input_ids, attention_mask, images, query_feats)
+                hidden, plan = self._splice(input_ids, attention_mask, images, query_feats, visual_memory, prefix_memory)
                 lengths, cu = plan["lengths"], plan["cu_seqlens"]
             B = len(lengths)
             kv = self._alloc_kv(lengths, reserve_new_tokens, plan["shared_prefix"] if inputs_embeds is None else 0)
@@ -299,23 +325,25 @@ class RevisionLlamaForCausalLM:
     def generate(self, input_ids, images=None, query_feats=None, do_sample=False, temperature=1.0, num_beams=1,
                  max_new_tokens=1024, use_cache=True, visual_memory=None, prefix_memory=None, output_scores=False,
                  return_dict_in_generate=False, output_hidden_states=False, attention_mask=None,
-                 eos_token_id="config", pad_token_id=None, stopping_criteria=None, **unused):
+                 eos_token_id="config", pad_token_id=None, stopping_criteria=None, seed: int = 0,
+                 retire_finished: bool = False, **unused):
+        """`seed`: key of the Philox stream used when do_sample=True.  `retire_finished`: drop rows that emitted EOS from the
+        decode batch (their remaining tokens are pad, as in the reference; their per-step entropies stop at EOS instead of
+        continuing over pad inputs as the reference's do)."""
         self._need_engine()
         if num_beams != 1:
             raise NotImplementedError("beam search is not part of the reference path (num_beams=1, inference.py:49)")
-        if visual_memory is not None or prefix_memory is not None:
-            raise NotImplementedError("the <memory> streaming branch is listed as 'next' in SURVEY.md section 8f")
+        if (visual_memory is None) != (prefix_memory is None):
+            raise RvlError("visual_memory and prefix_memory come together (vtimellm_arch.py:226-228)")
         if images is None:
             raise RvlError("generate() needs `images` (pre-extracted CLIP features)")
-        if do_sample and not self._warned_sampling:
-            warnings.warn("revisionllm_b200 decodes greedily (BASELINE.json north_star); do_sample/temperature are ignored")
-            self._warned_sampling = True
+        sampling = bool(do_sample) and temperature is not None and float(temperature) > 0.0
         eng, cfg = self.engine, self.config
         dev = self.device
         eos = cfg.eos_token_id if eos_token_id == "config" else eos_token_id
         pad = pad_token_id if pad_token_id is not None else (cfg.pad_token_id if cfg.pad_token_id is not None else (eos if eos is not None else 0))
         with torch.cuda.device(dev):
-            hidden, plan = self._splice(input_ids, attention_mask, images, query_feats)
+            hidden, plan = self._splice(input_ids, attention_mask, images, query_feats, visual_memory, prefix_memory)
             lengths, cu = plan["lengths"], plan["cu_seqlens"]
             B = len(lengths)
             room = cfg.max_position_embeddings - int(lengths.max())
@@ -329,25 +357,56 @@ class RevisionLlamaForCausalLM:
             logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
             eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
             del hidden
-            tokens = torch.empty((max_new, B), dtype=torch.int32, device=dev)
-            entropies = torch.empty((max_new, B), dtype=torch.float32, device=dev)
+            tokens = torch.full((max_new, B), int(pad), dtype=torch.int32, device=dev)
+            entropies = torch.full((max_new, B), float("nan"), dtype=torch.float32, device=dev)
             unfinished = torch.ones(B, dtype=torch.int32, device=dev) if eos is not None else None
             scores: List[torch.Tensor] = []
             n_steps = 0
+            active = None                          # original row ids of the live decode batch once rows have been retired
+            tok_t = ent_t = None
             for t in range(max_new):
-                eng.sample_greedy(logits, tokens[t], entropies[t], unfinished, -1 if eos is None else eos, pad)
+                n_live = logits.shape[0]
+                if active is None:
+                    tok_t, ent_t = tokens[t], entropies[t]
+                else:
+                    tok_t = torch.empty(n_live, dtype=torch.int32, device=dev)
+                    ent_t = torch.empty(n_live, dtype=torch.float32, device=dev)
+                if sampling:
+                    eng.sample_multinomial(logits, tok_t, float(temperature), seed, t, ent_t, unfinished, -1 if eos is None else eos, pad)
+                else:
+                    eng.sample_greedy(logits, tok_t, ent_t, unfinished, -1 if eos is None else eos, pad)
+                if active is not None:
+                    tokens[t].index_copy_(0, active, tok_t)
+                    entropies[t].index_copy_(0, active, ent_t)
                 if output_scores:
-                    scores.append(logits)
+                    if active is None:
+                        scores.append(logits)
+                    else:
+                        full = torch.zeros((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                        full.index_copy_(0, active, logits)
+                        scores.append(full)
                 n_steps = t + 1
-                if unfinished is not None and int(unfinished.sum().item()) == 0:     # vtimellm_llama.py:359-362
+                n_unf = int(unfinished.sum().item()) if unfinished is not None else n_live
+                if unfinished is not None and n_unf == 0:     # vtimellm_llama.py:359-362
                     break
                 if t == max_new - 1:
                     break
                 if t + 1 > kv.reserve:
-                    kv = self._grow_kv(kv, lengths, t + 1 + chunk)
-                if output_scores:
-                    logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
-                eng.decode_step(tokens[t], kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
+                    kv = self._grow_kv(kv, kv.lengths, t + 1 + chunk)       # kv.lengths: the rows still in the batch
+                if retire_finished and unfinished is not None and n_unf < n_live:
+                    # per-sequence retirement from the paged batch: only rows still generating go through the next step
+                    live = torch.nonzero(unfinished, as_tuple=False).flatten()
+                    active = live if active is None else active.index_select(0, live)
+                    kv_live = KVState(kv.page_table.index_select(0, live).contiguous(), kv.seq_lens.index_select(0, live).contiguous(),
+                                      kv.reserve, kv.lengths[live.cpu().numpy()])
+                    kv_live.steps, kv_live.shared_prefix = kv.steps, getattr(kv, "shared_prefix", 0)
+                    kv = kv_live
+                    tok_t = tok_t.index_select(0, live).contiguous()
+                    unfinished = unfinished.index_select(0, live).contiguous()
+                    logits = torch.empty((live.shape[0], cfg.vocab_size), dtype=torch.float32, device=dev)
+                elif output_scores:
+                    logits = torch.empty((n_live, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.decode_step(tok_t.contiguous(), kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
                 kv.steps += 1
             new_tokens = tokens[:n_steps].t().contiguous()
             ids_dev = input_ids.to(dev)

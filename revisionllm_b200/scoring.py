@@ -151,6 +151,14 @@ def get_entropy_statistics(engine: Engine, logits: torch.Tensor, q_begin: int = 
 
 
 def entropy_stats_from_steps(ent: torch.Tensor) -> torch.Tensor:
-    """ent [B, T'] per-step entropies (already produced on the device during decode) -> [B, 4]."""
-    std = ent.std(dim=1) if ent.shape[1] > 1 else torch.zeros(ent.shape[0], device=ent.device)
-    return torch.stack([ent.max(dim=1).values, ent.min(dim=1).values, ent.mean(dim=1), std], dim=1)
+    """ent [B, T'] per-step entropies (already produced on the device during decode) -> [B, 4] = (max, min, mean, std) as
+    in funs_get_feature_X.py:136-145.  NaN marks steps a row did not run (retired after EOS): they are left out."""
+    valid = ~torch.isnan(ent)
+    cnt = valid.sum(dim=1).clamp(min=1).to(ent.dtype)
+    zero = torch.zeros((), dtype=ent.dtype, device=ent.device)
+    mx = torch.where(valid, ent, torch.full_like(ent, float("-inf"))).max(dim=1).values
+    mn = torch.where(valid, ent, torch.full_like(ent, float("inf"))).min(dim=1).values
+    mean = torch.where(valid, ent, zero).sum(dim=1) / cnt
+    dev2 = torch.where(valid, (ent - mean[:, None]) ** 2, zero).sum(dim=1)
+    std = torch.sqrt(dev2 / (cnt - 1).clamp(min=1)) * (cnt > 1).to(ent.dtype)          # unbiased, 0 for a single step
+    return torch.stack([mx, mn, mean, std], dim=1)

@@ -90,6 +90,30 @@ def case_stage1(ref, name, cfg, n_seg, n_frames, n_pre, n_post, steps, ragged=Fa
     print(name, "embeds", tuple(embeds.shape), "tokens", toks[0].tolist())
 
 
+def case_stage1_memory(ref, name, cfg, n_seg, n_frames, n_mem, n_prefix, steps):
+    """The <memory> streaming branch (vtimellm_arch.py:208-232): ids hold -200 and -300, the memory block is
+    [embed_tokens(prefix_memory) ; mm_projector(visual_memory)]."""
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    feats = syn.make_features(n_seg, n_frames, cfg.adapter_dim, seed=21).float()
+    vis_mem = syn.make_features(n_seg, n_mem, cfg.adapter_dim, seed=22).float()
+    g = torch.Generator().manual_seed(23)
+    prefix = torch.randint(3, cfg.vocab, (n_seg, n_prefix), generator=g)
+    base = syn.make_prompt_ids(cfg, 6, 9, seed=24)
+    base = torch.cat([base[:-4], torch.tensor([ref.constants.MEMORY_TOKEN_INDEX]), base[-4:]])     # ... <video> text <memory> text
+    ids = base[None].repeat(n_seg, 1)
+    with torch.inference_mode():
+        r = model.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, feats, None, vis_mem, prefix, None)
+        embeds = r[4]
+        am = torch.ones(embeds.shape[:2], dtype=torch.bool)
+        logits_all, toks, scores = greedy_via_reference(model, embeds, am, steps)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), digest=syn.weights_digest(w), feats=feats.numpy(), vis_mem=vis_mem.numpy(),
+        prefix=prefix.numpy(), ids=ids.numpy(), embeds=embeds.numpy(), prefill_logits=logits_all.numpy().astype(np.float32),
+        tokens=toks.numpy(), scores=scores.numpy())
+    print(name, "embeds", tuple(embeds.shape), "tokens", toks[0].tolist())
+
+
 def case_clip_encoder(ref, name, cfg, V, T, Lq):
     w = syn.make_llama_weights(cfg, seed=0)
     cw = syn.make_clip_encoder_weights(cfg.hidden, seed=0)
@@ -173,6 +197,7 @@ def main():
     ref = ref_shim.load()
     case_stage1(ref, "stage1_tiny", syn.TINY, n_seg=3, n_frames=20, n_pre=6, n_post=9, steps=6)
     case_stage1(ref, "stage1_ragged", syn.TINY, n_seg=4, n_frames=12, n_pre=5, n_post=11, steps=4, ragged=True)
+    case_stage1_memory(ref, "stage1_memory", syn.TINY, n_seg=2, n_frames=10, n_mem=3, n_prefix=4, steps=4)
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
     case_scoring(ref, "scoring")
     case_prompt(ref, "prompt")

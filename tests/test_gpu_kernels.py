@@ -323,3 +323,72 @@ def test_cosine_topk_and_selection(eng, norm_axis):
     assert eng.select_topk(sc.cuda(), 5).tolist() == scoring_ref.select_topk_segments(sc.numpy(), 5).tolist() == [4, 1, 2, 5, 0]
     big = torch.randn(4096, generator=g)
     assert eng.select_topk(big.cuda(), 100).tolist() == scoring_ref.select_topk_segments(big.numpy(), 100).tolist()
+
+
+def test_merge_rank_kernel_reproduces_the_reference_ranking(eng, golden_dir):
+    """rvl_merge_rank (normalise, merge, min-max, cover filter, stable descending rank; fp64 on the device) on the synthetic
+    prediction logs of tests/golden/merge_metrics.json: ranked proposals, scores and the final recall metrics must equal what
+    the reference's metric_retrieval_forward.py produced."""
+    import json
+    import os
+    from oracle import metrics_ref
+    from revisionllm_b200 import metrics
+    g = json.load(open(os.path.join(golden_dir, "merge_metrics.json")))
+    ranked = []
+    for q in g["queries"]:
+        gl = q["gl"]
+        res = metrics.rank_query(eng, gl["answer"], q["cos"], q["ent"], gl["info"]["iou"], q["rl"]["info"]["frames"],
+                                 q["rl2"]["info"]["frames"], mode="add", normalize=True, minmax=True)
+        ref = metrics_ref.merge_with_retrieval(gl, q["rl"], q["rl2"])
+        sc = ref["info"]["scores"]
+        order = sorted(range(len(sc)), key=lambda k: sc[k], reverse=True)
+        assert res["ious"] == [ref["info"]["iou"][i] for i in order]
+        # scores: the golden logs carry cos / ent rounded through float32 on the way to the device
+        np.testing.assert_allclose(res["scores"], [sc[i] for i in order], rtol=0, atol=2e-6)
+        ranked.append(res["ious"])
+    got = metrics.grounding_metrics_stream(ranked)
+    for k, v in g["metrics"].items():
+        assert abs(got[k] - v) < 1e-9, (k, got[k], v)
+
+
+def test_sample_multinomial_philox_and_inverse_cdf(eng):
+    """rvl_sample_multinomial: the Philox words equal the oracle's (hence the Random123 known answers), the draw is the
+    inverse CDF of softmax(logits / T) at that variate, finished rows emit pad, entropy equals the greedy kernel's."""
+    from oracle import sampling_ref
+    B, V = 96, 2048
+    g = torch.Generator().manual_seed(21)
+    logits = (torch.randn(B, V, generator=g) * 2).cuda()
+    seed, step, T = 0x1234567855AA, 7, 0.8
+    tok = torch.empty(B, dtype=torch.int32, device="cuda")
+    ent = torch.empty(B, dtype=torch.float32, device="cuda")
+    words = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    unfinished = torch.ones(B, dtype=torch.int32, device="cuda")
+    unfinished[3] = 0
+    eng.sample_multinomial(logits, tok, T, seed, step, ent, unfinished, eos_id=2, pad_id=0, philox_out=words)
+    w = words.cpu().numpy().astype(np.uint32)
+    for b in (0, 1, 17, B - 1):
+        assert tuple(int(x) for x in w[b]) == sampling_ref.philox4x32_10((b, step, 0, 0), (seed & 0xFFFFFFFF, seed >> 32))
+    ref_tok, slack = sampling_ref.multinomial_draw(logits.cpu().numpy(), T, seed, step)
+    got = tok.cpu().tolist()
+    assert got[3] == 0                                              # finished row -> pad
+    for b in range(B):
+        if b == 3:
+            continue
+        assert got[b] == ref_tok[b] or (slack[b] < 1e-5 and abs(got[b] - ref_tok[b]) == 1), (b, got[b], ref_tok[b], slack[b])
+    tok2 = torch.empty(B, dtype=torch.int32, device="cuda")
+    ent2 = torch.empty(B, dtype=torch.float32, device="cuda")
+    eng.sample_greedy(logits, tok2, ent2)
+    assert torch.equal(ent, ent2)
+    # temperature 0.05 on a row with a clear winner is the argmax (what makes the reference's sampling near-deterministic)
+    peaked = logits.clone()
+    peaked[:, 11] += 20.0
+    eng.sample_multinomial(peaked, tok, 0.05, seed, step)
+    assert tok.cpu().tolist() == [11] * B
+    # frequencies follow the distribution: 8-way, 4096 rows, chi-square (7 dof) far below the 0.1 % tail of 24.3
+    p = torch.tensor([0.30, 0.20, 0.15, 0.12, 0.10, 0.07, 0.04, 0.02])
+    rows = p.log()[None].repeat(4096, 1).cuda().contiguous()
+    tk = torch.empty(4096, dtype=torch.int32, device="cuda")
+    eng.sample_multinomial(rows, tk, 1.0, 99, 0)
+    counts = torch.bincount(tk.cpu().long(), minlength=8).float()
+    chi2 = float(((counts - 4096 * p) ** 2 / (4096 * p)).sum())
+    assert chi2 < 24.3, chi2

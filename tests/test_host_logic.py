@@ -141,3 +141,30 @@ def test_product_path_fails_loudly_without_gpu():
         model.generate(torch.zeros(1, 4, dtype=torch.long), images=torch.zeros(1, 2, 768))
     with pytest.raises(_cabi.RvlError):
         model.float()
+
+
+def test_metrics_host_mirror_matches_oracle(golden_dir):
+    import json
+    from oracle import metrics_ref
+    from revisionllm_b200 import metrics
+    g = json.load(open(os.path.join(golden_dir, "merge_metrics.json")))
+    for c in g["iou_cases"]:
+        a = metrics.iou(c["answers"], tuple(c["gt"]), c["num_frames_clip"], c["num_frames_video"], c["scores"], c["plus_baseline"])
+        b = metrics_ref.iou(c["answers"], tuple(c["gt"]), c["num_frames_clip"], c["num_frames_video"], c["scores"], c["plus_baseline"])
+        assert a == b
+    merged = [metrics_ref.merge_with_retrieval(q["gl"], q["rl"], q["rl2"]) for q in g["queries"]]
+    ranked = []
+    for m in merged:
+        sc = m["info"]["scores"]
+        order = sorted(range(len(sc)), key=lambda k: sc[k], reverse=True)
+        ranked.append([m["info"]["iou"][i] for i in order])
+    got = metrics.grounding_metrics_stream(ranked)
+    for k, v in g["metrics"].items():
+        assert abs(got[k] - v) < 1e-9
+    q = g["queries"][0]
+    n = len(q["gl"]["answer"])
+    cov = metrics.cover_mask(n, q["rl"]["info"]["frames"])
+    ref = set()
+    for lo, hi in q["rl"]["info"]["frames"].values():
+        ref |= set(range(max(0, int(.4 * lo)), min(int(.4 * hi), n - 1)))
+    assert set(np.nonzero(cov)[0].tolist()) == ref

@@ -126,3 +126,55 @@ def test_windows_and_selection_rules():
     assert scoring_ref.parse_span("From 12 to 34.") == (12, 34)
     assert scoring_ref.parse_span("Not Present") is None
     assert scoring_ref.select_topk_segments(np.array([1.0, 3.0, 3.0, 2.0], np.float32), 2).tolist() == [1, 2]
+
+
+def test_iou_merge_and_ranking_metrics_match_reference(golden_dir):
+    """oracle/metrics_ref.py against tests/golden/merge_metrics.json: the reference's own `iou` outputs and the metrics its
+    metric_retrieval_forward.py script wrote for the same synthetic prediction files."""
+    import json
+    from oracle import metrics_ref
+    g = json.load(open(os.path.join(golden_dir, "merge_metrics.json")))
+    for c in g["iou_cases"]:
+        cf, ious, kept = metrics_ref.iou(c["answers"], tuple(c["gt"]), c["num_frames_clip"], c["num_frames_video"], c["scores"],
+                                         c["plus_baseline"])
+        assert {str(k): list(v) for k, v in cf.items()} == c["clip_frames"]
+        assert ious == c["ious"] and kept == c["kept_scores"]
+    merged = [metrics_ref.merge_with_retrieval(q["gl"], q["rl"], q["rl2"]) for q in g["queries"]]
+    got = metrics_ref.grounding_metrics_stream(merged)
+    assert set(got) == set(g["metrics"])
+    for k, v in g["metrics"].items():
+        assert abs(got[k] - v) < 1e-9, (k, got[k], v)
+    ratio = sum(len(m["answer"]) for m in merged) / sum(len(q["gl"]["answer"]) for q in g["queries"])
+    assert abs(ratio - g["selected_ratio"]) < 1e-12
+
+
+def test_memory_branch_splice_matches_reference(golden_dir):
+    """<memory> streaming branch of the splice (vtimellm_arch.py:208-232) against the fixture recorded from the reference."""
+    g = np.load(os.path.join(golden_dir, "stage1_memory.npz"))
+    w = syn.make_llama_weights(syn.TINY, seed=0)
+    assert syn.weights_digest(w) == str(g["digest"])
+    ids, feats = torch.from_numpy(g["ids"]), torch.from_numpy(g["feats"])
+    rows = splice_ref.splice(w, ids, splice_ref.mm_projector_linear(w, feats), visual_memory=torch.from_numpy(g["vis_mem"]),
+                             prefix_memory=torch.from_numpy(g["prefix"]))
+    got = torch.stack(rows)
+    assert got.shape == tuple(g["embeds"].shape)
+    np.testing.assert_allclose(got.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)
+    shape = llama_ref.LlamaShape(syn.TINY.hidden, syn.TINY.n_layers, syn.TINY.n_heads, syn.TINY.head_dim, syn.TINY.intermediate,
+                                 syn.TINY.vocab, syn.TINY.rms_eps, syn.TINY.rope_theta, syn.TINY.adapter_dim)
+    toks, scores = llama_ref.greedy_decode(w, shape, got, g["tokens"].shape[1], stop_on_eos=False)
+    assert toks.tolist() == g["tokens"].tolist()
+    np.testing.assert_allclose(torch.stack(scores).numpy(), g["scores"], rtol=2e-3, atol=2e-3)
+
+
+def test_philox_known_answers_and_sampling_rule():
+    from oracle import sampling_ref
+    for ctr, key, out in sampling_ref.KNOWN_ANSWERS:
+        assert sampling_ref.philox4x32_10(ctr, key) == out
+    # a peaked distribution at T = 0.05 is the argmax; a flat one follows the uniform variate
+    logits = np.zeros((4, 16), dtype=np.float32)
+    logits[:, 5] = 3.0
+    toks, _ = sampling_ref.multinomial_draw(logits, 0.05, seed=1, step=0)
+    assert toks == [5, 5, 5, 5]
+    flat = np.zeros((64, 8), dtype=np.float32)
+    toks, _ = sampling_ref.multinomial_draw(flat, 1.0, seed=3, step=2)
+    assert toks == [int(sampling_ref.uniform(3, 2, b) * 8) for b in range(64)]
