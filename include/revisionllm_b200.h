@@ -122,6 +122,13 @@ RVL_API int rvl_project_splice(rvl_handle* h, const void* feats, const int32_t* 
                        const int32_t* text_ids, const int32_t* text_dst, int32_t n_text,
                        float* hidden_out, int64_t total_tokens, rvl_stream stream);
 
+/* Window builder of the feature loader: out[i] (bf16 [n_rows, dim]) = features[frame_idx[i]] (fp32 [n_frames, dim]).
+ * Replaces the host-side `features[np.linspace(start, end, num_frames, dtype=int32)]` per window of
+ * eval_nlq_negative.py:224-235 / eval_nlq_retrieval_e2e2.py:262-277 and the later cast to bf16: the movie's features
+ * are copied to the GPU once, as stored, and every (overlapping) window is gathered there.  Indices are clamped. */
+RVL_API int rvl_gather_windows(rvl_handle* h, const float* features, int32_t n_frames, int32_t dim,
+                       const int32_t* frame_idx, int32_t n_rows, void* out, rvl_stream stream);
+
 /* Same splice for already-projected visual rows (stage-2: one ClipEncoder CLS row per segment,
  * vtimellm_arch.py:114-121): vis [n_vis, hidden] bf16 scattered to vis_dst rows. */
 RVL_API int rvl_splice_rows(rvl_handle* h, const void* vis, const int32_t* vis_dst, int32_t n_vis,

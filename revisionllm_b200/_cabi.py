@@ -51,6 +51,7 @@ PROTOTYPES = {
     "rvl_kv_bytes": (_SZ, [_P, _I32]),
     "rvl_set_kv": (C.c_int, [_P, _P, _I32]),
     "rvl_project_splice": (C.c_int, [_P, _P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
+    "rvl_gather_windows": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P, _P]),
     "rvl_splice_rows": (C.c_int, [_P, _P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
     "rvl_prefill": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _P, _I32, _P, _I32, _P]),
     "rvl_decode_step": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P]),

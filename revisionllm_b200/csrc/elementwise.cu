@@ -138,6 +138,30 @@ void launch_scatter_rows_bf16(const void* src, const int32_t* dst_rows, int n, i
   launch_k(scatter_rows_kernel, dim3(n), dim3(128), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), dst_rows, dim, out);
 }
 
+// ------------------------------------------------------------------------------------ window gather (feature loader)
+// out[i] (bf16) = src[idx[i]] (fp32): the per-window frame sampling `features[np.linspace(start, end, num_frames)]` of
+// revisionllm/eval/eval_nlq_negative.py:224-235 fused with the fp32 -> bf16 cast the reference does later with
+// `.to(torch.bfloat16)`; the movie's features cross PCIe once as stored (fp32) and the overlapping windows are built here.
+// HBM-bound: 4 B read + 2 B written per element; one CTA per output row.
+__global__ void gather_rows_f32_bf16_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n_src, int dim,
+                                            __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x;
+  int r = idx[i];
+  r = r < 0 ? 0 : (r >= n_src ? n_src - 1 : r);
+  const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<long long>(r) * dim);
+  uint2* o = reinterpret_cast<uint2*>(out + static_cast<long long>(i) * dim);
+  for (int v = threadIdx.x; v < (dim >> 2); v += blockDim.x) {
+    const float4 x = __ldg(s4 + v);
+    o[v] = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+  }
+}
+void launch_gather_rows_f32_bf16(const float* src, const int32_t* idx, int n_rows, int n_src, int dim, void* out, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  launch_k(gather_rows_f32_bf16_kernel, dim3(n_rows), dim3(192), 0, st, src, idx, n_src, dim, reinterpret_cast<__nv_bfloat16*>(out));
+}
+
 // ------------------------------------------------------------------------------------ token -> sequence map
 __global__ void token_seq_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict__ tok_seq,
                                  int32_t* __restrict__ last_rows, long long total) {

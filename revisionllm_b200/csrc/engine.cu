@@ -388,6 +388,14 @@ int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq, int32_t
   return check_cuda(h, "rvl_sample_greedy");
 }
 
+int rvl_gather_windows(rvl_handle* h, const float* features, int32_t n_frames, int32_t dim, const int32_t* frame_idx, int32_t n_rows,
+                       void* out, rvl_stream stream) {
+  if (!h || !features || !frame_idx || !out) return fail(h, RVL_ERR_INVALID, "rvl_gather_windows: null argument");
+  if (n_frames <= 0 || dim % 4) return fail(h, RVL_ERR_INVALID, "rvl_gather_windows: need n_frames > 0 and dim % 4 == 0");
+  launch_gather_rows_f32_bf16(features, frame_idx, n_rows, n_frames, dim, out, static_cast<cudaStream_t>(stream));
+  return check_cuda(h, "rvl_gather_windows");
+}
+
 int rvl_sample_multinomial(rvl_handle* h, const float* logits, int32_t n_seq, int32_t vocab, float temperature, uint64_t seed,
                             uint32_t step, int32_t* unfinished, int32_t eos_id, int32_t pad_id, int32_t* next_tokens,
                             float* entropy_out, uint32_t* philox_out, rvl_stream stream) {

@@ -76,6 +76,7 @@ void launch_scatter_rows_bf16(const void* src, const int32_t* dst_rows, int n, i
 void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const int32_t* tok_seq,
                     const int32_t* cu_seqlens, const int32_t* page_table, int max_pages, void* k_pages, void* v_pages,
                     int n_heads, int page_size, float theta, cudaStream_t st);
+void launch_gather_rows_f32_bf16(const float* src, const int32_t* idx, int n_rows, int n_src, int dim, void* out, cudaStream_t st);
 void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaStream_t st);
 void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, int32_t* last_rows, int64_t total,
                       cudaStream_t st);

@@ -168,6 +168,16 @@ class Engine:
                                                 _stream()), "rvl_project_splice")
         self.launches += (1 if n_feat else 0) + (1 if n_text else 0)
 
+    def gather_windows(self, features_f32, frame_idx):
+        """features [T, D] fp32 (device), frame_idx [...] int32 (device) -> bf16 [..., D]."""
+        _req(features_f32, torch.float32, "features"); _req(frame_idx, torch.int32, "frame_idx")
+        n = frame_idx.numel()
+        out = torch.empty(tuple(frame_idx.shape) + (features_f32.shape[1],), dtype=torch.bfloat16, device=features_f32.device)
+        self._check(self.lib.rvl_gather_windows(self.h, features_f32.data_ptr(), features_f32.shape[0], features_f32.shape[1],
+                                                frame_idx.data_ptr(), n, out.data_ptr(), _stream()), "rvl_gather_windows")
+        self.launches += 1
+        return out
+
     def splice_rows(self, vis, vis_dst, text_ids, text_dst, hidden_out):
         n_vis = 0 if vis is None else vis.shape[0]
         n_text = 0 if text_ids is None else text_ids.shape[0]
