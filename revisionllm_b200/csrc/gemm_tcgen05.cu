@@ -174,7 +174,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32]
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float g0 = v[2 * j], g1 = v[2 * j + 1];
-        o[j] = pack_bf16x2(g0 / (1.f + __expf(-g0)) * v[16 + 2 * j], g1 / (1.f + __expf(-g1)) * v[17 + 2 * j]);
+        o[j] = pack_bf16x2(__fdividef(g0, 1.f + __expf(-g0)) * v[16 + 2 * j], __fdividef(g1, 1.f + __expf(-g1)) * v[17 + 2 * j]);
       }
       uint4* dst = reinterpret_cast<uint4*>(out + static_cast<long long>(m) * args.ldc + (n0 >> 1));
       dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -190,7 +190,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& args, float (&v)[32]
         const float g = lower ? v[j] : got;
         const float u = lower ? got : v[j + 1];
         const int jj = j + (lower ? 0 : 1);
-        if (jj < nvalid && m_ok) col[static_cast<long long>(n0 + jj) * args.ldc] = __float2bfloat16(g / (1.f + __expf(-g)) * u);
+        if (jj < nvalid && m_ok) col[static_cast<long long>(n0 + jj) * args.ldc] = __float2bfloat16(__fdividef(g, 1.f + __expf(-g)) * u);
       }
     }
     return;
@@ -570,7 +570,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const float got = __shfl_xor_sync(0xffffffffu, lower ? v[j + 1] : v[j], 16);
                 const float g = lower ? v[j] : got;
                 const float u = lower ? got : v[j + 1];
-                const __nv_bfloat16 a = __float2bfloat16(g / (1.f + __expf(-g)) * u);
+                const __nv_bfloat16 a = __float2bfloat16(__fdividef(g, 1.f + __expf(-g)) * u);
                 st_shared_u16(base + j * 128, *reinterpret_cast<const uint16_t*>(&a));
               }
             } else if (args.mode == RVL_GEMM_OUT_BF16) {

@@ -121,6 +121,8 @@ class RevisionLlamaForCausalLM:
         self.dtype = torch.bfloat16
         self._warned_sampling = False
         self.clip_encoder = None
+        self.record_phase_events = False   # bench.py: CUDA events at the splice / prefill / decode boundaries of generate()
+        self.last_phase_events = None
         self.share_prefix_pages = True     # map the KV pages of a prompt prefix common to the whole batch once (see _alloc_kv)
 
     # ---- placement (eval_nlq_negative.py:144-148 does `model.bfloat16().cuda()`)
@@ -343,7 +345,12 @@ class RevisionLlamaForCausalLM:
         eos = cfg.eos_token_id if eos_token_id == "config" else eos_token_id
         pad = pad_token_id if pad_token_id is not None else (cfg.pad_token_id if cfg.pad_token_id is not None else (eos if eos is not None else 0))
         with torch.cuda.device(dev):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.record_phase_events else None
+            if ev:
+                ev[0].record()
             hidden, plan = self._splice(input_ids, attention_mask, images, query_feats, visual_memory, prefix_memory)
+            if ev:
+                ev[1].record()
             lengths, cu = plan["lengths"], plan["cu_seqlens"]
             B = len(lengths)
             room = cfg.max_position_embeddings - int(lengths.max())
@@ -356,6 +363,8 @@ class RevisionLlamaForCausalLM:
             cu_d = torch.from_numpy(cu).to(dev)
             logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
             eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
+            if ev:
+                ev[2].record()
             del hidden
             tokens = torch.full((max_new, B), int(pad), dtype=torch.int32, device=dev)
             entropies = torch.full((max_new, B), float("nan"), dtype=torch.float32, device=dev)
@@ -408,6 +417,9 @@ class RevisionLlamaForCausalLM:
                     logits = torch.empty((n_live, cfg.vocab_size), dtype=torch.float32, device=dev)
                 eng.decode_step(tok_t.contiguous(), kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
                 kv.steps += 1
+            if ev:
+                ev[3].record()
+                self.last_phase_events = ev      # splice start, prefill start, decode start, end (read after a synchronize)
             new_tokens = tokens[:n_steps].t().contiguous()
             ids_dev = input_ids.to(dev)
             sequences = torch.cat([ids_dev, new_tokens.to(ids_dev.dtype)], dim=1)     # prompt ids (placeholder echoed) + new

@@ -32,3 +32,27 @@ for N in (12288, 22016, 32000):
 for M in Ms:
     bench(M, 4096, 4096, mode=_cabi.GEMM_ADD_F32, split_k=4)
     bench(M, 4096, 11008, mode=_cabi.GEMM_ADD_F32, split_k=4)
+
+# gate/up GEMM of the decode step: fused SwiGLU epilogue vs GEMM + swiglu kernel
+def bench_gu(M, I=11008, K=4096, reps=20):
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    Ws = [torch.randn(2 * I, K, device="cuda").to(torch.bfloat16) for _ in range(4)]
+    act = torch.zeros(M, I, device="cuda", dtype=torch.bfloat16)
+    gu = torch.zeros(M, 2 * I, device="cuda", dtype=torch.bfloat16)
+    def fused(i):
+        eng.gemm(A, Ws[i % 4], out=act, flags=_cabi.GEMM_FLAG_SWAP | _cabi.GEMM_FLAG_SWIGLU | _cabi.GEMM_FLAG_W_CONST, ldc=I)
+    def unfused(i):
+        eng.gemm(A, Ws[i % 4], out=gu, flags=_cabi.GEMM_FLAG_SWAP | _cabi.GEMM_FLAG_W_CONST)
+        eng.swiglu(gu)
+    for name, fn in (("fused", fused), ("gemm+swiglu kernel", unfused)):
+        for i in range(3):
+            fn(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"[{tag}] gate/up M={M}: {name:20s} {e0.elapsed_time(e1) / reps * 1e3:7.1f} us", flush=True)
+for M in Ms:
+    bench_gu(M)

@@ -1,0 +1,25 @@
+"""Phase split of one stage-1 sweep step (180 segments, L=184, 16 tokens): splice+projector / prefill / decode / tail."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from revisionllm_b200 import sweep, synthetic as syn
+from revisionllm_b200.model import RevisionConfig, RevisionLlamaForCausalLM
+cfg = syn.VICUNA_7B
+model = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg), syn.make_llama_weights(cfg, seed=0, device="cuda")).bfloat16().cuda()
+model.record_phase_events = True
+feats = syn.make_features(180, 100, 768, seed=1).cuda()
+ids = syn.make_prompt_ids(cfg, seed=2).cuda()
+cls = torch.randn(768, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
+for i in range(4):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    sweep.score_segments(model, feats, ids, cls, 16, eos_token_id=None)
+    e1.record()
+    t_host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    ev = model.last_phase_events
+    print(f"step {i}: total {e0.elapsed_time(e1):7.2f} ms (host enqueue {1e3 * t_host:6.1f} ms) | before generate {e0.elapsed_time(ev[0]):6.2f} | "
+          f"splice {ev[0].elapsed_time(ev[1]):6.2f} | prefill {ev[1].elapsed_time(ev[2]):7.2f} | decode {ev[2].elapsed_time(ev[3]):7.2f} | "
+          f"tail {ev[3].elapsed_time(e1):6.2f}", flush=True)
