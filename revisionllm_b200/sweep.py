@@ -124,7 +124,8 @@ def stage1_sweep(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Op
 
 def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tensor, grounding_windows: Sequence[int],
                 batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16, perm_seed: Optional[int] = 0,
-                answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config") -> List[Dict]:
+                answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config",
+                max_calls_per_batch: int = 16) -> List[Dict]:
     """Stage-2 hierarchical pass (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:337-386).
 
     `windows` [N, T, 768]: the selected stage-2 windows (already restricted to `grounding_windows`).  For each
@@ -133,10 +134,14 @@ def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tens
     integer of the answer // zoom indexes the permuted chunk and is mapped back to a window id.
     The reference permutes with an unseeded torch.randperm (:348); here the permutation comes from
     `perm_seed` (None = identity) so runs are reproducible.
-    Returns one dict per generate() call: tokens, entropy stats (1/max, 1/mean as in :356-359), picked window."""
+    All chunks of all zoom levels are independent prompts, so they run as one batched generate() (up to
+    `max_calls_per_batch` rows; 1 restores the reference's one-call-per-chunk schedule).
+    Returns one dict per chunk (the reference's generate() calls, in its order): tokens, entropy stats (1/max, 1/mean as in
+    :356-359), picked window."""
     N = windows.shape[0]
     gen = torch.Generator().manual_seed(perm_seed) if perm_seed is not None else None
-    out: List[Dict] = []
+    # ---- plan every call first (same order of randperm draws as the sequential loop of the reference)
+    calls: List[Dict] = []
     for zoom in zooms:
         b = max(1, batch // zoom)
         n_chunks = (N + b - 1) // b
@@ -145,24 +150,39 @@ def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tens
             end = min(start + b, N)
             if end - start < b:
                 start = max(0, end - b)
-            feat = windows[start:end]
-            n = feat.shape[0]
+            n = end - start
             idx = torch.randperm(n, generator=gen) if gen is not None else torch.arange(n)
-            feat = feat[idx]
-            if zoom > 1:
-                feat = feat.repeat_interleave(zoom, dim=0)
-            res = model.generate(input_ids[None], images=feat[None], query_feats=query_feats, max_new_tokens=max_new_tokens,
+            rows = (start + idx).repeat_interleave(zoom) if zoom > 1 else (start + idx)
+            calls.append(dict(zoom=zoom, start=start, n=n, idx=idx, rows=rows))
+    # ---- the calls are independent prompts: those with the same number of visual rows go through ONE generate() as a
+    # batch (the reference runs them one by one with B = 1, where every decode step re-streams the 13 GB of weights)
+    results: List[Optional[Dict]] = [None] * len(calls)
+    groups: Dict[int, List[int]] = {}
+    for ci, c in enumerate(calls):
+        groups.setdefault(int(c["rows"].shape[0]), []).append(ci)
+    q_tok, q_mask = query_feats if query_feats is not None else (None, None)
+    for v_rows, members in groups.items():
+        for g0 in range(0, len(members), max_calls_per_batch):
+            part = members[g0: g0 + max_calls_per_batch]
+            feat = torch.stack([windows[calls[ci]["rows"].to(windows.device)] for ci in part])          # [calls, V, T, 768]
+            qf = None if q_tok is None else (q_tok.expand(len(part), -1, -1).contiguous(), q_mask.expand(len(part), -1).contiguous())
+            res = model.generate(input_ids[None].expand(len(part), -1), images=feat, query_feats=qf, max_new_tokens=max_new_tokens,
                                  output_scores=False, return_dict_in_generate=True, eos_token_id=eos_token_id)
-            new_tok = res["sequences"][0, input_ids.shape[0]:]
-            stats = scoring.entropy_stats_from_steps(res["entropies"])[0]
-            number = answer_number(new_tok) if answer_number is not None else None
-            picked = None
-            if number is not None:
-                j = number // zoom
-                if j < n:
-                    j = int(idx[j])
-                j = min(max(start + j, 0), len(grounding_windows) - 1)
-                picked = int(grounding_windows[j])
-            out.append(dict(zoom=zoom, start=start, perm=idx.tolist(), tokens=new_tok.tolist(), inv_max_entropy=1.0 / float(stats[0]),
-                            inv_mean_entropy=1.0 / float(stats[2]), window=picked))
+            stats_all = scoring.entropy_stats_from_steps(res["entropies"])
+            for r, ci in enumerate(part):
+                results[ci] = dict(tokens=res["sequences"][r, input_ids.shape[0]:], stats=stats_all[r])
+    out: List[Dict] = []
+    for c, r in zip(calls, results):
+        new_tok, stats = r["tokens"], r["stats"]
+        zoom, start, n, idx = c["zoom"], c["start"], c["n"], c["idx"]
+        number = answer_number(new_tok) if answer_number is not None else None
+        picked = None
+        if number is not None:
+            j = number // zoom
+            if j < n:
+                j = int(idx[j])
+            j = min(max(start + j, 0), len(grounding_windows) - 1)
+            picked = int(grounding_windows[j])
+        out.append(dict(zoom=zoom, start=start, perm=idx.tolist(), tokens=new_tok.tolist(), inv_max_entropy=1.0 / float(stats[0]),
+                        inv_mean_entropy=1.0 / float(stats[2]), window=picked))
     return out
