@@ -39,7 +39,6 @@ namespace rvl {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 192;
-constexpr int kGroupM = 16;  // tile rasterisation: 16 m-tiles share each n-tile sweep (L2 reuse)
 constexpr int kMaxStages = 12;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB per 128-row A tile and k-block
 constexpr int kEpiScratchBytes = 4 * 32 * 33 * 4;   // per epilogue warp a 32 x 33 fp32 transpose tile
@@ -53,6 +52,7 @@ struct GemmArgs {
   int M, N, K;          // A rows, B rows, reduction
   int tiles_m, tiles_n; // tiles_m counts (a_tiles x 128)-row tiles
   int k_blocks;         // ceil(K / 64)
+  int group_m;          // tile rasterisation: this many m-tiles share each n-tile sweep (their A slab stays in L2)
   int split_k;          // tile mode: k-range split (atomics into fp32 out, or partial buffers via split_stride)
   int a_tiles;          // 1 or 2: 128-row A tiles per CTA tile (they share the B tile)
   int bn;               // B rows per tile = MMA N (multiple of 16, <= 256)
@@ -89,11 +89,11 @@ struct WorkItem {
   int followers;
 };
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m_blk, int& n_blk) {
-  const int group = kGroupM * tiles_n;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& m_blk, int& n_blk) {
+  const int group = group_m * tiles_n;
   const int gid = t / group;
-  const int first_m = gid * kGroupM;
-  const int gsz = min(tiles_m - first_m, kGroupM);
+  const int first_m = gid * group_m;
+  const int gsz = min(tiles_m - first_m, group_m);
   const int r = t - gid * group;
   m_blk = first_m + r % gsz;
   n_blk = r / gsz;
@@ -108,7 +108,7 @@ __device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w
     if (tile >= tiles_mn * a.split_k) return false;
     const int kb_per_split = (a.k_blocks + a.split_k - 1) / a.split_k;
     w.ks = tile / tiles_mn;
-    tile_coords(tile - w.ks * tiles_mn, a.tiles_m, a.tiles_n, w.m_blk, w.n_blk);
+    tile_coords(tile - w.ks * tiles_mn, a.tiles_m, a.tiles_n, a.group_m, w.m_blk, w.n_blk);
     w.kb0 = w.ks * kb_per_split;
     w.kb1 = min(a.k_blocks, w.kb0 + kb_per_split);
     w.kind = 0;
@@ -125,7 +125,7 @@ __device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w
   const long long t_begin = static_cast<long long>(tile) * a.k_blocks;
   if (t_begin >= u1) return false;
   w.ks = 0;
-  tile_coords(tile, a.tiles_m, a.tiles_n, w.m_blk, w.n_blk);
+  tile_coords(tile, a.tiles_m, a.tiles_n, a.group_m, w.m_blk, w.n_blk);
   w.kb0 = static_cast<int>(max(u0, t_begin) - t_begin);
   w.kb1 = static_cast<int>(min(u1, t_begin + a.k_blocks) - t_begin);
   w.followers = 0;
@@ -740,7 +740,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int m_blk, n_blk;
-      tile_coords(tile, args.tiles_m, args.tiles_n, m_blk, n_blk);
+      tile_coords(tile, args.tiles_m, args.tiles_n, args.group_m, m_blk, n_blk);
       const int m0 = (m_blk * 2 + rank) * kBM, n0 = n_blk * BN + rank * kHalfN;
       for (int kb = 0; kb < args.k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -795,7 +795,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       int m_blk, n_blk;
-      tile_coords(tile, args.tiles_m, args.tiles_n, m_blk, n_blk);
+      tile_coords(tile, args.tiles_m, args.tiles_n, args.group_m, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = (m_blk * 2 + rank) * kBM + m_local;
@@ -921,6 +921,7 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   GemmArgs a{};
   a.K = static_cast<int>(c.K);
   a.k_blocks = static_cast<int>((c.K + kBK - 1) / kBK);
+  a.group_m = 16;
   a.ldc = c.ldc;
   a.out = c.out;
   a.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
@@ -1003,6 +1004,15 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     a.bn = 256;
     a.tiles_m = (a.M + 255) / 256;
     a.tiles_n = (a.N + 255) / 256;
+    {
+      // m-tiles per n-sweep (L2 reuse of the A slab against the weight streaming through).  Measured interleaved on B200 at
+      // 33120 tokens (tools/prefill_gemm_ab.py): 32 is 3-4 % faster than 16 for qkv / gate|up / down, 16 is best for the
+      // small o projection; the differences come from DRAM traffic (power), not from the tensor pipe.
+      const char* env_gm = getenv("RVL_GROUP_M");
+      long long gm = (c.N * c.K >= (32ll << 20)) ? 32 : 16;
+      if (env_gm) gm = atoi(env_gm);
+      a.group_m = static_cast<int>(gm < 2 ? 2 : (gm > 64 ? 64 : gm));
+    }
     a.stages = kSmemBudget / (kATileBytes + 128 * kBK * 2);
     if (a.stages > kMaxStages) a.stages = kMaxStages;
     CUtensorMap ta2, tb2;

@@ -81,13 +81,39 @@ def report(path, out):
     out.write("\n")
 
 
+def traffic(path, out_json, algorithmic_bytes):
+    """Average measured DRAM bytes (read + write) per launch over the kernels of one `--set full` report -> the
+    `roofline.traffic` value bench.py reports for the dominant kernel."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = []
+    for r in rows[2:]:
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += float(r[col[k]].replace(",", "")) * scale[units[col[k]]]
+        per.append(b)
+    json.dump({"prefill_gemm_dram_bytes_per_launch": sum(per) / len(per), "per_launch": per,
+               "prefill_gemm_algorithmic_bytes_per_launch": algorithmic_bytes,
+               "source": f"ncu --set full --clock-control none, {path.split('/')[-1]}: the 4 prefill GEMMs of one layer (qkv, o, gate|up+SwiGLU, down), "
+                         "dram__bytes_read.sum + dram__bytes_write.sum averaged per launch"}, open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--launches")
     ap.add_argument("--reports", nargs="*", default=[])
     ap.add_argument("--out", required=True)
     ap.add_argument("--title", default="ncu summary")
+    ap.add_argument("--traffic-report", help="--set full report of the dominant kernel's launches")
+    ap.add_argument("--traffic-out")
+    ap.add_argument("--algorithmic-bytes", type=float, default=0.0)
     a = ap.parse_args()
+    if a.traffic_report and a.traffic_out:
+        traffic(a.traffic_report, a.traffic_out, a.algorithmic_bytes)
     with open(a.out, "w") as f:
         f.write(f"# {a.title}\n\n")
         if a.launches:
