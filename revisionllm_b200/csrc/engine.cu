@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -29,6 +30,8 @@ struct rvl_handle {
   size_t stream_ws_bytes = 0;
   unsigned int* stream_flags = nullptr;  // [num_sms] epoch flags
   mutable unsigned int stream_epoch = 0;
+  unsigned int* grid_barrier = nullptr;  // arrival counter of the fused decode kernel (lives behind the flags)
+  mutable unsigned int grid_barrier_count = 0;
   float* partials = nullptr;             // [kMaxSplit][max_seqs][hidden] fp32 split-k partials of the decode o/down GEMMs
   int32_t *tok_seq = nullptr, *last_rows = nullptr;
   // kv
@@ -166,6 +169,8 @@ int rvl_set_workspace(rvl_handle* h, void* ws, size_t bytes, int64_t max_tokens,
   h->stream_flags = reinterpret_cast<unsigned int*>(b + l.stream_flags);
   h->partials = reinterpret_cast<float*>(b + l.partials);
   h->stream_epoch = 0;
+  h->grid_barrier = h->stream_flags + 200;
+  h->grid_barrier_count = 0;
   if (cudaMemset(h->stream_flags, 0, 1024) != cudaSuccess) return fail(h, RVL_ERR_CUDA, "rvl_set_workspace: cudaMemset failed");
   h->tok_seq = reinterpret_cast<int32_t*>(b + l.tok_seq); h->last_rows = reinterpret_cast<int32_t*>(b + l.last_rows);
   return RVL_OK;
@@ -356,6 +361,71 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
   const int64_t n = n_seq;
   float* hid = h->dec_hidden;
   launch_embed_rows(h->w.embed_tokens, token_ids, nullptr, n_seq, H, c.vocab, hid, st);
+  const char* env_fused = getenv("RVL_FUSED_DECODE");      // read per call: tests and tools toggle it
+  if (h->w.wgu_layout == 1 && n_seq <= 256 && H <= 8192 && !h->prof_on && env_fused && atoi(env_fused) == 1) {
+    // ---- EXPERIMENTAL fused path: one persistent kernel per attention boundary (csrc/decode_fused.cu).  Off by default:
+    // measured 9.56 / 3.50 ms per 7B decode step (B = 180 / 1) against 9.04 / 3.13 ms for the per-GEMM path - the five
+    // grid barriers per layer and the 4-5-way stream-K fix-up of the 32-tile o / down projections cost more than the six
+    // launches they replace.
+    auto launch = [&](FusedCall& fc) -> int {
+      fc.n_tokens = n_seq;
+      fc.stream_ws = h->stream_ws; fc.stream_ws_bytes = h->stream_ws_bytes; fc.stream_flags = h->stream_flags;
+      fc.epoch0 = h->stream_epoch + 1;
+      h->stream_epoch += fc.n_phases;
+      fc.grid_barrier = h->grid_barrier;
+      fc.grid_barrier_base = h->grid_barrier_count;
+      h->grid_barrier_count += static_cast<unsigned int>(fc.n_phases) * h->num_sms;
+      std::string err;
+      int r = decode_fused(fc, h->num_sms, st, &err);
+      return r ? fail(h, r, err) : RVL_OK;
+    };
+    // o / down projections: plain split-k into the partial buffers, summed into the residual by the RMSNorm phase that follows
+    // (a 32-tile GEMM dealt stream-K over 148 SMs needs a 4-5-way fix-up per tile: measured ~30 us per phase)
+    const int tiles_h = (H + 127) / 128;
+    int sk = h->num_sms / tiles_h;
+    if (sk > 4) sk = 4;
+    if (sk < 1) sk = 1;
+    auto norm = [&](const void* w, void* y, int n_partials) {
+      FusedPhase p; p.kind = 1; p.x = hid; p.norm_w = w; p.y = y; p.dim = H; p.eps = c.rms_eps; p.partials = h->partials; p.n_partials = n_partials;
+      return p;
+    };
+    auto resid = [&](const void* W, const void* act, int K) {
+      FusedPhase p; p.kind = 0; p.W = W; p.act = act; p.out = h->partials; p.features = H; p.K = K; p.ldc = H; p.out_kind = RVL_FUSED_OUT_F32;
+      p.split_k = (K / 64) / sk >= 4 ? sk : 1;
+      return p;
+    };
+    auto gemm = [&](const void* W, const void* act, void* out, int features, int K, int64_t ldc, int kind) {
+      FusedPhase p; p.kind = 0; p.W = W; p.act = act; p.out = out; p.features = features; p.K = K; p.ldc = ldc; p.out_kind = kind; return p;
+    };
+    {
+      FusedCall fc;
+      fc.n_phases = 2;
+      fc.ph[0] = norm(h->layers[0].ln1, h->xnorm, 0);
+      fc.ph[1] = gemm(h->layers[0].wqkv, h->xnorm, h->qkv, 3 * H, H, 3 * H, RVL_FUSED_OUT_BF16);
+      if ((rc = launch(fc))) return rc;
+    }
+    for (int l = 0; l < c.n_layers; ++l) {
+      const rvl_layer_weights& w = h->layers[l];
+      launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
+                         c.kv_page_size, 1, c.rope_theta, max_kv_len, st);
+      FusedCall fc;
+      fc.n_phases = 6;
+      fc.ph[0] = resid(w.wo, h->attn, H);
+      fc.ph[1] = norm(w.ln2, h->xnorm, fc.ph[0].split_k);
+      fc.ph[2] = gemm(w.wgu, h->xnorm, h->act, 2 * I, H, I, RVL_FUSED_OUT_SWIGLU);
+      fc.ph[3] = resid(w.wdown, h->act, I);
+      if (l + 1 < c.n_layers) {
+        fc.ph[4] = norm(h->layers[l + 1].ln1, h->xnorm, fc.ph[3].split_k);
+        fc.ph[5] = gemm(h->layers[l + 1].wqkv, h->xnorm, h->qkv, 3 * H, H, 3 * H, RVL_FUSED_OUT_BF16);
+      } else {
+        fc.ph[4] = norm(h->w.final_norm, h->xlast, fc.ph[3].split_k);
+        fc.ph[5] = gemm(h->w.lm_head, h->xlast, logits_out, c.vocab, H, c.vocab, RVL_FUSED_OUT_F32);
+      }
+      if ((rc = launch(fc))) return rc;
+    }
+    launch_k(inc_kernel, dim3((n_seq + 127) / 128), dim3(128), 0, st, seq_lens, static_cast<int>(n_seq));
+    return check_cuda(h, "rvl_decode_step");
+  }
   // o_proj / down_proj leave split-k partial sums in h->partials; the next RMSNorm adds them to the residual
   const int64_t pstride = n * H;
   int pending = 0;

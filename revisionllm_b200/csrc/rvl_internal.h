@@ -32,6 +32,41 @@ struct GemmCall {
 };
 int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err);
 
+// decode_fused.cu: the per-layer chain of the decode step as one persistent kernel (see the file header)
+constexpr int kFusedMaxPhases = 6;
+enum { RVL_FUSED_OUT_BF16 = 0, RVL_FUSED_OUT_SWIGLU = 1, RVL_FUSED_OUT_ADD_F32 = 2, RVL_FUSED_OUT_F32 = 3 };
+struct FusedPhase {
+  int kind = 0;                 // 0: GEMM, 1: RMSNorm
+  // GEMM: out[token][feature] (+)= act[token][:] . W[feature][:]
+  const void* W = nullptr;      // [features, K] bf16
+  const void* act = nullptr;    // [n_tokens, K] bf16
+  void* out = nullptr;          // bf16 / fp32 [n_tokens, ldc]
+  int features = 0, K = 0;
+  int64_t ldc = 0;
+  int out_kind = RVL_FUSED_OUT_BF16;
+  int split_k = 0;              // > 0: plain split-k, fp32 partial s of the tile goes to out + s * n_tokens * ldc (RVL_FUSED_OUT_F32)
+  // RMSNorm: x += sum of n_partials partial buffers [n_tokens, dim] (written back), y = x * rsqrt(mean(x^2) + eps) * norm_w
+  float* x = nullptr;
+  const float* partials = nullptr;
+  int n_partials = 0;
+  const void* norm_w = nullptr;
+  void* y = nullptr;
+  int dim = 0;
+  float eps = 0.f;
+};
+struct FusedCall {
+  int n_phases = 0;
+  int n_tokens = 0;
+  FusedPhase ph[kFusedMaxPhases];
+  float* stream_ws = nullptr;
+  size_t stream_ws_bytes = 0;
+  unsigned int* stream_flags = nullptr;
+  unsigned int epoch0 = 0;              // phase p uses epoch0 + p
+  unsigned int* grid_barrier = nullptr; // monotonic arrival counter
+  unsigned int grid_barrier_base = 0;   // its value before this launch (advances by n_phases * num_sms)
+};
+int decode_fused(const FusedCall& c, int num_sms, cudaStream_t st, std::string* err);
+
 // Programmatic dependent launch: RVL_PDL=0 in the environment switches it off (plain stream order).
 // Bit 0: the GEMM launches, bit 1: every other kernel.  Default 1: measured on B200 (decode step, 7B shape, B = 180 / 32)
 // 10.08 / 5.71 ms without, 9.72 / 5.18 ms with GEMMs only, 9.90 / 5.67 ms with everything - small kernels that become
