@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--segments", type=int, default=N_SEG)
     ap.add_argument("--no-stage2", action="store_true", help="skip the (untimed-in-value) stage-2 top-100 measurement")
+    ap.add_argument("--ragged-videos", type=int, default=0,
+                    help="also time a VidChapters-shaped ragged batch (BASELINE.json configs[4]) of this many videos, sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -347,6 +349,46 @@ def main():
                                      "note": "ClipEncoder (4 layers, d=768) + splice of 100 CLS tokens + Vicuna-7B prefill/decode, 16 tokens per call"}
         except Exception as e:      # stage 2 is reported, never allowed to take the headline number down
             line["stage2_top100"] = {"error": repr(e)[:200]}
+    # ---- BASELINE.json configs[4] (optional, reported beside the headline): VidChapters-shaped ragged batch - videos of
+    # 1-60 min at 2 fps, 500 s windows with 250 s stride sampled to <= 100 frames, queries of 8-32 tokens, varlen-packed,
+    # windows dealt to the ranks by length (sweep.shard_balanced), one all-gather of the records.
+    if args.ragged_videos > 0:
+        rng = np.random.default_rng(1)
+        windows, qlens = [], []
+        for v in range(args.ragged_videos):
+            n_feat = int(rng.uniform(1, 60) * 60 * 2)
+            if n_feat <= 1000:
+                spans = [(0, n_feat - 1)]
+            else:
+                spans = [(i * 500, min(i * 500 + 1000, n_feat - 1)) for i in range(int(np.ceil(n_feat / 500)) - 1)]
+            ql = int(rng.integers(8, 33))
+            for (a0, b0) in spans:
+                windows.append(min(100, b0 - a0 + 1))
+                qlens.append(ql)
+        gw = torch.Generator().manual_seed(11)
+        wins = [torch.randn(f, cfg.adapter_dim, generator=gw).to(torch.bfloat16).to(dev) for f in windows]
+        Ltxt = 1 + 37 + 1 + 32 + 14
+        rids = torch.zeros((len(wins), Ltxt), dtype=torch.int64)
+        ram = torch.zeros((len(wins), Ltxt), dtype=torch.bool)
+        for i, ql in enumerate(qlens):
+            row = torch.cat([torch.tensor([1]), torch.randint(3, cfg.vocab, (37,), generator=gw), torch.tensor([-200]),
+                             torch.randint(3, cfg.vocab, (ql + 14,), generator=gw)])
+            rids[i, : row.shape[0]] = row
+            ram[i, : row.shape[0]] = True
+
+        def ragged():
+            return sweep.ragged_sweep(model, wins, rids, ram, cls_dev, NEW_TOKENS, rank, world, max_tokens_per_batch=33120, eos_token_id=None)
+        ragged()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        ragged()
+        r1.record()
+        barrier()
+        rms = max_over_ranks(r0.elapsed_time(r1))
+        line["vidchapters_ragged"] = {"videos": args.ragged_videos, "windows": len(wins), "prompt_tokens": int(sum(w + q + 52 for w, q in zip(windows, qlens))),
+                                      "ms": rms, "windows_per_s": len(wins) / (rms * 1e-3), "new_tokens": NEW_TOKENS,
+                                      "note": "stage 1 over all windows of all videos, one pass, weights replicated, windows balanced by length"}
     # ---- CPU baseline beside it (rank 0, N=1): the oracle port on ONE segment, and full-size parity of that segment
     if keep_for_cpu:
         try:

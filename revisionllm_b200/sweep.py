@@ -28,6 +28,42 @@ def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
     return np.arange(rank, n, world, dtype=np.int64)
 
 
+def shard_balanced(lengths: Sequence[int], world: int) -> List[np.ndarray]:
+    """Ragged batches (VidChapters: windows of 1-100 frames, queries of 8-32 tokens): greedy length-balanced bin packing
+    (longest first onto the least loaded rank).  Deterministic - every rank computes the same
+    assignment from the same lengths: ties go to the lower index / lower rank.  Returns one ascending index array per rank."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.lexsort((np.arange(lengths.shape[0]), -lengths))          # by length descending, then index
+    load = np.zeros(world, dtype=np.int64)
+    bins: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = int(np.argmin(load))                                          # first minimum = lowest rank on ties
+        bins[r].append(int(i))
+        load[r] += int(lengths[i])
+    return [np.asarray(sorted(b), dtype=np.int64) for b in bins]
+
+
+def allgather_indexed(local: torch.Tensor, shards: Sequence[np.ndarray], rank: int, world: int, group=None) -> torch.Tensor:
+    """All-gather for an arbitrary (but globally known) assignment: rank r holds the records of `shards[r]` in that order;
+    every rank receives all records in global index order.  One collective, padded to the largest shard."""
+    n_total = int(sum(len(s) for s in shards))
+    if world == 1:
+        out = torch.empty((n_total, local.shape[1]), dtype=local.dtype, device=local.device)
+        out[torch.from_numpy(shards[0]).to(local.device)] = local
+        return out
+    import torch.distributed as dist
+    per = max(len(s) for s in shards)
+    buf = torch.full((per, local.shape[1]), -1, dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    gathered = torch.empty((world * per, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    out = torch.empty((n_total, local.shape[1]), dtype=local.dtype, device=local.device)
+    for r, idx in enumerate(shards):
+        if len(idx):
+            out[torch.from_numpy(idx).to(local.device)] = gathered[r * per: r * per + len(idx)]
+    return out
+
+
 def pack_records(tokens: torch.Tensor, spans: torch.Tensor, h_mean: torch.Tensor, h_max: torch.Tensor,
                  cos: torch.Tensor) -> torch.Tensor:
     """tokens [n, T'<=16] int32, spans [n, 2] int32 (-1 = 'Not Present'), h_mean/h_max/cos [n] fp32 ->
@@ -120,6 +156,45 @@ def stage1_sweep(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Op
         cos = unpack_records(allrec)["cos"]
         res.stage2_indices = scoring.select_topk_segments(model.engine, cos, stage2_topk)
     return res
+
+
+def ragged_sweep(model, windows: Sequence[torch.Tensor], input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                 cls: Optional[torch.Tensor], max_new_tokens: int = 16, rank: int = 0, world: int = 1, group=None,
+                 max_tokens_per_batch: int = 1 << 16, eos_token_id="config") -> torch.Tensor:
+    """BASELINE.json config 5 (VidChapters-shaped): windows with different frame counts `windows[i]` [F_i, 768] and
+    right-padded prompts `input_ids` [n, Ltxt] / `attention_mask` of different lengths, varlen-packed.  Windows are dealt
+    to the ranks by `shard_balanced` on their spliced lengths, each rank scores its share in packed batches of at most
+    `max_tokens_per_batch` prompt tokens, and one `allgather_indexed` returns all records in window order."""
+    n = len(windows)
+    am = attention_mask.bool()
+    lengths = [int(am[i].sum()) - 1 + int(windows[i].shape[0]) for i in range(n)]
+    shards = shard_balanced(lengths, world)
+    mine = shards[rank]
+    eng, dev = model.engine, model.device
+    recs = []
+    start = 0
+    while start < len(mine):
+        tok, end = 0, start
+        while end < len(mine) and (end == start or tok + lengths[mine[end]] <= max_tokens_per_batch):
+            tok += lengths[mine[end]]
+            end += 1
+        sel = [int(i) for i in mine[start:end]]
+        imgs = [windows[i] for i in sel]
+        out = model.generate(input_ids[sel], images=imgs, attention_mask=am[sel], max_new_tokens=max_new_tokens, output_scores=False,
+                             return_dict_in_generate=True, eos_token_id=eos_token_id)
+        new_tok = out["sequences"][:, input_ids.shape[1]:].to(torch.int32)
+        stats = scoring.entropy_stats_from_steps(out["entropies"])
+        if cls is not None:
+            rows = torch.cat([w.reshape(-1, w.shape[-1]) for w in imgs]).to(dev, torch.bfloat16).contiguous()
+            offs = torch.tensor(np.concatenate([[0], np.cumsum([w.shape[0] for w in imgs])]), dtype=torch.int32, device=dev)
+            cos, _ = eng.cosine_topk(rows, offs, cls.to(dev, torch.bfloat16).contiguous(), k=3, max_seg_rows=max(w.shape[0] for w in imgs))
+        else:
+            cos = torch.zeros(len(sel), dtype=torch.float32, device=dev)
+        spans = torch.full((len(sel), 2), -1, dtype=torch.int32, device=dev)
+        recs.append(pack_records(new_tok, spans, stats[:, 2], stats[:, 0], cos))
+        start = end
+    local = torch.cat(recs, dim=0) if recs else torch.empty((0, REC_WORDS), dtype=torch.int32, device=dev)
+    return allgather_indexed(local, shards, rank, world, group)
 
 
 def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tensor, grounding_windows: Sequence[int],

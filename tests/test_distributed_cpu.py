@@ -35,6 +35,47 @@ def _worker(rank, world, port, n_total, q):
         dist.destroy_process_group()
 
 
+def _worker_ragged(rank, world, port, lengths, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = sweep.shard_balanced(lengths, world)
+        mine = shards[rank]
+        local = torch.stack([torch.full((sweep.REC_WORDS,), int(i) * 7, dtype=torch.int32) for i in mine]) if len(mine) else \
+            torch.empty((0, sweep.REC_WORDS), dtype=torch.int32)
+        q.put((rank, sweep.allgather_indexed(local, shards, rank, world).numpy(), [s.tolist() for s in shards]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_sharding_and_indexed_allgather_world2_gloo():
+    """Ragged (VidChapters-shaped) batches: length-balanced bin packing + the one all-gather that restores global order."""
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(20, 140, size=37).tolist()
+    for world in (1, 2, 3, 8):
+        shards = sweep.shard_balanced(lengths, world)
+        flat = sorted(i for s in shards for i in s.tolist())
+        assert flat == list(range(37))                                          # every window exactly once
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)                          # LPT bound
+        assert all(s.tolist() == sorted(s.tolist()) for s in shards)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ragged, args=(r, world, port, lengths, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(got[0][1], got[1][1])
+    assert got[0][2] == got[1][2]                                               # same assignment computed on every rank
+    assert got[0][1][:, 0].tolist() == [i * 7 for i in range(37)]
+
+
 def test_allgather_records_world2_gloo():
     world, n_total = 2, 7          # uneven shards: rank 0 gets 4, rank 1 gets 3
     ctx = mp.get_context("spawn")
