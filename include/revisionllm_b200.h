@@ -143,10 +143,16 @@ RVL_API int rvl_splice_rows(rvl_handle* h, const void* vis, const int32_t* vis_d
  *   cu_seqlens   [n_seq+1] int32 device
  *   page_table   [n_seq, max_pages] int32 device (KV page ids per sequence)
  *   logits_out   fp32 [n_seq, vocab] (last token of each sequence) or, when all_logits != 0,
- *                [total_tokens, vocab] */
+ *                [total_tokens, vocab]
+ *   seq_pos0     optional int32 [n_seq] device: sequence i's own rows start at position seq_pos0[i]; its positions
+ *                [0, seq_pos0[i]) are the rows [seq_ctx_row[i], +seq_pos0[i]) of the same packed stream - a prompt prefix
+ *                shared by the batch that is embedded, projected and written to (shared) KV pages ONCE, as its own
+ *                sequence, and attended to by every sequence that names it (max_seqlen counts positions, context included).
+ *   seq_ctx_row  optional int32 [n_seq] device, see seq_pos0 (both NULL: every sequence is self-contained) */
 RVL_API int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t n_seq,
                 int64_t total_tokens, int32_t max_seqlen, const int32_t* page_table, int32_t max_pages,
-                float* logits_out, int32_t all_logits, rvl_stream stream);
+                float* logits_out, int32_t all_logits, const int32_t* seq_pos0, const int32_t* seq_ctx_row,
+                rvl_stream stream);
 
 /* One KV-cached decode step for n_seq sequences (one new token each).
  * Replaces the step t>0 forward: vtimellm_arch.py:88-100 (position = tokens so far)

@@ -53,30 +53,38 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 // Tile in smem: [rows][128] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
 __device__ __forceinline__ uint32_t tile_off(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
 
-// Load a 64 x 128 tile; rows >= n_valid are zero-filled.
-__device__ __forceinline__ void load_tile(uint8_t* smem_tile, const __nv_bfloat16* g_row0, long long row_stride,
-                                          int n_valid, int tid) {
+// Load the 64 x 128 tile of positions [pos0, pos0 + 64) of one sequence; positions >= L are zero-filled.  A sequence's
+// positions [0, ctx_len) live in the rows of its context (a prompt prefix shared with other sequences, computed once),
+// positions >= ctx_len in its own rows: `ctx` / `own` point at column 0 of position 0 / position ctx_len.
+__device__ __forceinline__ void load_tile(uint8_t* smem_tile, const __nv_bfloat16* ctx, const __nv_bfloat16* own, int ctx_len,
+                                          long long row_stride, int pos0, int L, int tid) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int idx = tid + i * 128;
     const int r = idx >> 4, c = idx & 15;
-    const bool ok = r < n_valid;
-    const __nv_bfloat16* src = g_row0 + (ok ? r : 0) * row_stride + c * 8;
-    cp_async16(smem_tile + tile_off(r, c), src, ok);
+    const int pos = pos0 + r;
+    const bool ok = pos < L;
+    const __nv_bfloat16* src = !ok ? own : (pos < ctx_len ? ctx + pos * row_stride : own + (pos - ctx_len) * row_stride);
+    cp_async16(smem_tile + tile_off(r, c), src + c * 8, ok);
   }
 }
 
 __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ out,
                                                             const int32_t* __restrict__ cu_seqlens, int n_heads,
-                                                            float scale_log2) {
+                                                            float scale_log2, const int32_t* __restrict__ seq_pos0,
+                                                            const int32_t* __restrict__ seq_ctx_row) {
   pdl_trigger();
   pdl_wait();
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int s0 = cu_seqlens[seq];
-  const int L = cu_seqlens[seq + 1] - s0;
+  // optional external context: positions [0, p0) of this sequence are the rows [c0, c0 + p0) of the packed stream (a prompt
+  // prefix shared by the batch, projected once); the sequence's own rows hold positions p0 .. L - 1
+  const int p0 = seq_pos0 ? seq_pos0[seq] : 0;
+  const int c0 = seq_ctx_row ? seq_ctx_row[seq] : 0;
+  const int L = p0 + cu_seqlens[seq + 1] - s0;
   const int q0 = qt * kQT;
-  if (q0 >= L) return;
+  if (q0 >= L || q0 + kQT <= p0) return;      // past the end, or a query tile that lies entirely inside the context
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;          // [2][64][128]
@@ -84,14 +92,13 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = n_heads * kD;
   const long long stride = 3LL * H;
-  const __nv_bfloat16* qbase = qkv + (static_cast<long long>(s0) + q0) * stride + head * kD;
-  const __nv_bfloat16* kbase = qkv + static_cast<long long>(s0) * stride + H + head * kD;
-  const __nv_bfloat16* vbase = kbase + H;
+  const __nv_bfloat16* own = qkv + static_cast<long long>(s0) * stride + head * kD;      // position p0, q columns
+  const __nv_bfloat16* ctx = qkv + static_cast<long long>(c0) * stride + head * kD;      // position 0, q columns
 
   const int n_tiles = min((L + kKT - 1) / kKT, qt + 1);  // causal: keys <= q0 + 63
-  load_tile(sQ, qbase, stride, min(kQT, L - q0), tid);
-  load_tile(sK, kbase, stride, min(kKT, L), tid);
-  load_tile(sV, vbase, stride, min(kKT, L), tid);
+  load_tile(sQ, ctx, own, p0, stride, q0, L, tid);
+  load_tile(sK, ctx + H, own + H, p0, stride, 0, L, tid);
+  load_tile(sV, ctx + 2 * H, own + 2 * H, p0, stride, 0, L, tid);
   cp_async_commit();
 
   uint32_t qf[8][4];
@@ -105,8 +112,8 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
     const int buf = j & 1;
     if (j + 1 < n_tiles) {
       const int k0n = (j + 1) * kKT;
-      load_tile(sK + (buf ^ 1) * 16384, kbase + k0n * stride, stride, min(kKT, L - k0n), tid);
-      load_tile(sV + (buf ^ 1) * 16384, vbase + k0n * stride, stride, min(kKT, L - k0n), tid);
+      load_tile(sK + (buf ^ 1) * 16384, ctx + H, own + H, p0, stride, k0n, L, tid);
+      load_tile(sV + (buf ^ 1) * 16384, ctx + 2 * H, own + 2 * H, p0, stride, k0n, L, tid);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -207,9 +214,9 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int qr = q0 + warp * 16 + g + h * 8;
-    if (qr < L) {
+    if (qr < L && qr >= p0) {                  // context positions are produced by the context's own sequence
       const float inv = 1.f / l_run[h];
-      __nv_bfloat16* dst = out + (static_cast<long long>(s0) + qr) * H + head * kD;
+      __nv_bfloat16* dst = out + (static_cast<long long>(s0) + (qr - p0)) * H + head * kD;
 #pragma unroll
       for (int nt = 0; nt < 16; ++nt) {
         *reinterpret_cast<uint32_t*>(dst + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][2 * h] * inv, o[nt][2 * h + 1] * inv);
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
 }
 
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row) {
   if (n_seq <= 0 || max_seqlen <= 0) return;
   static bool attr = false;
   constexpr int smem = 16384 * 5;
@@ -230,7 +237,7 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
   dim3 grid((max_seqlen + kQT - 1) / kQT, n_heads, n_seq);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kD));
   launch_k(attn_prefill_kernel, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
-           reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2);
+           reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2, seq_pos0, seq_ctx_row);
 }
 
 // ------------------------------------------------------------------------------------------- decode

@@ -196,14 +196,16 @@ __global__ void __launch_bounds__(128) rope_kv_kernel(__nv_bfloat16* __restrict_
                                                        const int32_t* __restrict__ cu_seqlens,
                                                        const int32_t* __restrict__ page_table, int max_pages,
                                                        __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
-                                                       int n_heads, int page_size, float theta) {
+                                                       int n_heads, int page_size, float theta,
+                                                       const int32_t* __restrict__ seq_pos0) {
   constexpr int D = 128;
   __shared__ float s_cos[D / 2], s_sin[D / 2];
   pdl_trigger();
   pdl_wait();
   const long long tok = blockIdx.x;
   const int seq = tok_seq ? tok_seq[tok] : static_cast<int>(tok);
-  const int pos = positions ? positions[tok] : static_cast<int>(tok - cu_seqlens[seq]);
+  // seq_pos0: the sequence's own rows start at this position (the positions before it belong to a shared context)
+  const int pos = positions ? positions[tok] : static_cast<int>(tok - cu_seqlens[seq]) + (seq_pos0 ? seq_pos0[seq] : 0);
   if (threadIdx.x < D / 2) {
     // inv_freq_i = theta^(-2i/D)  (LlamaRotaryEmbedding), angle in fp32 like the reference
     const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * threadIdx.x) / static_cast<float>(D));
@@ -255,11 +257,11 @@ __global__ void __launch_bounds__(128) rope_kv_kernel(__nv_bfloat16* __restrict_
 }
 void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const int32_t* tok_seq,
                     const int32_t* cu_seqlens, const int32_t* page_table, int max_pages, void* k_pages, void* v_pages,
-                    int n_heads, int page_size, float theta, cudaStream_t st) {
+                    int n_heads, int page_size, float theta, cudaStream_t st, const int32_t* seq_pos0) {
   if (n_tokens <= 0) return;
   launch_k(rope_kv_kernel, dim3(static_cast<unsigned>(n_tokens)), dim3(128), 0, st, reinterpret_cast<__nv_bfloat16*>(qkv), positions,
            tok_seq, cu_seqlens, page_table, max_pages, reinterpret_cast<__nv_bfloat16*>(k_pages),
-           reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, theta);
+           reinterpret_cast<__nv_bfloat16*>(v_pages), n_heads, page_size, theta, seq_pos0);
 }
 
 // ------------------------------------------------------------------------------------ SwiGLU

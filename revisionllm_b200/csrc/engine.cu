@@ -302,7 +302,7 @@ static int ready(const rvl_handle* h, const char* who) {
 
 int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t n_seq, int64_t total_tokens,
                 int32_t max_seqlen, const int32_t* page_table, int32_t max_pages, float* logits_out, int32_t all_logits,
-                rvl_stream stream) {
+                const int32_t* seq_pos0, const int32_t* seq_ctx_row, rvl_stream stream) {
   int rc = ready(h, "rvl_prefill");
   if (rc) return rc;
   if (!hidden || !cu_seqlens || !page_table || !logits_out) return fail(h, RVL_ERR_INVALID, "rvl_prefill: null argument");
@@ -319,11 +319,11 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
     launch_rmsnorm(hidden, w.ln1, h->xnorm, T, H, c.rms_eps, nullptr, st);
     if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, T, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_rope_kv(h->qkv, T, nullptr, h->tok_seq, cu_seqlens, page_table, max_pages, k_pages(h, l), v_pages(h, l),
-                   c.n_heads, c.kv_page_size, c.rope_theta, st);
+                   c.n_heads, c.kv_page_size, c.rope_theta, st, seq_pos0);
     {
       // causal FLOPs need the per-sequence lengths (device side); use the uniform-length bound T*max_seqlen
       ProfScope ps(h, st, RVL_PROF_ATTN_PREFILL, 2.0 * T * max_seqlen * H, 2.0 * T * 4 * H);
-      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st);
+      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row);
     }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hidden, T, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
     launch_rmsnorm(hidden, w.ln2, h->xnorm, T, H, c.rms_eps, nullptr, st);

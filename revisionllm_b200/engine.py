@@ -189,14 +189,15 @@ class Engine:
                     "rvl_splice_rows")
         self.launches += (1 if n_vis else 0) + (1 if n_text else 0)
 
-    def prefill(self, hidden, cu_seqlens, n_seq, max_seqlen, page_table, logits_out, all_logits=False):
+    def prefill(self, hidden, cu_seqlens, n_seq, max_seqlen, page_table, logits_out, all_logits=False, seq_pos0=None,
+                seq_ctx_row=None):
         _req(hidden, torch.float32, "hidden"); _req(cu_seqlens, torch.int32, "cu_seqlens")
         _req(page_table, torch.int32, "page_table"); _req(logits_out, torch.float32, "logits_out")
         T = hidden.shape[0]
         self.ensure_workspace(T, n_seq)
         self._check(self.lib.rvl_prefill(self.h, hidden.data_ptr(), cu_seqlens.data_ptr(), n_seq, T, max_seqlen,
                                          page_table.data_ptr(), page_table.shape[1], logits_out.data_ptr(),
-                                         1 if all_logits else 0, _stream()), "rvl_prefill")
+                                         1 if all_logits else 0, _ptr(seq_pos0), _ptr(seq_ctx_row), _stream()), "rvl_prefill")
         self.launches += 1 + (8 if self.wgu_interleaved else 9) * self.cfg.n_layers + 2
 
     def decode_step(self, token_ids, seq_lens, page_table, logits_out, max_kv_len: int = 0):

@@ -123,6 +123,7 @@ class RevisionLlamaForCausalLM:
         self.clip_encoder = None
         self.record_phase_events = False   # bench.py: CUDA events at the splice / prefill / decode boundaries of generate()
         self.last_phase_events = None
+        self.share_prefix_compute = False  # also COMPUTE that prefix once (see _share_prefix_rows); opt-in
         self.share_prefix_pages = True     # map the KV pages of a prompt prefix common to the whole batch once (see _alloc_kv)
 
     # ---- placement (eval_nlq_negative.py:144-148 does `model.bfloat16().cuda()`)
@@ -187,7 +188,37 @@ class RevisionLlamaForCausalLM:
         B, F, D = images.shape                           # stage 1: [B, F, 768] through the Linear projector (:125)
         return images.to(dev, torch.bfloat16).reshape(B * F, D).contiguous(), [F] * B, False
 
-    def _splice(self, input_ids, attention_mask, images, query_feats, visual_memory=None, prefix_memory=None):
+    def _share_prefix_rows(self, plan) -> None:
+        """Opt-in (`share_prefix_compute`): the whole pages of a text prefix common to every sequence of the batch are computed
+        ONCE.  The packed stream becomes [prefix (P rows) | seq 0 from position P | seq 1 from position P | ...]; the prefix is
+        one more sequence whose K/V go to the shared pages, and every real sequence names it as its attention context
+        (`seq_pos0` / `seq_ctx_row` of rvl_prefill).  Row-wise kernels (GEMMs, norms, SwiGLU) never see the difference and the
+        attention tiles stay aligned to absolute positions, so every logit keeps its bits - (B - 1) * P rows of work disappear
+        (32 of 184 positions for the 1-hour sweep).  Off by default: the headline benchmark computes every segment in full,
+        like the reference."""
+        ps = self.engine.cfg.kv_page_size
+        lengths = plan["lengths"].astype(np.int64)
+        B = lengths.shape[0]
+        P = (min(int(plan["shared_prefix"]), int(lengths.min()) - 1) // ps) * ps
+        if B < 2 or P < ps:
+            return
+        cu = plan["cu_seqlens"].astype(np.int64)
+        new_start = np.concatenate([[P], P + np.cumsum(lengths - P)])                  # first own row of sequence b; [-1] = total
+        def remap(dst):
+            b = np.searchsorted(cu, dst, side="right") - 1
+            pos = dst - cu[b]
+            keep = (pos >= P) | (b == 0)
+            return keep, np.where(pos < P, pos, new_start[b] + pos - P)
+        kt, nt = remap(plan["text_dst"].astype(np.int64))
+        kv_, nv = remap(plan["vis_dst"].astype(np.int64))
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        plan["text_ids"], plan["text_dst"] = i32(plan["text_ids"][kt]), i32(nt[kt])
+        plan["vis_src"], plan["vis_dst"] = i32(plan["vis_src"][kv_]), i32(nv[kv_])
+        plan["cu_seqlens"] = i32(np.concatenate([[0], new_start]))                     # B + 1 sequences: the prefix first
+        plan["ctx_len"] = P
+
+    def _splice(self, input_ids, attention_mask, images, query_feats, visual_memory=None, prefix_memory=None,
+                share_compute: bool = False):
         """Projector + splice into a packed fp32 residual stream.  Returns (hidden [T, H], plan)."""
         eng = self.engine
         rows, n_vis, projected = self._visual_blocks(images, query_feats)
@@ -219,6 +250,9 @@ class RevisionLlamaForCausalLM:
             n_vis = [n for _ in range(B) for n in (F, M)]
         plan = plan_splice(ids_np, n_vis, am_np, self.config.tokenizer_model_max_length, constants.IMAGE_TOKEN_INDEX)
         plan["shared_prefix"] = min(self._common_text_prefix(ids_np, am_np), int(plan["lengths"].min()))
+        plan["ctx_len"] = 0
+        if share_compute:
+            self._share_prefix_rows(plan)
         dev = self.device
         T = int(plan["cu_seqlens"][-1])
         hidden = torch.empty((T, self.config.hidden_size), dtype=torch.float32, device=dev)
@@ -348,7 +382,8 @@ class RevisionLlamaForCausalLM:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.record_phase_events else None
             if ev:
                 ev[0].record()
-            hidden, plan = self._splice(input_ids, attention_mask, images, query_feats, visual_memory, prefix_memory)
+            hidden, plan = self._splice(input_ids, attention_mask, images, query_feats, visual_memory, prefix_memory,
+                                        share_compute=self.share_prefix_compute)
             if ev:
                 ev[1].record()
             lengths, cu = plan["lengths"], plan["cu_seqlens"]
@@ -361,8 +396,22 @@ class RevisionLlamaForCausalLM:
             chunk = max_new if max_new <= 64 else 64
             kv = self._alloc_kv(lengths, chunk, plan["shared_prefix"])
             cu_d = torch.from_numpy(cu).to(dev)
-            logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
-            eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
+            P = int(plan["ctx_len"])
+            if P:
+                # B + 1 sequences: the shared prefix (its K/V fill the shared pages), then every segment from position P on
+                ps = eng.cfg.kv_page_size
+                table = torch.zeros((B + 1, kv.page_table.shape[1]), dtype=torch.int32, device=dev)
+                table[0, : P // ps] = kv.page_table[0, : P // ps]
+                table[1:] = kv.page_table
+                pos0 = torch.full((B + 1,), P, dtype=torch.int32, device=dev)
+                pos0[0] = 0
+                all_last = torch.empty((B + 1, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.prefill(hidden, cu_d, B + 1, int(lengths.max()), table, all_last, all_logits=False, seq_pos0=pos0,
+                            seq_ctx_row=torch.zeros(B + 1, dtype=torch.int32, device=dev))
+                logits = all_last[1:].contiguous()
+            else:
+                logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
             if ev:
                 ev[2].record()
             del hidden
