@@ -10,7 +10,14 @@ model.record_phase_events = True
 feats = syn.make_features(180, 100, 768, seed=1).cuda()
 ids = syn.make_prompt_ids(cfg, seed=2).cuda()
 cls = torch.randn(768, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
-for i in range(4):
+AB = os.environ.get("AB_ENV")          # e.g. AB_ENV=RVL_ROPE_EPILOGUE: odd steps run with it set to 0
+acc = {0: [], 1: []}
+for i in range(9 if AB else 4):
+    if AB:
+        if i % 2:
+            os.environ[AB] = "0"
+        else:
+            os.environ.pop(AB, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -23,3 +30,9 @@ for i in range(4):
     print(f"step {i}: total {e0.elapsed_time(e1):7.2f} ms (host enqueue {1e3 * t_host:6.1f} ms) | before generate {e0.elapsed_time(ev[0]):6.2f} | "
           f"splice {ev[0].elapsed_time(ev[1]):6.2f} | prefill {ev[1].elapsed_time(ev[2]):7.2f} | decode {ev[2].elapsed_time(ev[3]):7.2f} | "
           f"tail {ev[3].elapsed_time(e1):6.2f}", flush=True)
+    if AB and i > 0:
+        acc[i % 2].append((ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), e0.elapsed_time(e1)))
+if AB:
+    for k, name in ((0, "default"), (1, AB + "=0")):
+        n = len(acc[k])
+        print(f"{name:28s} prefill {sum(a[0] for a in acc[k]) / n:7.2f} ms  decode {sum(a[1] for a in acc[k]) / n:7.2f} ms  total {sum(a[2] for a in acc[k]) / n:7.2f} ms")
