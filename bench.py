@@ -41,6 +41,16 @@ WEIGHT_BYTES_PER_STEP = 13.214e9
 KV_BYTES_PER_TOKEN = 0.524288e6
 
 
+def workload_config(segments_per_rank_step: int, seq_len: int, world: int) -> dict:
+    """`config` of the JSON line - the same for this repo's arm and for the reference arm."""
+    return {"workload": "stage1_sweep_1h_movie (BASELINE.json configs[1]): 180 segments x 100 frames, L=184, "
+                        "projector+splice+prefill+16 greedy decode steps+entropy+cosine top-3",
+            "model": "Vicuna-7B shape (Llama-2-7B), random-init planted weights", "segments_per_rank_step": segments_per_rank_step,
+            "seq_len": seq_len, "new_tokens": NEW_TOKENS, "parallelism": f"segment-parallel dp{world}",
+            "l2": "inputs larger than L2: 13.2 GB of weights are streamed every prefill/decode pass",
+            "decoding": "greedy (north star); KV pages of the prompt prefix common to the batch are mapped once"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -131,8 +141,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "stage1_sweep_1h_movie", "segments": N_SEG, "frames": N_FRAMES, "seq_len": 184,
-                       "new_tokens": NEW_TOKENS, "sample": "1 segment per step"},
+            "config": dict(workload_config(N_SEG, int(ids.shape[0]) - 1 + N_FRAMES, 1),
+                           sample="CPU arm: each step scores 1 of the 180 segments (fp32 oracle port, all host threads)"),
             "cpu_baseline": {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
                              "sample": f"1 segment (L=184, {NEW_TOKENS} greedy tokens) per step, fp32, torch {torch.__version__}"},
             "e2e": {"value": val, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -307,12 +317,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "stage1_sweep_1h_movie (BASELINE.json configs[1]): 180 segments x 100 frames, L=184, "
-                               "projector+splice+prefill+16 greedy decode steps+entropy+cosine top-3",
-                   "model": "Vicuna-7B shape (Llama-2-7B), random-init planted weights", "segments_per_rank_step": n_local,
-                   "seq_len": seq_len, "new_tokens": NEW_TOKENS, "parallelism": f"segment-parallel dp{world}",
-                   "l2": "inputs larger than L2: 13.2 GB of weights are streamed every prefill/decode pass",
-                   "decoding": "greedy (north star); KV pages of the prompt prefix common to the batch are mapped once"},
+        "config": workload_config(n_local, seq_len, world),
         "prefill_tokens_per_s": units_per_step * seq_len * args.steps / (dev_ms * 1e-3),
         "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,

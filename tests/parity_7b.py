@@ -1,8 +1,8 @@
 """Full-size parity evidence (north star: tokens identical on >= 99 % of segments, logits within a stated bf16 tolerance):
 N segments of the 1-hour sweep at the Vicuna-7B shape, CUDA path (batched) vs the fp32 CPU oracle (one segment at a time).
-Writes one JSON line; run on the GPU box:  python tools/parity_7b.py 8 > gpurun_out/parity_7b.json"""
+Writes one JSON line; run on the GPU box:  python tests/parity_7b.py 8 > gpurun_out/parity_7b.json"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import torch
 from oracle import llama_ref, splice_ref
 from revisionllm_b200 import synthetic as syn
