@@ -20,7 +20,9 @@ namespace rvl {
 // Algorithmic bytes per row: dim*4 (read) + dim*2 (write) (+ dim*2 weight, L2 resident).
 // Optional fused split-k reduction (decode): the row is first completed with the partial sums the preceding
 // weight-streaming GEMM left in `partials` ([n_partials][rows][dim] fp32) and written back as the new residual.
-template <int THREADS, int kMaxVec>   // kMaxVec float4 per thread: dim <= THREADS * kMaxVec * 4
+// kPartials compiles the split-k reduction in; the prefill variant stays at 54 registers / 28 CTAs per SM without it (with the
+// partial-sum registers in the same kernel it measured 87 registers, 14 CTAs and 244 instead of 113 us per 33120 x 4096 launch)
+template <int THREADS, int kMaxVec, bool kPartials>   // kMaxVec float4 per thread: dim <= THREADS * kMaxVec * 4
 __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const __nv_bfloat16* __restrict__ w,
                                                            __nv_bfloat16* __restrict__ y, int dim, float eps,
                                                            const int32_t* __restrict__ rows,
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
     const int idx = threadIdx.x + i * THREADS;
     if (idx < nvec) {
       c[i] = xr[idx];
-      if (n_partials > 0) {
+      if (kPartials && n_partials > 0) {
         // all partial loads are issued before the first add: one round trip instead of n_partials
         float4 q[kMaxPartials];
 #pragma unroll
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
         for (int p = 0; p < kMaxPartials; ++p)
           if (p < n_partials) { c[i].x += q[p].x; c[i].y += q[p].y; c[i].z += q[p].z; c[i].w += q[p].w; }
       }
-      if (x_out) reinterpret_cast<float4*>(x_out + src_row * dim)[idx] = c[i];
+      if (kPartials && x_out) reinterpret_cast<float4*>(x_out + src_row * dim)[idx] = c[i];
       ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
     }
   }
@@ -84,14 +86,19 @@ void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int 
   const long long ps = partial_stride;
   // few rows (decode): one float4 per thread so that a row's loads are all in flight at once (the 128-thread
   // variant took 9.7 us for 180 rows with 4 split-k partials - latency, not bandwidth)
-  if (n_rows <= 1024 && dim >= 2048)
-    launch_k(rmsnorm_kernel<1024, 2>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+  const bool reduce = n_partials > 0 || x_out != nullptr;
+  if (n_rows <= 1024 && dim >= 2048 && reduce)
+    launch_k(rmsnorm_kernel<1024, 2, true>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+  else if (n_rows <= 1024 && dim >= 2048)
+    launch_k(rmsnorm_kernel<1024, 2, false>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+  else if (reduce)
+    launch_k(rmsnorm_kernel<256, 8, true>, dim3(static_cast<unsigned>(n_rows)), dim3(256), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
   else if (dim <= 128 * 32)
     // many rows (prefill): 128 threads x 8 float4, 28 CTAs per SM - measured 113 us per 33120 x 4096 launch (82 % of DRAM
     // peak); a 512-thread variant with the same bytes per thread ran at 250 us
-    launch_k(rmsnorm_kernel<128, 8>, dim3(static_cast<unsigned>(n_rows)), dim3(128), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+    launch_k(rmsnorm_kernel<128, 8, false>, dim3(static_cast<unsigned>(n_rows)), dim3(128), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
   else
-    launch_k(rmsnorm_kernel<256, 8>, dim3(static_cast<unsigned>(n_rows)), dim3(256), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+    launch_k(rmsnorm_kernel<256, 8, false>, dim3(static_cast<unsigned>(n_rows)), dim3(256), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
 }
 
 // ------------------------------------------------------------------------------------ embedding / splice rows
