@@ -240,6 +240,184 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
            reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2, seq_pos0, seq_ctx_row);
 }
 
+// ------------------------------------------------------------------------------------------- small MHA, head_dim 96
+// nn.MultiheadAttention of the stage-2 ClipEncoder (revisionllm/model/adapter/transformer.py:210-223,271-305): 8 heads x 96
+// dims, non-causal, fixed Tq / Tk per launch, optional key-padding mask, K / V optionally taken from another sequence index
+// (all windows of a query share the query's text tokens).  Same structure as attn_prefill_kernel - 64 query rows per CTA,
+// 64-key tiles in shared memory with cp.async double buffering, QK^T and PV on mma.sync, online softmax in registers - with
+// six 16-dim k-steps instead of eight; rows keep the 256-byte pitch of the 128-dim tiles so the swizzle is unchanged.
+// Replaces the CUDA-core kernel of round 1 (3.7 ms per self-attention launch for 700 windows x 251 tokens).
+constexpr int kD96 = 96;
+
+__device__ __forceinline__ void load_tile96(uint8_t* smem_tile, const __nv_bfloat16* base, long long row_stride, int n_valid, int tid) {
+  // 64 rows x 12 chunks of 16 B
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int idx = tid + i * 128;
+    const int r = idx / 12, c = idx - r * 12;
+    const bool ok = r < n_valid;
+    cp_async16(smem_tile + tile_off(r, c), base + (ok ? r : 0) * row_stride + c * 8, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128) mha96_mma_kernel(const __nv_bfloat16* __restrict__ q, long long q_stride,
+                                                         const __nv_bfloat16* __restrict__ k, long long k_stride,
+                                                         const __nv_bfloat16* __restrict__ v, long long v_stride,
+                                                         __nv_bfloat16* __restrict__ out, long long out_stride, int Tq, int Tk,
+                                                         const int32_t* __restrict__ kv_seq_idx,
+                                                         const float* __restrict__ key_mask, float scale_log2) {
+  const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int q0 = qt * kQT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;          // [2][64][128 (96 used)]
+  uint8_t* sV = smem + 16384 * 3;
+  __shared__ float s_mask[2][kKT];     // additive key mask of the two tiles in flight (0 / -inf)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kv_seq = kv_seq_idx ? kv_seq_idx[seq] : seq;
+  const __nv_bfloat16* qbase = q + (static_cast<long long>(seq) * Tq + q0) * q_stride + head * kD96;
+  const __nv_bfloat16* kbase = k + static_cast<long long>(kv_seq) * Tk * k_stride + head * kD96;
+  const __nv_bfloat16* vbase = v + static_cast<long long>(kv_seq) * Tk * v_stride + head * kD96;
+  const float* mbase = key_mask ? key_mask + static_cast<long long>(kv_seq) * Tk : nullptr;
+  const int n_tiles = (Tk + kKT - 1) / kKT;
+  load_tile96(sQ, qbase, q_stride, min(kQT, Tq - q0), tid);
+  load_tile96(sK, kbase, k_stride, min(kKT, Tk), tid);
+  load_tile96(sV, vbase, v_stride, min(kKT, Tk), tid);
+  cp_async_commit();
+  if (tid < kKT) s_mask[0][tid] = (tid < Tk && (!mbase || mbase[tid] != 0.f)) ? 0.f : -INFINITY;
+
+  uint32_t qf[6][4];
+  float o[12][4];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int g = lane >> 2, t4 = lane & 3;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_tiles) {
+      const int k0n = (j + 1) * kKT;
+      load_tile96(sK + (buf ^ 1) * 16384, kbase + k0n * k_stride, k_stride, min(kKT, Tk - k0n), tid);
+      load_tile96(sV + (buf ^ 1) * 16384, vbase + k0n * v_stride, v_stride, min(kKT, Tk - k0n), tid);
+      cp_async_commit();
+      if (tid < kKT) s_mask[buf ^ 1][tid] = (k0n + tid < Tk && (!mbase || mbase[k0n + tid] != 0.f)) ? 0.f : -INFINITY;
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (j == 0) {
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ) + tile_off(r, ks * 2 + (lane >> 4)));
+    }
+    const uint32_t kaddr = smem_u32(sK + buf * 16384);
+    const uint32_t vaddr = smem_u32(sV + buf * 16384);
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        ldmatrix_x4(b, kaddr + tile_off(key, ks * 2 + ((lane >> 3) & 1)));
+        mma_bf16_16816(s[2 * np], qf[ks], b[0], b[1]);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], b[2], b[3]);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float add = s_mask[buf][nt * 8 + t4 * 2 + (e & 1)];
+        s[nt][e] = s[nt][e] * scale_log2 + add;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      mnew[h] = fmaxf(m_run[h], mx[h]);
+      const float msafe = mnew[h] == -INFINITY ? 0.f : mnew[h];
+      corr[h] = exp2f(m_run[h] - msafe);
+      m_run[h] = mnew[h];
+      mnew[h] = msafe;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = exp2f(s[nt][e] - mnew[e >> 1]);
+        s[nt][e] = p;
+        rs[e >> 1] += p;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * corr[h] + rs[h];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
+      pa[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
+      pa[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 6; ++dp) {
+        uint32_t b[4];
+        const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4_trans(b, vaddr + tile_off(key, dp * 2 + (lane >> 4)));
+        mma_bf16_16816(o[2 * dp], pa, b[0], b[1]);
+        mma_bf16_16816(o[2 * dp + 1], pa, b[2], b[3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int qr = q0 + warp * 16 + g + h * 8;
+    if (qr < Tq) {
+      const float inv = 1.f / l_run[h];
+      __nv_bfloat16* dst = out + (static_cast<long long>(seq) * Tq + qr) * out_stride + head * kD96;
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt)
+        *reinterpret_cast<uint32_t*>(dst + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][2 * h] * inv, o[nt][2 * h + 1] * inv);
+    }
+  }
+}
+
+int launch_mha96(const void* q, long long q_stride, const void* k, long long k_stride, const void* v, long long v_stride, void* out,
+                 long long out_stride, int n_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx, const float* key_mask,
+                 cudaStream_t st) {
+  static bool attr = false;
+  constexpr int smem = 16384 * 5;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mha96_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return RVL_ERR_CUDA;
+    attr = true;
+  }
+  dim3 grid((Tq + kQT - 1) / kQT, n_heads, n_seq);
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kD96));
+  mha96_mma_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(q), q_stride, reinterpret_cast<const __nv_bfloat16*>(k),
+                                            k_stride, reinterpret_cast<const __nv_bfloat16*>(v), v_stride,
+                                            reinterpret_cast<__nv_bfloat16*>(out), out_stride, Tq, Tk, kv_seq_idx, key_mask, scale_log2);
+  return cudaGetLastError() == cudaSuccess ? RVL_OK : RVL_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------------------------------- decode
 // grid (n_heads, n_seq), 128 threads: one query row per (sequence, head) against the paged KV cache.
 //   phase 0 (kFused): RoPE of this step's q and k (rotate-half, fp32 sincosf like LlamaRotaryEmbedding, results rounded

@@ -82,102 +82,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   }
 }
 
-// ------------------------------------------------------------------------------------ small MHA, head_dim 96
-// grid (n_heads, n_seq, ceil(Tq / 128)), 256 threads: thread pair (2r, 2r+1) owns query row r of the chunk,
-// each thread 48 of the 96 dims.  K/V rows of (kv sequence, head) live in shared memory as bf16.
-constexpr int kHD = 96;
-constexpr int kHalf = 48;
-
-__global__ void __launch_bounds__(256) mha96_kernel(const __nv_bfloat16* __restrict__ q, long long q_stride,
-                                                     const __nv_bfloat16* __restrict__ k, long long k_stride,
-                                                     const __nv_bfloat16* __restrict__ v, long long v_stride,
-                                                     __nv_bfloat16* __restrict__ out, long long out_stride, int Tq, int Tk,
-                                                     const int32_t* __restrict__ kv_seq_idx,
-                                                     const float* __restrict__ key_mask, float scale) {
-  extern __shared__ __align__(16) uint8_t smem_mha[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_mha);       // [Tk][96]
-  __nv_bfloat16* sV = sK + static_cast<size_t>(Tk) * kHD;               // [Tk][96]
-  float* sMask = reinterpret_cast<float*>(sV + static_cast<size_t>(Tk) * kHD);  // [Tk] additive (0 / -inf)
-  const int head = blockIdx.x, seq = blockIdx.y;
-  const int kv_seq = kv_seq_idx ? kv_seq_idx[seq] : seq;
-  const int tid = threadIdx.x;
-  // stage K, V (12 x 16 B per row)
-  for (int i = tid; i < Tk * 12; i += 256) {
-    const int r = i / 12, c = i - r * 12;
-    const long long krow = static_cast<long long>(kv_seq) * Tk + r;
-    reinterpret_cast<uint4*>(sK)[i] = __ldg(reinterpret_cast<const uint4*>(k + krow * k_stride + head * kHD) + c);
-    reinterpret_cast<uint4*>(sV)[i] = __ldg(reinterpret_cast<const uint4*>(v + krow * v_stride + head * kHD) + c);
-  }
-  for (int i = tid; i < Tk; i += 256)
-    sMask[i] = (key_mask == nullptr || key_mask[static_cast<long long>(kv_seq) * Tk + i] != 0.f) ? 0.f : -INFINITY;
-  __syncthreads();
-  const int qr = blockIdx.z * 128 + (tid >> 1);
-  const int half = tid & 1;
-  const bool active = qr < Tq;
-  const long long qrow = static_cast<long long>(seq) * Tq + (active ? qr : 0);
-  float qf[kHalf], acc[kHalf];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(q + qrow * q_stride + head * kHD + half * kHalf);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const uint4 t = __ldg(qp + c);
-      qf[c * 8 + 0] = bf16_lo(t.x) * scale; qf[c * 8 + 1] = bf16_hi(t.x) * scale;
-      qf[c * 8 + 2] = bf16_lo(t.y) * scale; qf[c * 8 + 3] = bf16_hi(t.y) * scale;
-      qf[c * 8 + 4] = bf16_lo(t.z) * scale; qf[c * 8 + 5] = bf16_hi(t.z) * scale;
-      qf[c * 8 + 6] = bf16_lo(t.w) * scale; qf[c * 8 + 7] = bf16_hi(t.w) * scale;
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < kHalf; ++d) acc[d] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  for (int j0 = 0; j0 < Tk; j0 += 4) {
-    float s[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = j0 + jj;
-      float d = 0.f;
-      if (j < Tk) {
-        const uint32_t* kr = reinterpret_cast<const uint32_t*>(sK + static_cast<size_t>(j) * kHD + half * kHalf);
-#pragma unroll
-        for (int e = 0; e < kHalf / 2; ++e) {
-          const uint32_t kk = kr[e];
-          d += qf[2 * e] * bf16_lo(kk) + qf[2 * e + 1] * bf16_hi(kk);
-        }
-      }
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      s[jj] = (j < Tk) ? d + sMask[j] : -INFINITY;
-    }
-    const float cm = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-    const float m_new = fmaxf(m_run, cm);
-    if (m_new == -INFINITY) continue;   // everything so far masked
-    const float corr = __expf(m_run - m_new);
-    l_run *= corr;
-#pragma unroll
-    for (int d = 0; d < kHalf; ++d) acc[d] *= corr;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = j0 + jj;
-      const float p = __expf(s[jj] - m_new);   // exp(-inf) = 0 for masked / out-of-range keys
-      l_run += p;
-      if (j < Tk) {
-        const uint32_t* vr = reinterpret_cast<const uint32_t*>(sV + static_cast<size_t>(j) * kHD + half * kHalf);
-#pragma unroll
-        for (int e = 0; e < kHalf / 2; ++e) {
-          const uint32_t vv = vr[e];
-          acc[2 * e] += p * bf16_lo(vv);
-          acc[2 * e + 1] += p * bf16_hi(vv);
-        }
-      }
-    }
-    m_run = m_new;
-  }
-  if (active) {
-    const float inv = 1.f / l_run;
-    uint32_t* op = reinterpret_cast<uint32_t*>(out + qrow * out_stride + head * kHD + half * kHalf);
-#pragma unroll
-    for (int e = 0; e < kHalf / 2; ++e) op[e] = pack_bf16x2(acc[2 * e] * inv, acc[2 * e + 1] * inv);
-  }
-}
+// (the head_dim-96 attention of the adapter lives in attention.cu: mha96_mma_kernel)
 
 }  // namespace rvl
 
@@ -204,20 +109,8 @@ int rvl_mha96(rvl_handle* h, const void* q, int64_t q_stride, const void* k, int
   (void)h;
   if (!q || !k || !v || !out || n_seq <= 0 || Tq <= 0 || Tk <= 0) return RVL_ERR_INVALID;
   if (q_stride % 8 || k_stride % 8 || v_stride % 8 || out_stride % 2) return RVL_ERR_INVALID;
-  const size_t smem = static_cast<size_t>(Tk) * kHD * 2 * 2 + static_cast<size_t>(Tk) * 4;
-  if (smem > 200 * 1024) return RVL_ERR_INVALID;   // Tk <= ~520
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    if (cudaFuncSetAttribute(mha96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-      return RVL_ERR_CUDA;
-    attr = smem;
-  }
-  dim3 grid(n_heads, n_seq, (Tq + 127) / 128);
-  mha96_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q), q_stride, reinterpret_cast<const __nv_bfloat16*>(k), k_stride,
-      reinterpret_cast<const __nv_bfloat16*>(v), v_stride, reinterpret_cast<__nv_bfloat16*>(out), out_stride, Tq, Tk,
-      kv_seq_idx, key_mask, 1.0f / sqrtf(static_cast<float>(kHD)));
-  return cudaGetLastError() == cudaSuccess ? RVL_OK : RVL_ERR_CUDA;
+  return launch_mha96(q, q_stride, k, k_stride, v, v_stride, out, out_stride, n_seq, n_heads, Tq, Tk, kv_seq_idx, key_mask,
+                      static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -121,6 +121,9 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
                         int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused, float theta,
                         int max_kv_len, cudaStream_t st);
+int launch_mha96(const void* q, long long q_stride, const void* k, long long k_stride, const void* v, long long v_stride, void* out,
+                 long long out_stride, int n_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx, const float* key_mask,
+                 cudaStream_t st);
 // sampling.cu
 void launch_sample_greedy(const float* logits, int n_seq, int vocab, int32_t* unfinished, int eos_id, int pad_id,
                           int32_t* next_tokens, float* entropy_out, int32_t* seq_lens, int32_t* n_unfinished,
