@@ -176,7 +176,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from revisionllm_b200 import _cabi, scoring, sweep, synthetic as syn
+    from revisionllm_b200 import scoring, sweep, synthetic as syn
     from revisionllm_b200.model import RevisionConfig, RevisionLlamaForCausalLM
     cfg = syn.VICUNA_7B
     n_seg = args.segments

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import dataclasses
 from enum import Enum, auto
-from typing import List, Optional
+from typing import Optional
 
 
 class SeparatorStyle(Enum):

@@ -11,7 +11,7 @@ String parsing stays on the host (as in the reference); normalisation, merge, fi
 from __future__ import annotations
 
 import re
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -16,9 +16,8 @@ Differences, all deliberate and documented in DESIGN.md:
 from __future__ import annotations
 
 import math
-import warnings
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from dataclasses import dataclass
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
@@ -119,7 +118,6 @@ class RevisionLlamaForCausalLM:
         self.engine: Optional[Engine] = None
         self.device = torch.device("cpu")
         self.dtype = torch.bfloat16
-        self._warned_sampling = False
         self.clip_encoder = None
         self.record_phase_events = False   # bench.py: CUDA events at the splice / prefill / decode boundaries of generate()
         self.last_phase_events = None

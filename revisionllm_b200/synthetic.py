@@ -21,7 +21,7 @@ from __future__ import annotations
 import hashlib
 import math
 from dataclasses import dataclass, asdict
-from typing import Dict, Optional, Tuple
+from typing import Dict
 
 import torch
 
