@@ -832,6 +832,231 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------- CTA-pair, weight streaming
+// Weight-streaming orientation with MANY tokens (decode at 65 - 256 sequences): the activation tile (tokens x 64, 24 KB at
+// 180 tokens) is re-fetched from L2 for every 16 KB weight tile, and one SM ingests at most ~75 B/clk from L2 + HBM together
+// (tools/probes/tma_probe2.cu) - at the 1.1 - 1.3 GHz the power-capped chip runs inside the sweep that is 40 KB per ~530
+// cycles = ~0.45 us per k-block and SM, i.e. ~4.4 TB/s of weights with every SM pulling: ingest-bound, not HBM-bound.  Here
+// two CTAs of a cluster share the activation tile through tcgen05.mma.cta_group::2: each loads its own 128 weight rows
+// and HALF of the token rows (28 KB per k-block), the even CTA issues M = 256 MMAs for both, each CTA keeps the accumulator
+// of its own 128 weight rows in its TMEM and runs the staged TMA-store epilogue for them.  Work units are (256-row weight
+// tile, k-split) pairs dealt round-robin to the clusters; split-k partials go to the caller's partial buffers.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
+  const int kStages = args.stages;
+  const int BN = args.bn;                       // tokens (MMA N), multiple of 16
+  const int half_rows = BN >> 1;
+  const int b_half_bytes = half_rows * kBK * 2;
+  const int stage_bytes = kATileBytes + b_half_bytes;
+  const int acc_cols = args.sub_stride;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kATileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kATileBytes + ((b_half_bytes + 1023) & ~1023)));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint8_t* stage_out = reinterpret_cast<uint8_t*>(bars) + 512;
+  const int b_slot_bytes = (b_half_bytes + 1023) & ~1023;        // every B slot starts on a 1024-byte swizzle boundary
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();
+
+  const int n_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int tiles = args.tiles_m;                               // 256-row weight tiles
+  const int n_units = tiles * args.split_k;
+  const int kb_per_split = (args.k_blocks + args.split_k - 1) / args.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
+    int stage = 0;
+    uint32_t phase = 0;
+    // weight tiles of the first k-blocks go out before the kernel that produces the activations is known to be finished
+    int pre = 0;
+    if (args.prefetch_a) {
+      for (int u = cluster_id; u < n_units && pre < kStages; u += n_clusters) {
+        const int ks = u / tiles, tile = u - ks * tiles;
+        const int kb0 = ks * kb_per_split, kb1 = min(args.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1 && pre < kStages; ++kb, ++pre) {
+          if (elect_one()) {
+            const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[pre]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[pre], 2 * stage_bytes);
+            tma_load_2d_pair_hint(smem_a + pre * kATileBytes, &tmap_a, full_leader, kb * kBK, (tile * 2 + static_cast<int>(rank)) * kBM, pol_a);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    pdl_wait();
+    int n_iter = 0;
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+      const int ks = u / tiles, tile = u - ks * tiles;
+      const int kb0 = ks * kb_per_split, kb1 = min(args.k_blocks, kb0 + kb_per_split);
+      const int m0 = (tile * 2 + static_cast<int>(rank)) * kBM;
+      for (int kb = kb0; kb < kb1; ++kb, ++n_iter) {
+        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+        if (n_iter < pre) {
+          if (elect_one()) tma_load_2d_pair_hint(smem_b + stage * b_slot_bytes, &tmap_b, full_leader, kb * kBK, static_cast<int>(rank) * half_rows, pol_b);
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+            tma_load_2d_pair_hint(smem_a + stage * kATileBytes, &tmap_a, full_leader, kb * kBK, m0, pol_a);
+            tma_load_2d_pair_hint(smem_b + stage * b_slot_bytes, &tmap_b, full_leader, kb * kBK, static_cast<int>(rank) * half_rows, pol_b);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------------------------------------------------- MMA issuer (leader CTA only)
+      const uint32_t idesc = umma_idesc_bf16(256, static_cast<uint32_t>(BN));
+      const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem_a));
+      const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem_b));
+      const uint64_t a_step = static_cast<uint64_t>(kATileBytes >> 4), b_step = static_cast<uint64_t>(b_slot_bytes >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        const int ks = u / tiles;
+        const int kb0 = ks * kb_per_split, kb1 = min(args.k_blocks, kb0 + kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + a_step * stage;
+            const uint64_t b_desc = b_desc0 + b_step * stage;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (both CTAs: own 128 weight rows), staged TMA stores
+    pdl_wait();
+    const int quarter = warp & 3;
+    const int m_local = quarter * 32 + lane;
+    const int n_chunks = (BN + 31) >> 5;
+    const uint32_t stg = smem_u32(stage_out);
+    const int cpg = args.staged;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+      const int ks = u / tiles, tile = u - ks * tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int feat0 = (tile * 2 + static_cast<int>(rank)) * kBM;
+      for (int c0 = 0; c0 < n_chunks; c0 += cpg) {
+        if (threadIdx.x == 64) bulk_wait_read_all();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int c1 = min(c0 + cpg, n_chunks);
+        for (int c = c0; c < c1; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == n_chunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          }
+          const int lc = c - c0;
+          if (args.swiglu) {
+            const bool lower = lane < 16;
+            const uint32_t base = stg + lc * (32 * 128) + (quarter * 16 + (lane & 15)) * 2 + (lower ? 0 : 128);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float vj = __uint_as_float(r[j]), vj1 = __uint_as_float(r[j + 1]);
+              const float got = __shfl_xor_sync(0xffffffffu, lower ? vj1 : vj, 16);
+              const float g = lower ? vj : got;
+              const float uu = lower ? got : vj1;
+              const __nv_bfloat16 a = __float2bfloat16(__fdividef(g, 1.f + __expf(-g)) * uu);
+              st_shared_u16(base + j * 128, *reinterpret_cast<const uint16_t*>(&a));
+            }
+          } else if (args.mode == RVL_GEMM_OUT_BF16) {
+            const uint32_t base = stg + lc * (32 * 256) + m_local * 2;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const __nv_bfloat16 a = __float2bfloat16(__uint_as_float(r[j]));
+              st_shared_u16(base + j * 256, *reinterpret_cast<const uint16_t*>(&a));
+            }
+          } else {
+            const uint32_t base = stg + lc * (32 * 512) + m_local * 4;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_shared_f32(base + j * 512, __uint_as_float(r[j]));
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int chunk_bytes = args.swiglu ? 32 * 128 : (args.mode == RVL_GEMM_OUT_BF16 ? 32 * 256 : 32 * 512);
+          for (int c = c0; c < c1; ++c) {
+            const int tok0 = c * 32;
+            if (tok0 < args.N) tma_store_3d(&tmap_out, stage_out + (c - c0) * chunk_bytes, args.swiglu ? (feat0 >> 1) : feat0, tok0, ks);
+          }
+          bulk_commit_group();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (threadIdx.x == 64) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -957,7 +1182,12 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   const int waves = (a.tiles_m + num_sms - 1) / num_sms;
   const bool ragged = a.tiles_m > num_sms && a.tiles_m < 0.7 * waves * num_sms;
   const bool force_sk = (env_sk && atoi(env_sk) == 2) || (c.flags & RVL_GEMM_FLAG_STREAMK);
-  if (swap && c.stream_ws && c.stream_flags && sk == 1 && a.tiles_n == 1 && !a.rowmap && !partials && a.a_tiles == 1 &&
+  // many tokens: the CTA-pair weight-streaming kernel takes the GEMM (tile mode / split-k partials), no stream-K
+  static const char* env_spair0 = getenv("RVL_SPAIR");
+  const bool spair_candidate = swap && a.N > 64 && a.M >= 256 && (num_sms % 2 == 0) && !c.bias && !c.rowmap && !a.relu &&
+                               c.out_mode != RVL_GEMM_ADD_F32 && !force_sk && !ragged && !(env_spair0 && atoi(env_spair0) == 0);
+  // (ragged tile counts - gate|up: 86 pair tiles on 74 clusters - stay on the single-CTA stream-K path: 42 vs 44.5 us)
+  if (!spair_candidate && swap && c.stream_ws && c.stream_flags && sk == 1 && a.tiles_n == 1 && !a.rowmap && !partials && a.a_tiles == 1 &&
       (ragged || force_sk)) {
     const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
     const int ctas = static_cast<int>(total < num_sms ? total : num_sms);
@@ -1034,6 +1264,39 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     cudaError_t e2 = launch_gemm_k(gemm_bf16_pair_kernel, dim3(grid2), dim3(kGemmThreads), smem2, st, ta2, tb2, a);
     if (e2 == cudaSuccess) e2 = cudaGetLastError();
     if (e2 != cudaSuccess) { *err = std::string("gemm pair launch: ") + cudaGetErrorString(e2); return RVL_ERR_CUDA; }
+    return RVL_OK;
+  }
+  // CTA-pair weight streaming (see gemm_stream_pair_kernel): many tokens, staged outputs, no stream-K
+  static const char* env_spair = getenv("RVL_SPAIR");
+  if (swap && a.staged && !a.stream_k && a.N > 64 && a.tiles_n == 1 && a.a_tiles == 1 && (num_sms % 2 == 0) && a.M >= 256 &&
+      !(env_spair && atoi(env_spair) == 0)) {
+    CUtensorMap pa_map, pb_map, po_map;
+    a.tiles_m = (a.M + 255) / 256;
+    const int half_bytes = ((a.bn / 2) * kBK * 2 + 1023) & ~1023;
+    a.stages = kSmemBudgetStaged / (kATileBytes + half_bytes);
+    if (a.stages > kMaxStages) a.stages = kMaxStages;
+    a.acc_stages = 2;
+    int rcp = make_tmap(&pa_map, pa, a.M, c.K, kBM, err);
+    if (rcp) return rcp;
+    rcp = make_tmap(&pb_map, pb, a.N, c.K, a.bn / 2, err);
+    if (rcp) return rcp;
+    rcp = make_tmap_out(&po_map, c.out, a.swiglu ? a.M / 2 : a.M, a.N, a.split_stride > 0 ? a.split_k : 1, c.ldc, a.split_stride,
+                        a.swiglu ? 64 : 128, out_f32, err);
+    if (rcp) return rcp;
+    static bool sp_attr = false;
+    if (!sp_attr) {
+      if (cudaFuncSetAttribute(gemm_stream_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        *err = "cudaFuncSetAttribute(stream pair kernel) failed"; return RVL_ERR_CUDA;
+      }
+      sp_attr = true;
+    }
+    const int smem_sp = a.stages * (kATileBytes + half_bytes) + 1024 + 512 + kStageOutBytes;
+    const int units = a.tiles_m * a.split_k;
+    const int grid_sp = 2 * (units < num_sms / 2 ? units : num_sms / 2);
+    if (env_dbg) fprintf(stderr, "rvl gemm stream-pair: rows=%d tokens=%d K=%d bn=%d stages=%d split_k=%d grid=%d\n", a.M, a.N, a.K, a.bn, a.stages, a.split_k, grid_sp);
+    cudaError_t esp = launch_gemm_k(gemm_stream_pair_kernel, dim3(grid_sp), dim3(kGemmThreads), smem_sp, st, pa_map, pb_map, po_map, a);
+    if (esp == cudaSuccess) esp = cudaGetLastError();
+    if (esp != cudaSuccess) { *err = std::string("gemm stream-pair launch: ") + cudaGetErrorString(esp); return RVL_ERR_CUDA; }
     return RVL_OK;
   }
   CUtensorMap ta, tb, tout;
