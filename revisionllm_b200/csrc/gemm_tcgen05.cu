@@ -101,7 +101,9 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 
 // idx-th work item of this CTA; false when there is none.  All three roles call it with the same arguments.
 template <bool kStreamK>
-__device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w) {
+__device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w, int vid = -1) {
+  // vid: the CTA's index among the CTAs that share the work (blockIdx.x, or the cluster index for the CTA-pair kernels)
+  if (vid < 0) vid = static_cast<int>(blockIdx.x);
   const int tiles_mn = a.tiles_m * a.tiles_n;
   if (!kStreamK) {
     const int tile = blockIdx.x + idx * gridDim.x;
@@ -117,7 +119,7 @@ __device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w
   }
   // stream-K: units are (tile, k-block) in tile-major order; this CTA owns [u0, u1)
   const long long total = static_cast<long long>(tiles_mn) * a.k_blocks;
-  const long long u0 = static_cast<long long>(blockIdx.x) * a.units_per_cta;
+  const long long u0 = static_cast<long long>(vid) * a.units_per_cta;
   const long long u1 = min(total, u0 + a.units_per_cta);
   if (u0 >= u1) return false;
   const int t_first = static_cast<int>(u0 / a.k_blocks);
@@ -135,7 +137,7 @@ __device__ __forceinline__ bool get_work(const GemmArgs& a, int idx, WorkItem& w
     w.kind = 2;  // later CTAs hold the rest: CTAs blockIdx.x+1 .. whose ranges start inside this tile
     const long long t_end = t_begin + a.k_blocks;
     int f = 0;
-    while ((static_cast<long long>(blockIdx.x) + f + 1) * a.units_per_cta < t_end) ++f;
+    while ((static_cast<long long>(vid) + f + 1) * a.units_per_cta < t_end) ++f;
     w.followers = f;
   } else {
     w.kind = 0;
@@ -898,6 +900,21 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int tiles = args.tiles_m;                               // 256-row weight tiles
   const int n_units = tiles * args.split_k;
   const int kb_per_split = (args.k_blocks + args.split_k - 1) / args.split_k;
+  // it-th work item of this cluster: stream-K (k-blocks of all tiles dealt evenly to the clusters, partial tiles fixed up
+  // through the workspace exactly as in gemm_bf16_tcgen05_kernel<1, true>, per CTA of the pair) or (tile, k-split) units
+  auto next_item = [&](int it, WorkItem& w) -> bool {
+    if (args.stream_k) return get_work<true>(args, it, w, cluster_id);
+    const int u = cluster_id + it * n_clusters;
+    if (u >= n_units) return false;
+    w.ks = u / tiles;
+    w.m_blk = u - w.ks * tiles;
+    w.n_blk = 0;
+    w.kb0 = w.ks * kb_per_split;
+    w.kb1 = min(args.k_blocks, w.kb0 + kb_per_split);
+    w.kind = 0;
+    w.followers = 0;
+    return true;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -907,14 +924,13 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     // weight tiles of the first k-blocks go out before the kernel that produces the activations is known to be finished
     int pre = 0;
     if (args.prefetch_a) {
-      for (int u = cluster_id; u < n_units && pre < kStages; u += n_clusters) {
-        const int ks = u / tiles, tile = u - ks * tiles;
-        const int kb0 = ks * kb_per_split, kb1 = min(args.k_blocks, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1 && pre < kStages; ++kb, ++pre) {
+      WorkItem w;
+      for (int it = 0; pre < kStages && next_item(it, w); ++it) {
+        for (int kb = w.kb0; kb < w.kb1 && pre < kStages; ++kb, ++pre) {
           if (elect_one()) {
             const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[pre]), 0);
             if (leader) mbar_arrive_expect_tx(&full_bar[pre], 2 * stage_bytes);
-            tma_load_2d_pair_hint(smem_a + pre * kATileBytes, &tmap_a, full_leader, kb * kBK, (tile * 2 + static_cast<int>(rank)) * kBM, pol_a);
+            tma_load_2d_pair_hint(smem_a + pre * kATileBytes, &tmap_a, full_leader, kb * kBK, (w.m_blk * 2 + static_cast<int>(rank)) * kBM, pol_a);
           }
           __syncwarp();
         }
@@ -922,11 +938,10 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
     pdl_wait();
     int n_iter = 0;
-    for (int u = cluster_id; u < n_units; u += n_clusters) {
-      const int ks = u / tiles, tile = u - ks * tiles;
-      const int kb0 = ks * kb_per_split, kb1 = min(args.k_blocks, kb0 + kb_per_split);
-      const int m0 = (tile * 2 + static_cast<int>(rank)) * kBM;
-      for (int kb = kb0; kb < kb1; ++kb, ++n_iter) {
+    WorkItem w;
+    for (int it = 0; next_item(it, w); ++it) {
+      const int m0 = (w.m_blk * 2 + static_cast<int>(rank)) * kBM;
+      for (int kb = w.kb0; kb < w.kb1; ++kb, ++n_iter) {
         const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
         if (n_iter < pre) {
           if (elect_one()) tma_load_2d_pair_hint(smem_b + stage * b_slot_bytes, &tmap_b, full_leader, kb * kBK, static_cast<int>(rank) * half_rows, pol_b);
@@ -953,9 +968,9 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = cluster_id; u < n_units; u += n_clusters) {
-        const int ks = u / tiles;
-        const int kb0 = ks * kb_per_split, kb1 = min(args.k_blocks, kb0 + kb_per_split);
+      WorkItem w;
+      for (int it = 0; next_item(it, w); ++it) {
+        const int kb0 = w.kb0, kb1 = w.kb1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
@@ -987,12 +1002,46 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const int cpg = args.staged;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = cluster_id; u < n_units; u += n_clusters) {
-      const int ks = u / tiles, tile = u - ks * tiles;
+    WorkItem w;
+    for (int it = 0; next_item(it, w); ++it) {
+      const int ks = w.ks, tile = w.m_blk;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
       const int feat0 = (tile * 2 + static_cast<int>(rank)) * kBM;
+      if (w.kind == 1) {
+        // tail piece of a stream-K tile: publish this CTA's fp32 partial (register order) and raise its flag
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == n_chunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          }
+          float4* dst = reinterpret_cast<float4*>(args.ws) + (static_cast<long long>(blockIdx.x) * 8 + c) * (8 * 128) + m_local;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q * 128] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                       __uint_as_float(r[q * 4 + 3]));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) st_release(args.flags + blockIdx.x, args.epoch);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      if (w.kind == 2) {
+        // head piece: the same-rank CTAs of the following clusters hold the rest of the k-range
+        for (int f = 1; f <= w.followers; ++f) {
+          const unsigned int* fl = args.flags + blockIdx.x + 2 * f;
+          unsigned int spins = 0;
+          while (ld_acquire(fl) != args.epoch) {
+            if (++spins > (1u << 26)) mbar_timeout(nullptr, 0xdead);
+          }
+        }
+      }
       for (int c0 = 0; c0 < n_chunks; c0 += cpg) {
         if (threadIdx.x == 64) bulk_wait_read_all();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1005,6 +1054,20 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          }
+          for (int f = 1; f <= w.followers; ++f) {               // stream-K head: add the followers' partials in a fixed order
+            const float4* src = reinterpret_cast<const float4*>(args.ws) +
+                                (static_cast<long long>(blockIdx.x + 2 * f) * 8 + c) * (8 * 128) + m_local;
+            float4 pp[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pp[q] = __ldcg(src + q * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              r[q * 4] = __float_as_uint(__uint_as_float(r[q * 4]) + pp[q].x);
+              r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + pp[q].y);
+              r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + pp[q].z);
+              r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + pp[q].w);
+            }
           }
           const int lc = c - c0;
           if (args.swiglu) {
@@ -1183,10 +1246,9 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   const bool ragged = a.tiles_m > num_sms && a.tiles_m < 0.7 * waves * num_sms;
   const bool force_sk = (env_sk && atoi(env_sk) == 2) || (c.flags & RVL_GEMM_FLAG_STREAMK);
   // many tokens: the CTA-pair weight-streaming kernel takes the GEMM (tile mode / split-k partials), no stream-K
-  static const char* env_spair0 = getenv("RVL_SPAIR");
+  const char* env_spair0 = getenv("RVL_SPAIR");              // read per call: in-process A/B
   const bool spair_candidate = swap && a.N > 64 && a.M >= 256 && (num_sms % 2 == 0) && !c.bias && !c.rowmap && !a.relu &&
-                               c.out_mode != RVL_GEMM_ADD_F32 && !force_sk && !ragged && !(env_spair0 && atoi(env_spair0) == 0);
-  // (ragged tile counts - gate|up: 86 pair tiles on 74 clusters - stay on the single-CTA stream-K path: 42 vs 44.5 us)
+                               c.out_mode != RVL_GEMM_ADD_F32 && !force_sk && !(env_spair0 && atoi(env_spair0) == 0);
   if (!spair_candidate && swap && c.stream_ws && c.stream_flags && sk == 1 && a.tiles_n == 1 && !a.rowmap && !partials && a.a_tiles == 1 &&
       (ragged || force_sk)) {
     const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
@@ -1267,11 +1329,32 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     return RVL_OK;
   }
   // CTA-pair weight streaming (see gemm_stream_pair_kernel): many tokens, staged outputs, no stream-K
-  static const char* env_spair = getenv("RVL_SPAIR");
-  if (swap && a.staged && !a.stream_k && a.N > 64 && a.tiles_n == 1 && a.a_tiles == 1 && (num_sms % 2 == 0) && a.M >= 256 &&
+  const char* env_spair = getenv("RVL_SPAIR");
+  if (swap && a.staged && spair_candidate && a.tiles_n == 1 && a.a_tiles == 1 && (num_sms % 2 == 0) && a.M >= 256 &&
       !(env_spair && atoi(env_spair) == 0)) {
     CUtensorMap pa_map, pb_map, po_map;
     a.tiles_m = (a.M + 255) / 256;
+    // a ragged last wave of 256-row tiles (gate|up: 86 tiles on 74 clusters): deal the k-blocks out evenly (stream-K).
+    // Measured at 180 tokens: gate|up 39.7 us against 44.6 us in tile mode (42.1 us on the single-CTA stream-K kernel); for
+    // less than one wave (qkv: 48 tiles, 26.0 vs 30.2 us) or nearly full waves (lm_head: 125 tiles, 49.9 vs 51.6 us) tile mode wins.
+    const char* env_spsk = getenv("RVL_SPAIR_STREAMK");
+    const int clusters = num_sms / 2;
+    const int pair_waves = (a.tiles_m + clusters - 1) / clusters;
+    const bool pair_ragged = a.tiles_m > clusters && a.tiles_m < 0.7 * pair_waves * clusters;
+    a.stream_k = 0;
+    if (c.stream_ws && c.stream_flags && sk == 1 && !partials && !(env_spsk && atoi(env_spsk) == 0) &&
+        static_cast<size_t>(num_sms) * 8 * 8 * 128 * 16 <= c.stream_ws_bytes && (pair_ragged || (env_spsk && atoi(env_spsk) == 2))) {
+      const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
+      const int cl = num_sms / 2;
+      int upc = static_cast<int>((total + cl - 1) / cl);
+      if (upc < 8 && total >= 8) upc = 8;
+      a.stream_k = 1;
+      a.units_per_cta = upc;
+      a.ws = c.stream_ws;
+      a.flags = c.stream_flags;
+      a.epoch = c.stream_epoch;
+      a.ws_ld = a.sub_stride;
+    }
     const int half_bytes = ((a.bn / 2) * kBK * 2 + 1023) & ~1023;
     a.stages = kSmemBudgetStaged / (kATileBytes + half_bytes);
     if (a.stages > kMaxStages) a.stages = kMaxStages;
@@ -1291,7 +1374,8 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
       sp_attr = true;
     }
     const int smem_sp = a.stages * (kATileBytes + half_bytes) + 1024 + 512 + kStageOutBytes;
-    const int units = a.tiles_m * a.split_k;
+    const int units = a.stream_k ? static_cast<int>((static_cast<long long>(a.tiles_m) * a.k_blocks + a.units_per_cta - 1) / a.units_per_cta)
+                                 : a.tiles_m * a.split_k;
     const int grid_sp = 2 * (units < num_sms / 2 ? units : num_sms / 2);
     if (env_dbg) fprintf(stderr, "rvl gemm stream-pair: rows=%d tokens=%d K=%d bn=%d stages=%d split_k=%d grid=%d\n", a.M, a.N, a.K, a.bn, a.stages, a.split_k, grid_sp);
     cudaError_t esp = launch_gemm_k(gemm_stream_pair_kernel, dim3(grid_sp), dim3(kGemmThreads), smem_sp, st, pa_map, pb_map, po_map, a);

@@ -19,10 +19,17 @@ ids = syn.make_prompt_ids(cfg, seed=2)
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6531.9
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("RVL_"))
+AB = os.environ.get("AB_ENV")      # e.g. AB_ENV=RVL_SPAIR: odd repetitions run with it set to 0 (the library reads it per call)
 for B in [int(b) for b in args.batches.split(",")]:
     feats = syn.make_features(B, 100, 768, seed=1).cuda()
     best = None
-    for rep in range(args.reps):
+    ab = {0: [], 1: []}
+    for rep in range(args.reps if not AB else 2 * args.reps + 1):
+        if AB:
+            if rep % 2:
+                os.environ[AB] = "0"
+            else:
+                os.environ.pop(AB, None)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         out = model(ids[None].expand(B, -1), images=feats, logits_to_keep=1, reserve_new_tokens=64)
         kv = out.past_key_values
@@ -38,6 +45,12 @@ for B in [int(b) for b in args.batches.split(",")]:
         torch.cuda.synchronize()
         ms = e[0].elapsed_time(e[1]) / args.steps
         best = ms if best is None else min(best, ms)
+        if AB and rep > 0:
+            ab[rep % 2].append(ms)
+    if AB:
+        print(f"B={B}: default {sum(ab[0]) / len(ab[0]):.3f} ms (min {min(ab[0]):.3f}) | {AB}=0 {sum(ab[1]) / len(ab[1]):.3f} ms (min {min(ab[1]):.3f})", flush=True)
+        os.environ.pop(AB, None)
+        continue
     L = ids.shape[0] - 1 + 100
     bytes_step = 13.214e9 + B * 0.524288e6 * (L + args.steps / 2 + 1)
     print(f"[{tag}] B={B:4d}: {best:7.3f} ms/decode step   {bytes_step / best / 1e6:7.0f} GB/s = {bytes_step / best / 1e6 / peak:.3f} of HBM peak", flush=True)
