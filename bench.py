@@ -375,7 +375,31 @@ def main():
             dt2 = time.perf_counter() - t0
             line["stage2_top100"] = {"ms_per_query": 1e3 * dt2, "generate_calls": len(r2), "windows": 100, "frames_per_window": 250,
                                      "zooms": [4, 2, 1], "selected_first5": top[:5].tolist(),
-                                     "note": "ClipEncoder (4 layers, d=768) + splice of 100 CLS tokens + Vicuna-7B prefill/decode, 16 tokens per call"}
+                                     "note": "ClipEncoder (4 layers, d=768; each distinct window once) + splice of 100 CLS tokens + Vicuna-7B prefill/decode, 16 tokens per call"}
+            # the same pass batched across 8 queries of one rank (sweep.stage2_pass_queries): the chunks of all queries share
+            # the decode steps, so the 13 GB of weights stream once per step for 56 prompts instead of 7
+            NQ = 8
+            qs = [dict(windows=syn.make_features(100, 250, cfg.adapter_dim, seed=40 + k).to(dev),
+                       query_feats=(torch.randn(1, 32, cfg.adapter_dim, generator=gq).to(torch.bfloat16), q_mask),
+                       input_ids=syn.make_prompt_ids(cfg, seed=50 + k), grounding_windows=top.tolist(), perm_seed=k) for k in range(NQ)]
+
+            def stage2_multi():
+                return sweep.stage2_pass_queries(model, qs, batch=100, zooms=(4, 2, 1), max_new_tokens=NEW_TOKENS, eos_token_id=None)
+            stage2_multi()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rq = stage2_multi()
+            torch.cuda.synchronize()
+            dtq = time.perf_counter() - t0
+            line["stage2_top100"]["batched_across_queries"] = {"queries": NQ, "ms_per_query": 1e3 * dtq / NQ,
+                                                               "generate_calls_batched": sum(len(r) for r in rq)}
+            for it in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                sweep.stage2_pass(model, wins, (q_tok, q_mask), ids2, grounding_windows=top.tolist(), batch=100, zooms=(4, 2, 1),
+                                  max_new_tokens=NEW_TOKENS, perm_seed=0, eos_token_id=None, dedup=False)
+                torch.cuda.synchronize()
+                line["stage2_top100"]["ms_per_query_stacked_repeats"] = 1e3 * (time.perf_counter() - t0)
         except Exception as e:      # stage 2 is reported, never allowed to take the headline number down
             line["stage2_top100"] = {"error": repr(e)[:200]}
     # ---- BASELINE.json configs[4] (optional, reported beside the headline): VidChapters-shaped ragged batch - videos of

@@ -28,6 +28,18 @@ from .engine import Engine, EngineConfig, plan_splice
 
 
 @dataclass
+class WindowBank:
+    """Stage-2 hierarchy input without the repetition: the reference stacks every window once per zoom repeat and per chunk
+    into `images [b, v, t, 768]` (eval_nlq_retrieval_e2e2.py:348-352) and runs the ClipEncoder adapter over all copies.  The
+    CLS row of a window depends only on (window, query), so here `windows [U, t, 768]` holds each distinct pair once,
+    `text_index [U]` names the row of `query_feats` it attends to, and `rows [b, v]` says which of the U CLS rows fills each
+    visual position of each prompt.  Pass it as `images=` to generate() / forward()."""
+    windows: torch.Tensor
+    rows: torch.Tensor
+    text_index: torch.Tensor
+
+
+@dataclass
 class RevisionConfig:
     """Subset of the HF/VTimeLLM config the reference touches (vtimellm_arch.py:106,172,241,257,291)."""
     hidden_size: int = 4096
@@ -172,6 +184,14 @@ class RevisionLlamaForCausalLM:
             n_vis = [int(im.shape[0]) for im in images]
             rows = torch.cat([im.reshape(-1, im.shape[-1]) for im in images], dim=0)
             return rows.to(dev, torch.bfloat16).contiguous(), n_vis, False
+        if isinstance(images, WindowBank):               # hierarchy input with every distinct (window, query) pair stored once
+            if self.clip_encoder is None:
+                raise RvlError("a WindowBank needs the stage-2 ClipEncoder adapter (pass clip_encoder_state)")
+            q_tok, q_mask = query_feats
+            b, v = images.rows.shape
+            cls_u = self.clip_encoder(images.windows.to(dev, torch.bfloat16).contiguous(), q_tok.to(dev, torch.bfloat16), q_mask.to(dev),
+                                      images.text_index.to(dev, torch.int32).contiguous())              # [U, hidden] bf16
+            return cls_u.index_select(0, images.rows.reshape(-1).to(dev, torch.int64)).contiguous(), [v] * b, True
         if images.dim() == 4:                            # hierarchy: [b, v, t, d] -> one CLS row per segment (:114-121)
             if self.clip_encoder is None:
                 raise RvlError("4-D `images` need the stage-2 ClipEncoder adapter (pass clip_encoder_state)")

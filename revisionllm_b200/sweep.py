@@ -11,12 +11,13 @@ data-path collective: weights are replicated, segments are independent.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import scoring
+from .model import WindowBank
 
 REC_TOKENS = 16
 # int32 words: 16 tokens | n_tokens | span_start | span_end | H_mean | H_max | cos   (floats stored as raw bits)
@@ -197,25 +198,9 @@ def ragged_sweep(model, windows: Sequence[torch.Tensor], input_ids: torch.Tensor
     return allgather_indexed(local, shards, rank, world, group)
 
 
-def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tensor, grounding_windows: Sequence[int],
-                batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16, perm_seed: Optional[int] = 0,
-                answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config",
-                max_calls_per_batch: int = 16) -> List[Dict]:
-    """Stage-2 hierarchical pass (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:337-386).
-
-    `windows` [N, T, 768]: the selected stage-2 windows (already restricted to `grounding_windows`).  For each
-    zoom in (4, 2, 1): chunks of batch // zoom windows, permuted, each repeated `zoom` times, go through ONE
-    generate() call as a [1, batch, T, 768] hierarchy input (one ClipEncoder CLS token per window); the first
-    integer of the answer // zoom indexes the permuted chunk and is mapped back to a window id.
-    The reference permutes with an unseeded torch.randperm (:348); here the permutation comes from
-    `perm_seed` (None = identity) so runs are reproducible (SURVEY.md H6).
-    All chunks of all zoom levels are independent prompts, so they run as one batched generate() (up to
-    `max_calls_per_batch` rows; 1 restores the reference's one-call-per-chunk schedule).
-    Returns one dict per chunk (the reference's generate() calls, in its order): tokens, entropy stats (1/max, 1/mean as in
-    :356-359), picked window."""
-    N = windows.shape[0]
-    gen = torch.Generator().manual_seed(perm_seed) if perm_seed is not None else None
-    # ---- plan every call first (same order of randperm draws as the sequential loop of the reference)
+def _stage2_plan(N: int, batch: int, zooms: Sequence[int], gen: Optional[torch.Generator]) -> List[Dict]:
+    """The generate() calls of one query's hierarchical pass, in the reference's order (e2e2:337-386): for each zoom,
+    chunks of batch // zoom windows (the last chunk is shifted back to full size), permuted, each window repeated `zoom` times."""
     calls: List[Dict] = []
     for zoom in zooms:
         b = max(1, batch // zoom)
@@ -229,23 +214,10 @@ def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tens
             idx = torch.randperm(n, generator=gen) if gen is not None else torch.arange(n)
             rows = (start + idx).repeat_interleave(zoom) if zoom > 1 else (start + idx)
             calls.append(dict(zoom=zoom, start=start, n=n, idx=idx, rows=rows))
-    # ---- the calls are independent prompts: those with the same number of visual rows go through ONE generate() as a
-    # batch (the reference runs them one by one with B = 1, where every decode step re-streams the 13 GB of weights)
-    results: List[Optional[Dict]] = [None] * len(calls)
-    groups: Dict[int, List[int]] = {}
-    for ci, c in enumerate(calls):
-        groups.setdefault(int(c["rows"].shape[0]), []).append(ci)
-    q_tok, q_mask = query_feats if query_feats is not None else (None, None)
-    for v_rows, members in groups.items():
-        for g0 in range(0, len(members), max_calls_per_batch):
-            part = members[g0: g0 + max_calls_per_batch]
-            feat = torch.stack([windows[calls[ci]["rows"].to(windows.device)] for ci in part])          # [calls, V, T, 768]
-            qf = None if q_tok is None else (q_tok.expand(len(part), -1, -1).contiguous(), q_mask.expand(len(part), -1).contiguous())
-            res = model.generate(input_ids[None].expand(len(part), -1), images=feat, query_feats=qf, max_new_tokens=max_new_tokens,
-                                 output_scores=False, return_dict_in_generate=True, eos_token_id=eos_token_id)
-            stats_all = scoring.entropy_stats_from_steps(res["entropies"])
-            for r, ci in enumerate(part):
-                results[ci] = dict(tokens=res["sequences"][r, input_ids.shape[0]:], stats=stats_all[r])
+    return calls
+
+
+def _stage2_finish(calls: List[Dict], results: List[Dict], grounding_windows: Sequence[int], answer_number) -> List[Dict]:
     out: List[Dict] = []
     for c, r in zip(calls, results):
         new_tok, stats = r["tokens"], r["stats"]
@@ -260,4 +232,106 @@ def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tens
             picked = int(grounding_windows[j])
         out.append(dict(zoom=zoom, start=start, perm=idx.tolist(), tokens=new_tok.tolist(), inv_max_entropy=1.0 / float(stats[0]),
                         inv_mean_entropy=1.0 / float(stats[2]), window=picked))
+    return out
+
+
+def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tensor, grounding_windows: Sequence[int],
+                batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16, perm_seed: Optional[int] = 0,
+                answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config",
+                max_calls_per_batch: int = 16, dedup: bool = True) -> List[Dict]:
+    """Stage-2 hierarchical pass (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:337-386).
+
+    `windows` [N, T, 768]: the selected stage-2 windows (already restricted to `grounding_windows`).  For each
+    zoom in (4, 2, 1): chunks of batch // zoom windows, permuted, each repeated `zoom` times, go through ONE
+    generate() call as a [1, batch, T, 768] hierarchy input (one ClipEncoder CLS token per window); the first
+    integer of the answer // zoom indexes the permuted chunk and is mapped back to a window id.
+    The reference permutes with an unseeded torch.randperm (:348); here the permutation comes from
+    `perm_seed` (None = identity) so runs are reproducible (SURVEY.md H6).
+    All chunks of all zoom levels are independent prompts, so they run as one batched generate() (up to
+    `max_calls_per_batch` rows; 1 restores the reference's one-call-per-chunk schedule), and the adapter sees every window
+    once (`dedup`, see stage2_pass_queries; False stacks the zoom repeats like the reference).
+    Returns one dict per chunk (the reference's generate() calls, in its order): tokens, entropy stats (1/max, 1/mean as in
+    :356-359), picked window."""
+    q = dict(windows=windows, query_feats=query_feats, input_ids=input_ids, grounding_windows=grounding_windows, perm_seed=perm_seed)
+    return stage2_pass_queries(model, [q], batch, zooms, max_new_tokens, answer_number, eos_token_id, max_calls_per_batch, dedup=dedup)[0]
+
+
+def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16,
+                        answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config",
+                        max_calls_per_batch: int = 64, rank: int = 0, world: int = 1, dedup: bool = True) -> List[Optional[List[Dict]]]:
+    """Stage 2 for SEVERAL queries at once (north star: "one GPU per query, batched across queries").
+
+    Each entry of `queries` holds what `stage2_pass` takes for one query: `windows` [N, T, 768], `query_feats`
+    ((tokens [1, Lq, 768], mask [1, Lq]) or None), `input_ids` [L], `grounding_windows`, optional `perm_seed`.
+    Query i belongs to rank i mod world (no exchange step: a query's result stays on its rank; the other entries of the
+    returned list are None).  Every chunk of every zoom level of every local query is an independent prompt, so they are
+    batched across queries into generate() calls of up to `max_calls_per_batch` rows: the 13 GB of weights are streamed once
+    per decode step for all of them instead of once per chunk.  Prompts of different lengths are right-padded and masked;
+    query features of different lengths are padded with masked rows.  Per query the result equals `stage2_pass`'s.
+    `dedup` (default): the ClipEncoder adapter sees every distinct (query, window) pair once instead of once per zoom repeat
+    and per chunk (7 x fewer adapter rows for zooms (4, 2, 1)); False feeds the stacked copies like the reference."""
+    mine = [qi for qi in range(len(queries)) if qi % world == rank]
+    jobs: List[Tuple[int, int]] = []                       # (query, call)
+    plans: Dict[int, List[Dict]] = {}
+    for qi in mine:
+        q = queries[qi]
+        seed = q.get("perm_seed", 0)
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        plans[qi] = _stage2_plan(int(q["windows"].shape[0]), batch, zooms, gen)
+        jobs += [(qi, ci) for ci in range(len(plans[qi]))]
+    results: Dict[Tuple[int, int], Dict] = {}
+    groups: Dict[Tuple[int, int, bool], List[Tuple[int, int]]] = {}
+    for (qi, ci) in jobs:                                   # one generate() needs equal visual rows / frames per row
+        w = queries[qi]["windows"]
+        key = (int(plans[qi][ci]["rows"].shape[0]), int(w.shape[1]), queries[qi].get("query_feats") is not None)
+        groups.setdefault(key, []).append((qi, ci))
+    for (v_rows, _, has_q), members in groups.items():
+        for g0 in range(0, len(members), max_calls_per_batch):
+            part = members[g0: g0 + max_calls_per_batch]
+            L = max(int(queries[qi]["input_ids"].shape[0]) for (qi, _) in part)
+            ids = torch.zeros((len(part), L), dtype=torch.int64)
+            am = torch.zeros((len(part), L), dtype=torch.bool)
+            for r, (qi, _) in enumerate(part):
+                row = queries[qi]["input_ids"].cpu()
+                ids[r, : row.shape[0]] = row
+                am[r, : row.shape[0]] = True
+            part_q = sorted({qi for (qi, _) in part})
+            qf = None
+            if has_q:
+                Lq = max(int(queries[qi]["query_feats"][0].shape[1]) for qi in part_q)
+                t0, m0 = queries[part_q[0]]["query_feats"]
+                qt = torch.zeros((len(part_q), Lq, t0.shape[-1]), dtype=t0.dtype, device=t0.device)
+                qm = torch.zeros((len(part_q), Lq), dtype=m0.dtype, device=m0.device)
+                for r, qi in enumerate(part_q):
+                    t, m = queries[qi]["query_feats"]
+                    qt[r, : t.shape[1]] = t[0]
+                    qm[r, : m.shape[1]] = m[0]
+                qf = (qt, qm)
+            if has_q and dedup:
+                # every distinct (query, window) of this batch goes through the adapter once; zoom repeats and the chunks of
+                # the three zoom levels that show the same window reuse its CLS row (model.WindowBank)
+                base, banks, text_index = {}, [], []
+                for r, qi in enumerate(part_q):
+                    used = torch.unique(torch.cat([plans[qi][ci]["rows"] for (qj, ci) in part if qj == qi]))
+                    lut = torch.full((int(queries[qi]["windows"].shape[0]),), -1, dtype=torch.int64)
+                    lut[used] = torch.arange(used.shape[0]) + sum(int(b.shape[0]) for b in banks)
+                    base[qi] = lut
+                    banks.append(queries[qi]["windows"][used.to(queries[qi]["windows"].device)])
+                    text_index += [r] * int(used.shape[0])
+                feat = WindowBank(torch.cat(banks), torch.stack([base[qi][plans[qi][ci]["rows"]] for (qi, ci) in part]),
+                                  torch.tensor(text_index, dtype=torch.int32))
+            else:
+                feat = torch.stack([queries[qi]["windows"][plans[qi][ci]["rows"].to(queries[qi]["windows"].device)] for (qi, ci) in part])
+                if has_q:                                   # one text row per prompt, as generate() expects for 4-D images
+                    pos = {qi: r for r, qi in enumerate(part_q)}
+                    sel = torch.tensor([pos[qi] for (qi, _) in part])
+                    qf = (qf[0][sel.to(qf[0].device)], qf[1][sel.to(qf[1].device)])
+            res = model.generate(ids, images=feat, query_feats=qf, attention_mask=None if bool(am.all()) else am,
+                                 max_new_tokens=max_new_tokens, output_scores=False, return_dict_in_generate=True, eos_token_id=eos_token_id)
+            stats_all = scoring.entropy_stats_from_steps(res["entropies"])
+            for r, job in enumerate(part):
+                results[job] = dict(tokens=res["sequences"][r, L:], stats=stats_all[r])
+    out: List[Optional[List[Dict]]] = [None] * len(queries)
+    for qi in mine:
+        out[qi] = _stage2_finish(plans[qi], [results[(qi, ci)] for ci in range(len(plans[qi]))], queries[qi]["grounding_windows"], answer_number)
     return out
