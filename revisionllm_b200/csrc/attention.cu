@@ -86,9 +86,11 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
   const int q0 = qt * kQT;
   if (q0 >= L || q0 + kQT <= p0) return;      // past the end, or a query tile that lies entirely inside the context
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;          // [2][64][128]
-  uint8_t* sV = smem + 16384 * 3;      // [2][64][128]
+  // 64 KB: K [2][64][128] | V [2][64][128]; the Q tile borrows K's second buffer until its fragments sit in registers
+  // (three CTAs per SM instead of two - the kernel is bound by the latency of each CTA's first loads, not by bandwidth)
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + 16384 * 2;
+  uint8_t* sQ = smem + 16384;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = n_heads * kD;
   const long long stride = 3LL * H;
@@ -110,21 +112,30 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
 
   for (int j = 0; j < n_tiles; ++j) {
     const int buf = j & 1;
-    if (j + 1 < n_tiles) {
-      const int k0n = (j + 1) * kKT;
-      load_tile(sK + (buf ^ 1) * 16384, ctx + H, own + H, p0, stride, k0n, L, tid);
-      load_tile(sV + (buf ^ 1) * 16384, ctx + 2 * H, own + 2 * H, p0, stride, k0n, L, tid);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
     if (j == 0) {
+      cp_async_wait<0>();
+      __syncthreads();
       // Q fragments (A operand, 16 rows of this warp x 16 dims per k-step)
       const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ) + tile_off(r, ks * 2 + (lane >> 4)));
+      if (n_tiles > 1) {
+        __syncthreads();                 // every warp holds its Q fragments: K's second buffer may be overwritten
+        load_tile(sK + 16384, ctx + H, own + H, p0, stride, kKT, L, tid);
+        load_tile(sV + 16384, ctx + 2 * H, own + 2 * H, p0, stride, kKT, L, tid);
+        cp_async_commit();
+      }
+    } else {
+      if (j + 1 < n_tiles) {
+        const int k0n = (j + 1) * kKT;
+        load_tile(sK + (buf ^ 1) * 16384, ctx + H, own + H, p0, stride, k0n, L, tid);
+        load_tile(sV + (buf ^ 1) * 16384, ctx + 2 * H, own + 2 * H, p0, stride, k0n, L, tid);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
     }
     const uint32_t kaddr = smem_u32(sK + buf * 16384);
     const uint32_t vaddr = smem_u32(sV + buf * 16384);
@@ -229,7 +240,7 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
                          cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row) {
   if (n_seq <= 0 || max_seqlen <= 0) return;
   static bool attr = false;
-  constexpr int smem = 16384 * 5;
+  constexpr int smem = 16384 * 4;
   if (!attr) {
     cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
@@ -269,9 +280,9 @@ __global__ void __launch_bounds__(128) mha96_mma_kernel(const __nv_bfloat16* __r
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int q0 = qt * kQT;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;          // [2][64][128 (96 used)]
-  uint8_t* sV = smem + 16384 * 3;
+  uint8_t* sK = smem;                  // [2][64][128 (96 used)]
+  uint8_t* sV = smem + 16384 * 2;
+  uint8_t* sQ = smem + 16384;          // borrows K's second buffer until the Q fragments are in registers (3 CTAs per SM)
   __shared__ float s_mask[2][kKT];     // additive key mask of the two tiles in flight (0 / -inf)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kv_seq = kv_seq_idx ? kv_seq_idx[seq] : seq;
@@ -295,21 +306,31 @@ __global__ void __launch_bounds__(128) mha96_mma_kernel(const __nv_bfloat16* __r
 
   for (int j = 0; j < n_tiles; ++j) {
     const int buf = j & 1;
-    if (j + 1 < n_tiles) {
-      const int k0n = (j + 1) * kKT;
-      load_tile96(sK + (buf ^ 1) * 16384, kbase + k0n * k_stride, k_stride, min(kKT, Tk - k0n), tid);
-      load_tile96(sV + (buf ^ 1) * 16384, vbase + k0n * v_stride, v_stride, min(kKT, Tk - k0n), tid);
-      cp_async_commit();
-      if (tid < kKT) s_mask[buf ^ 1][tid] = (k0n + tid < Tk && (!mbase || mbase[k0n + tid] != 0.f)) ? 0.f : -INFINITY;
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
     if (j == 0) {
+      cp_async_wait<0>();
+      __syncthreads();
       const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
       for (int ks = 0; ks < 6; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ) + tile_off(r, ks * 2 + (lane >> 4)));
+      if (n_tiles > 1) {
+        __syncthreads();
+        load_tile96(sK + 16384, kbase + kKT * k_stride, k_stride, min(kKT, Tk - kKT), tid);
+        load_tile96(sV + 16384, vbase + kKT * v_stride, v_stride, min(kKT, Tk - kKT), tid);
+        cp_async_commit();
+        if (tid < kKT) s_mask[1][tid] = (kKT + tid < Tk && (!mbase || mbase[kKT + tid] != 0.f)) ? 0.f : -INFINITY;
+      }
+    } else {
+      if (j + 1 < n_tiles) {
+        const int k0n = (j + 1) * kKT;
+        load_tile96(sK + (buf ^ 1) * 16384, kbase + k0n * k_stride, k_stride, min(kKT, Tk - k0n), tid);
+        load_tile96(sV + (buf ^ 1) * 16384, vbase + k0n * v_stride, v_stride, min(kKT, Tk - k0n), tid);
+        cp_async_commit();
+        if (tid < kKT) s_mask[buf ^ 1][tid] = (k0n + tid < Tk && (!mbase || mbase[k0n + tid] != 0.f)) ? 0.f : -INFINITY;
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
     }
     const uint32_t kaddr = smem_u32(sK + buf * 16384);
     const uint32_t vaddr = smem_u32(sV + buf * 16384);
@@ -405,7 +426,7 @@ int launch_mha96(const void* q, long long q_stride, const void* k, long long k_s
                  long long out_stride, int n_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx, const float* key_mask,
                  cudaStream_t st) {
   static bool attr = false;
-  constexpr int smem = 16384 * 5;
+  constexpr int smem = 16384 * 4;
   if (!attr) {
     if (cudaFuncSetAttribute(mha96_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return RVL_ERR_CUDA;
     attr = true;
