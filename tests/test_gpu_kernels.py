@@ -131,6 +131,46 @@ def test_gemm_stream_k_exact_and_modes(eng_ws, M, N, K):
     assert _relerr(outb.float().cpu(), ref) < 1e-2
 
 
+PAIR_STREAM_SHAPES = [
+    # tokens, features, K : > 64 tokens in the weight-streaming orientation -> gemm_stream_pair_kernel (cta_group::2)
+    (180, 4096, 4096),     # 16 pair tiles, split-k units
+    (180, 12288, 4096),    # qkv: 48 pair tiles
+    (180, 22016, 4096),    # gate|up size: 86 pair tiles on 74 clusters -> stream-K units inside the pair kernel
+    (128, 32000, 4096),    # lm_head: 125 pair tiles
+    (100, 1280, 512),      # features not a multiple of 256 (the odd CTA of the last cluster owns no rows)
+    (65, 256, 64),         # smallest case the policy sends here: one pair tile, one k-block
+    (250, 4352, 1024),     # 17 pair tiles, ragged token chunk (250 = 7 x 32 + 26)
+]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_STREAM_SHAPES)
+def test_gemm_pair_weight_streaming_exact(eng_ws, M, N, K, monkeypatch):
+    """CTA-pair weight-streaming GEMM: integer inputs, so fp32 accumulation is exact whatever the split of the k-blocks -
+    tile / split-k units, stream-K units forced on and off, against the single-CTA kernel and the fp32 reference."""
+    from revisionllm_b200 import _cabi
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randint(-3, 4, (M, K), generator=g).to(torch.bfloat16)
+    W = torch.randint(-3, 4, (N, K), generator=g).to(torch.bfloat16)
+    ref = F.linear(A.float(), W.float())
+    Ad, Wd = A.cuda(), W.cuda()
+    FL = _cabi.GEMM_FLAG_SWAP | _cabi.GEMM_FLAG_W_CONST
+    for sk_env in (None, "0", "2"):                        # policy default, stream-K units never, always
+        if sk_env is None:
+            monkeypatch.delenv("RVL_SPAIR_STREAMK", raising=False)
+        else:
+            monkeypatch.setenv("RVL_SPAIR_STREAMK", sk_env)
+        for rep in range(2):                               # stream-K flags are re-used with a new epoch
+            out = torch.full((M, N), float("nan"), device="cuda")
+            eng_ws.gemm(Ad, Wd, out=out, out_mode=_cabi.GEMM_OUT_F32, flags=FL)
+            assert torch.equal(out.cpu(), ref), f"pair stream fp32 {M}x{N}x{K} env={sk_env} rep={rep}: {(out.cpu() - ref).abs().max()}"
+        outb = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        eng_ws.gemm(Ad, Wd, out=outb, flags=FL)
+        assert torch.equal(outb.cpu(), ref.to(torch.bfloat16)), f"pair stream bf16 {M}x{N}x{K} env={sk_env}"
+    monkeypatch.setenv("RVL_SPAIR", "0")                   # the single-CTA kernel gives the same bits
+    out1 = eng_ws.gemm(Ad, Wd, out_mode=_cabi.GEMM_OUT_F32, flags=FL)
+    assert torch.equal(out1.cpu(), ref)
+
+
 def _interleave_gate_up(gate, up):
     """rvl_weights.wgu_layout 1: blocks of 32 rows = [16 gate rows | 16 up rows]."""
     I = gate.shape[0]
