@@ -139,7 +139,9 @@ RVL_API int rvl_splice_rows(rvl_handle* h, const void* vis, const int32_t* vis_d
  * Replaces transformers LlamaModel/LlamaForCausalLM.forward reached from
  * vtimellm_llama.py:79-90 at step 0 (RMSNorm, QKV, RoPE, KV write, causal attention,
  * O, SwiGLU MLP, final norm, lm_head).
- *   hidden       [total_tokens, hidden] fp32 in/out (residual stream, overwritten)
+ *   hidden       [total_tokens, hidden] fp32 in/out (residual stream, overwritten; with all_logits == 0 the o projection
+ *                and the MLP of the LAST layer run on the last row of each sequence only - nothing else reads the other
+ *                rows - so on return `hidden` holds the input of the last layer, not its output)
  *   cu_seqlens   [n_seq+1] int32 device
  *   page_table   [n_seq, max_pages] int32 device (KV page ids per sequence)
  *   logits_out   fp32 [n_seq, vocab] (last token of each sequence) or, when all_logits != 0,

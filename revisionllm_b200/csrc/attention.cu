@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
                                                             __nv_bfloat16* __restrict__ out,
                                                             const int32_t* __restrict__ cu_seqlens, int n_heads,
                                                             float scale_log2, const int32_t* __restrict__ seq_pos0,
-                                                            const int32_t* __restrict__ seq_ctx_row) {
+                                                            const int32_t* __restrict__ seq_ctx_row, int only_last) {
   pdl_trigger();
   pdl_wait();
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
   const int L = p0 + cu_seqlens[seq + 1] - s0;
   const int q0 = qt * kQT;
   if (q0 >= L || q0 + kQT <= p0) return;      // past the end, or a query tile that lies entirely inside the context
+  if (only_last && q0 + kQT < L) return;      // last decoder layer of a generation prefill: only the last position is consumed
   extern __shared__ __align__(128) uint8_t smem[];
   // 64 KB: K [2][64][128] | V [2][64][128]; the Q tile borrows K's second buffer until its fragments sit in registers
   // (three CTAs per SM instead of two - the kernel is bound by the latency of each CTA's first loads, not by bandwidth)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
 }
 
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
-                         cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row) {
+                         cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row, int only_last) {
   if (n_seq <= 0 || max_seqlen <= 0) return;
   static bool attr = false;
   constexpr int smem = 16384 * 4;
@@ -248,7 +249,7 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
   dim3 grid((max_seqlen + kQT - 1) / kQT, n_heads, n_seq);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kD));
   launch_k(attn_prefill_kernel, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
-           reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2, seq_pos0, seq_ctx_row);
+           reinterpret_cast<__nv_bfloat16*>(out), cu_seqlens, n_heads, scale_log2, seq_pos0, seq_ctx_row, only_last);
 }
 
 // ------------------------------------------------------------------------------------------- small MHA, head_dim 96

@@ -193,6 +193,25 @@ void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, in
            static_cast<long long>(total));
 }
 
+// Last decoder layer of a generation prefill: only the last position of each sequence goes on, so its attention row
+// (bf16) and its residual row (fp32) are copied out of the packed stream and the rest of the layer runs on n_seq rows.
+__global__ void __launch_bounds__(256) gather_last_rows_kernel(const uint4* __restrict__ attn, const float4* __restrict__ hidden,
+                                                               const int32_t* __restrict__ rows, int dim, uint4* __restrict__ attn_out,
+                                                               float4* __restrict__ hidden_out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long src = rows[blockIdx.x];
+  const int na = dim / 8, nh = dim / 4;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) attn_out[static_cast<long long>(blockIdx.x) * na + i] = attn[src * na + i];
+  for (int i = threadIdx.x; i < nh; i += blockDim.x) hidden_out[static_cast<long long>(blockIdx.x) * nh + i] = hidden[src * nh + i];
+}
+void launch_gather_last_rows(const void* attn, const float* hidden, const int32_t* rows, int n_rows, int dim, void* attn_out,
+                             float* hidden_out, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  launch_k(gather_last_rows_kernel, dim3(n_rows), dim3(256), 0, st, reinterpret_cast<const uint4*>(attn),
+           reinterpret_cast<const float4*>(hidden), rows, dim, reinterpret_cast<uint4*>(attn_out), reinterpret_cast<float4*>(hidden_out));
+}
+
 // ------------------------------------------------------------------------------------ RoPE + KV write
 // In-place rotate-half RoPE on q and k of qkv [T, 3*H] (bf16) and write of the rotated k and of v into
 // the paged cache [page][head][slot][128].  One CTA per token; cos/sin computed once per token in fp32

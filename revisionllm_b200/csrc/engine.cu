@@ -314,16 +314,36 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
   const int64_t T = total_tokens;
   const int H = c.hidden, I = c.intermediate;
   launch_token_seq(cu_seqlens, n_seq, h->tok_seq, h->last_rows, T, st);
+  const char* env_fl = getenv("RVL_FULL_LAST_LAYER");      // diagnostic, read per call: 1 = run the last layer on every row
+  const bool env_full_last = env_fl && atoi(env_fl) == 1;
   for (int l = 0; l < c.n_layers; ++l) {
     const rvl_layer_weights& w = h->layers[l];
     launch_rmsnorm(hidden, w.ln1, h->xnorm, T, H, c.rms_eps, nullptr, st);
     if ((rc = linear(h, h->xnorm, w.wqkv, nullptr, h->qkv, T, 3 * H, H, 3 * H, RVL_GEMM_OUT_BF16, 0, nullptr, st))) return rc;
     launch_rope_kv(h->qkv, T, nullptr, h->tok_seq, cu_seqlens, page_table, max_pages, k_pages(h, l), v_pages(h, l),
                    c.n_heads, c.kv_page_size, c.rope_theta, st, seq_pos0);
+    // Generation prefill, last layer: every position's K / V is cached above, but only the LAST position's hidden state is
+    // ever read (final norm + lm_head on the last rows), so attention runs for the query tile that holds it and the o
+    // projection and the MLP run on n_seq gathered rows instead of T (1/32 of the o / gate|up / down FLOPs of a 7B prefill).
+    const bool last_only = !all_logits && l == c.n_layers - 1 && H % 8 == 0 && !env_full_last;
     {
       // causal FLOPs need the per-sequence lengths (device side); use the uniform-length bound T*max_seqlen
       ProfScope ps(h, st, RVL_PROF_ATTN_PREFILL, 2.0 * T * max_seqlen * H, 2.0 * T * 4 * H);
-      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row);
+      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row, last_only ? 1 : 0);
+    }
+    if (last_only) {
+      const int64_t n = n_seq;
+      float* hid = h->dec_hidden;
+      float* part = n <= 256 ? h->partials : nullptr;       // split-k partial buffers exist for the weight-streaming orientation
+      int pending = 0;
+      launch_gather_last_rows(h->attn, hidden, h->last_rows, n_seq, H, h->xlast, hid, st);
+      if ((rc = linear(h, h->xlast, w.wo, nullptr, hid, n, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st, part, &pending))) return rc;
+      launch_rmsnorm(hid, w.ln2, h->xnorm, n, H, c.rms_eps, nullptr, st, h->partials, pending, n * H, pending ? hid : nullptr);
+      if ((rc = gate_up(h, w, n, st))) return rc;
+      if ((rc = linear(h, h->act, w.wdown, nullptr, hid, n, H, I, H, RVL_GEMM_ADD_F32, 0, nullptr, st, part, &pending))) return rc;
+      launch_rmsnorm(hid, h->w.final_norm, h->xlast, n, H, c.rms_eps, nullptr, st, h->partials, pending, n * H, pending ? hid : nullptr);
+      if ((rc = linear(h, h->xlast, h->w.lm_head, nullptr, logits_out, n, c.vocab, H, c.vocab, RVL_GEMM_OUT_F32, 0, nullptr, st))) return rc;
+      return check_cuda(h, "rvl_prefill");
     }
     if ((rc = linear(h, h->attn, w.wo, nullptr, hidden, T, H, H, H, RVL_GEMM_ADD_F32, 0, nullptr, st))) return rc;
     launch_rmsnorm(hidden, w.ln2, h->xnorm, T, H, c.rms_eps, nullptr, st);

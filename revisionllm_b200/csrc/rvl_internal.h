@@ -112,12 +112,14 @@ void launch_rope_kv(void* qkv, int64_t n_tokens, const int32_t* positions, const
                     const int32_t* cu_seqlens, const int32_t* page_table, int max_pages, void* k_pages, void* v_pages,
                     int n_heads, int page_size, float theta, cudaStream_t st, const int32_t* seq_pos0 = nullptr);
 void launch_gather_rows_f32_bf16(const float* src, const int32_t* idx, int n_rows, int n_src, int dim, void* out, cudaStream_t st);
+void launch_gather_last_rows(const void* attn, const float* hidden, const int32_t* rows, int n_rows, int dim, void* attn_out,
+                             float* hidden_out, cudaStream_t st);
 void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaStream_t st);
 void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, int32_t* last_rows, int64_t total,
                       cudaStream_t st);
 // attention.cu
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
-                         cudaStream_t st, const int32_t* seq_pos0 = nullptr, const int32_t* seq_ctx_row = nullptr);
+                         cudaStream_t st, const int32_t* seq_pos0 = nullptr, const int32_t* seq_ctx_row = nullptr, int only_last = 0);
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
                         int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused, float theta,
                         int max_kv_len, cudaStream_t st);

@@ -198,7 +198,7 @@ class Engine:
         self._check(self.lib.rvl_prefill(self.h, hidden.data_ptr(), cu_seqlens.data_ptr(), n_seq, T, max_seqlen,
                                          page_table.data_ptr(), page_table.shape[1], logits_out.data_ptr(),
                                          1 if all_logits else 0, _ptr(seq_pos0), _ptr(seq_ctx_row), _stream()), "rvl_prefill")
-        self.launches += 1 + (8 if self.wgu_interleaved else 9) * self.cfg.n_layers + 2
+        self.launches += 1 + (8 if self.wgu_interleaved else 9) * self.cfg.n_layers + 2 + (0 if all_logits else 1)   # + last-row gather
 
     def decode_step(self, token_ids, seq_lens, page_table, logits_out, max_kv_len: int = 0):
         _req(token_ids, torch.int32, "token_ids"); _req(seq_lens, torch.int32, "seq_lens")

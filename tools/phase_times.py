@@ -10,12 +10,15 @@ model.record_phase_events = True
 feats = syn.make_features(180, 100, 768, seed=1).cuda()
 ids = syn.make_prompt_ids(cfg, seed=2).cuda()
 cls = torch.randn(768, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
-AB = os.environ.get("AB_ENV")          # e.g. AB_ENV=RVL_ROPE_EPILOGUE: odd steps run with it set to 0
+AB = os.environ.get("AB_ENV")          # e.g. AB_ENV=RVL_PDL (odd steps run with it set to 0) or AB_ENV=RVL_FULL_LAST_LAYER:1
+AB_VAL = "0"
+if AB and ":" in AB:
+    AB, AB_VAL = AB.split(":")
 acc = {0: [], 1: []}
-for i in range(9 if AB else 4):
+for i in range(13 if AB else 4):
     if AB:
         if i % 2:
-            os.environ[AB] = "0"
+            os.environ[AB] = AB_VAL
         else:
             os.environ.pop(AB, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,6 +36,6 @@ for i in range(9 if AB else 4):
     if AB and i > 0:
         acc[i % 2].append((ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), e0.elapsed_time(e1)))
 if AB:
-    for k, name in ((0, "default"), (1, AB + "=0")):
+    for k, name in ((0, "default"), (1, AB + "=" + AB_VAL)):
         n = len(acc[k])
         print(f"{name:28s} prefill {sum(a[0] for a in acc[k]) / n:7.2f} ms  decode {sum(a[1] for a in acc[k]) / n:7.2f} ms  total {sum(a[2] for a in acc[k]) / n:7.2f} ms")
