@@ -55,21 +55,29 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c) { return static_cast<
 
 // Load the 64 x 128 tile of positions [pos0, pos0 + 64) of one sequence; positions >= L are zero-filled.  A sequence's
 // positions [0, ctx_len) live in the rows of its context (a prompt prefix shared with other sequences, computed once),
-// positions >= ctx_len in its own rows: `ctx` / `own` point at column 0 of position 0 / position ctx_len.
-__device__ __forceinline__ void load_tile(uint8_t* smem_tile, const __nv_bfloat16* ctx, const __nv_bfloat16* own, int ctx_len,
+// positions >= ctx_len in its own rows: `ctx` points at column 0 of position 0, `own_adj` at where position 0 WOULD be if
+// the own rows started there (own - ctx_len rows), so both cases are base + pos * row_stride.  Each thread copies chunk
+// (tid & 15) of rows (tid >> 4) + 8 i: the swizzled shared-memory address advances by 2 KB per i, and the address math
+// is ~10 instructions per cp.async (the first version spent 44, more than half of the kernel's instructions).
+__device__ __forceinline__ void load_tile(uint8_t* smem_tile, const __nv_bfloat16* ctx, const __nv_bfloat16* own_adj, int ctx_len,
                                           long long row_stride, int pos0, int L, int tid) {
+  const int r0 = tid >> 4, c = tid & 15;
+  const uint32_t sbase = smem_u32(smem_tile) + tile_off(r0, c);
+  const int p_first = pos0 + r0;
+  ctx += c * 8;
+  own_adj += c * 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int idx = tid + i * 128;
-    const int r = idx >> 4, c = idx & 15;
-    const int pos = pos0 + r;
+    const int pos = p_first + i * 8;
     const bool ok = pos < L;
-    const __nv_bfloat16* src = !ok ? own : (pos < ctx_len ? ctx + pos * row_stride : own + (pos - ctx_len) * row_stride);
-    cp_async16(smem_tile + tile_off(r, c), src + c * 8, ok);
+    const int pc = ok ? pos : L - 1;           // keep the (unread) source address inside the sequence
+    const __nv_bfloat16* src = (pc < ctx_len ? ctx : own_adj) + static_cast<long long>(pc) * row_stride;
+    const int sz = ok ? 16 : 0;                // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + i * 2048), "l"(src), "r"(sz) : "memory");
   }
 }
 
-__global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 3) attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ out,
                                                             const int32_t* __restrict__ cu_seqlens, int n_heads,
                                                             float scale_log2, const int32_t* __restrict__ seq_pos0,
@@ -95,8 +103,8 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const __nv_bfloat16* 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = n_heads * kD;
   const long long stride = 3LL * H;
-  const __nv_bfloat16* own = qkv + static_cast<long long>(s0) * stride + head * kD;      // position p0, q columns
-  const __nv_bfloat16* ctx = qkv + static_cast<long long>(c0) * stride + head * kD;      // position 0, q columns
+  const __nv_bfloat16* own = qkv + (static_cast<long long>(s0) - p0) * stride + head * kD;  // where position 0 would be (own rows start at p0), q columns
+  const __nv_bfloat16* ctx = qkv + static_cast<long long>(c0) * stride + head * kD;        // position 0 of the context, q columns
 
   const int n_tiles = min((L + kKT - 1) / kKT, qt + 1);  // causal: keys <= q0 + 63
   load_tile(sQ, ctx, own, p0, stride, q0, L, tid);
