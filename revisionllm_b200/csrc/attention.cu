@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "rvl_internal.h"
+#include <cstdlib>
 #include "rvl_ptx.cuh"
 
 namespace rvl {
@@ -462,7 +463,8 @@ int launch_mha96(const void* q, long long q_stride, const void* k, long long k_s
 // kU: 16-key groups whose K loads are in flight together (phase 1) - and 2 kU 8-key groups of V (phase 3).  kU = 4 (64 registers,
 // 8 CTAs per SM) is the measured optimum on B200: kU = 12 (one round trip per context, 128 registers, 4 CTAs per SM) ran
 // the 7B decode step at 10.7 ms against 9.3 ms.
-template <bool kFused, int kU = 4>
+constexpr int kPtSmem = 128;     // page ids kept in shared memory by the register decode kernel (4096 tokens at 32 per page)
+template <bool kFused, int kU = 4, int kPS = 0>
 __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ seq_lens,
                                                            const int32_t* __restrict__ page_table, int max_pages,
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
   __shared__ float s_stat[8];
   __shared__ __align__(16) float s_q[kD];               // this step's (rotated) query, bf16-rounded values
   __shared__ __align__(16) __nv_bfloat16 s_knew[kD];    // this step's rotated key
+  __shared__ int32_t s_pt[kPtSmem];                     // this sequence's page ids: one global read instead of one per key group
   pdl_trigger();
   pdl_wait();
   const int head = blockIdx.x, seq = blockIdx.y;
@@ -481,6 +484,13 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
   const int n_keys = pos + 1;                  // includes the token appended this step
   const int H = n_heads * kD;
   const int32_t* pt = page_table + static_cast<long long>(seq) * max_pages;
+  // kPS: compile-time page size (32 in every shipped configuration) - shifts and masks instead of integer divisions in
+  // front of every K / V load; 0 = use the runtime value
+  const int ps = kPS ? kPS : page_size;
+  const int n_pages = (n_keys + ps - 1) / ps;
+  const bool pt_smem = n_pages <= kPtSmem;
+  if (pt_smem && tid < n_pages) s_pt[tid] = pt[tid];     // visible after the __syncthreads of phase 0
+  auto page_of = [&](int key) { const int i = key / ps; return pt_smem ? s_pt[i] : pt[i]; };
   const __nv_bfloat16* row = qkv + static_cast<long long>(seq) * 3 * H + head * kD;
 
   // ---- phase 0
@@ -497,8 +507,8 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
       s_knew[tid + 64] = __float2bfloat16(k1 * cs + k0 * sn);
     }
     __syncthreads();
-    const int page = pt[pos / page_size];
-    const long long slot = ((static_cast<long long>(page) * n_heads + head) * page_size + pos % page_size) * kD;
+    const int page = pt[pos / ps];
+    const long long slot = ((static_cast<long long>(page) * n_heads + head) * ps + pos % ps) * kD;
     if (tid < 16) {
       reinterpret_cast<uint4*>(k_pages + slot)[tid] = reinterpret_cast<const uint4*>(s_knew)[tid];
     } else if (tid < 32) {
@@ -531,8 +541,8 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
             kp = reinterpret_cast<const uint4*>(s_knew) + dg * 2;        // not yet visible through the read-only path
             kv[u][0] = kp[0]; kv[u][1] = kp[1];
           } else {
-            const int page = pt[key / page_size];
-            kp = reinterpret_cast<const uint4*>(k_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dg * 16);
+            const int page = page_of(key);
+            kp = reinterpret_cast<const uint4*>(k_pages + ((static_cast<long long>(page) * n_heads + head) * ps + key % ps) * kD + dg * 16);
             kv[u][0] = __ldg(kp); kv[u][1] = __ldg(kp + 1);
           }
         }
@@ -586,8 +596,8 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
           if (kFused && key == pos) {
             vv[u] = *reinterpret_cast<const uint4*>(row + 2 * H + dv);
           } else {
-            const int page = pt[key / page_size];
-            vv[u] = __ldg(reinterpret_cast<const uint4*>(v_pages + ((static_cast<long long>(page) * n_heads + head) * page_size + key % page_size) * kD + dv));
+            const int page = page_of(key);
+            vv[u] = __ldg(reinterpret_cast<const uint4*>(v_pages + ((static_cast<long long>(page) * n_heads + head) * ps + key % ps) * kD + dv));
           }
           pp[u] = s_scores[key];
         }
@@ -844,7 +854,19 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
   if (smem > 40000 && smem > attr_smem_r) {
     cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_kernel<true, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_kernel<false, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem_r = smem;
+  }
+  const char* env_ps = getenv("RVL_ATTN_PS32");          // diagnostic, read per call: 0 = runtime page size arithmetic
+  if (page_size == 32 && !(env_ps && atoi(env_ps) == 0)) {
+    if (fused)
+      launch_k(attn_decode_kernel<true, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+               scale, theta);
+    else
+      launch_k(attn_decode_kernel<false, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+               scale, theta);
+    return;
   }
   if (fused)
     launch_k(attn_decode_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
