@@ -474,7 +474,6 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
   __shared__ float s_red[8][kD];
   __shared__ float s_stat[8];
   __shared__ __align__(16) float s_q[kD];               // this step's (rotated) query, bf16-rounded values
-  __shared__ __align__(16) __nv_bfloat16 s_knew[kD];    // this step's rotated key
   __shared__ int32_t s_pt[kPtSmem];                     // this sequence's page ids: one global read instead of one per key group
   pdl_trigger();
   pdl_wait();
@@ -495,6 +494,10 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
 
   // ---- phase 0
   if (kFused) {
+    // the rotated key goes straight to its cache slot and v is copied there, so that after ONE barrier every thread finds
+    // this step's token in the cache like any other key (plain loads below: the read-only path would not see these writes)
+    const int page = pt[pos / ps];
+    const long long slot = ((static_cast<long long>(page) * n_heads + head) * ps + pos % ps) * kD;
     if (tid < kD / 2) {
       const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * tid) / static_cast<float>(kD));
       float sn, cs;
@@ -503,21 +506,15 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
       const float k0 = __bfloat162float(row[H + tid]), k1 = __bfloat162float(row[H + tid + 64]);
       s_q[tid] = __bfloat162float(__float2bfloat16(q0 * cs - q1 * sn));
       s_q[tid + 64] = __bfloat162float(__float2bfloat16(q1 * cs + q0 * sn));
-      s_knew[tid] = __float2bfloat16(k0 * cs - k1 * sn);
-      s_knew[tid + 64] = __float2bfloat16(k1 * cs + k0 * sn);
-    }
-    __syncthreads();
-    const int page = pt[pos / ps];
-    const long long slot = ((static_cast<long long>(page) * n_heads + head) * ps + pos % ps) * kD;
-    if (tid < 16) {
-      reinterpret_cast<uint4*>(k_pages + slot)[tid] = reinterpret_cast<const uint4*>(s_knew)[tid];
-    } else if (tid < 32) {
-      reinterpret_cast<uint4*>(v_pages + slot)[tid - 16] = reinterpret_cast<const uint4*>(row + 2 * H)[tid - 16];
+      k_pages[slot + tid] = __float2bfloat16(k0 * cs - k1 * sn);
+      k_pages[slot + tid + 64] = __float2bfloat16(k1 * cs + k0 * sn);
+    } else if (tid < kD / 2 + 16) {
+      reinterpret_cast<uint4*>(v_pages + slot)[tid - kD / 2] = reinterpret_cast<const uint4*>(row + 2 * H)[tid - kD / 2];
     }
   } else {
     s_q[tid] = __bfloat162float(row[tid]);
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- phase 1
   {
@@ -536,15 +533,9 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
         const int key = kbase + u * 16 + ksub;
         kv[u][0] = kv[u][1] = make_uint4(0u, 0u, 0u, 0u);
         if (key < n_keys) {
-          const uint4* kp;
-          if (kFused && key == pos) {
-            kp = reinterpret_cast<const uint4*>(s_knew) + dg * 2;        // not yet visible through the read-only path
-            kv[u][0] = kp[0]; kv[u][1] = kp[1];
-          } else {
-            const int page = page_of(key);
-            kp = reinterpret_cast<const uint4*>(k_pages + ((static_cast<long long>(page) * n_heads + head) * ps + key % ps) * kD + dg * 16);
-            kv[u][0] = __ldg(kp); kv[u][1] = __ldg(kp + 1);
-          }
+          const int page = page_of(key);
+          const uint4* kp = reinterpret_cast<const uint4*>(k_pages + ((static_cast<long long>(page) * n_heads + head) * ps + key % ps) * kD + dg * 16);
+          kv[u][0] = kp[0]; kv[u][1] = kp[1];
         }
       }
 #pragma unroll
@@ -593,12 +584,8 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
         vv[u] = make_uint4(0u, 0u, 0u, 0u);
         pp[u] = 0.f;
         if (key < n_keys) {
-          if (kFused && key == pos) {
-            vv[u] = *reinterpret_cast<const uint4*>(row + 2 * H + dv);
-          } else {
-            const int page = page_of(key);
-            vv[u] = __ldg(reinterpret_cast<const uint4*>(v_pages + ((static_cast<long long>(page) * n_heads + head) * ps + key % ps) * kD + dv));
-          }
+          const int page = page_of(key);
+          vv[u] = *reinterpret_cast<const uint4*>(v_pages + ((static_cast<long long>(page) * n_heads + head) * ps + key % ps) * kD + dv);
           pp[u] = s_scores[key];
         }
       }
