@@ -51,6 +51,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// 2^x on the SFU (2 ulp, flushes denormals, -inf -> +0): the probabilities are rounded to bf16 for the PV product anyway
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Tile in smem: [rows][128] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
 __device__ __forceinline__ uint32_t tile_off(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
 
@@ -164,38 +171,44 @@ __global__ void __launch_bounds__(128, 3) attn_prefill_kernel(const __nv_bfloat1
         mma_bf16_16816(s[2 * np + 1], qf[ks], b[2], b[3]);
       }
     }
-    // ---- mask + online softmax (rows g and g+8 of this warp's 16)
+    // ---- mask + online softmax (rows g and g+8 of this warp's 16).  The scores stay unscaled: the scale is positive, so
+    // the row maximum is taken on the raw values and 1/sqrt(d) * log2(e) rides in the FFMA in front of each ex2.
     const int k0 = j * kKT;
     const int qrow0 = q0 + warp * 16 + g;  // local query index of c0/c1; c2/c3 are +8
+    if (k0 + kKT - 1 > q0 + warp * 16 || k0 + kKT > L) {   // warp-uniform: tiles below the diagonal and inside L need no mask
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = k0 + nt * 8 + t4 * 2 + (e & 1);
+          const int qr = qrow0 + (e >> 1) * 8;
+          if (!(key <= qr && key < L)) s[nt][e] = -INFINITY;
+        }
+      }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = k0 + nt * 8 + t4 * 2 + (e & 1);
-        const int qr = qrow0 + (e >> 1) * 8;
-        const bool ok = key <= qr && key < L;
-        s[nt][e] = ok ? s[nt][e] * scale_log2 : -INFINITY;
-        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
-      }
+      for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
     }
-    float corr[2], mnew[2];
+    float corr[2], mneg[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-      mnew[h] = fmaxf(m_run[h], mx[h]);
-      const float msafe = mnew[h] == -INFINITY ? 0.f : mnew[h];
-      corr[h] = exp2f(m_run[h] - msafe);  // m_run = -inf -> 0
-      m_run[h] = mnew[h];
-      mnew[h] = msafe;
+      const float mnew = fmaxf(m_run[h], mx[h] * scale_log2);
+      const float msafe = mnew == -INFINITY ? 0.f : mnew;
+      corr[h] = ex2_approx(m_run[h] - msafe);  // m_run = -inf -> 0
+      m_run[h] = mnew;
+      mneg[h] = -msafe;
     }
     float rs[2] = {0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float p = exp2f(s[nt][e] - mnew[e >> 1]);
+        const float p = ex2_approx(fmaf(s[nt][e], scale_log2, mneg[e >> 1]));
         s[nt][e] = p;
         rs[e >> 1] += p;
       }

@@ -55,6 +55,17 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
       ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
     }
   }
+  // few rows (decode): the weight vector is fetched before the reduction so that its L2 latency is not paid after the barrier
+  constexpr bool kEarlyW = kMaxVec <= 2;
+  const uint2* wr = reinterpret_cast<const uint2*>(w);
+  uint2 wv_early[kEarlyW ? kMaxVec : 1];
+  if (kEarlyW) {
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int idx = threadIdx.x + i * THREADS;
+      if (idx < nvec) wv_early[i] = __ldg(wr + idx);
+    }
+  }
   __shared__ float red[THREADS / 32];
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -64,12 +75,11 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_kernel(const float* x, const 
   for (int i = 0; i < THREADS / 32; ++i) tot += red[i];
   const float inv = rsqrtf(tot / static_cast<float>(dim) + eps);
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(blockIdx.x) * dim);
-  const uint2* wr = reinterpret_cast<const uint2*>(w);
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int idx = threadIdx.x + i * THREADS;
     if (idx < nvec) {
-      const uint2 wv = __ldg(wr + idx);
+      const uint2 wv = kEarlyW ? wv_early[i] : __ldg(wr + idx);
       uint2 o;
       o.x = pack_bf16x2(bf16_lo(wv.x) * (c[i].x * inv), bf16_hi(wv.x) * (c[i].y * inv));
       o.y = pack_bf16x2(bf16_lo(wv.y) * (c[i].z * inv), bf16_hi(wv.y) * (c[i].w * inv));
