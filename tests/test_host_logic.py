@@ -168,3 +168,70 @@ def test_metrics_host_mirror_matches_oracle(golden_dir):
     for lo, hi in q["rl"]["info"]["frames"].values():
         ref |= set(range(max(0, int(.4 * lo)), min(int(.4 * hi), n - 1)))
     assert set(np.nonzero(cov)[0].tolist()) == ref
+
+
+class _FakeStage2Model:
+    """Stands in for the CUDA model in the stage-2 drivers: every prompt's new tokens are a deterministic function of its
+    prompt ids (unpadded), its visual rows in order and its query features, so the drivers' batching, padding, window
+    de-duplication and rank assignment can be checked on the CPU."""
+
+    def __init__(self):
+        self.calls = []
+
+    def generate(self, ids, images=None, query_feats=None, attention_mask=None, max_new_tokens=3, **kw):
+        from revisionllm_b200.model import WindowBank
+        B, L = ids.shape
+        self.calls.append(B)
+        if isinstance(images, WindowBank):
+            per_window = images.windows.float().sum(dim=(1, 2))                       # [U]
+            qsum = (query_feats[0].float() * query_feats[1][..., None].float()).sum(dim=(1, 2))   # [Q]
+            per_window = per_window + 7.0 * qsum[images.text_index.long()]
+            vis = per_window[images.rows]                                               # [B, V]
+        else:
+            vis = images.float().sum(dim=(2, 3))
+            if query_feats is not None:
+                vis = vis + 7.0 * (query_feats[0].float() * query_feats[1][..., None].float()).sum(dim=(1, 2))[:, None]
+        order = torch.arange(1, vis.shape[1] + 1, dtype=torch.float32)
+        am = torch.ones_like(ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
+        code = (vis * order).sum(dim=1) + (ids.clamp(min=0) * am).sum(dim=1).float()
+        new = torch.stack([(code * (t + 1)).round().long() % 97 for t in range(max_new_tokens)], dim=1)
+        ent = torch.rand(B, max_new_tokens, generator=torch.Generator().manual_seed(0)) + 0.5
+        return {"sequences": torch.cat([ids, new], dim=1), "entropies": ent}
+
+
+def test_stage2_drivers_batch_pad_dedup_and_shard_like_the_sequential_schedule():
+    g = torch.Generator().manual_seed(5)
+    queries = []
+    for k, (nw, L, lq) in enumerate([(7, 14, 5), (5, 11, 3), (9, 14, 5), (4, 9, 2)]):
+        ids = torch.randint(3, 500, (L,), generator=g)
+        ids[4] = -200
+        queries.append(dict(windows=torch.randint(-3, 4, (nw, 6, 8), generator=g).float(),
+                            query_feats=(torch.randint(-2, 3, (1, lq, 8), generator=g).float(), torch.ones(1, lq)),
+                            input_ids=ids, grounding_windows=list(range(100 * k, 100 * k + nw)), perm_seed=k))
+    kw = dict(batch=4, zooms=(2, 1), max_new_tokens=3, answer_number=lambda t: int(t[0]) % 4, eos_token_id=None)
+    key = lambda res: [(r["zoom"], r["start"], r["perm"], r["tokens"], r["window"]) for r in res]
+    # the reference's schedule: one generate() per chunk, stacked zoom repeats
+    seq_model = _FakeStage2Model()
+    seq = [sweep.stage2_pass(seq_model, q["windows"], q["query_feats"], q["input_ids"], q["grounding_windows"], perm_seed=k,
+                             max_calls_per_batch=1, dedup=False, **kw) for k, q in enumerate(queries)]
+    assert all(b == 1 for b in seq_model.calls)
+    # batched across queries, windows de-duplicated, prompts and query features of different lengths padded + masked
+    multi_model = _FakeStage2Model()
+    multi = sweep.stage2_pass_queries(multi_model, queries, **kw)
+    assert [key(r) for r in multi] == [key(r) for r in seq]
+    assert sum(multi_model.calls) == sum(seq_model.calls) and len(multi_model.calls) < len(seq_model.calls)
+    # stacked copies instead of the bank: same answers
+    stacked = sweep.stage2_pass_queries(_FakeStage2Model(), queries, dedup=False, **kw)
+    assert [key(r) for r in stacked] == [key(r) for r in seq]
+    # a batch bound splits the work, query i belongs to rank i mod world
+    small = sweep.stage2_pass_queries(_FakeStage2Model(), queries, max_calls_per_batch=3, **kw)
+    assert [key(r) for r in small] == [key(r) for r in seq]
+    for rank in range(2):
+        part = sweep.stage2_pass_queries(_FakeStage2Model(), queries, rank=rank, world=2, **kw)
+        for qi in range(len(queries)):
+            assert (part[qi] is None) == (qi % 2 != rank)
+            if part[qi] is not None:
+                assert key(part[qi]) == key(seq[qi])
+    # every window picked maps back into its own query's grounding windows
+    for k, res in enumerate(multi):
+        assert all(r["window"] in queries[k]["grounding_windows"] for r in res)
