@@ -58,6 +58,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Blackwell packed fp32 FMA: d.{x,y} = a.{x,y} * b.{x,y} + c.{x,y} in one instruction (FFMA2)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 // Tile in smem: [rows][128] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
 __device__ __forceinline__ uint32_t tile_off(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
 
@@ -555,9 +567,10 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
       for (int u = 0; u < kU; ++u) {
         const int key = kbase + u * 16 + ksub;
         const uint32_t kw[8] = {kv[u][0].x, kv[u][0].y, kv[u][0].z, kv[u][0].w, kv[u][1].x, kv[u][1].y, kv[u][1].z, kv[u][1].w};
-        float acc = 0.f;
+        float2 acc2 = make_float2(0.f, 0.f);       // even / odd dims accumulate side by side in one FFMA2 per bf16 pair
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc += qf[2 * e] * bf16_lo(kw[e]) + qf[2 * e + 1] * bf16_hi(kw[e]);
+        for (int e = 0; e < 8; ++e) acc2 = ffma2(make_float2(qf[2 * e], qf[2 * e + 1]), make_float2(bf16_lo(kw[e]), bf16_hi(kw[e])), acc2);
+        float acc = acc2.x + acc2.y;
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -587,7 +600,7 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
   {
     const int grp = tid >> 4;                  // 8 key groups
     const int dv = (tid & 15) * 8;             // dims [dv, dv + 8)
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     for (int kbase = 0; kbase < n_keys; kbase += 16 * kU) {
       uint4 vv[2 * kU];
       float pp[2 * kU];
@@ -604,15 +617,15 @@ __global__ void __launch_bounds__(128, 8) attn_decode_kernel(const __nv_bfloat16
       }
 #pragma unroll
       for (int u = 0; u < 2 * kU; ++u) {
-        const float p = pp[u];
-        acc[0] += p * bf16_lo(vv[u].x); acc[1] += p * bf16_hi(vv[u].x);
-        acc[2] += p * bf16_lo(vv[u].y); acc[3] += p * bf16_hi(vv[u].y);
-        acc[4] += p * bf16_lo(vv[u].z); acc[5] += p * bf16_hi(vv[u].z);
-        acc[6] += p * bf16_lo(vv[u].w); acc[7] += p * bf16_hi(vv[u].w);
+        const float2 p = make_float2(pp[u], pp[u]);
+        acc[0] = ffma2(p, make_float2(bf16_lo(vv[u].x), bf16_hi(vv[u].x)), acc[0]);
+        acc[1] = ffma2(p, make_float2(bf16_lo(vv[u].y), bf16_hi(vv[u].y)), acc[1]);
+        acc[2] = ffma2(p, make_float2(bf16_lo(vv[u].z), bf16_hi(vv[u].z)), acc[2]);
+        acc[3] = ffma2(p, make_float2(bf16_lo(vv[u].w), bf16_hi(vv[u].w)), acc[3]);
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s_red[grp][dv + e] = acc[e];
+    for (int e = 0; e < 4; ++e) { s_red[grp][dv + 2 * e] = acc[e].x; s_red[grp][dv + 2 * e + 1] = acc[e].y; }
   }
   __syncthreads();
   {
