@@ -830,6 +830,7 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
                         float theta, int max_kv_len, cudaStream_t st) {
   if (n_seq <= 0) return;
   dim3 grid(n_heads, n_seq);
+  const bool pdl_dec = pdl_few_rows(n_seq, 8);
   const float scale = 1.0f / sqrtf(static_cast<float>(kD));
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
@@ -855,10 +856,10 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
       attr_smem = 432 * (2 * kD * 2 + 4);
     }
     if (fused)
-      launch_k(attn_decode_staged_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads,
+      launch_pdl(pdl_dec, attn_decode_staged_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads,
                page_size, scale, theta, cap);
     else
-      launch_k(attn_decode_staged_kernel<false>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads,
+      launch_pdl(pdl_dec, attn_decode_staged_kernel<false>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads,
                page_size, scale, theta, cap);
     return;
   }
@@ -874,18 +875,18 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
   const char* env_ps = getenv("RVL_ATTN_PS32");          // diagnostic, read per call: 0 = runtime page size arithmetic
   if (page_size == 32 && !(env_ps && atoi(env_ps) == 0)) {
     if (fused)
-      launch_k(attn_decode_kernel<true, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+      launch_pdl(pdl_dec, attn_decode_kernel<true, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
                scale, theta);
     else
-      launch_k(attn_decode_kernel<false, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+      launch_pdl(pdl_dec, attn_decode_kernel<false, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
                scale, theta);
     return;
   }
   if (fused)
-    launch_k(attn_decode_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+    launch_pdl(pdl_dec, attn_decode_kernel<true>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
              scale, theta);
   else
-    launch_k(attn_decode_kernel<false>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
+    launch_pdl(pdl_dec, attn_decode_kernel<false>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
              scale, theta);
 }
 

@@ -97,10 +97,11 @@ void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int 
   // few rows (decode): one float4 per thread so that a row's loads are all in flight at once (the 128-thread
   // variant took 9.7 us for 180 rows with 4 split-k partials - latency, not bandwidth)
   const bool reduce = n_partials > 0 || x_out != nullptr;
+  const bool pdl_few = pdl_few_rows(n_rows, 4);
   if (n_rows <= 1024 && dim >= 2048 && reduce)
-    launch_k(rmsnorm_kernel<1024, 2, true>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+    launch_pdl(pdl_few, rmsnorm_kernel<1024, 2, true>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
   else if (n_rows <= 1024 && dim >= 2048)
-    launch_k(rmsnorm_kernel<1024, 2, false>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
+    launch_pdl(pdl_few, rmsnorm_kernel<1024, 2, false>, dim3(static_cast<unsigned>(n_rows)), dim3(1024), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
   else if (reduce)
     launch_k(rmsnorm_kernel<256, 8, true>, dim3(static_cast<unsigned>(n_rows)), dim3(256), 0, st, x, wp, yp, dim, eps, rows, partials, n_partials, ps, x_out);
   else if (dim <= 128 * 32)

@@ -71,9 +71,19 @@ int decode_fused(const FusedCall& c, int num_sms, cudaStream_t st, std::string* 
 // Bit 0: the GEMM launches, bit 1: every other kernel.  Default 1: measured on B200 (decode step, 7B shape, B = 180 / 32)
 // 10.08 / 5.71 ms without, 9.72 / 5.18 ms with GEMMs only, 9.90 / 5.67 ms with everything - small kernels that become
 // resident early only squat on the SM while the GEMM before them is still streaming.
+// Bit 2: the few-row (decode) RMSNorm only, bit 3: the decode attention kernels only.  Read per call so that tools can A/B in
+// one process.
 inline int pdl_mask() {
-  static const int m = [] { const char* e = getenv("RVL_PDL"); return e ? atoi(e) : 1; }();
-  return m;
+  const char* e = getenv("RVL_PDL");
+  return e ? atoi(e) : 1;
+}
+// Decode-step RMSNorm (bit 2) and attention (bit 3): early launch pays for few rows - measured per 7B decode step with both
+// on: 3.12 -> 3.01 ms at B = 1, 4.24 -> 4.13 at 23, 5.36 -> 5.08 at 56, 6.43 -> 6.28 at 96 - and costs at B = 180
+// (8.50 -> 8.77 ms: the 1024-thread RMSNorm CTAs cannot share an SM with a streaming GEMM CTA).  Default: on up to 128 rows.
+inline bool pdl_few_rows(long long rows, int bit) {
+  const char* e = getenv("RVL_PDL");
+  if (e) return (atoi(e) & (2 | bit)) != 0;
+  return rows <= 128;
 }
 // Launch `kernel` so that it may start while the previous kernel of `st` is still running (it must call pdl_wait()
 // before touching anything earlier kernels write; see rvl_ptx.cuh).

@@ -19,7 +19,10 @@ ids = syn.make_prompt_ids(cfg, seed=2)
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6531.9
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("RVL_"))
-AB = os.environ.get("AB_ENV")      # e.g. AB_ENV=RVL_SPAIR: odd repetitions run with it set to 0 (the library reads it per call)
+AB = os.environ.get("AB_ENV")      # e.g. AB_ENV=RVL_SPAIR (odd repetitions run with it set to 0) or AB_ENV=RVL_PDL:5; read per call by the library
+AB_VAL = "0"
+if AB and ":" in AB:
+    AB, AB_VAL = AB.split(":")
 for B in [int(b) for b in args.batches.split(",")]:
     feats = syn.make_features(B, 100, 768, seed=1).cuda()
     best = None
@@ -27,7 +30,7 @@ for B in [int(b) for b in args.batches.split(",")]:
     for rep in range(args.reps if not AB else 2 * args.reps + 1):
         if AB:
             if rep % 2:
-                os.environ[AB] = "0"
+                os.environ[AB] = AB_VAL
             else:
                 os.environ.pop(AB, None)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -51,7 +54,7 @@ for B in [int(b) for b in args.batches.split(",")]:
         if AB and rep > 0:
             ab[rep % 2].append(ms)
     if AB:
-        print(f"B={B}: default {sum(ab[0]) / len(ab[0]):.3f} ms (min {min(ab[0]):.3f}) | {AB}=0 {sum(ab[1]) / len(ab[1]):.3f} ms (min {min(ab[1]):.3f})", flush=True)
+        print(f"B={B}: default {sum(ab[0]) / len(ab[0]):.3f} ms (min {min(ab[0]):.3f}) | {AB}={AB_VAL} {sum(ab[1]) / len(ab[1]):.3f} ms (min {min(ab[1]):.3f})", flush=True)
         os.environ.pop(AB, None)
         continue
     L = ids.shape[0] - 1 + 100
