@@ -274,7 +274,7 @@ def main():
     # decode step t reads K and V of (seq_len + t + 1) tokens per sequence, all layers
     attn_d_bytes = sum(n_local * KV_BYTES_PER_TOKEN * (seq_len + t + 1) for t in range(NEW_TOKENS - 1))
     roofline = {
-        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (prefill GEMMs: qkv, o, gate|up, down, projector)",
+        "bound": "tensor", "kernel": "gemm_bf16_pair_kernel (token-major tcgen05 GEMMs of the prefill: qkv, o, gate|up + SwiGLU, down, projector)",
         "achieved": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else None,
         "peak": pk["tf_sust"], "unit": "TFLOP/s", "peak_source": pk["src"] + ", sustained bf16",
         "frac": (gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / pk["tf_sust"]) if gemm["ms"] > 0 else None,
@@ -289,11 +289,14 @@ def main():
     # step is made of.  Decode: 15 steps, each streams the 13.2 GB of weights once and reads K/V of every cached token.
     dec_steps = NEW_TOKENS - 1
     dec_bytes = dec_steps * WEIGHT_BYTES_PER_STEP + attn_d_bytes
-    tf_prefill = n_local * seq_len * FLOP_PER_TOKEN / (phase_ms["prefill"] * 1e-3) / 1e12
+    # executed GEMM FLOPs: the o projection and the MLP of the LAST layer run on the last row of each sequence only
+    # (csrc/engine.cu rvl_prefill; 2 * (H*H + 3*H*I) FLOP per skipped row), so they are not counted for the other rows
+    skipped = n_local * (seq_len - 1) * 2.0 * (cfg.hidden * cfg.hidden + 3.0 * cfg.hidden * cfg.intermediate)
+    tf_prefill = (n_local * seq_len * FLOP_PER_TOKEN - skipped) / (phase_ms["prefill"] * 1e-3) / 1e12
     roofline["phases"] = {
         "splice_ms": phase_ms["splice"], "prefill_ms": phase_ms["prefill"], "decode_ms": phase_ms["decode"],
         "prefill": {"bound": "tensor", "achieved": tf_prefill, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf_prefill / pk["tf_sust"],
-                    "note": "all of prefill (GEMMs + attention + RMSNorm + RoPE/KV write + lm_head on last rows) against the GEMM FLOPs only"},
+                    "note": "all of prefill (GEMMs + attention + RMSNorm + RoPE/KV write + lm_head on last rows) against the executed GEMM FLOPs only"},
         "decode": {"bound": "hbm", "ms_per_step": phase_ms["decode"] / dec_steps, "achieved": dec_bytes / (phase_ms["decode"] * 1e-3) / 1e9,
                    "peak": pk["hbm"], "unit": "GB/s", "frac": dec_bytes / (phase_ms["decode"] * 1e-3) / 1e9 / pk["hbm"],
                    "note": "15 decode steps + 16 sampling kernels; bytes = weights once per step + K/V of every cached token"},
