@@ -351,6 +351,24 @@ def main():
         line["shared_prefix_compute"] = {"error": repr(e)[:200]}
     finally:
         model.share_prefix_compute = False
+    # ---- the reference's own windowing of a 1-hour MAD movie (eval_nlq_negative.py:226-235: 250 frames per window, stride
+    # half a window -> 57 windows, L = 334), reported beside the headline, not part of `value`
+    try:
+        feats_mad = syn.make_features(57, 250, cfg.adapter_dim, seed=21).to(dev)
+        for _ in range(2):
+            sweep.score_segments(model, feats_mad, ids_dev, cls_dev, NEW_TOKENS, eos_token_id=None)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(args.steps):
+            sweep.score_segments(model, feats_mad, ids_dev, cls_dev, NEW_TOKENS, eos_token_id=None)
+        m1.record()
+        torch.cuda.synchronize()
+        mad_ms = m0.elapsed_time(m1) / args.steps
+        line["mad_windows_57x250"] = {"ms_per_movie_query": mad_ms, "windows_per_s": 57 / (mad_ms * 1e-3), "prompt_len": seq_len - N_FRAMES + 250,
+                                      "note": "one rank, 57 windows x 250 frames x 16 greedy tokens (the reference's MAD windowing)"}
+        del feats_mad
+    except Exception as e:
+        line["mad_windows_57x250"] = {"error": repr(e)[:200]}
     # ---- stage 2 (BASELINE.json configs[3], reported beside the headline, not part of `value`): top-100 segments by
     # cosine score -> 250-frame windows through the ClipEncoder adapter (one CLS token per window) -> one ~180-token
     # prompt per zoom level (4, 2, 1), 16 greedy tokens each.  One query per rank.
@@ -379,6 +397,19 @@ def main():
             line["stage2_top100"] = {"ms_per_query": 1e3 * dt2, "generate_calls": len(r2), "windows": 100, "frames_per_window": 250,
                                      "zooms": [4, 2, 1], "selected_first5": top[:5].tolist(),
                                      "note": "ClipEncoder (4 layers, d=768; each distinct window once) + splice of 100 CLS tokens + Vicuna-7B prefill/decode, 16 tokens per call"}
+            # stage2_long_33: the top-33 windows of the same query (zooms 4 / 2 / 1 over chunks of 33 // zoom windows)
+            top33 = scoring.select_topk_segments(eng, cos, 33)
+
+            def stage2_33():
+                return sweep.stage2_pass(model, wins[:33], (q_tok, q_mask), ids2, grounding_windows=top33.tolist(), batch=33,
+                                         zooms=(4, 2, 1), max_new_tokens=NEW_TOKENS, perm_seed=0, eos_token_id=None)
+            stage2_33()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r33 = stage2_33()
+            torch.cuda.synchronize()
+            line["stage2_top33"] = {"ms_per_query": 1e3 * (time.perf_counter() - t0), "generate_calls": len(r33), "windows": 33,
+                                    "frames_per_window": 250, "zooms": [4, 2, 1]}
             # the same pass batched across 8 queries of one rank (sweep.stage2_pass_queries): the chunks of all queries share
             # the decode steps, so the 13 GB of weights stream once per step for 56 prompts instead of 7
             NQ = 8

@@ -32,10 +32,11 @@ class WindowBank:
     """Stage-2 hierarchy input without the repetition: the reference stacks every window once per zoom repeat and per chunk
     into `images [b, v, t, 768]` (eval_nlq_retrieval_e2e2.py:348-352) and runs the ClipEncoder adapter over all copies.  The
     CLS row of a window depends only on (window, query), so here `windows [U, t, 768]` holds each distinct pair once,
-    `text_index [U]` names the row of `query_feats` it attends to, and `rows [b, v]` says which of the U CLS rows fills each
-    visual position of each prompt.  Pass it as `images=` to generate() / forward()."""
+    `text_index [U]` names the row of `query_feats` it attends to, and `rows [b, v]` (or a list of b index vectors when the
+    prompts hold different numbers of windows) says which of the U CLS rows fills each visual position of each prompt.
+    Pass it as `images=` to generate() / forward()."""
     windows: torch.Tensor
-    rows: torch.Tensor
+    rows: object
     text_index: torch.Tensor
 
 
@@ -188,10 +189,15 @@ class RevisionLlamaForCausalLM:
             if self.clip_encoder is None:
                 raise RvlError("a WindowBank needs the stage-2 ClipEncoder adapter (pass clip_encoder_state)")
             q_tok, q_mask = query_feats
-            b, v = images.rows.shape
+            if isinstance(images.rows, (list, tuple)):          # prompts with different numbers of visual positions
+                n_vis = [int(r.shape[0]) for r in images.rows]
+                flat = torch.cat([r.reshape(-1) for r in images.rows])
+            else:
+                b, v = images.rows.shape
+                n_vis, flat = [v] * b, images.rows.reshape(-1)
             cls_u = self.clip_encoder(images.windows.to(dev, torch.bfloat16).contiguous(), q_tok.to(dev, torch.bfloat16), q_mask.to(dev),
                                       images.text_index.to(dev, torch.int32).contiguous())              # [U, hidden] bf16
-            return cls_u.index_select(0, images.rows.reshape(-1).to(dev, torch.int64)).contiguous(), [v] * b, True
+            return cls_u.index_select(0, flat.to(dev, torch.int64)).contiguous(), n_vis, True
         if images.dim() == 4:                            # hierarchy: [b, v, t, d] -> one CLS row per segment (:114-121)
             if self.clip_encoder is None:
                 raise RvlError("4-D `images` need the stage-2 ClipEncoder adapter (pass clip_encoder_state)")

@@ -283,7 +283,9 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
     groups: Dict[Tuple[int, int, bool], List[Tuple[int, int]]] = {}
     for (qi, ci) in jobs:                                   # one generate() needs equal visual rows / frames per row
         w = queries[qi]["windows"]
-        key = (int(plans[qi][ci]["rows"].shape[0]), int(w.shape[1]), queries[qi].get("query_feats") is not None)
+        has_q = queries[qi].get("query_feats") is not None
+        # the window bank takes prompts with different numbers of visual rows in one batch; stacked 4-D images need them equal
+        key = (0 if (has_q and dedup) else int(plans[qi][ci]["rows"].shape[0]), int(w.shape[1]), has_q)
         groups.setdefault(key, []).append((qi, ci))
     for (v_rows, _, has_q), members in groups.items():
         for g0 in range(0, len(members), max_calls_per_batch):
@@ -318,7 +320,8 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
                     base[qi] = lut
                     banks.append(queries[qi]["windows"][used.to(queries[qi]["windows"].device)])
                     text_index += [r] * int(used.shape[0])
-                feat = WindowBank(torch.cat(banks), torch.stack([base[qi][plans[qi][ci]["rows"]] for (qi, ci) in part]),
+                rows = [base[qi][plans[qi][ci]["rows"]] for (qi, ci) in part]
+                feat = WindowBank(torch.cat(banks), torch.stack(rows) if len({int(r.shape[0]) for r in rows}) == 1 else rows,
                                   torch.tensor(text_index, dtype=torch.int32))
             else:
                 feat = torch.stack([queries[qi]["windows"][plans[qi][ci]["rows"].to(queries[qi]["windows"].device)] for (qi, ci) in part])

@@ -186,14 +186,16 @@ class _FakeStage2Model:
             per_window = images.windows.float().sum(dim=(1, 2))                       # [U]
             qsum = (query_feats[0].float() * query_feats[1][..., None].float()).sum(dim=(1, 2))   # [Q]
             per_window = per_window + 7.0 * qsum[images.text_index.long()]
-            vis = per_window[images.rows]                                               # [B, V]
+            rows = list(images.rows) if isinstance(images.rows, (list, tuple)) else list(images.rows.unbind(0))
+            vis = [per_window[r] for r in rows]                                         # B x [V_b]
         else:
-            vis = images.float().sum(dim=(2, 3))
+            v4 = images.float().sum(dim=(2, 3))
             if query_feats is not None:
-                vis = vis + 7.0 * (query_feats[0].float() * query_feats[1][..., None].float()).sum(dim=(1, 2))[:, None]
-        order = torch.arange(1, vis.shape[1] + 1, dtype=torch.float32)
+                v4 = v4 + 7.0 * (query_feats[0].float() * query_feats[1][..., None].float()).sum(dim=(1, 2))[:, None]
+            vis = list(v4.unbind(0))
         am = torch.ones_like(ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
-        code = (vis * order).sum(dim=1) + (ids.clamp(min=0) * am).sum(dim=1).float()
+        code = torch.stack([(v * torch.arange(1, v.shape[0] + 1, dtype=torch.float32)).sum() for v in vis]) + \
+            (ids.clamp(min=0) * am).sum(dim=1).float()
         new = torch.stack([(code * (t + 1)).round().long() % 97 for t in range(max_new_tokens)], dim=1)
         ent = torch.rand(B, max_new_tokens, generator=torch.Generator().manual_seed(0)) + 0.5
         return {"sequences": torch.cat([ids, new], dim=1), "entropies": ent}
@@ -202,7 +204,7 @@ class _FakeStage2Model:
 def test_stage2_drivers_batch_pad_dedup_and_shard_like_the_sequential_schedule():
     g = torch.Generator().manual_seed(5)
     queries = []
-    for k, (nw, L, lq) in enumerate([(7, 14, 5), (5, 11, 3), (9, 14, 5), (4, 9, 2)]):
+    for k, (nw, L, lq) in enumerate([(7, 14, 5), (5, 11, 3), (9, 14, 5), (4, 9, 2), (3, 12, 4)]):   # 3 windows: a 3-row prompt among 4-row ones
         ids = torch.randint(3, 500, (L,), generator=g)
         ids[4] = -200
         queries.append(dict(windows=torch.randint(-3, 4, (nw, 6, 8), generator=g).float(),
