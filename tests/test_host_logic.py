@@ -237,3 +237,44 @@ def test_stage2_drivers_batch_pad_dedup_and_shard_like_the_sequential_schedule()
     # every window picked maps back into its own query's grounding windows
     for k, res in enumerate(multi):
         assert all(r["window"] in queries[k]["grounding_windows"] for r in res)
+
+
+class _FakeSweepModel:
+    """generate() for the ragged-sweep driver on the CPU: new tokens are a function of each window's content and prompt."""
+    engine = None
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.batches = []
+
+    def generate(self, ids, images=None, attention_mask=None, max_new_tokens=4, **kw):
+        am = attention_mask.bool()
+        self.batches.append(sum(int(am[i].sum()) - 1 + int(images[i].shape[0]) for i in range(ids.shape[0])))
+        code = torch.stack([im.float().sum() for im in images]) + (ids.clamp(min=0) * am).sum(dim=1).float()
+        new = torch.stack([(code * (t + 1)).round().long() % 89 for t in range(max_new_tokens)], dim=1)
+        ent = torch.full((ids.shape[0], max_new_tokens), 0.25)
+        return {"sequences": torch.cat([ids, new], dim=1), "entropies": ent}
+
+
+def test_ragged_sweep_packs_by_token_budget_and_keeps_window_order():
+    g = torch.Generator().manual_seed(9)
+    n = 23
+    frames = [int(x) for x in torch.randint(1, 60, (n,), generator=g)]
+    windows = [torch.randint(-3, 4, (f, 8), generator=g).float() for f in frames]
+    L = 12
+    ids = torch.randint(3, 300, (n, L), generator=g)
+    ids[:, 3] = -200
+    am = torch.ones(n, L, dtype=torch.bool)
+    for i in range(n):
+        am[i, L - (i % 4):] = False if i % 4 else am[i, L:]          # right padding of 0..3 positions
+    budget = 150
+    model = _FakeSweepModel()
+    rec = sweep.ragged_sweep(model, windows, ids, am, None, max_new_tokens=4, rank=0, world=1, max_tokens_per_batch=budget, eos_token_id=None)
+    got = sweep.unpack_records(rec)["tokens"][:, :4]
+    # one window at a time gives the same tokens, in window order
+    for i in range(n):
+        one = _FakeSweepModel().generate(ids[i:i + 1], images=[windows[i]], attention_mask=am[i:i + 1], max_new_tokens=4)
+        assert got[i].tolist() == one["sequences"][0, L:].tolist(), i
+    # every packed batch respects the token budget unless it holds a single over-long window
+    assert len(model.batches) > 1 and all(b <= budget for b in model.batches)
+    assert sum(model.batches) == sum(int(am[i].sum()) - 1 + frames[i] for i in range(n))
