@@ -278,3 +278,48 @@ def test_ragged_sweep_packs_by_token_budget_and_keeps_window_order():
     # every packed batch respects the token budget unless it holds a single over-long window
     assert len(model.batches) > 1 and all(b <= budget for b in model.batches)
     assert sum(model.batches) == sum(int(am[i].sum()) - 1 + frames[i] for i in range(n))
+
+
+def test_shared_prefix_plan_remap_is_a_compact_relabelling():
+    """model._share_prefix_rows: the packed stream becomes [prefix | seq 0 from P | seq 1 from P | ...].  Checked on the plan
+    alone: every destination row is used exactly once, the prefix rows carry sequence 0's first P items, every other
+    item keeps its order inside its sequence, and nothing but the duplicated prefix items disappears."""
+    from types import SimpleNamespace
+    from revisionllm_b200.model import RevisionLlamaForCausalLM as M
+    B, F, ps = 5, 40, 32
+    g = np.random.default_rng(3)
+    pre = g.integers(3, 900, size=37)                                   # common system prompt: 37 ids -> P = 32
+    ids = np.stack([np.concatenate([pre, [-200], g.integers(3, 900, size=9 + 0)]) for _ in range(B)]).astype(np.int64)
+    n_vis = [F - 3 * i for i in range(B)]                               # ragged visual blocks
+    plan = plan_splice(ids, n_vis)
+    plan["shared_prefix"] = min(M._common_text_prefix(ids, None), int(plan["lengths"].min()))
+    plan["ctx_len"] = 0
+    assert plan["shared_prefix"] == 37
+    before = {k: plan[k].copy() for k in ("cu_seqlens", "text_ids", "text_dst", "vis_src", "vis_dst", "lengths")}
+    M._share_prefix_rows(SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps))), plan)
+    P = plan["ctx_len"]
+    assert P == 32
+    cu = plan["cu_seqlens"]
+    lengths = before["lengths"].astype(np.int64)
+    assert cu.tolist() == np.concatenate([[0, P], P + np.cumsum(lengths - P)]).tolist()      # B + 1 sequences, the prefix first
+    dst = np.concatenate([plan["text_dst"], plan["vis_dst"]])
+    assert sorted(dst.tolist()) == list(range(int(cu[-1])))                                    # every row written exactly once
+    # prefix rows = the first P text ids of sequence 0, in order
+    order = np.argsort(plan["text_dst"])
+    assert plan["text_ids"][order][:P].tolist() == pre[:P].tolist()
+    # each sequence keeps its items from position P on, in order: compare with the unshared plan
+    ocu = before["cu_seqlens"].astype(np.int64)
+    for b in range(B):
+        lo, hi = ocu[b] + P, ocu[b + 1]
+        old_t = [(d - lo, t) for d, t in zip(before["text_dst"], before["text_ids"]) if lo <= d < hi]
+        new_t = [(d - cu[b + 1], t) for d, t in zip(plan["text_dst"], plan["text_ids"]) if cu[b + 1] <= d < cu[b + 2]]
+        assert sorted(old_t) == sorted(new_t), b
+        old_v = [(d - lo, s) for d, s in zip(before["vis_dst"], before["vis_src"]) if lo <= d < hi]
+        new_v = [(d - cu[b + 1], s) for d, s in zip(plan["vis_dst"], plan["vis_src"]) if cu[b + 1] <= d < cu[b + 2]]
+        assert sorted(old_v) == sorted(new_v), b
+    # a batch of one, or a common prefix shorter than a page, is left alone
+    small = plan_splice(ids[:, 10:], n_vis)
+    small["shared_prefix"], small["ctx_len"] = 27, 0
+    keep = small["cu_seqlens"].copy()
+    M._share_prefix_rows(SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps))), small)
+    assert small["ctx_len"] == 0 and np.array_equal(small["cu_seqlens"], keep)
