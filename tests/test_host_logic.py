@@ -323,3 +323,33 @@ def test_shared_prefix_plan_remap_is_a_compact_relabelling():
     keep = small["cu_seqlens"].copy()
     M._share_prefix_rows(SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps))), small)
     assert small["ctx_len"] == 0 and np.array_equal(small["cu_seqlens"], keep)
+
+
+def test_kv_page_table_shares_whole_prefix_pages_only():
+    """model._alloc_kv: pages filled entirely by the common prompt prefix are mapped once for all sequences; every other page
+    belongs to exactly one sequence; every sequence can hold its prompt plus the reserved new tokens."""
+    from types import SimpleNamespace
+    from revisionllm_b200.model import RevisionLlamaForCausalLM as M
+    ps = 32
+    asked = []
+    stub = SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps), ensure_kv=asked.append),
+                           device=torch.device("cpu"), share_prefix_pages=True)
+    lengths = np.array([184, 184, 150, 97, 70], dtype=np.int64)
+    kv = M._alloc_kv(stub, lengths, extra=16, shared_prefix=70)          # 70 common positions -> 2 whole pages
+    table = kv.page_table.numpy()
+    need = [int(np.ceil((l + 16) / ps)) for l in lengths]
+    assert table.shape == (5, max(need))
+    assert (table[:, :2] == table[0, :2]).all() and table[0, :2].tolist() == [0, 1]
+    own = [table[i, 2:need[i]].tolist() for i in range(5)]
+    flat = [p for row in own for p in row]
+    assert len(flat) == len(set(flat)) and not set(flat) & {0, 1}        # disjoint, and never a shared page
+    assert asked == [2 + len(flat)] and max(flat) == asked[0] - 1         # the pool is asked for exactly what is mapped
+    # a prefix longer than the shortest prompt shares only that prompt's whole pages; one sequence shares nothing
+    kv = M._alloc_kv(stub, np.array([184, 40], dtype=np.int64), extra=16, shared_prefix=100)
+    t = kv.page_table.numpy()
+    assert (t[:, 0] == 0).all() and t[0, 1] != t[1, 1]
+    kv = M._alloc_kv(stub, np.array([184], dtype=np.int64), extra=16, shared_prefix=100)
+    assert kv.page_table.numpy()[0].tolist() == list(range(int(np.ceil(200 / ps))))
+    stub.share_prefix_pages = False
+    t = M._alloc_kv(stub, lengths, extra=16, shared_prefix=70).page_table.numpy()
+    assert len({int(p) for i in range(5) for p in t[i, :need[i]]}) == sum(need)
