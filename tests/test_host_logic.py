@@ -353,3 +353,45 @@ def test_kv_page_table_shares_whole_prefix_pages_only():
     stub.share_prefix_pages = False
     t = M._alloc_kv(stub, lengths, extra=16, shared_prefix=70).page_table.numpy()
     assert len({int(p) for i in range(5) for p in t[i, :need[i]]}) == sum(need)
+
+
+def test_checkpoint_readers_and_key_cleanup(tmp_path):
+    """checkpoint.load_hf_checkpoint over every directory layout builder.py's `from_pretrained` accepts (sharded / single,
+    safetensors / .bin) and the key clean-up of builder.py:12-15."""
+    import json
+    from safetensors.torch import save_file
+    from revisionllm_b200 import checkpoint
+    from revisionllm_b200._cabi import RvlError
+    g = torch.Generator().manual_seed(1)
+    sd = {f"model.layers.{i}.mlp.up_proj.weight": torch.randn(4, 3, generator=g).to(torch.bfloat16) for i in range(4)}
+    sd["lm_head.weight"] = torch.randn(5, 3, generator=g).to(torch.bfloat16)
+    keys = sorted(sd)
+    same = lambda a: set(a) == set(sd) and all(torch.equal(a[k], sd[k]) for k in sd)
+    # sharded safetensors with an index
+    d = tmp_path / "st_sharded"; os.makedirs(d)
+    parts = {"model-00001-of-00002.safetensors": keys[:2], "model-00002-of-00002.safetensors": keys[2:]}
+    for f, ks in parts.items():
+        save_file({k: sd[k] for k in ks}, str(d / f))
+    json.dump({"weight_map": {k: f for f, ks in parts.items() for k in ks}}, open(d / "model.safetensors.index.json", "w"))
+    assert same(checkpoint.load_hf_checkpoint(str(d)))
+    # sharded .bin with an index
+    d = tmp_path / "bin_sharded"; os.makedirs(d)
+    parts = {"pytorch_model-00001-of-00002.bin": keys[:3], "pytorch_model-00002-of-00002.bin": keys[3:]}
+    for f, ks in parts.items():
+        torch.save({k: sd[k] for k in ks}, d / f)
+    json.dump({"weight_map": {k: f for f, ks in parts.items() for k in ks}}, open(d / "pytorch_model.bin.index.json", "w"))
+    assert same(checkpoint.load_hf_checkpoint(str(d)))
+    # single files
+    d = tmp_path / "st_single"; os.makedirs(d)
+    save_file(sd, str(d / "model.safetensors"))
+    assert same(checkpoint.load_hf_checkpoint(str(d)))
+    d = tmp_path / "bin_single"; os.makedirs(d)
+    torch.save(sd, d / "pytorch_model.bin")
+    assert same(checkpoint.load_hf_checkpoint(str(d)))
+    d = tmp_path / "empty"; os.makedirs(d)
+    with pytest.raises(RvlError):
+        checkpoint.load_hf_checkpoint(str(d))
+    # builder.py:12-15: strip "base_model." and, if any key then starts with "model.model.", one more "model."
+    raw = {"base_model.model.model.norm.weight": 1, "base_model.model.model.mm_projector.bias": 2, "base_model.model.lm_head.weight": 3}
+    assert checkpoint.strip_lora_prefixes(raw) == {"model.norm.weight": 1, "model.mm_projector.bias": 2, "lm_head.weight": 3}
+    assert checkpoint.strip_lora_prefixes({"model.norm.weight": 1}) == {"model.norm.weight": 1}
