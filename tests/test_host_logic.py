@@ -395,3 +395,33 @@ def test_checkpoint_readers_and_key_cleanup(tmp_path):
     raw = {"base_model.model.model.norm.weight": 1, "base_model.model.model.mm_projector.bias": 2, "base_model.model.lm_head.weight": 3}
     assert checkpoint.strip_lora_prefixes(raw) == {"model.norm.weight": 1, "model.mm_projector.bias": 2, "lm_head.weight": 3}
     assert checkpoint.strip_lora_prefixes({"model.norm.weight": 1}) == {"model.norm.weight": 1}
+
+
+def test_feature_store_reads_blobs_written_by_the_reference_writer(golden_dir, tmp_path):
+    """features.FeatureStore against LMDB values produced by the reference's own `dumps_npz` (tests/golden/make_golden_blobs.py),
+    its own writer, a directory of .npy files, and the failure modes."""
+    from revisionllm_b200 import features as ft
+    from revisionllm_b200._cabi import RvlError
+    g = np.load(os.path.join(golden_dir, "feature_blobs.npz"))
+    store = ft.FeatureStore({"movie": g["video_blob"].tobytes(), "q": g["query_blob"].tobytes()})
+    assert store.kind == "dict"
+    v = store.video("movie")
+    assert v.dtype == np.float32 and np.array_equal(v, g["features"])
+    tok, cls = store.query("q")
+    assert np.array_equal(tok, g["token_features"]) and np.array_equal(cls, g["cls_features"])
+    with pytest.raises(KeyError):
+        store.video("absent")
+    # our writer produces blobs the same reader (np.load on the bytes, eval_nlq_negative.py:193-197) accepts
+    again = ft.loads_npz(ft.dumps_npz({"features": g["features"]}))
+    assert np.array_equal(again["features"], g["features"])
+    # bare .npy per video (VidChapters, eval_nlq_negative.py:198-200)
+    np.save(tmp_path / "vid7.npy", g["features"])
+    npy = ft.FeatureStore(str(tmp_path))
+    assert npy.kind == "npy" and np.array_equal(npy.video("vid7"), g["features"])
+    # an LMDB environment needs the `lmdb` module, which this image does not have: loud failure, no fallback
+    try:
+        import lmdb  # noqa: F401
+    except ImportError:
+        os.makedirs(tmp_path / "env")
+        with pytest.raises(RvlError):
+            ft.FeatureStore(str(tmp_path / "env"))
