@@ -425,3 +425,39 @@ def test_feature_store_reads_blobs_written_by_the_reference_writer(golden_dir, t
         os.makedirs(tmp_path / "env")
         with pytest.raises(RvlError):
             ft.FeatureStore(str(tmp_path / "env"))
+
+
+def test_window_builders_match_tables_produced_by_the_reference_source(golden_dir):
+    """tests/golden/windows.json holds what the reference's own window-building source lines (eval_nlq_negative.py:224-240,
+    eval_nlq_retrieval_e2e2.py:262-294, exec'd by make_golden_windows.py) produce; the host mirrors and the oracle must agree."""
+    import json
+    g = json.load(open(os.path.join(golden_dir, "windows.json")))
+    for c in g["stage1"]:
+        clip_length = c["debug_window"] * c["feature_fps"]
+        for impl in (scoring.stage1_windows, scoring_ref.stage1_windows):
+            idx = impl(c["ctx_l"], clip_length, c["num_frames"])
+            rows = idx.tolist()
+            if c["baseline"]:
+                rows = [rows[1]]                                          # --baseline keeps window 1 only (:228)
+            if c["plus_baseline"]:                                        # the whole-video row of --plus_baseline (:237-240)
+                rows = rows + [np.linspace(0, c["ctx_l"] - 1, c["num_frames"], dtype=np.int32).tolist()]
+            assert rows == c["windows"], (impl.__module__, c["ctx_l"], clip_length)
+    for c in g["stage2"]:
+        clip_length = c["debug_window"] * c["feature_fps"]
+        for mod in (scoring, scoring_ref):
+            idx, times = mod.stage2_windows(c["ctx_l"], clip_length, c["num_frames"], c["stride"])
+            assert [list(t) for t in times] == c["times"] and idx.shape[0] == c["n_windows"]
+            if c["stage1_answers"] is None:
+                sel = list(range(idx.shape[0]))                           # no stage-1 log: every window (:293-294)
+            else:
+                sel = mod.stage2_select_windows(c["stage1_answers"], idx.shape[0], c["batch"], c["stride"])
+            want = c["grounding_windows"]
+            if c["stage1_answers"] is not None and len(want) >= c["batch"] and want != sorted(want):
+                # no padding needed: the reference keeps `list(set(...))` as CPython's set iterates it (it only sorts after
+                # padding, :289) and then permutes the windows at random anyway (:348); the mirrors return the same windows sorted
+                assert sorted(sel) == sorted(want) and sel == sorted(sel)
+            else:
+                assert sel == want, (mod.__name__, c["ctx_l"], c["batch"])
+            # negative ids (a positive stage-1 window 0 maps to -3..-1) index from the end, like the reference's list indexing
+            first = [int(idx[i][0]) for i in want]
+            assert first == c["selected_first_frames"]
