@@ -199,9 +199,14 @@ def ragged_sweep(model, windows: Sequence[torch.Tensor], input_ids: torch.Tensor
 
 
 def _stage2_plan(N: int, batch: int, zooms: Sequence[int], gen: Optional[torch.Generator]) -> List[Dict]:
-    """The generate() calls of one query's hierarchical pass, in the reference's order (e2e2:337-386): for each zoom,
-    chunks of batch // zoom windows (the last chunk is shifted back to full size), permuted, each window repeated `zoom` times."""
+    """The generate() calls of one query's hierarchical pass, in the reference's order (e2e2:337-353): for each zoom,
+    chunks of batch // zoom windows (the last chunk is shifted back to full size), permuted, each window repeated `zoom` times.
+    With fewer windows than one chunk the shifted start goes negative and the reference's `features[start:end]` follows
+    Python's slicing rules (20 windows, chunks of 25: start = -5 keeps the LAST five; 12 windows: start = -13 keeps all);
+    `start` is kept as computed because the answer is mapped back through `starts[i] + j` (:373).  Pinned by
+    tests/golden/stage2_plan.json, which the reference's own loop produced."""
     calls: List[Dict] = []
+    ids = torch.arange(N)
     for zoom in zooms:
         b = max(1, batch // zoom)
         n_chunks = (N + b - 1) // b
@@ -209,10 +214,11 @@ def _stage2_plan(N: int, batch: int, zooms: Sequence[int], gen: Optional[torch.G
             start = i * b
             end = min(start + b, N)
             if end - start < b:
-                start = max(0, end - b)
-            n = end - start
+                start = end - b
+            chunk = ids[start:end]
+            n = int(chunk.shape[0])
             idx = torch.randperm(n, generator=gen) if gen is not None else torch.arange(n)
-            rows = (start + idx).repeat_interleave(zoom) if zoom > 1 else (start + idx)
+            rows = chunk[idx].repeat_interleave(zoom) if zoom > 1 else chunk[idx]
             calls.append(dict(zoom=zoom, start=start, n=n, idx=idx, rows=rows))
     return calls
 

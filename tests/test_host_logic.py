@@ -461,3 +461,18 @@ def test_window_builders_match_tables_produced_by_the_reference_source(golden_di
             # negative ids (a positive stage-1 window 0 maps to -3..-1) index from the end, like the reference's list indexing
             first = [int(idx[i][0]) for i in want]
             assert first == c["selected_first_frames"]
+
+
+def test_stage2_call_plan_matches_the_reference_loop(golden_dir):
+    """sweep._stage2_plan against tests/golden/stage2_plan.json (the reference's own zoom loop, exec'd by
+    make_golden_stage2_plan.py): chunk starts, permutations (same generator seed) and the windows of every call, including
+    the cases with fewer windows than one chunk, where the reference's negative slice start applies."""
+    import json
+    g = json.load(open(os.path.join(golden_dir, "stage2_plan.json")))
+    for c in g["cases"]:
+        gen = torch.Generator().manual_seed(c["seed"])
+        plan = sweep._stage2_plan(c["n_windows"], c["batch"], (4, 2, 1), gen)
+        assert [p["zoom"] for p in plan] == c["zooms"]
+        assert [p["start"] for p in plan] == c["starts"], (c["n_windows"], c["batch"])
+        assert [p["idx"].tolist() for p in plan] == c["perms"]
+        assert [p["rows"].tolist() for p in plan] == c["call_windows"]
