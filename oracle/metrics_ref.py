@@ -3,6 +3,8 @@
 Plain-Python restatement of the reference's answer -> proposal -> score -> rank rules:
   * `iou`                      /root/reference/revisionllm/eval/eval_nlq_negative.py:79-112
   * `merge_scores`             ... eval_nlq_negative.py:317-336 (lives in oracle/scoring_ref.py)
+  * `stage2_iou`               /root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:109-139 (pinned by
+                               tests/golden/stage2_iou.json: the reference's own function, lifted with `ast`)
   * `merge_with_retrieval`     /root/reference/revisionllm/eval/metric_retrieval_forward.py:104-177 (the `--single` branch,
                                buffer = 0; the script's main block, restated as a function)
   * `grounding_metrics_stream` /root/reference/revisionllm/eval/metric_retrieval_forward.py:35-56
@@ -46,6 +48,32 @@ def iou(outputs: Sequence[str], gt: Tuple[float, float], num_frames_clip: int, n
         union = max(t, e) - min(f, s)
         ious.append(round(inter / union, 2))
     return clip_frames, ious, kept_scores
+
+
+def stage2_iou(outputs: Sequence[str], gt: Sequence[float], num_frames_video: int, starts: Sequence[int],
+               indexes: Sequence[Sequence[int]], hierarchy_zooms: Sequence[int], grounding_windows: Sequence[int]):
+    """/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:109-139, statement by statement."""
+    frames = []
+    clip_frames = {}
+    for i, output in enumerate(outputs):
+        m = re.search(r"(\d+)", output)
+        if m:
+            n = int(m.group(1))
+            n = n // hierarchy_zooms[i]                                   # :117
+            if n < len(indexes[i]):                                       # :118-119
+                n = int(indexes[i][n])
+            n = starts[i] + n                                             # :120
+            n = max(0, n)
+            n = min(len(grounding_windows) - 1, n)
+            n = grounding_windows[n]                                      # :123
+            to = n
+            n = max(0, n - 1)
+            to = min(num_frames_video, to + 1)
+            clip_frames[i] = (int(n), int(to))
+            frames.append((n, to))
+    s, e = min(gt), max(gt)
+    hits = [max(0, min(t, e) - max(f, s)) for f, t in frames]
+    return clip_frames, [1] if sum(hits) > 0 else [0]
 
 
 def merge_with_retrieval(gl: dict, rl: dict, rl2: Optional[dict], buffer: int = 0) -> dict:

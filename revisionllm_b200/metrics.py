@@ -2,6 +2,7 @@
 
 Host-side mirror of the reference's evaluation tail, written for this code base:
   * `iou`                      /root/reference/revisionllm/eval/eval_nlq_negative.py:79-112
+  * `stage2_frames`            /root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:109-139 (the stage-2 script's `iou`)
   * `cover_mask`               /root/reference/revisionllm/eval/metric_retrieval_forward.py:119-135 (windows kept by stage 2)
   * `rank_query`               eval_nlq_negative.py:317-336 + metric_retrieval_forward.py:137-160, numeric part on the GPU
                                (`rvl_merge_rank`)
@@ -52,6 +53,35 @@ def iou(outputs: Sequence[str], gt: Tuple[float, float], num_frames_clip: int, n
         ious.append(round(inter / (max(t, e) - min(f, s)), 2))
     kept = [scores[w] for w, _, _ in rows] if len(scores) > 0 else []
     return clip_frames, ious, kept
+
+
+_INT = re.compile(r"(\d+)")
+
+
+def stage2_frames(outputs: Sequence[str], gt: Sequence[float], num_frames_video: int, starts: Sequence[int],
+                  indexes: Sequence[Sequence[int]], hierarchy_zooms: Sequence[int], grounding_windows: Sequence[int]):
+    """The stage-2 script's `iou` (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:109-139): the first integer
+    of answer i, divided by the call's zoom, indexes the call's permuted chunk; `starts[i] +` that, clamped, indexes
+    `grounding_windows`; the window w becomes the frame range (max(0, w - 1), min(num_frames_video, w + 1)) of the stage-2
+    log (`clip_frames`, what `cover_mask` consumes), and the query counts as a hit when any range overlaps [min(gt), max(gt)].
+    Same return value as the reference: ({call: (from, to)}, [1] or [0]).  `starts` / `indexes` / `hierarchy_zooms` are the
+    per-call lists of the zoom loop (`sweep.stage2_pass` returns them as `start` / `perm` / `zoom`)."""
+    clip_frames: Dict[int, Tuple[int, int]] = {}
+    s, e = min(gt), max(gt)
+    overlap = 0
+    for i, text in enumerate(outputs):
+        m = _INT.search(text)
+        if m is None:
+            continue
+        j = int(m.group(1)) // hierarchy_zooms[i]
+        if j < len(indexes[i]):
+            j = int(indexes[i][j])
+        j = min(len(grounding_windows) - 1, max(0, starts[i] + j))
+        w = int(grounding_windows[j])
+        lo, hi = max(0, w - 1), min(num_frames_video, w + 1)
+        clip_frames[i] = (lo, hi)
+        overlap += max(0, min(hi, e) - max(lo, s))
+    return clip_frames, [1] if overlap > 0 else [0]
 
 
 def cover_mask(n_windows: int, stage2_frames: Dict, buffer: int = 0) -> np.ndarray:

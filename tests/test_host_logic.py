@@ -476,3 +476,34 @@ def test_stage2_call_plan_matches_the_reference_loop(golden_dir):
         assert [p["start"] for p in plan] == c["starts"], (c["n_windows"], c["batch"])
         assert [p["idx"].tolist() for p in plan] == c["perms"]
         assert [p["rows"].tolist() for p in plan] == c["call_windows"]
+
+
+def test_stage2_frames_match_the_reference_iou(golden_dir):
+    """metrics.stage2_frames and the oracle's stage2_iou against tests/golden/stage2_iou.json (the stage-2 script's own `iou`,
+    lifted by make_golden_stage2_iou.py); the window `sweep._stage2_finish` reports is the one those frames are built around."""
+    import json
+    from oracle import metrics_ref
+    from revisionllm_b200 import metrics
+    g = json.load(open(os.path.join(golden_dir, "stage2_iou.json")))
+    assert any(c["hit"] == [1] for c in g["cases"]) and any(c["hit"] == [0] for c in g["cases"])
+    for c in g["cases"]:
+        args = (c["outputs"], c["gt"], c["num_frames_video"], c["starts"], c["indexes"], c["hierarchy_zooms"], c["grounding_windows"])
+        want = {int(k): tuple(v) for k, v in c["clip_frames"].items()}
+        for fn in (metrics.stage2_frames, metrics_ref.stage2_iou):
+            frames, hit = fn(*args)
+            assert {k: tuple(v) for k, v in frames.items()} == want and hit == c["hit"], fn.__module__
+        # the driver's own mapping (first integer // zoom -> permuted chunk -> grounding window)
+        calls = [dict(zoom=z, start=s0, n=len(ix), idx=torch.tensor(ix)) for z, s0, ix in zip(c["hierarchy_zooms"], c["starts"], c["indexes"])]
+        results = [dict(tokens=torch.tensor([0]), stats=torch.tensor([1.0, 1.0, 1.0, 0.0])) for _ in calls]
+        texts = iter(c["outputs"])
+
+        def number(_tok):
+            m = re.search(r"(\d+)", next(texts))
+            return int(m.group(1)) if m else None
+        out = sweep._stage2_finish(calls, results, c["grounding_windows"], number)
+        for i, r in enumerate(out):
+            if i in want:
+                w = r["window"]
+                assert (max(0, w - 1), min(c["num_frames_video"], w + 1)) == want[i]
+            else:
+                assert r["window"] is None
