@@ -507,3 +507,18 @@ def test_stage2_frames_match_the_reference_iou(golden_dir):
                 assert (max(0, w - 1), min(c["num_frames_video"], w + 1)) == want[i]
             else:
                 assert r["window"] is None
+
+
+def test_inline_merge_matches_the_reference_source(golden_dir):
+    """scoring.merge_scores (and the oracle's) against tests/golden/merge_inline.json: the reference's own normalise + merge
+    lines (eval_nlq_negative.py:321-335), exec'd by make_golden_merge.py.  Bit-exact: the same Python float arithmetic."""
+    import json
+    g = json.load(open(os.path.join(golden_dir, "merge_inline.json")))
+    for c in g["cases"]:
+        for mod in (scoring, scoring_ref):
+            if c["score"] == "cosine_sim":                         # 'entropy' not in args.score: the (normalised) cosine score alone
+                cos = c["score_cos"]
+                got = [v / max(cos) for v in cos] if (c["normalize"] and cos) else list(cos)
+            else:
+                got = mod.merge_scores(c["score_cos"], c["scores_entropy"], mode=c["score_merge"], normalize=c["normalize"])
+            assert got == c["scores"], (mod.__name__, c["score"], c["score_merge"], c["normalize"], len(c["score_cos"]))
