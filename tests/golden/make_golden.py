@@ -90,6 +90,30 @@ def case_stage1(ref, name, cfg, n_seg, n_frames, n_pre, n_post, steps, ragged=Fa
     print(name, "embeds", tuple(embeds.shape), "tokens", toks[0].tolist())
 
 
+def case_stage1_truncated(ref, name, cfg, n_seg, n_frames, n_pre, n_post, max_len):
+    """`tokenizer_model_max_length` (vtimellm_arch.py:239-243): every spliced row is cut to max_len positions - inside the
+    visual block for the long rows, not at all for the short ones - then right-padded (:245-276).  Splice only."""
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    model.config.tokenizer_model_max_length = max_len
+    feats = syn.make_features(n_seg, n_frames, cfg.adapter_dim, seed=31).float()
+    base = syn.make_prompt_ids(cfg, n_pre, n_post, seed=32)
+    ids = base[None].repeat(n_seg, 1)
+    Ltxt = ids.shape[1]
+    attn = torch.ones(n_seg, Ltxt, dtype=torch.bool)
+    for b in range(n_seg):
+        cut = (b * 5) % 9                        # 0 .. 8 trailing text ids masked out
+        if cut:
+            attn[b, Ltxt - cut:] = False
+            ids[b, Ltxt - cut:] = 0
+    with torch.inference_mode():
+        r = model.prepare_inputs_labels_for_multimodal(ids, None, attn, None, None, feats, None, None, None, None)
+        _, pos, am, _, embeds, _ = r
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), digest=syn.weights_digest(w), feats=feats.numpy(), ids=ids.numpy(), attn=attn.numpy(),
+                        max_len=np.int64(max_len), embeds=embeds.numpy(), embeds_mask=am.bool().numpy())
+    print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
+
+
 def case_stage1_memory(ref, name, cfg, n_seg, n_frames, n_mem, n_prefix, steps):
     """The <memory> streaming branch (vtimellm_arch.py:208-232): ids hold -200 and -300, the memory block is
     [embed_tokens(prefix_memory) ; mm_projector(visual_memory)]."""
@@ -198,6 +222,9 @@ def main():
     case_stage1(ref, "stage1_tiny", syn.TINY, n_seg=3, n_frames=20, n_pre=6, n_post=9, steps=6)
     case_stage1(ref, "stage1_ragged", syn.TINY, n_seg=4, n_frames=12, n_pre=5, n_post=11, steps=4, ragged=True)
     case_stage1_memory(ref, "stage1_memory", syn.TINY, n_seg=2, n_frames=10, n_mem=3, n_prefix=4, steps=4)
+    if "--all" in sys.argv or "truncated" in sys.argv:
+        case_stage1_truncated(ref, "stage1_truncated", syn.TINY, n_seg=4, n_frames=14, n_pre=5, n_post=12, max_len=17)
+        case_stage1_truncated(ref, "stage1_truncated_text", syn.TINY, n_seg=3, n_frames=6, n_pre=5, n_post=12, max_len=19)
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
     case_scoring(ref, "scoring")
     case_prompt(ref, "prompt")

@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import clip_encoder_ref, llama_ref, scoring_ref, splice_ref
@@ -178,3 +179,32 @@ def test_philox_known_answers_and_sampling_rule():
     flat = np.zeros((64, 8), dtype=np.float32)
     toks, _ = sampling_ref.multinomial_draw(flat, 1.0, seed=3, step=2)
     assert toks == [int(sampling_ref.uniform(3, 2, b) * 8) for b in range(64)]
+
+
+@pytest.mark.parametrize("name", ["stage1_truncated", "stage1_truncated_text"])
+def test_truncation_to_tokenizer_model_max_length_matches_reference(golden_dir, name):
+    """`config.tokenizer_model_max_length` (vtimellm_arch.py:239-243) cuts every spliced row - inside the visual block in the
+    first fixture, inside the trailing text / not at all in the second.  The oracle's splice and the product's host index
+    plan (`engine.plan_splice`, replayed here with plain gathers) must both reproduce the reference's padded embeddings."""
+    from revisionllm_b200.engine import plan_splice
+    g = _load(golden_dir, name)
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    assert syn.weights_digest(w) == str(g["digest"])
+    feats, ids, attn = torch.from_numpy(g["feats"]), torch.from_numpy(g["ids"]), torch.from_numpy(g["attn"])
+    max_len = int(g["max_len"])
+    img = splice_ref.mm_projector_linear(w, feats)
+    emb = splice_ref.splice(w, ids, img, attention_mask=attn, max_length=max_len)
+    x, m, _ = splice_ref.right_pad(emb)
+    np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)
+    assert m.numpy().tolist() == g["embeds_mask"].tolist()
+    # the product's plan: text ids -> embedding rows, visual source rows -> projected rows, both scattered to packed rows
+    plan = plan_splice(ids.numpy(), [feats.shape[1]] * feats.shape[0], attn.numpy(), max_length=max_len)
+    assert plan["lengths"].tolist() == g["embeds_mask"].sum(1).tolist()
+    T = int(plan["cu_seqlens"][-1])
+    packed = torch.zeros(T, x.shape[2])
+    packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"].float()[torch.from_numpy(plan["text_ids"]).long()]
+    packed[torch.from_numpy(plan["vis_dst"]).long()] = img.reshape(-1, img.shape[-1]).float()[torch.from_numpy(plan["vis_src"]).long()]
+    cu = plan["cu_seqlens"]
+    for b in range(ids.shape[0]):
+        np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : cu[b + 1] - cu[b]], rtol=1e-5, atol=1e-5)
