@@ -114,6 +114,26 @@ def case_stage1_truncated(ref, name, cfg, n_seg, n_frames, n_pre, n_post, max_le
     print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
 
 
+def case_stage1_no_placeholder(ref, name, cfg, n_seg, n_frames, n_pre, n_post, rows_without):
+    """A batch in which some rows hold no <video> placeholder (vtimellm_arch.py:168-176): such a row is text only, but it
+    still consumes its visual block (`cur_image_idx += 1`), so the following rows keep theirs.  Splice only."""
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    feats = syn.make_features(n_seg, n_frames, cfg.adapter_dim, seed=41).float()
+    base = syn.make_prompt_ids(cfg, n_pre, n_post, seed=42)
+    ids = base[None].repeat(n_seg, 1)
+    for b in rows_without:
+        ids[b][ids[b] == ref.constants.IMAGE_TOKEN_INDEX] = 7 + b
+    with torch.inference_mode():
+        r = model.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, feats, None, None, None, None)
+        _, _, am, _, embeds, _ = r
+    if am is None:
+        am = torch.ones(embeds.shape[:2], dtype=torch.bool)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), digest=syn.weights_digest(w), feats=feats.numpy(), ids=ids.numpy(),
+                        embeds=embeds.numpy(), embeds_mask=am.bool().numpy())
+    print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
+
+
 def case_stage1_memory(ref, name, cfg, n_seg, n_frames, n_mem, n_prefix, steps):
     """The <memory> streaming branch (vtimellm_arch.py:208-232): ids hold -200 and -300, the memory block is
     [embed_tokens(prefix_memory) ; mm_projector(visual_memory)]."""
@@ -225,6 +245,7 @@ def main():
     if "--all" in sys.argv or "truncated" in sys.argv:
         case_stage1_truncated(ref, "stage1_truncated", syn.TINY, n_seg=4, n_frames=14, n_pre=5, n_post=12, max_len=17)
         case_stage1_truncated(ref, "stage1_truncated_text", syn.TINY, n_seg=3, n_frames=6, n_pre=5, n_post=12, max_len=19)
+        case_stage1_no_placeholder(ref, "stage1_no_placeholder", syn.TINY, n_seg=4, n_frames=9, n_pre=5, n_post=8, rows_without=(1, 3))
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
     case_scoring(ref, "scoring")
     case_prompt(ref, "prompt")

@@ -208,3 +208,28 @@ def test_truncation_to_tokenizer_model_max_length_matches_reference(golden_dir, 
     cu = plan["cu_seqlens"]
     for b in range(ids.shape[0]):
         np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : cu[b + 1] - cu[b]], rtol=1e-5, atol=1e-5)
+
+
+def test_rows_without_placeholder_match_reference(golden_dir):
+    """vtimellm_arch.py:168-176: a row without <video> is text only and still consumes its visual block, so the next rows
+    keep theirs.  Oracle splice and the product's index plan against the reference's padded embeddings."""
+    from revisionllm_b200.engine import plan_splice
+    g = _load(golden_dir, "stage1_no_placeholder")
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    assert syn.weights_digest(w) == str(g["digest"])
+    feats, ids = torch.from_numpy(g["feats"]), torch.from_numpy(g["ids"])
+    img = splice_ref.mm_projector_linear(w, feats)
+    emb = splice_ref.splice(w, ids, img)
+    lens = [e.shape[0] for e in emb]
+    assert sorted(set(lens)) == [ids.shape[1], ids.shape[1] - 1 + feats.shape[1]]           # text-only rows are shorter
+    x, _, _ = splice_ref.right_pad(emb)
+    np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)                  # zero padding behind the short rows
+    plan = plan_splice(ids.numpy(), [feats.shape[1]] * feats.shape[0])
+    assert plan["lengths"].tolist() == lens
+    packed = torch.zeros(int(plan["cu_seqlens"][-1]), x.shape[2])
+    packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"].float()[torch.from_numpy(plan["text_ids"]).long()]
+    packed[torch.from_numpy(plan["vis_dst"]).long()] = img.reshape(-1, img.shape[-1]).float()[torch.from_numpy(plan["vis_src"]).long()]
+    cu = plan["cu_seqlens"]
+    for b in range(ids.shape[0]):
+        np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : lens[b]], rtol=1e-5, atol=1e-5)
