@@ -134,6 +134,30 @@ def case_stage1_no_placeholder(ref, name, cfg, n_seg, n_frames, n_pre, n_post, r
     print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
 
 
+def case_stage1_image_list(ref, name, cfg, frames, n_pre, n_post):
+    """`images` as a LIST of [F_i, 768] tensors with different F_i (vtimellm_arch.py:102-109: one projector call over the
+    concatenation, split back per row), prompts right-padded with an attention mask - the VidChapters-shaped ragged batch."""
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    n_seg = len(frames)
+    images = [syn.make_features(1, f, cfg.adapter_dim, seed=50 + i)[0].float() for i, f in enumerate(frames)]
+    base = syn.make_prompt_ids(cfg, n_pre, n_post, seed=52)
+    ids = base[None].repeat(n_seg, 1)
+    Ltxt = ids.shape[1]
+    attn = torch.ones(n_seg, Ltxt, dtype=torch.bool)
+    for b in range(n_seg):
+        cut = (b * 2) % 5
+        if cut:
+            attn[b, Ltxt - cut:] = False
+            ids[b, Ltxt - cut:] = 0
+    with torch.inference_mode():
+        r = model.prepare_inputs_labels_for_multimodal(ids, None, attn, None, None, images, None, None, None, None)
+        _, _, am, _, embeds, _ = r
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), digest=syn.weights_digest(w), frames=np.array(frames),
+                        images=torch.cat(images).numpy(), ids=ids.numpy(), attn=attn.numpy(), embeds=embeds.numpy(), embeds_mask=am.bool().numpy())
+    print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
+
+
 def case_stage1_memory(ref, name, cfg, n_seg, n_frames, n_mem, n_prefix, steps):
     """The <memory> streaming branch (vtimellm_arch.py:208-232): ids hold -200 and -300, the memory block is
     [embed_tokens(prefix_memory) ; mm_projector(visual_memory)]."""
@@ -246,6 +270,7 @@ def main():
         case_stage1_truncated(ref, "stage1_truncated", syn.TINY, n_seg=4, n_frames=14, n_pre=5, n_post=12, max_len=17)
         case_stage1_truncated(ref, "stage1_truncated_text", syn.TINY, n_seg=3, n_frames=6, n_pre=5, n_post=12, max_len=19)
         case_stage1_no_placeholder(ref, "stage1_no_placeholder", syn.TINY, n_seg=4, n_frames=9, n_pre=5, n_post=8, rows_without=(1, 3))
+        case_stage1_image_list(ref, "stage1_image_list", syn.TINY, frames=(11, 3, 1, 17, 8), n_pre=5, n_post=9)
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
     case_scoring(ref, "scoring")
     case_prompt(ref, "prompt")

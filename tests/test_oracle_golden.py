@@ -233,3 +233,31 @@ def test_rows_without_placeholder_match_reference(golden_dir):
     cu = plan["cu_seqlens"]
     for b in range(ids.shape[0]):
         np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : lens[b]], rtol=1e-5, atol=1e-5)
+
+
+def test_list_of_images_with_ragged_frame_counts_matches_reference(golden_dir):
+    """vtimellm_arch.py:102-109: `images` as a list of [F_i, 768] tensors (one projector call, split per row) with right-padded
+    prompts - the VidChapters-shaped batch.  Oracle splice and the product's index plan against the reference's embeddings."""
+    from revisionllm_b200.engine import plan_splice
+    g = _load(golden_dir, "stage1_image_list")
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    assert syn.weights_digest(w) == str(g["digest"])
+    frames = [int(f) for f in g["frames"]]
+    flat = torch.from_numpy(g["images"])
+    images = list(torch.split(flat, frames, dim=0))
+    ids, attn = torch.from_numpy(g["ids"]), torch.from_numpy(g["attn"])
+    proj = [splice_ref.mm_projector_linear(w, im[None])[0] for im in images]
+    emb = splice_ref.splice(w, ids, proj, attention_mask=attn)
+    x, m, _ = splice_ref.right_pad(emb)
+    np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)
+    assert m.numpy().tolist() == g["embeds_mask"].tolist()
+    plan = plan_splice(ids.numpy(), frames, attn.numpy())
+    assert plan["lengths"].tolist() == g["embeds_mask"].sum(1).tolist()
+    allproj = torch.cat(proj).float()
+    packed = torch.zeros(int(plan["cu_seqlens"][-1]), x.shape[2])
+    packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"].float()[torch.from_numpy(plan["text_ids"]).long()]
+    packed[torch.from_numpy(plan["vis_dst"]).long()] = allproj[torch.from_numpy(plan["vis_src"]).long()]
+    cu = plan["cu_seqlens"]
+    for b in range(ids.shape[0]):
+        np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : cu[b + 1] - cu[b]], rtol=1e-5, atol=1e-5)
