@@ -158,6 +158,30 @@ def case_stage1_image_list(ref, name, cfg, frames, n_pre, n_post):
     print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
 
 
+def case_decode_fixup(ref, name, cfg):
+    """The one-token branch of prepare_inputs_labels_for_multimodal (vtimellm_arch.py:88-100): the prompt-time mask is
+    extended with ones up to the cache length + 1 and the position of the new token is sum(mask) - 1 - for right-padded
+    rows the padding hole stays in the mask and the new token's position follows the row's own length."""
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    rows = {}
+    for key, (lens, past_len) in dict(step1=((9, 6, 9, 4), 9), step3=((9, 6, 9, 4), 11), full=((7, 7), 7)).items():
+        B, L = len(lens), max(lens)
+        mask = torch.zeros(B, L, dtype=torch.long)
+        for b, n in enumerate(lens):
+            mask[b, :n] = 1
+        if key == "step3":                       # two earlier steps already appended their ones
+            mask = torch.cat([mask, torch.ones(B, 2, dtype=torch.long)], dim=1)
+        past = ((torch.zeros(B, cfg.n_heads, past_len, cfg.head_dim), torch.zeros(B, cfg.n_heads, past_len, cfg.head_dim)),)
+        ids = torch.full((B, 1), 5, dtype=torch.long)
+        with torch.inference_mode():
+            r = model.prepare_inputs_labels_for_multimodal(ids, None, mask, past, None, torch.zeros(B, 2, cfg.adapter_dim), None, None, None, None)
+        rows[key + "_mask_in"], rows[key + "_past_len"] = mask.numpy(), np.int64(past_len)
+        rows[key + "_mask_out"], rows[key + "_pos_out"] = r[2].numpy(), r[1].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rows)
+    print(name, {k: v.tolist() for k, v in rows.items() if k.endswith("pos_out")})
+
+
 def case_stage1_memory(ref, name, cfg, n_seg, n_frames, n_mem, n_prefix, steps):
     """The <memory> streaming branch (vtimellm_arch.py:208-232): ids hold -200 and -300, the memory block is
     [embed_tokens(prefix_memory) ; mm_projector(visual_memory)]."""
@@ -271,6 +295,7 @@ def main():
         case_stage1_truncated(ref, "stage1_truncated_text", syn.TINY, n_seg=3, n_frames=6, n_pre=5, n_post=12, max_len=19)
         case_stage1_no_placeholder(ref, "stage1_no_placeholder", syn.TINY, n_seg=4, n_frames=9, n_pre=5, n_post=8, rows_without=(1, 3))
         case_stage1_image_list(ref, "stage1_image_list", syn.TINY, frames=(11, 3, 1, 17, 8), n_pre=5, n_post=9)
+        case_decode_fixup(ref, "decode_fixup", syn.TINY)
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
     case_scoring(ref, "scoring")
     case_prompt(ref, "prompt")

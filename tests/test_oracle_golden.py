@@ -261,3 +261,15 @@ def test_list_of_images_with_ragged_frame_counts_matches_reference(golden_dir):
     cu = plan["cu_seqlens"]
     for b in range(ids.shape[0]):
         np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : cu[b + 1] - cu[b]], rtol=1e-5, atol=1e-5)
+
+
+def test_decode_step_fixup_matches_reference(golden_dir):
+    """vtimellm_arch.py:88-100 run by the reference itself: mask extended to cache length + 1, position = sum(mask) - 1.
+    For right-padded rows that is the row's OWN length plus the steps already decoded - the `seq_lens` the CUDA decode step
+    uses as position and KV slot of the new token."""
+    g = _load(golden_dir, "decode_fixup")
+    for key, lens, done in (("step1", (9, 6, 9, 4), 0), ("step3", (9, 6, 9, 4), 2), ("full", (7, 7), 0)):
+        am, pos = splice_ref.decode_step_fixup(torch.from_numpy(g[key + "_mask_in"]), int(g[key + "_past_len"]))
+        assert am.numpy().tolist() == g[key + "_mask_out"].tolist()
+        assert pos.numpy().tolist() == g[key + "_pos_out"].tolist()
+        assert [[n + done] for n in lens] == g[key + "_pos_out"].tolist()
