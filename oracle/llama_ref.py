@@ -137,6 +137,15 @@ def embed_tokens(w: Dict[str, torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
     return w["model.embed_tokens.weight"].float()[ids]
 
 
+def eos_bookkeeping(next_tokens: torch.Tensor, unfinished: torch.Tensor, eos_token_id: int, pad_token_id: int
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One step of the reference's EOS rule (/root/reference/revisionllm/model/vtimellm_llama.py:340-356): rows that have
+    finished emit `pad_token_id`; a row finishes with the step in which it emits EOS.  Returns (tokens appended this step,
+    updated unfinished flags).  Pinned by tests/golden/eos_rule.json (the reference's own lines, exec'd)."""
+    tokens = next_tokens * unfinished + pad_token_id * (1 - unfinished)
+    return tokens, unfinished * (tokens != eos_token_id).long()
+
+
 def greedy_decode(
     w: Dict[str, torch.Tensor],
     shape: LlamaShape,
@@ -169,8 +178,7 @@ def greedy_decode(
         scores.append(logits.clone())
         nxt = torch.argmax(logits, dim=-1)
         if stop_on_eos and eos_token_id is not None:
-            nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
-            unfinished = unfinished * (nxt != eos_token_id).long()
+            nxt, unfinished = eos_bookkeeping(nxt, unfinished, eos_token_id, pad_token_id)
         toks.append(nxt)
         if stop_on_eos and unfinished.max() == 0:
             break

@@ -273,3 +273,22 @@ def test_decode_step_fixup_matches_reference(golden_dir):
         assert am.numpy().tolist() == g[key + "_mask_out"].tolist()
         assert pos.numpy().tolist() == g[key + "_pos_out"].tolist()
         assert [[n + done] for n in lens] == g[key + "_pos_out"].tolist()
+
+
+def test_eos_bookkeeping_matches_reference_lines(golden_dir):
+    """llama_ref.eos_bookkeeping (the rule inside the oracle's greedy loop, and the one `sample_greedy_kernel` implements on the
+    device) against tests/golden/eos_rule.json: the reference's own `sample()` lines 340-362, exec'd step by step."""
+    import json
+    g = json.load(open(os.path.join(golden_dir, "eos_rule.json")))
+    assert any(c["stopped_after_step"] is not None for c in g["cases"]) and any(c["stopped_after_step"] is None for c in g["cases"])
+    for c in g["cases"]:
+        raw = torch.tensor(c["raw"])
+        unfinished = torch.ones(raw.shape[1], dtype=torch.long)
+        for t in range(len(c["appended"])):
+            tok, unfinished = llama_ref.eos_bookkeeping(raw[t], unfinished, c["eos"], c["pad"])
+            assert tok.tolist() == c["appended"][t] and unfinished.tolist() == c["unfinished"][t], (c["eos"], t)
+            if int(unfinished.max()) == 0:
+                assert c["stopped_after_step"] == t
+                break
+        else:
+            assert c["stopped_after_step"] is None
