@@ -93,9 +93,9 @@ extern "C" {
 int rvl_layernorm(rvl_handle* h, const float* x, const void* w, const void* b, float* y_f32, void* y_bf16,
                   const float* pos, void* y_pos_bf16, int64_t rows, int32_t dim, int32_t period, float eps,
                   rvl_stream stream) {
-  (void)h;
-  if (!x || rows <= 0) return RVL_ERR_INVALID;
-  if (dim % 4 || dim > 1024 || (w != nullptr) != (b != nullptr) || (y_pos_bf16 && (!pos || period <= 0))) return RVL_ERR_INVALID;
+  if (!x || rows <= 0) return report_error(h, RVL_ERR_INVALID, "rvl_layernorm: null argument");
+  if (dim % 4 || dim > 1024 || (w != nullptr) != (b != nullptr) || (y_pos_bf16 && (!pos || period <= 0)))
+    return report_error(h, RVL_ERR_INVALID, "rvl_layernorm: dim must be a multiple of 4 and <= 1024, weight and bias come together, y_pos needs pos and period");
   layernorm_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<const __nv_bfloat16*>(b), y_f32,
       reinterpret_cast<__nv_bfloat16*>(y_bf16), pos, reinterpret_cast<__nv_bfloat16*>(y_pos_bf16), rows, dim,
@@ -106,9 +106,9 @@ int rvl_layernorm(rvl_handle* h, const float* x, const void* w, const void* b, f
 int rvl_mha96(rvl_handle* h, const void* q, int64_t q_stride, const void* k, int64_t k_stride, const void* v,
               int64_t v_stride, void* out, int64_t out_stride, int32_t n_seq, int32_t n_heads, int32_t Tq, int32_t Tk,
               const int32_t* kv_seq_idx, const float* key_mask, rvl_stream stream) {
-  (void)h;
-  if (!q || !k || !v || !out || n_seq <= 0 || Tq <= 0 || Tk <= 0) return RVL_ERR_INVALID;
-  if (q_stride % 8 || k_stride % 8 || v_stride % 8 || out_stride % 2) return RVL_ERR_INVALID;
+  if (!q || !k || !v || !out || n_seq <= 0 || Tq <= 0 || Tk <= 0) return report_error(h, RVL_ERR_INVALID, "rvl_mha96: null argument");
+  if (q_stride % 8 || k_stride % 8 || v_stride % 8 || out_stride % 2)
+    return report_error(h, RVL_ERR_INVALID, "rvl_mha96: q / k / v row strides must be multiples of 8 elements, the out stride of 2");
   return launch_mha96(q, q_stride, k, k_stride, v, v_stride, out, out_stride, n_seq, n_heads, Tq, Tk, kv_seq_idx, key_mask,
                       static_cast<cudaStream_t>(stream));
 }

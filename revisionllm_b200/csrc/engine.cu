@@ -68,6 +68,10 @@ static int fail(const rvl_handle* h, int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+namespace rvl {
+// error reporting for the entry points that live in other translation units (clip_encoder.cu)
+int report_error(const rvl_handle* h, int code, const char* msg) { return fail(h, code, msg); }
+}  // namespace rvl
 static int check_cuda(const rvl_handle* h, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, RVL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));

@@ -110,6 +110,9 @@ inline cudaError_t launch_gemm_k(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return launch_pdl((pdl_mask() & 1) != 0, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
+// engine.cu: sets rvl_last_error (handle and thread) and returns `code`
+int report_error(const rvl_handle* h, int code, const char* msg);
+
 // elementwise.cu
 // y = rmsnorm(x + sum_p partials[p]) ; when x_out != null the summed row is written back (residual update)
 void launch_rmsnorm(const float* x, const void* w, void* y, int64_t n_rows, int dim, float eps, const int32_t* rows,

@@ -522,3 +522,31 @@ def test_inline_merge_matches_the_reference_source(golden_dir):
             else:
                 got = mod.merge_scores(c["score_cos"], c["scores_entropy"], mode=c["score_merge"], normalize=c["normalize"])
             assert got == c["scores"], (mod.__name__, c["score"], c["score_merge"], c["normalize"], len(c["score_cos"]))
+
+
+def test_every_entry_point_rejects_a_null_handle_without_a_gpu():
+    """Error behaviour of the C ABI (include/revisionllm_b200.h): a call with a NULL handle / NULL buffers returns a negative
+    rvl_status and leaves a message in rvl_last_error - no crash, no CUDA call, so this runs on the CPU-only box."""
+    lib = _cabi.load()
+    skipped = {"rvl_abi_version", "rvl_last_error", "rvl_destroy", "rvl_create", "rvl_workspace_bytes", "rvl_kv_bytes",
+               "rvl_debug_gemm_timestamps", "rvl_debug_fused_timestamps"}
+    checked = 0
+    for name, (restype, argtypes) in _cabi.PROTOTYPES.items():
+        if name in skipped:
+            continue
+        args = []
+        for t in argtypes:
+            if t is ctypes.c_void_p or hasattr(t, "contents") or (hasattr(t, "_type_") and not isinstance(t._type_, str)):
+                args.append(None)
+            elif t in (ctypes.c_float, ctypes.c_double):
+                args.append(t(0.0))
+            else:
+                args.append(t(0))
+        rc = getattr(lib, name)(*args)
+        assert isinstance(rc, int) and rc < 0, (name, rc)
+        msg = lib.rvl_last_error(None)
+        assert msg and name.encode() in msg, (name, msg)
+        checked += 1
+    assert checked >= 20
+    assert lib.rvl_create(None, None) < 0
+    lib.rvl_destroy(None)                                  # a no-op, not a crash
