@@ -550,3 +550,27 @@ def test_every_entry_point_rejects_a_null_handle_without_a_gpu():
     assert checked >= 20
     assert lib.rvl_create(None, None) < 0
     lib.rvl_destroy(None)                                  # a no-op, not a crash
+
+
+def test_rvl_create_validates_the_configuration_before_touching_cuda():
+    """include/revisionllm_b200.h `rvl_create`: configurations the kernels do not cover are refused with a message naming the
+    reason (checked before any CUDA call, so the CPU-only box sees them); a valid configuration then fails loudly for want of
+    a GPU - there is no CPU fallback."""
+    lib = _cabi.load()
+    good = dict(hidden=4096, n_layers=32, n_heads=32, head_dim=128, intermediate=11008, vocab=32000, adapter_dim=768, max_pos=4096,
+                kv_page_size=32, device=0, rms_eps=1e-5, rope_theta=10000.0)
+
+    def create(**over):
+        cfg = _cabi.rvl_config(**{**good, **over})
+        h = ctypes.c_void_p()
+        rc = lib.rvl_create(ctypes.byref(cfg), ctypes.byref(h))
+        return rc, (lib.rvl_last_error(None) or b"").decode(), h
+    for over, needle in ((dict(head_dim=64, hidden=2048), "head_dim must be 128"), (dict(hidden=4224), "hidden != n_heads*head_dim"),
+                         (dict(intermediate=11000), "unsupported dimensions"), (dict(vocab=32001), "unsupported dimensions"),
+                         (dict(adapter_dim=770), "unsupported dimensions"), (dict(kv_page_size=0), "bad kv_page_size"),
+                         (dict(kv_page_size=512), "bad kv_page_size")):
+        rc, msg, h = create(**over)
+        assert rc < 0 and needle in msg and not h.value, (over, rc, msg)
+    if not torch.cuda.is_available():
+        rc, msg, h = create()
+        assert rc < 0 and "no CUDA device" in msg and "no CPU fallback" in msg and not h.value
