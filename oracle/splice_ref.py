@@ -115,7 +115,8 @@ def splice(
         pos = torch.where(ids == IMAGE_TOKEN_INDEX)[0].tolist()
         if len(pos) == 0:
             # :168-176 - text only; the image slot is consumed but contributes 0 rows
-            out.append(emb[ids])
+            e = emb[ids]
+            out.append(e[:max_length] if max_length is not None else e)    # :239-243 truncates every row, text-only ones too
             cur_image += 1
             continue
         bounds = [-1] + pos + [ids.shape[0]]

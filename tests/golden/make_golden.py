@@ -114,11 +114,13 @@ def case_stage1_truncated(ref, name, cfg, n_seg, n_frames, n_pre, n_post, max_le
     print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
 
 
-def case_stage1_no_placeholder(ref, name, cfg, n_seg, n_frames, n_pre, n_post, rows_without):
+def case_stage1_no_placeholder(ref, name, cfg, n_seg, n_frames, n_pre, n_post, rows_without, max_len=None):
     """A batch in which some rows hold no <video> placeholder (vtimellm_arch.py:168-176): such a row is text only, but it
     still consumes its visual block (`cur_image_idx += 1`), so the following rows keep theirs.  Splice only."""
     w = syn.make_llama_weights(cfg, seed=0)
     model = ref_shim.build_reference_model(ref, cfg, w)
+    if max_len is not None:
+        model.config.tokenizer_model_max_length = max_len       # :239-243 cuts the text-only rows as well
     feats = syn.make_features(n_seg, n_frames, cfg.adapter_dim, seed=41).float()
     base = syn.make_prompt_ids(cfg, n_pre, n_post, seed=42)
     ids = base[None].repeat(n_seg, 1)
@@ -130,7 +132,7 @@ def case_stage1_no_placeholder(ref, name, cfg, n_seg, n_frames, n_pre, n_post, r
     if am is None:
         am = torch.ones(embeds.shape[:2], dtype=torch.bool)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), digest=syn.weights_digest(w), feats=feats.numpy(), ids=ids.numpy(),
-                        embeds=embeds.numpy(), embeds_mask=am.bool().numpy())
+                        embeds=embeds.numpy(), embeds_mask=am.bool().numpy(), max_len=np.int64(-1 if max_len is None else max_len))
     print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
 
 
@@ -294,6 +296,7 @@ def main():
         case_stage1_truncated(ref, "stage1_truncated", syn.TINY, n_seg=4, n_frames=14, n_pre=5, n_post=12, max_len=17)
         case_stage1_truncated(ref, "stage1_truncated_text", syn.TINY, n_seg=3, n_frames=6, n_pre=5, n_post=12, max_len=19)
         case_stage1_no_placeholder(ref, "stage1_no_placeholder", syn.TINY, n_seg=4, n_frames=9, n_pre=5, n_post=8, rows_without=(1, 3))
+        case_stage1_no_placeholder(ref, "stage1_no_placeholder_truncated", syn.TINY, n_seg=4, n_frames=9, n_pre=5, n_post=8, rows_without=(1, 3), max_len=11)
         case_stage1_image_list(ref, "stage1_image_list", syn.TINY, frames=(11, 3, 1, 17, 8), n_pre=5, n_post=9)
         case_decode_fixup(ref, "decode_fixup", syn.TINY)
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)

@@ -574,3 +574,41 @@ def test_rvl_create_validates_the_configuration_before_touching_cuda():
     if not torch.cuda.is_available():
         rc, msg, h = create()
         assert rc < 0 and "no CUDA device" in msg and "no CPU fallback" in msg and not h.value
+
+
+def test_plan_splice_equals_oracle_splice_on_random_ragged_batches():
+    """engine.plan_splice (the product's host index plan, vectorised fast path and general loop) replayed with plain gathers
+    against oracle/splice_ref.splice over 60 random batches: masks, rows without a placeholder, frame counts from 0 to 9,
+    truncation inside the text in front of, inside, and behind the visual block."""
+    rng = np.random.default_rng(11)
+    H, V = 16, 64
+    w = {"model.embed_tokens.weight": torch.from_numpy(rng.standard_normal((V, H)).astype(np.float32))}
+    for case in range(60):
+        B = int(rng.integers(1, 6))
+        Ltxt = int(rng.integers(4, 12))
+        ids = rng.integers(3, V, size=(B, Ltxt)).astype(np.int64)
+        has = rng.random(B) < (0.75 if case % 3 else 1.0)                  # every third case: all rows have a placeholder (fast path)
+        for b in range(B):
+            if has[b]:
+                ids[b, int(rng.integers(0, Ltxt))] = -200
+        mask = None
+        if case % 2:
+            mask = np.ones((B, Ltxt), dtype=bool)
+            for b in range(B):
+                cut = int(rng.integers(0, 3))
+                if cut:
+                    keep = ids[b] == -200
+                    mask[b, Ltxt - cut:] = keep[Ltxt - cut:]                 # never mask the placeholder itself away
+        frames = [int(rng.integers(0 if case % 5 == 0 else 1, 10)) for _ in range(B)]
+        max_len = None if case % 4 else int(rng.integers(2, Ltxt + 6))
+        proj = [torch.from_numpy(rng.standard_normal((f, H)).astype(np.float32)) for f in frames]
+        want = splice_ref.splice(w, torch.from_numpy(ids), proj, attention_mask=None if mask is None else torch.from_numpy(mask), max_length=max_len)
+        plan = plan_splice(ids, frames, mask, max_length=max_len)
+        assert plan["lengths"].tolist() == [e.shape[0] for e in want], case
+        allproj = torch.cat(proj) if sum(frames) else torch.zeros(0, H)
+        packed = torch.full((int(plan["cu_seqlens"][-1]), H), float("nan"))
+        packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"][torch.from_numpy(plan["text_ids"]).long()]
+        packed[torch.from_numpy(plan["vis_dst"]).long()] = allproj[torch.from_numpy(plan["vis_src"]).long()]
+        cu = plan["cu_seqlens"]
+        for b in range(B):
+            assert torch.equal(packed[cu[b]:cu[b + 1]], want[b]), (case, b)

@@ -210,22 +210,25 @@ def test_truncation_to_tokenizer_model_max_length_matches_reference(golden_dir, 
         np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : cu[b + 1] - cu[b]], rtol=1e-5, atol=1e-5)
 
 
-def test_rows_without_placeholder_match_reference(golden_dir):
+@pytest.mark.parametrize("name", ["stage1_no_placeholder", "stage1_no_placeholder_truncated"])
+def test_rows_without_placeholder_match_reference(golden_dir, name):
     """vtimellm_arch.py:168-176: a row without <video> is text only and still consumes its visual block, so the next rows
     keep theirs.  Oracle splice and the product's index plan against the reference's padded embeddings."""
     from revisionllm_b200.engine import plan_splice
-    g = _load(golden_dir, "stage1_no_placeholder")
+    g = _load(golden_dir, name)
     cfg = syn.TINY
     w = syn.make_llama_weights(cfg, seed=0)
     assert syn.weights_digest(w) == str(g["digest"])
     feats, ids = torch.from_numpy(g["feats"]), torch.from_numpy(g["ids"])
+    max_len = None if int(g["max_len"]) < 0 else int(g["max_len"])        # the truncated fixture cuts the text-only rows too (:239-243)
     img = splice_ref.mm_projector_linear(w, feats)
-    emb = splice_ref.splice(w, ids, img)
+    emb = splice_ref.splice(w, ids, img, max_length=max_len)
     lens = [e.shape[0] for e in emb]
-    assert sorted(set(lens)) == [ids.shape[1], ids.shape[1] - 1 + feats.shape[1]]           # text-only rows are shorter
+    full = [ids.shape[1], ids.shape[1] - 1 + feats.shape[1]]                                  # text-only rows are shorter
+    assert sorted(set(lens)) == sorted({min(n, max_len) if max_len else n for n in full})
     x, _, _ = splice_ref.right_pad(emb)
     np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)                  # zero padding behind the short rows
-    plan = plan_splice(ids.numpy(), [feats.shape[1]] * feats.shape[0])
+    plan = plan_splice(ids.numpy(), [feats.shape[1]] * feats.shape[0], max_length=max_len)
     assert plan["lengths"].tolist() == lens
     packed = torch.zeros(int(plan["cu_seqlens"][-1]), x.shape[2])
     packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"].float()[torch.from_numpy(plan["text_ids"]).long()]
