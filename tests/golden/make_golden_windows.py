@@ -59,6 +59,31 @@ def main():
                                   times=[[int(a), int(b)] for a, b in ns["times"]], grounding_windows=[int(i) for i in ns["grounding_windows"]],
                                   selected_first_frames=[int(w[0, 0]) for w in ns["clip_feats"]],
                                   n_windows=len(ns["windowidx"])))
+    # random small cases: every stride, batches below / at / above the number of positive windows
+    rng2 = np.random.default_rng(1)
+    while len(out["stage2"]) < 46:
+        window, fps = int(rng2.integers(5, 40)), int(rng2.integers(1, 6))
+        clip_length = window * fps
+        stride = int(rng2.integers(2, 7))
+        if clip_length // stride == 0 or clip_length // 2 == 0:
+            continue
+        T = int(rng2.integers(clip_length + 2, 40 * clip_length))
+        nf = int(rng2.integers(2, 12))
+        batch = int(rng2.integers(1, 60))
+        n_stage1 = math.ceil(T / (clip_length // 2)) - 1
+        p_pos = float(rng2.uniform(0, 1))
+        answers = ["From 3 to 9" if rng2.random() < p_pos else "Not Present" for _ in range(n_stage1)]
+        ns = {"np": np, "math": math, "features": np.arange(T, dtype=np.int64)[:, None], "id": "q0", "batch": batch,
+              "grounding_dict": {"q0": {"answer": answers}},
+              "args": SimpleNamespace(debug_window=window, feature_fps=fps, num_frames=nf, stride=stride)}
+        try:
+            exec(s2_src, ns)
+        except (ValueError, IndexError):          # slice step 0 / window id outside the list: the reference skips the query (bare except, :338)
+            continue
+        out["stage2"].append(dict(ctx_l=T, debug_window=window, feature_fps=fps, num_frames=nf, stride=stride, batch=batch, stage1_answers=answers,
+                                  times=[[int(a), int(b)] for a, b in ns["times"]], grounding_windows=[int(i) for i in ns["grounding_windows"]],
+                                  selected_first_frames=[int(w[0, 0]) for w in ns["clip_feats"]],
+                                  n_windows=len(ns["windowidx"])))
     json.dump(out, open(os.path.join(HERE, "windows.json"), "w"))
     print(out["source"], [len(c["windows"]) for c in out["stage1"]], [(c["n_windows"], len(c["grounding_windows"])) for c in out["stage2"]])
 

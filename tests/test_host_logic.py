@@ -612,3 +612,39 @@ def test_plan_splice_equals_oracle_splice_on_random_ragged_batches():
         cu = plan["cu_seqlens"]
         for b in range(B):
             assert torch.equal(packed[cu[b]:cu[b + 1]], want[b]), (case, b)
+
+
+def test_window_and_selection_mirrors_equal_the_oracle_on_random_inputs():
+    """Host mirrors (revisionllm_b200.scoring) against the oracle restatements over 200 random configurations each - lengths
+    shorter than one window, windows that do not divide the video, every stride, batches below / at / above the number of
+    positive windows (the slice-step-0 case the reference would crash on is skipped: step = int(rest / missing) == 0)."""
+    rng = np.random.default_rng(17)
+    for _ in range(200):
+        ctx = int(rng.integers(2, 20000))
+        clip = int(rng.integers(2, 1500))
+        nf = int(rng.integers(1, 260))
+        stride = int(rng.integers(1, 7))
+        if clip // 2 == 0 or clip // stride == 0:
+            continue
+        np.testing.assert_array_equal(scoring.stage1_windows(ctx, clip, nf), scoring_ref.stage1_windows(ctx, clip, nf))
+        a, ta = scoring.stage2_windows(ctx, clip, nf, stride)
+        b, tb = scoring_ref.stage2_windows(ctx, clip, nf, stride)
+        np.testing.assert_array_equal(a, b)
+        assert [tuple(t) for t in ta] == [tuple(t) for t in tb]
+    for _ in range(200):
+        n1 = int(rng.integers(1, 80))
+        stride = int(rng.integers(2, 7))
+        n2 = int(rng.integers(1, 200))
+        batch = int(rng.integers(1, 120))
+        p = float(rng.uniform(0, 1))
+        answers = ["From 1 to 2" if rng.random() < p else "Not Present" for _ in range(n1)]
+        got = scoring.stage2_select_windows(answers, n2, batch, stride)
+        want = scoring_ref.stage2_select_windows(answers, n2, batch, stride)
+        assert got == want, (n1, stride, n2, batch)
+    for _ in range(100):
+        n = int(rng.integers(1, 40))
+        cos = [float(v) for v in rng.uniform(0.01, 1, size=n)]
+        ent = [float(v) for v in rng.uniform(0.05, 4, size=n)]
+        for mode in ("add", "multiply", "neg"):
+            for normalize in (True, False):
+                assert scoring.merge_scores(cos, ent, mode, normalize) == scoring_ref.merge_scores(cos, ent, mode, normalize)
