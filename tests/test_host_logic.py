@@ -648,3 +648,22 @@ def test_window_and_selection_mirrors_equal_the_oracle_on_random_inputs():
         for mode in ("add", "multiply", "neg"):
             for normalize in (True, False):
                 assert scoring.merge_scores(cos, ent, mode, normalize) == scoring_ref.merge_scores(cos, ent, mode, normalize)
+
+
+def test_placeholder_tokenisation_matches_reference_on_more_prompts(golden_dir):
+    """mm_utils.tokenizer_image_token against tests/golden/prompt_more.json (the reference's own function, run by
+    make_golden_prompts.py): several <video> placeholders, <memory> with and without trailing text, tokenizers with and
+    without BOS."""
+    import json
+
+    class NoBos(syn.StubTokenizer):
+        def __call__(self, text):
+            r = super().__call__(text)
+            r.input_ids = r.input_ids[1:]
+            return r
+    g = json.load(open(os.path.join(golden_dir, "prompt_more.json")))
+    assert len(g["cases"]) >= 12
+    for c in g["cases"]:
+        tok = syn.StubTokenizer(32000) if c["bos"] else NoBos(32000)
+        assert mm_utils.tokenizer_image_token(c["prompt"], tok, -200) == c["ids"], (c["prompt"], c["bos"])
+        assert mm_utils.tokenizer_image_token(c["prompt"], tok, -200, return_tensors="pt").tolist() == c["ids"]
