@@ -667,3 +667,43 @@ def test_placeholder_tokenisation_matches_reference_on_more_prompts(golden_dir):
         tok = syn.StubTokenizer(32000) if c["bos"] else NoBos(32000)
         assert mm_utils.tokenizer_image_token(c["prompt"], tok, -200) == c["ids"], (c["prompt"], c["bos"])
         assert mm_utils.tokenizer_image_token(c["prompt"], tok, -200, return_tensors="pt").tolist() == c["ids"]
+
+
+def test_inference_surface_matches_the_reference_function(golden_dir):
+    """revisionllm_b200.inference.inference against tests/golden/inference_surface.json (the reference's own `inference()`,
+    lifted by make_golden_inference.py, run with a recording fake model): same ids and batch handed to generate(), same
+    keyword surface (sampling is opt-in here - greedy is the north star - and `do_sample=True` restores the reference's
+    arguments), same decoded / stripped / stop-string-trimmed answers, same list-vs-string rule, `<memory>` appended to the
+    query when a visual memory is given."""
+    import json
+    from revisionllm_b200.inference import inference
+
+    class FakeModel:
+        def __init__(self, new_tokens):
+            self.new_tokens = torch.tensor(new_tokens)
+
+        def generate(self, input_ids, **kw):
+            self.seen = (input_ids.cpu().tolist(), list(kw["images"].shape), kw)
+            return {"sequences": torch.cat([input_ids.cpu(), self.new_tokens], dim=1), "scores": ()}
+    g = json.load(open(os.path.join(golden_dir, "inference_surface.json")))
+    tok = syn.StubTokenizer(32000)
+    tok.inv[tok._word("</s>")] = "</s>"
+    assert any(isinstance(c["outputs"], str) for c in g["cases"]) and any("</s>" not in str(c["outputs"]) for c in g["cases"])
+    for c in g["cases"]:
+        model = FakeModel(c["new_tokens"])
+        B = c["batch"]
+        vm = torch.zeros(B, 2, 8) if c["memory"] else None
+        pm = torch.zeros(B, 3, dtype=torch.long) if c["memory"] else None
+        out, mo = inference(model, torch.zeros(B, 4, 8), None, c["query"], tok, visual_memory=vm, prefix_memory=pm,
+                            return_list=c["return_list"], do_sample=True)
+        assert out == c["outputs"], c["query"]
+        ids, shape, kw = model.seen
+        assert ids == c["generate"]["input_ids"] and shape == c["generate"]["images_shape"]
+        assert mo["sequences"].tolist() == c["sequences"]
+        want = c["generate"]["kwargs"]
+        for k in ("do_sample", "temperature", "num_beams", "max_new_tokens", "use_cache", "output_scores", "return_dict_in_generate"):
+            assert kw[k] == want[k], k
+        assert (kw.get("visual_memory") is not None) == c["generate"]["has_visual_memory"]
+        # the default call decodes greedily with everything else unchanged
+        inference(model, torch.zeros(B, 4, 8), None, c["query"], tok, visual_memory=vm, prefix_memory=pm, return_list=c["return_list"])
+        assert model.seen[2]["do_sample"] is False and model.seen[0] == ids
