@@ -707,3 +707,25 @@ def test_inference_surface_matches_the_reference_function(golden_dir):
         # the default call decodes greedily with everything else unchanged
         inference(model, torch.zeros(B, 4, 8), None, c["query"], tok, visual_memory=vm, prefix_memory=pm, return_list=c["return_list"])
         assert model.seen[2]["do_sample"] is False and model.seen[0] == ids
+
+
+def test_shard_balanced_invariants_on_random_lengths():
+    """sweep.shard_balanced (greedy length-balanced bin packing of ragged windows onto ranks): every index exactly once,
+    deterministic, no rank above the greedy bound (mean + longest item), world = 1 keeps the order of a full sort."""
+    rng = np.random.default_rng(23)
+    for _ in range(100):
+        n = int(rng.integers(0, 400))
+        world = int(rng.integers(1, 9))
+        lengths = [int(v) for v in rng.integers(1, 700, size=n)]
+        shards = sweep.shard_balanced(lengths, world)
+        assert len(shards) == world
+        flat = sorted(int(i) for s in shards for i in s)
+        assert flat == list(range(n))
+        again = sweep.shard_balanced(lengths, world)
+        assert all(np.array_equal(a, b) for a, b in zip(shards, again))
+        if n:
+            loads = [sum(lengths[int(i)] for i in s) for s in shards]
+            assert max(loads) <= sum(lengths) / world + max(lengths)
+            assert max(len(s) for s in shards) - min(len(s) for s in shards) <= max(1, n)   # no rank starves while work remains
+            if n >= world:
+                assert min(len(s) for s in shards) >= 1
