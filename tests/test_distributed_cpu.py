@@ -93,3 +93,63 @@ def test_allgather_records_world2_gloo():
     assert un["tokens"][:, 0].tolist() == [i * 100 for i in range(n_total)]
     assert un["spans"][:, 0].tolist() == list(range(n_total))
     assert un["cos"].tolist() == [float(i) - 3.0 for i in range(n_total)]
+
+
+class _FakeSweepModel:
+    """generate() stand-in for the sweep drivers on the CPU: the new tokens are a function of each window and prompt."""
+    engine = None
+    device = torch.device("cpu")
+
+    def generate(self, ids, images=None, attention_mask=None, max_new_tokens=4, **kw):
+        am = attention_mask.bool()
+        code = torch.stack([im.float().sum() for im in images]) + (ids.clamp(min=0) * am).sum(dim=1).float()
+        new = torch.stack([(code * (t + 1)).round().long() % 89 for t in range(max_new_tokens)], dim=1)
+        return {"sequences": torch.cat([ids, new], dim=1), "entropies": torch.full((ids.shape[0], max_new_tokens), 0.25)}
+
+
+def _ragged_inputs():
+    g = torch.Generator().manual_seed(9)
+    n, L = 19, 10
+    frames = [int(x) for x in torch.randint(1, 50, (n,), generator=g)]
+    windows = [torch.randint(-3, 4, (f, 8), generator=g).float() for f in frames]
+    ids = torch.randint(3, 300, (n, L), generator=g)
+    ids[:, 2] = -200
+    am = torch.ones(n, L, dtype=torch.bool)
+    for i in range(n):
+        if i % 3:
+            am[i, L - (i % 3):] = False
+    return windows, ids, am
+
+
+def _worker_ragged_sweep(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        windows, ids, am = _ragged_inputs()
+        rec = sweep.ragged_sweep(_FakeSweepModel(), windows, ids, am, None, max_new_tokens=4, rank=rank, world=world,
+                                 max_tokens_per_batch=120, eos_token_id=None)
+        q.put((rank, rec.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_sweep_driver_world2_gloo_equals_one_rank():
+    """The whole ragged-sweep driver on two ranks (each scores its length-balanced share in token-budget batches, one
+    indexed all-gather) returns on every rank the table one rank computes alone."""
+    windows, ids, am = _ragged_inputs()
+    alone = sweep.ragged_sweep(_FakeSweepModel(), windows, ids, am, None, max_new_tokens=4, rank=0, world=1,
+                               max_tokens_per_batch=120, eos_token_id=None).numpy()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ragged_sweep, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(got[0], got[1])
+    np.testing.assert_array_equal(got[0], alone)
