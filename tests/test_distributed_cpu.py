@@ -153,3 +153,53 @@ def test_ragged_sweep_driver_world2_gloo_equals_one_rank():
         assert p.exitcode == 0
     np.testing.assert_array_equal(got[0], got[1])
     np.testing.assert_array_equal(got[0], alone)
+
+
+class _FakeDenseModel:
+    engine = None
+    device = torch.device("cpu")
+
+    def generate(self, ids, images=None, max_new_tokens=4, **kw):
+        code = images.float().sum(dim=(1, 2)) + ids.clamp(min=0).sum(dim=1).float()
+        new = torch.stack([(code * (t + 1)).round().long() % 83 for t in range(max_new_tokens)], dim=1)
+        ent = (code[:, None] % 7 + 1.0) * torch.arange(1, max_new_tokens + 1)[None] * 0.125
+        return {"sequences": torch.cat([ids, new], dim=1), "entropies": ent}
+
+
+def _worker_stage1(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(4)
+        segs = torch.randint(-3, 4, (11, 6, 8), generator=g).to(torch.bfloat16)
+        ids = torch.randint(3, 300, (9,), generator=g)
+        res = sweep.stage1_sweep(_FakeDenseModel(), segs, ids, None, max_new_tokens=4, rank=rank, world=world, batch=3, eos_token_id=None)
+        q.put((rank, res.records.numpy(), res.local_indices.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stage1_sweep_driver_world2_gloo_equals_one_rank():
+    """sweep.stage1_sweep on two ranks: segment i goes to rank i mod 2, each rank scores its share in batches of 3, one
+    all-gather of the fixed-size records - every rank ends with the table a single rank computes."""
+    g = torch.Generator().manual_seed(4)
+    segs = torch.randint(-3, 4, (11, 6, 8), generator=g).to(torch.bfloat16)
+    ids = torch.randint(3, 300, (9,), generator=g)
+    alone = sweep.stage1_sweep(_FakeDenseModel(), segs, ids, None, max_new_tokens=4, rank=0, world=1, batch=3, eos_token_id=None)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_stage1, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {r: (rec, idx) for r, rec, idx in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(got[0][0], got[1][0])
+    np.testing.assert_array_equal(got[0][0], alone.records.numpy())
+    assert got[0][1] == [0, 2, 4, 6, 8, 10] and got[1][1] == [1, 3, 5, 7, 9]
+    un = sweep.unpack_records(alone.records)
+    assert un["tokens"].shape[0] == 11 and torch.isfinite(un["h_mean"]).all()
