@@ -729,3 +729,33 @@ def test_shard_balanced_invariants_on_random_lengths():
             assert max(len(s) for s in shards) - min(len(s) for s in shards) <= max(1, n)   # no rank starves while work remains
             if n >= world:
                 assert min(len(s) for s in shards) >= 1
+
+
+def test_window_loader_index_logic_matches_the_reference_tables(golden_dir):
+    """features.WindowLoader.stage1_windows with the upload and the device gather replaced by their CPU meaning (row t of
+    the features holds t, gather = fancy indexing): the windows it asks the device for are the reference's
+    (tests/golden/windows.json, produced by the reference's own lines), `--plus_baseline` row included."""
+    import json
+    from types import SimpleNamespace
+    from revisionllm_b200 import features as ft
+
+    class CpuLoader(ft.WindowLoader):
+        def __init__(self):
+            self.engine = SimpleNamespace(device=torch.device("cpu"), gather_windows=lambda dev, idx: dev[idx.long()])
+            self.dim = 1
+
+        def upload(self, features):
+            return torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+    g = json.load(open(os.path.join(golden_dir, "windows.json")))
+    loader = CpuLoader()
+    checked = 0
+    for c in g["stage1"]:
+        if c["baseline"]:
+            continue                                     # --baseline re-samples the features first (:220-222), not a loader mode
+        feats = np.arange(c["ctx_l"], dtype=np.float32)[:, None]
+        out = loader.stage1_windows(feats, c["debug_window"] * c["feature_fps"], c["num_frames"], plus_baseline=c["plus_baseline"])
+        assert out[:, :, 0].long().tolist() == c["windows"], (c["ctx_l"], c["plus_baseline"])
+        checked += 1
+    assert checked >= 4
+    one = loader.stage1_windows(np.arange(77, dtype=np.float32)[:, None], 500, 10, small_video=True)
+    assert one[:, :, 0].long().tolist() == [np.linspace(0, 76, 10, dtype=np.int32).tolist()]
