@@ -1,6 +1,7 @@
 """CPU tests of the host-side mirror (no GPU): prompt/tokenisation, splice planning, windows,
 selection rules, record packing, C-ABI surface."""
 import ctypes
+import math
 import os
 import re
 import subprocess
@@ -759,3 +760,65 @@ def test_window_loader_index_logic_matches_the_reference_tables(golden_dir):
     assert checked >= 4
     one = loader.stage1_windows(np.arange(77, dtype=np.float32)[:, None], 500, 10, small_video=True)
     assert one[:, :, 0].long().tolist() == [np.linspace(0, 76, 10, dtype=np.int32).tolist()]
+
+
+class _CpuAdapterEngine:
+    """The three entry points the ClipEncoder host code drives (rvl_gemm_bf16, rvl_layernorm, rvl_mha96) restated in torch
+    on the CPU with their documented meaning (include/revisionllm_b200.h), so that `clip_encoder.ClipEncoder.__call__` -
+    which weights, which biases, which output modes, in which order - can be checked without a GPU."""
+    device = torch.device("cpu")
+
+    def gemm(self, A, W, bias=None, out=None, out_mode=_cabi.GEMM_OUT_BF16, flags=0, **kw):
+        y = A.float() @ W.float().t()
+        if bias is not None:
+            y = y + bias.float()
+        if flags & _cabi.GEMM_FLAG_RELU:
+            y = y.clamp(min=0)
+        if out is None:
+            out = torch.empty(y.shape, dtype=torch.bfloat16 if out_mode == _cabi.GEMM_OUT_BF16 else torch.float32)
+        if out_mode == _cabi.GEMM_ADD_F32:
+            out += y
+        else:
+            out.copy_(y.to(out.dtype))
+        return out
+
+    def layernorm(self, x, w=None, b=None, y_f32=None, y_bf16=None, pos=None, y_pos_bf16=None, period=0, eps=1e-5):
+        y = x.float()
+        if w is not None:
+            y = torch.nn.functional.layer_norm(y, (x.shape[1],), w.float(), b.float(), eps)
+        y = y.clone()
+        if y_pos_bf16 is not None:
+            rows = torch.arange(x.shape[0]) % period
+            y_pos_bf16.copy_((y + pos.float()[rows]).to(torch.bfloat16))
+        if y_bf16 is not None:
+            y_bf16.copy_(y.to(torch.bfloat16))
+        if y_f32 is not None:
+            y_f32.copy_(y)
+
+    def mha96(self, q, k, v, out, n_seq, n_heads, Tq, Tk, kv_seq_idx=None, key_mask=None):
+        d = q.shape[1] // n_heads
+        qh = q.float().reshape(n_seq, Tq, n_heads, d).permute(0, 2, 1, 3)
+        sel = torch.arange(n_seq) if kv_seq_idx is None else kv_seq_idx.long()
+        kh = k.float().reshape(-1, Tk, n_heads, d)[sel].permute(0, 2, 1, 3)
+        vh = v.float().reshape(-1, Tk, n_heads, d)[sel].permute(0, 2, 1, 3)
+        s = qh @ kh.transpose(-1, -2) / math.sqrt(d)
+        if key_mask is not None:
+            s = s.masked_fill(key_mask.reshape(-1, Tk)[sel][:, None, None, :] == 0, float("-inf"))
+        o = torch.softmax(s, dim=-1) @ vh
+        out.copy_(o.permute(0, 2, 1, 3).reshape(n_seq * Tq, n_heads * d).to(torch.bfloat16))
+
+
+def test_clip_encoder_host_orchestration_matches_reference_fixture(golden_dir):
+    """clip_encoder.ClipEncoder.__call__ over a CPU stand-in for the three device entry points, against the reference's
+    own adapter output (tests/golden/clip_encoder_tiny.npz): pins the host side of stage 2 - projections, position
+    embeddings, global token, post-norm order, shared text K/V through `seg_text_idx`, key mask, CLS projection."""
+    from revisionllm_b200.clip_encoder import ClipEncoder
+    g = np.load(os.path.join(golden_dir, "clip_encoder_tiny.npz"), allow_pickle=True)
+    cw = syn.make_clip_encoder_weights(syn.TINY.hidden, seed=0)
+    enc = ClipEncoder(_CpuAdapterEngine(), cw)
+    frames, q, qmask = torch.from_numpy(g["frames"]), torch.from_numpy(g["q"]), torch.from_numpy(g["qmask"])
+    idx = torch.ones(frames.shape[0], dtype=torch.int32)             # every window attends to text row 1 (masked tail), as in the fixture
+    got = enc(frames.to(torch.bfloat16), q.to(torch.bfloat16), qmask, idx).float()
+    want = torch.from_numpy(g["cls_out"])
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 3e-2, err                                            # bf16 weights / activations against the fp32 reference
