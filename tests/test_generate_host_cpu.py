@@ -41,14 +41,21 @@ class CpuEngine:
         # the page that holds the sequence's LAST prompt position is never a shared prefix page
         return int(table_row[(int(seq_len) - 1) // self.cfg.kv_page_size])
 
+    def splice_rows(self, vis, vis_dst, text_ids, text_dst, hidden):
+        hidden[text_dst.long()] = self.w["model.embed_tokens.weight"][text_ids.long()]
+        hidden[vis_dst.long()] = vis.float()
+
     def prefill(self, hidden, cu, n_seq, max_seqlen, page_table, logits_out, all_logits=False, seq_pos0=None, seq_ctx_row=None):
-        assert seq_pos0 is None and not all_logits
+        assert seq_pos0 is None
         self.calls.append(("prefill", n_seq))
         for b in range(n_seq):
             x = hidden[int(cu[b]):int(cu[b + 1])][None]
             cache = llama_ref.KVCache(self.shape.n_layers)
             h = llama_ref.decoder_stack(self.w, self.shape, x, cache)
-            logits_out[b] = llama_ref.lm_head(self.w, h[:, -1])[0]
+            if all_logits:
+                logits_out[int(cu[b]):int(cu[b + 1])] = llama_ref.lm_head(self.w, h[0])
+            else:
+                logits_out[b] = llama_ref.lm_head(self.w, h[:, -1])[0]
             self.caches[self._key(page_table[b], x.shape[1])] = (cache, x.shape[1])
 
     def decode_step(self, tok, seq_lens, page_table, logits, max_kv_len=0):
@@ -65,6 +72,46 @@ class CpuEngine:
             if p in self.caches:
                 return p
         raise KeyError(table_row.tolist())
+
+    # ---- the three entry points the ClipEncoder host code drives, with their documented meaning
+    def gemm(self, A, W, bias=None, out=None, out_mode=0, flags=0, **kw):
+        from revisionllm_b200 import _cabi
+        y = A.float() @ W.float().t()
+        if bias is not None:
+            y = y + bias.float()
+        if flags & _cabi.GEMM_FLAG_RELU:
+            y = y.clamp(min=0)
+        if out is None:
+            out = torch.empty(y.shape, dtype=torch.bfloat16 if out_mode == _cabi.GEMM_OUT_BF16 else torch.float32)
+        if out_mode == _cabi.GEMM_ADD_F32:
+            out += y
+        else:
+            out.copy_(y.to(out.dtype))
+        return out
+
+    def layernorm(self, x, w=None, b=None, y_f32=None, y_bf16=None, pos=None, y_pos_bf16=None, period=0, eps=1e-5):
+        y = x.float()
+        if w is not None:
+            y = torch.nn.functional.layer_norm(y, (x.shape[1],), w.float(), b.float(), eps)
+        y = y.clone()
+        if y_pos_bf16 is not None:
+            y_pos_bf16.copy_((y + pos.float()[torch.arange(x.shape[0]) % period]).to(torch.bfloat16))
+        if y_bf16 is not None:
+            y_bf16.copy_(y.to(torch.bfloat16))
+        if y_f32 is not None:
+            y_f32.copy_(y)
+
+    def mha96(self, q, k, v, out, n_seq, n_heads, Tq, Tk, kv_seq_idx=None, key_mask=None):
+        d = q.shape[1] // n_heads
+        qh = q.float().reshape(n_seq, Tq, n_heads, d).permute(0, 2, 1, 3)
+        sel = torch.arange(n_seq) if kv_seq_idx is None else kv_seq_idx.long()
+        kh = k.float().reshape(-1, Tk, n_heads, d)[sel].permute(0, 2, 1, 3)
+        vh = v.float().reshape(-1, Tk, n_heads, d)[sel].permute(0, 2, 1, 3)
+        s = qh @ kh.transpose(-1, -2) / float(d) ** 0.5
+        if key_mask is not None:
+            s = s.masked_fill(key_mask.reshape(-1, Tk)[sel][:, None, None, :] == 0, float("-inf"))
+        o = torch.softmax(s, dim=-1) @ vh
+        out.copy_(o.permute(0, 2, 1, 3).reshape(n_seq * Tq, n_heads * d).to(torch.bfloat16))
 
     def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
         nxt = torch.argmax(logits, dim=-1)
@@ -160,3 +207,94 @@ def test_generate_ragged_batch_and_argument_errors(cpu_model):
         m.generate(ids, images=images, num_beams=2)
     with pytest.raises(RvlError):
         m.generate(ids, images=images, visual_memory=torch.zeros(3, 2, cfg.adapter_dim))
+
+
+def test_forward_api_prefill_logits_and_one_token_steps(cpu_model):
+    """forward(): all-position logits (right padded), logits_to_keep=1, then 1-token steps with past_key_values - the
+    LlamaForCausalLM.forward surface the reference's generate() drives (vtimellm_llama.py:38-90)."""
+    m, w, cfg = cpu_model
+    feats = syn.make_features(2, 6, cfg.adapter_dim, seed=3)
+    ids = syn.make_prompt_ids(cfg, 6, 9, seed=2)[None].repeat(2, 1)
+    shape = m.engine.shape
+    x = torch.stack(splice_ref.splice(w, ids, splice_ref.mm_projector_linear(w, feats)))
+    cache = llama_ref.KVCache(shape.n_layers)
+    ref_all = llama_ref.lm_head(w, llama_ref.decoder_stack(w, shape, x, cache))
+    full = m.forward(input_ids=ids, images=feats)
+    np.testing.assert_allclose(full.logits.numpy(), ref_all.numpy(), rtol=2e-4, atol=2e-4)
+    last = m.forward(input_ids=ids, images=feats, logits_to_keep=1, reserve_new_tokens=8)
+    np.testing.assert_allclose(last.logits[:, 0].numpy(), ref_all[:, -1].numpy(), rtol=2e-4, atol=2e-4)
+    kv = last.past_key_values
+    tok = ref_all[:, -1].argmax(-1)
+    for _ in range(3):
+        ref_step = llama_ref.lm_head(w, llama_ref.decoder_stack(w, shape, llama_ref.embed_tokens(w, tok)[:, None], cache)[:, -1])
+        out = m.forward(input_ids=tok[:, None], past_key_values=kv)
+        np.testing.assert_allclose(out.logits[:, 0].numpy(), ref_step.numpy(), rtol=2e-4, atol=2e-4)
+        kv = out.past_key_values
+        tok = ref_step.argmax(-1)
+    assert kv.steps == 3 and kv.seq_lens.tolist() == [x.shape[1] + 3] * 2
+
+
+def test_memory_branch_through_generate(cpu_model):
+    """`visual_memory` / `prefix_memory` (vtimellm_arch.py:208-232) through generate(): the -300 placeholder becomes the
+    prefix ids plus a second visual block; tokens equal the oracle's, which a reference fixture pins."""
+    m, w, cfg = cpu_model
+    B = 2
+    feats = syn.make_features(B, 7, cfg.adapter_dim, seed=21)
+    mem = syn.make_features(B, 3, cfg.adapter_dim, seed=22)
+    prefix = torch.randint(3, cfg.vocab, (B, 4), generator=torch.Generator().manual_seed(23))
+    base = syn.make_prompt_ids(cfg, 6, 9, seed=24)
+    base = torch.cat([base[:-4], torch.tensor([-300]), base[-4:]])
+    ids = base[None].repeat(B, 1)
+    out = m.generate(ids, images=feats, visual_memory=mem, prefix_memory=prefix, max_new_tokens=3, return_dict_in_generate=True, eos_token_id=None)
+    emb = splice_ref.splice(w, ids, splice_ref.mm_projector_linear(w, feats), visual_memory=mem.float(), prefix_memory=prefix)
+    toks, _ = llama_ref.greedy_decode(w, m.engine.shape, torch.stack(emb), 3, stop_on_eos=False)
+    assert out["sequences"][:, ids.shape[1]:].tolist() == toks.tolist()
+    assert out["prompt_lengths"].tolist() == [e.shape[0] for e in emb]
+
+
+def test_stage2_hierarchy_and_window_bank_through_generate(monkeypatch):
+    """Stage-2 input through generate() on the CPU stand-ins: `images [b, v, t, 768]` + `query_feats` (one ClipEncoder CLS token
+    per window spliced at <video>) equals the oracle's adapter + splice + greedy loop, and a `WindowBank` that stores each
+    distinct (window, query) pair once - rows of different lengths included - gives the same tokens as the stacked copies."""
+    from oracle import clip_encoder_ref
+    from revisionllm_b200.clip_encoder import ClipEncoder
+    from revisionllm_b200.model import WindowBank
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    cw = syn.make_clip_encoder_weights(cfg.hidden, seed=0)
+    m = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg, clip_adapter=True, clip_adapter_text=True, hierarchy=True), dict(w), None)
+    m.engine = CpuEngine(cfg, w)
+    m.device = torch.device("cpu")
+    m.clip_encoder = ClipEncoder(m.engine, cw)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    g = torch.Generator().manual_seed(3)
+    wins = syn.make_features(5, 6, 768, seed=9)                                   # 5 distinct windows of 6 frames
+    q_tok = torch.randn(2, 4, 768, generator=g).to(torch.bfloat16)
+    q_mask = torch.ones(2, 4)
+    q_mask[1, 3:] = 0
+    ids = syn.make_prompt_ids(cfg, 6, 9, seed=2)
+    rows = torch.tensor([[0, 0, 1, 1], [4, 2, 3, 3]])                             # zoom-style repeats; prompt 0 -> query 0, prompt 1 -> query 1
+    stacked = wins[rows]                                                          # [2, 4, 6, 768]
+    out_s = m.generate(ids[None].repeat(2, 1), images=stacked, query_feats=(q_tok, q_mask), max_new_tokens=3,
+                       return_dict_in_generate=True, eos_token_id=None)
+    # oracle: adapter per (window, its prompt's query) -> CLS rows -> splice -> greedy
+    seg_text = torch.tensor([0, 0, 0, 0, 1, 1, 1, 1])
+    cls = clip_encoder_ref.clip_encoder_cls(cw, stacked.reshape(8, 6, 768).float(), q_tok.float()[seg_text], q_mask[seg_text])
+    x = torch.stack(splice_ref.splice(w, ids[None].repeat(2, 1), cls.reshape(2, 4, -1)))
+    toks, _ = llama_ref.greedy_decode(w, m.engine.shape, x, 3, stop_on_eos=False)
+    assert out_s["sequences"][:, ids.shape[0]:].tolist() == toks.tolist()
+    # the bank: windows 0, 1 belong to query 0, windows 4, 2, 3 to query 1 - each pair once
+    bank = WindowBank(windows=wins[torch.tensor([0, 1, 4, 2, 3])], rows=torch.tensor([[0, 0, 1, 1], [2, 3, 4, 4]]),
+                      text_index=torch.tensor([0, 0, 1, 1, 1], dtype=torch.int32))
+    out_b = m.generate(ids[None].repeat(2, 1), images=bank, query_feats=(q_tok, q_mask), max_new_tokens=3,
+                       return_dict_in_generate=True, eos_token_id=None)
+    assert out_b["sequences"].tolist() == out_s["sequences"].tolist()
+    # prompts with different numbers of windows in one batch
+    ragged = WindowBank(windows=bank.windows, rows=[torch.tensor([0, 0, 1, 1]), torch.tensor([2, 3])], text_index=bank.text_index)
+    out_r = m.generate(ids[None].repeat(2, 1), images=ragged, query_feats=(q_tok, q_mask), max_new_tokens=3,
+                       return_dict_in_generate=True, eos_token_id=None)
+    assert out_r["prompt_lengths"].tolist() == [ids.shape[0] - 1 + 4, ids.shape[0] - 1 + 2]
+    assert out_r["sequences"][0].tolist() == out_s["sequences"][0].tolist()
+    alone = m.generate(ids[None], images=wins[torch.tensor([4, 2])][None], query_feats=(q_tok[1:2], q_mask[1:2]), max_new_tokens=3,
+                       return_dict_in_generate=True, eos_token_id=None)
+    assert out_r["sequences"][1].tolist() == alone["sequences"][0].tolist()
