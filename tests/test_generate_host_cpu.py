@@ -298,3 +298,35 @@ def test_stage2_hierarchy_and_window_bank_through_generate(monkeypatch):
     alone = m.generate(ids[None], images=wins[torch.tensor([4, 2])][None], query_feats=(q_tok[1:2], q_mask[1:2]), max_new_tokens=3,
                        return_dict_in_generate=True, eos_token_id=None)
     assert out_r["sequences"][1].tolist() == alone["sequences"][0].tolist()
+
+
+def test_stage2_pass_schedules_agree_on_the_cpu_model(monkeypatch):
+    """sweep.stage2_pass over the real model class on the CPU stand-ins: all chunks of all zoom levels in one batched
+    generate() with every distinct window through the adapter once == the reference's schedule (one generate() per chunk,
+    stacked zoom repeats), a window count below one chunk included (the reference's negative-slice case)."""
+    from revisionllm_b200 import sweep
+    from revisionllm_b200.clip_encoder import ClipEncoder
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    m = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg, clip_adapter=True, clip_adapter_text=True, hierarchy=True), dict(w), None)
+    m.engine = CpuEngine(cfg, w)
+    m.device = torch.device("cpu")
+    m.clip_encoder = ClipEncoder(m.engine, syn.make_clip_encoder_weights(cfg.hidden, seed=0))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    g = torch.Generator().manual_seed(5)
+    q = (torch.randn(1, 4, 768, generator=g).to(torch.bfloat16), torch.ones(1, 4))
+    ids = syn.make_prompt_ids(cfg, 6, 9, seed=2)
+    key = lambda res: [(r["zoom"], r["start"], r["perm"], r["tokens"], r["window"]) for r in res]
+    for n_windows in (7, 3):
+        wins = syn.make_features(n_windows, 5, 768, seed=30 + n_windows)
+        kw = dict(grounding_windows=list(range(10, 10 + n_windows)), batch=4, zooms=(2, 1), max_new_tokens=3, perm_seed=1,
+                  answer_number=lambda t: int(t[0]) % 4, eos_token_id=None)
+        m.engine.calls.clear()
+        fast = sweep.stage2_pass(m, wins, q, ids, **kw)
+        n_fast = sum(1 for kind, _ in m.engine.calls if kind == "prefill")
+        m.engine.calls.clear()
+        slow = sweep.stage2_pass(m, wins, q, ids, max_calls_per_batch=1, dedup=False, **kw)
+        n_slow = sum(1 for kind, _ in m.engine.calls if kind == "prefill")
+        assert key(fast) == key(slow), n_windows
+        assert n_fast == 1 and n_slow == len(slow)                              # one batched generate() against one per chunk
+        assert all(r["window"] in kw["grounding_windows"] for r in fast)
