@@ -46,16 +46,23 @@ class CpuEngine:
         hidden[vis_dst.long()] = vis.float()
 
     def prefill(self, hidden, cu, n_seq, max_seqlen, page_table, logits_out, all_logits=False, seq_pos0=None, seq_ctx_row=None):
-        assert seq_pos0 is None
         self.calls.append(("prefill", n_seq))
+        self.prefill_rows = int(cu[n_seq])
         for b in range(n_seq):
             x = hidden[int(cu[b]):int(cu[b + 1])][None]
+            if seq_pos0 is not None and int(seq_pos0[b]) > 0:
+                # positions [0, pos0) of this sequence are the rows [ctx_row, ctx_row + pos0) of the packed stream (include/
+                # revisionllm_b200.h, rvl_prefill): the shared prompt prefix, embedded once
+                c0, p0 = int(seq_ctx_row[b]), int(seq_pos0[b])
+                x = torch.cat([hidden[c0:c0 + p0][None], x], dim=1)
             cache = llama_ref.KVCache(self.shape.n_layers)
             h = llama_ref.decoder_stack(self.w, self.shape, x, cache)
             if all_logits:
                 logits_out[int(cu[b]):int(cu[b + 1])] = llama_ref.lm_head(self.w, h[0])
             else:
                 logits_out[b] = llama_ref.lm_head(self.w, h[:, -1])[0]
+            if seq_pos0 is not None and int(seq_pos0[b]) == 0:
+                continue                                 # the shared prefix itself: its K/V live on in every sequence that names it
             self.caches[self._key(page_table[b], x.shape[1])] = (cache, x.shape[1])
 
     def decode_step(self, tok, seq_lens, page_table, logits, max_kv_len=0):
@@ -330,3 +337,26 @@ def test_stage2_pass_schedules_agree_on_the_cpu_model(monkeypatch):
         assert key(fast) == key(slow), n_windows
         assert n_fast == 1 and n_slow == len(slow)                              # one batched generate() against one per chunk
         assert all(r["window"] in kw["grounding_windows"] for r in fast)
+
+
+def test_shared_prefix_compute_changes_nothing_but_the_rows_computed(cpu_model):
+    """`share_prefix_compute`: the whole pages of the prompt prefix common to the batch are embedded once ([prefix | seq 0 from
+    P | seq 1 from P | ...], B + 1 sequences with `seq_pos0` / `seq_ctx_row`).  On the CPU stand-in: same tokens and the same
+    logits to the bit, (B - 1) * P fewer rows through the prefill, and the shared pages mapped once in the page table."""
+    m, w, cfg = cpu_model
+    B, F = 4, 6
+    feats = syn.make_features(B, F, cfg.adapter_dim, seed=8)
+    ids = syn.make_prompt_ids(cfg, 40, 7, seed=9)[None].repeat(B, 1)        # 40 text ids in front of <video>: P = 32
+    kw = dict(images=feats, max_new_tokens=3, output_scores=True, return_dict_in_generate=True, eos_token_id=None)
+    plain = m.generate(ids, **kw)
+    rows_plain = m.engine.prefill_rows
+    m.share_prefix_compute = True
+    shared = m.generate(ids, **kw)
+    rows_shared = m.engine.prefill_rows
+    m.share_prefix_compute = False
+    assert shared["sequences"].tolist() == plain["sequences"].tolist()
+    assert torch.equal(torch.stack(shared["scores"]), torch.stack(plain["scores"]))
+    assert rows_plain - rows_shared == (B - 1) * 32
+    assert m.engine.calls.count(("prefill", B + 1)) == 1                    # the prefix went through as one more sequence
+    table = shared["past_key_values"].page_table
+    assert (table[:, 0] == table[0, 0]).all() and len(set(table[:, 1].tolist())) == B
