@@ -360,3 +360,92 @@ def test_shared_prefix_compute_changes_nothing_but_the_rows_computed(cpu_model):
     assert m.engine.calls.count(("prefill", B + 1)) == 1                    # the prefix went through as one more sequence
     table = shared["past_key_values"].page_table
     assert (table[:, 0] == table[0, 0]).all() and len(set(table[:, 1].tolist())) == B
+
+
+class PagedCpuEngine(CpuEngine):
+    """Like CpuEngine, but K / V really live in the paged pool with the product's layout ([layer][k|v][page][head][slot][d],
+    bf16, `engine._kv`) and every step reads them back THROUGH the page table - so a wrong table, a missing page after the pool
+    grew, or a shared page that is not really shared shows up as wrong tokens."""
+
+    def __init__(self, cfg, w):
+        super().__init__(cfg, w)
+        self._kv = None
+        self.cfg.n_heads, self.cfg.head_dim, self.cfg.n_layers = cfg.n_heads, cfg.head_dim, cfg.n_layers
+
+    def ensure_kv(self, n_pages):
+        if self._kv is not None and self.n_pages >= n_pages:
+            return
+        c = self.cfg
+        self._kv = torch.zeros(2 * c.n_layers * n_pages * c.n_heads * c.kv_page_size * c.head_dim, dtype=torch.bfloat16).view(torch.uint8)
+        self.n_pages = n_pages
+
+    def _pool(self, layer, which):
+        c = self.cfg
+        per = self.n_pages * c.n_heads * c.kv_page_size * c.head_dim
+        flat = self._kv.view(torch.bfloat16)
+        return flat[(2 * layer + which) * per:(2 * layer + which + 1) * per].view(self.n_pages, c.n_heads, c.kv_page_size, c.head_dim)
+
+    def _store(self, table_row, cache, first_pos):
+        ps = self.cfg.kv_page_size
+        for layer in range(self.cfg.n_layers):
+            for which, t in ((0, cache.k[layer]), (1, cache.v[layer])):
+                pool = self._pool(layer, which)
+                for p in range(first_pos, t.shape[2]):
+                    pool[int(table_row[p // ps]), :, p % ps] = t[0, :, p].to(torch.bfloat16)
+
+    def _load(self, table_row, n):
+        ps = self.cfg.kv_page_size
+        cache = llama_ref.KVCache(self.cfg.n_layers)
+        pages = table_row[: (n + ps - 1) // ps].long()
+        for layer in range(self.cfg.n_layers):
+            k = self._pool(layer, 0)[pages].permute(1, 0, 2, 3).reshape(self.cfg.n_heads, -1, self.cfg.head_dim)[:, :n]
+            v = self._pool(layer, 1)[pages].permute(1, 0, 2, 3).reshape(self.cfg.n_heads, -1, self.cfg.head_dim)[:, :n]
+            cache.k[layer], cache.v[layer] = k[None].float(), v[None].float()
+        return cache
+
+    def prefill(self, hidden, cu, n_seq, max_seqlen, page_table, logits_out, all_logits=False, seq_pos0=None, seq_ctx_row=None):
+        assert seq_pos0 is None and not all_logits
+        self.calls.append(("prefill", n_seq))
+        for b in range(n_seq):
+            x = hidden[int(cu[b]):int(cu[b + 1])][None]
+            cache = llama_ref.KVCache(self.shape.n_layers)
+            h = llama_ref.decoder_stack(self.w, self.shape, x, cache)
+            logits_out[b] = llama_ref.lm_head(self.w, h[:, -1])[0]
+            self._store(page_table[b], cache, 0)
+
+    def decode_step(self, tok, seq_lens, page_table, logits, max_kv_len=0):
+        self.calls.append(("decode", tok.shape[0]))
+        for b in range(tok.shape[0]):
+            n = int(seq_lens[b])
+            assert n < page_table.shape[1] * self.cfg.kv_page_size, "page table too small for this position"
+            cache = self._load(page_table[b], n)
+            h = llama_ref.decoder_stack(self.w, self.shape, llama_ref.embed_tokens(self.w, tok[b:b + 1].long())[:, None], cache)
+            logits[b] = llama_ref.lm_head(self.w, h[:, -1])[0]
+            self._store(page_table[b], cache, n)
+        seq_lens += 1
+
+
+def test_paged_kv_tables_shared_pages_and_growth_past_the_first_reservation(monkeypatch):
+    """generate() over the paged stand-in: 40 common text ids in front of <video> put one whole page under every sequence
+    (mapped once, `share_prefix_pages`), and 70 new tokens outgrow the first 64-token reservation so the pool is re-paged
+    mid-generation (`_grow_kv`).  Tokens must equal the un-paged oracle loop in both cases, with and without page sharing."""
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    B = 3
+    feats = syn.make_features(B, 5, cfg.adapter_dim, seed=12)
+    ids = syn.make_prompt_ids(cfg, 40, 6, seed=13)[None].repeat(B, 1)
+    for steps in (6, 70):
+        want, _ = _oracle(w, cfg, ids, feats, steps, stop_on_eos=False)
+        for share in (True, False):
+            m = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg), dict(w))
+            m.engine = PagedCpuEngine(cfg, w)
+            m.device = torch.device("cpu")
+            m.share_prefix_pages = share
+            out = m.generate(ids, images=feats, max_new_tokens=steps, return_dict_in_generate=True, eos_token_id=None)
+            got = out["sequences"][:, ids.shape[1]:]
+            same = (got == want).all(dim=0).long().cumprod(0).sum().item()          # leading steps on which every row agrees
+            assert same == steps, (steps, share, same)                               # bf16 K/V storage must not flip a planted token
+            table = out["past_key_values"].page_table
+            assert (len(set(table[:, 0].tolist())) == 1) == share
+            assert table.shape[1] * 32 >= ids.shape[1] - 1 + 5 + steps
