@@ -120,6 +120,19 @@ class CpuEngine:
         o = torch.softmax(s, dim=-1) @ vh
         out.copy_(o.permute(0, 2, 1, 3).reshape(n_seq * Tq, n_heads * d).to(torch.bfloat16))
 
+    def sample_multinomial(self, logits, next_tokens, temperature, seed, step, entropy=None, unfinished=None, eos_id=2, pad_id=2):
+        from oracle import sampling_ref
+        self.calls.append(("sample", (round(float(temperature), 6), int(seed), int(step))))
+        toks, _ = sampling_ref.multinomial_draw(logits.numpy(), float(temperature), int(seed), int(step))
+        nxt = torch.tensor(toks)
+        if entropy is not None:
+            p = torch.softmax(logits.float(), dim=-1)                 # the entropy is of the un-tempered distribution (raw scores, :321)
+            entropy.copy_(-(p * torch.log(p + 1e-10)).sum(-1))
+        if unfinished is not None and eos_id >= 0:
+            nxt, unf = llama_ref.eos_bookkeeping(nxt, unfinished.long(), eos_id, pad_id)
+            unfinished.copy_(unf.to(unfinished.dtype))
+        next_tokens.copy_(nxt.to(next_tokens.dtype))
+
     def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
         nxt = torch.argmax(logits, dim=-1)
         if entropy is not None:
@@ -449,3 +462,26 @@ def test_paged_kv_tables_shared_pages_and_growth_past_the_first_reservation(monk
             table = out["past_key_values"].page_table
             assert (len(set(table[:, 0].tolist())) == 1) == share
             assert table.shape[1] * 32 >= ids.shape[1] - 1 + 5 + steps
+
+
+def test_sampling_arguments_reach_the_engine(cpu_model):
+    """`do_sample=True, temperature=0.05, seed=s` (the reference's own rule, inference.py:47-48): every step calls the
+    multinomial entry point with (temperature, seed, step index) - the Philox counter layout documented in the header - and
+    the draw is reproducible per seed; temperature 0 or do_sample=False fall back to greedy."""
+    m, w, cfg = cpu_model
+    feats = syn.make_features(3, 6, cfg.adapter_dim, seed=1)
+    ids = syn.make_prompt_ids(cfg, 6, 9, seed=2)[None].repeat(3, 1)
+    kw = dict(images=feats, max_new_tokens=4, return_dict_in_generate=True, eos_token_id=None)
+    m.engine.calls.clear()
+    a = m.generate(ids, do_sample=True, temperature=0.05, seed=11, **kw)
+    assert [c[1] for c in m.engine.calls if c[0] == "sample"] == [(0.05, 11, t) for t in range(4)]
+    b = m.generate(ids, do_sample=True, temperature=0.05, seed=11, **kw)
+    assert a["sequences"].tolist() == b["sequences"].tolist()
+    hot_a = m.generate(ids, do_sample=True, temperature=50.0, seed=1, **kw)["sequences"]
+    hot_b = m.generate(ids, do_sample=True, temperature=50.0, seed=2, **kw)["sequences"]
+    assert hot_a.tolist() != hot_b.tolist()                                  # a flat distribution: the seed decides
+    greedy = m.generate(ids, **kw)["sequences"]
+    m.engine.calls.clear()
+    assert m.generate(ids, do_sample=True, temperature=0.0, **kw)["sequences"].tolist() == greedy.tolist()
+    assert not [c for c in m.engine.calls if c[0] == "sample"]
+    assert a["sequences"].tolist() == greedy.tolist()                        # at T = 0.05 the planted chain wins every draw
