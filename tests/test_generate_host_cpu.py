@@ -120,6 +120,16 @@ class CpuEngine:
         o = torch.softmax(s, dim=-1) @ vh
         out.copy_(o.permute(0, 2, 1, 3).reshape(n_seq * Tq, n_heads * d).to(torch.bfloat16))
 
+    def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True):
+        from oracle import scoring_ref
+        offs = seg_offsets.tolist()
+        scores = [scoring_ref.cosine_topk_score(frames[offs[i]:offs[i + 1]], cls, k, norm_axis=norm_axis)[0] for i in range(len(offs) - 1)]
+        return torch.tensor(scores, dtype=torch.float32), None
+
+    def select_topk(self, scores, k):
+        from oracle import scoring_ref
+        return torch.from_numpy(np.ascontiguousarray(scoring_ref.select_topk_segments(scores.numpy(), k))).to(torch.int32)
+
     def sample_multinomial(self, logits, next_tokens, temperature, seed, step, entropy=None, unfinished=None, eos_id=2, pad_id=2):
         from oracle import sampling_ref
         self.calls.append(("sample", (round(float(temperature), 6), int(seed), int(step))))
@@ -485,3 +495,26 @@ def test_sampling_arguments_reach_the_engine(cpu_model):
     assert m.generate(ids, do_sample=True, temperature=0.0, **kw)["sequences"].tolist() == greedy.tolist()
     assert not [c for c in m.engine.calls if c[0] == "sample"]
     assert a["sequences"].tolist() == greedy.tolist()                        # at T = 0.05 the planted chain wins every draw
+
+
+def test_stage1_sweep_records_over_the_cpu_model(cpu_model):
+    """sweep.stage1_sweep over the real model class on the CPU stand-in: per-segment records (tokens, entropy statistics,
+    cosine top-3 score) in batches, and the stage-2 selection on top - against the oracle's pieces."""
+    from oracle import scoring_ref
+    from revisionllm_b200 import sweep
+    m, w, cfg = cpu_model
+    n, F = 7, 6
+    segs = syn.make_features(n, F, cfg.adapter_dim, seed=14)
+    ids = syn.make_prompt_ids(cfg, 6, 9, seed=2)
+    cls = torch.randn(cfg.adapter_dim, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    res = sweep.stage1_sweep(m, segs, ids, cls, max_new_tokens=4, batch=3, eos_token_id=None, stage2_topk=3)
+    un = sweep.unpack_records(res.records)
+    toks, scores = _oracle(w, cfg, ids[None].repeat(n, 1), segs, 4, stop_on_eos=False)
+    assert un["tokens"][:, :4].tolist() == toks.tolist()
+    ent = torch.stack([scoring_ref.step_entropy(s) for s in scores], dim=1)            # [n, steps]
+    np.testing.assert_allclose(un["h_mean"].numpy(), ent.mean(1).numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(un["h_max"].numpy(), ent.max(1).values.numpy(), rtol=1e-4, atol=1e-5)
+    want_cos = [scoring_ref.cosine_topk_score(segs[i], cls, 3)[0] for i in range(n)]
+    np.testing.assert_allclose(un["cos"].numpy(), np.array(want_cos, dtype=np.float32), rtol=1e-6)
+    assert res.stage2_indices.tolist() == scoring_ref.select_topk_segments(np.array(want_cos, dtype=np.float32), 3).tolist()
+    assert [c for c in m.engine.calls if c[0] == "prefill"] == [("prefill", 3), ("prefill", 3), ("prefill", 1)]
