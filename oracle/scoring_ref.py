@@ -123,15 +123,16 @@ def nonoverlap_segments(ctx_l: int, num_frames: int) -> np.ndarray:
 def stage2_select_windows(stage1_answers: Sequence[str], n_stage2_windows: int, batch: int, stride: int = 5) -> List[int]:
     """eval_nlq_retrieval_e2e2.py:278-294: stage-1 windows whose answer is not
     'Not Present', mapped from the stride-2 grid to the stride-`stride` grid,
-    de-duplicated (set order made deterministic by sorting), padded with evenly
-    spaced other windows up to `batch`, sorted."""
+    de-duplicated with `list(set(...))` exactly as the reference does (:284 - when no padding follows, the list keeps
+    CPython's set iteration order, which is a function of the inserted values only), padded with evenly spaced other
+    windows up to `batch` and sorted in that case (:285-290)."""
     gw: List[int] = []
     for i, a in enumerate(stage1_answers):
         if a != "Not Present":
             lo = math.floor((i - 1) * (stride / 2))
             hi = math.ceil((i - 1) * (stride / 2) + (stride / 2))
             gw.extend(range(lo, hi))
-    gw = sorted(set(gw))
+    gw = list(set(gw))
     if batch > len(gw):
         non = [i for i in range(n_stage2_windows) if i not in gw]
         if len(non) > 0:

@@ -56,18 +56,21 @@ def nonoverlap_segments(ctx_l: int, num_frames: int) -> np.ndarray:
 
 
 def stage2_select_windows(stage1_answers: Sequence[str], n_stage2_windows: int, batch: int, stride: int = 5) -> List[int]:
-    """Positive stage-1 windows mapped to the stride-`stride` grid, padded with evenly spaced others."""
-    chosen = set()
+    """Positive stage-1 windows mapped to the stride-`stride` grid, padded with evenly spaced others
+    (eval_nlq_retrieval_e2e2.py:278-294).  Order: sorted when padding was needed (:289); otherwise the order in which a
+    Python set of the mapped ids iterates, exactly as the reference's `list(set(...))` leaves it (:284) - ids below zero
+    (a positive stage-1 window 0) index from the end of the window list, as they do there."""
+    mapped: List[int] = []
     for i, ans in enumerate(stage1_answers):
         if ans == "Not Present":
             continue
         lo = math.floor((i - 1) * (stride / 2))
         hi = math.ceil((i - 1) * (stride / 2) + (stride / 2))
-        chosen.update(range(lo, hi))
-    picked = sorted(chosen)
+        mapped.extend(range(lo, hi))
+    picked = list(set(mapped))
     missing = batch - len(picked)
     if missing > 0:
-        rest = [i for i in range(n_stage2_windows) if i not in chosen]
+        rest = [i for i in range(n_stage2_windows) if i not in picked]
         if rest:
             step = int(len(rest) / missing)
             rest = rest[::step][:missing] if step > 0 else rest[:missing]
