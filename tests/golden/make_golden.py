@@ -160,6 +160,24 @@ def case_stage1_image_list(ref, name, cfg, frames, n_pre, n_post):
     print(name, "embeds", tuple(embeds.shape), "row lengths", am.sum(1).tolist())
 
 
+def case_two_placeholders(ref, name, cfg):
+    """A row with TWO <video> placeholders consumes two visual blocks, the next row the one after (`cur_image_idx`,
+    vtimellm_arch.py:178-207); `images` is a list with one entry per placeholder."""
+    w = syn.make_llama_weights(cfg, seed=0)
+    model = ref_shim.build_reference_model(ref, cfg, w)
+    frames = (3, 5, 2)
+    images = [syn.make_features(1, f, cfg.adapter_dim, seed=60 + i)[0].float() for i, f in enumerate(frames)]
+    base = syn.make_prompt_ids(cfg, 4, 8, seed=62)
+    ids = base[None].repeat(2, 1)
+    ids[0, 9] = ref.constants.IMAGE_TOKEN_INDEX                 # a second placeholder further down row 0
+    with torch.inference_mode():
+        r = model.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, images, None, None, None, None)
+        embeds = r[4]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), digest=syn.weights_digest(w), frames=np.array(frames),
+                        images=torch.cat(images).numpy(), ids=ids.numpy(), embeds=embeds.numpy())
+    print(name, "embeds", tuple(embeds.shape))
+
+
 def case_decode_fixup(ref, name, cfg):
     """The one-token branch of prepare_inputs_labels_for_multimodal (vtimellm_arch.py:88-100): the prompt-time mask is
     extended with ones up to the cache length + 1 and the position of the new token is sum(mask) - 1 - for right-padded
@@ -299,6 +317,7 @@ def main():
         case_stage1_no_placeholder(ref, "stage1_no_placeholder_truncated", syn.TINY, n_seg=4, n_frames=9, n_pre=5, n_post=8, rows_without=(1, 3), max_len=11)
         case_stage1_image_list(ref, "stage1_image_list", syn.TINY, frames=(11, 3, 1, 17, 8), n_pre=5, n_post=9)
         case_decode_fixup(ref, "decode_fixup", syn.TINY)
+        case_two_placeholders(ref, "stage1_two_placeholders", syn.TINY)
     case_clip_encoder(ref, "clip_encoder_tiny", syn.TINY, V=5, T=12, Lq=7)
     case_scoring(ref, "scoring")
     case_prompt(ref, "prompt")

@@ -818,3 +818,35 @@ def test_clip_encoder_host_orchestration_matches_reference_fixture(golden_dir):
     want = torch.from_numpy(g["cls_out"])
     err = float((got - want).abs().max() / want.abs().max())
     assert err < 3e-2, err                                            # bf16 weights / activations against the fp32 reference
+
+
+def test_plan_splice_with_several_placeholders_per_row_equals_oracle():
+    """Rows with 0, 1, 2 or 3 <video> placeholders: visual blocks are consumed in order, one per placeholder (a row without
+    one still consumes a block, vtimellm_arch.py:168-176).  The general (non-vectorised) path of engine.plan_splice against
+    oracle/splice_ref.splice on 40 random batches, truncation included."""
+    rng = np.random.default_rng(29)
+    H, V = 8, 50
+    w = {"model.embed_tokens.weight": torch.from_numpy(rng.standard_normal((V, H)).astype(np.float32))}
+    for case in range(40):
+        B = int(rng.integers(1, 5))
+        Ltxt = int(rng.integers(5, 11))
+        ids = rng.integers(3, V, size=(B, Ltxt)).astype(np.int64)
+        n_blocks = 0
+        for b in range(B):
+            k = int(rng.integers(0, 4))
+            for pos in rng.choice(Ltxt, size=k, replace=False):
+                ids[b, int(pos)] = -200
+            n_blocks += max(k, 1)
+        frames = [int(rng.integers(1, 6)) for _ in range(n_blocks)]
+        max_len = None if case % 3 else int(rng.integers(3, Ltxt + 8))
+        proj = [torch.from_numpy(rng.standard_normal((f, H)).astype(np.float32)) for f in frames]
+        want = splice_ref.splice(w, torch.from_numpy(ids), proj, max_length=max_len)
+        plan = plan_splice(ids, frames, None, max_length=max_len)
+        assert plan["lengths"].tolist() == [e.shape[0] for e in want], case
+        allproj = torch.cat(proj)
+        packed = torch.full((int(plan["cu_seqlens"][-1]), H), float("nan"))
+        packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"][torch.from_numpy(plan["text_ids"]).long()]
+        packed[torch.from_numpy(plan["vis_dst"]).long()] = allproj[torch.from_numpy(plan["vis_src"]).long()]
+        cu = plan["cu_seqlens"]
+        for b in range(B):
+            assert torch.equal(packed[cu[b]:cu[b + 1]], want[b]), (case, b)

@@ -295,3 +295,29 @@ def test_eos_bookkeeping_matches_reference_lines(golden_dir):
                 break
         else:
             assert c["stopped_after_step"] is None
+
+
+def test_two_placeholders_in_one_row_match_reference(golden_dir):
+    """vtimellm_arch.py:178-207: a row with two <video> placeholders consumes two visual blocks and the next row the block
+    after them.  Oracle splice and the product's index plan (general path) against the reference's padded embeddings."""
+    from revisionllm_b200.engine import plan_splice
+    g = _load(golden_dir, "stage1_two_placeholders")
+    w = syn.make_llama_weights(syn.TINY, seed=0)
+    assert syn.weights_digest(w) == str(g["digest"])
+    frames = [int(f) for f in g["frames"]]
+    images = list(torch.split(torch.from_numpy(g["images"]), frames, dim=0))
+    ids = torch.from_numpy(g["ids"])
+    proj = [splice_ref.mm_projector_linear(w, im[None])[0] for im in images]
+    emb = splice_ref.splice(w, ids, proj)
+    assert [e.shape[0] for e in emb] == [ids.shape[1] - 2 + frames[0] + frames[1], ids.shape[1] - 1 + frames[2]]
+    x, _, _ = splice_ref.right_pad(emb)
+    np.testing.assert_allclose(x.numpy(), g["embeds"], rtol=1e-5, atol=1e-5)
+    plan = plan_splice(ids.numpy(), frames)
+    assert plan["lengths"].tolist() == [e.shape[0] for e in emb]
+    allproj = torch.cat(proj).float()
+    packed = torch.zeros(int(plan["cu_seqlens"][-1]), x.shape[2])
+    packed[torch.from_numpy(plan["text_dst"]).long()] = w["model.embed_tokens.weight"].float()[torch.from_numpy(plan["text_ids"]).long()]
+    packed[torch.from_numpy(plan["vis_dst"]).long()] = allproj[torch.from_numpy(plan["vis_src"]).long()]
+    cu = plan["cu_seqlens"]
+    for b in range(2):
+        np.testing.assert_allclose(packed[cu[b]:cu[b + 1]].numpy(), g["embeds"][b, : cu[b + 1] - cu[b]], rtol=1e-5, atol=1e-5)
