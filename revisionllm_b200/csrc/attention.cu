@@ -839,8 +839,8 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
   // Few (sequence, head) rows (stage 2 runs one query at a time): latency matters, the staged kernel wins (B = 1: 3.25 vs
   // 3.50 ms per 7B decode step); many rows: 8 register-staged CTAs per SM overlap better than 2 staged ones (B = 180: 9.4
   // vs 9.9 ms).  RVL_ATTN_DECODE = "regs" / "staged" forces one of them.
-  static const char* env = getenv("RVL_ATTN_DECODE");
-  const char mode = env ? env[0] : (n_seq * n_heads >= 1024 ? 'r' : 's');
+  const int forced = tuning().attn_decode;
+  const char mode = forced ? static_cast<char>(forced) : (n_seq * n_heads >= 1024 ? 'r' : 's');
   if (mode == 's') {
     // staged kernel: K and V rows of the whole context (or of a 432-key chunk) in shared memory.  Up to 220 keys two
     // CTAs share an SM (one computes while the other's copies are in flight).
@@ -872,8 +872,7 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
     cudaFuncSetAttribute(attn_decode_kernel<false, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem_r = smem;
   }
-  const char* env_ps = getenv("RVL_ATTN_PS32");          // diagnostic, read per call: 0 = runtime page size arithmetic
-  if (page_size == 32 && !(env_ps && atoi(env_ps) == 0)) {
+  if (page_size == 32 && tuning().attn_ps32 != 0) {          // RVL_ATTN_PS32=0 (diagnostic): runtime page size arithmetic
     if (fused)
       launch_pdl(pdl_dec, attn_decode_kernel<true, 4, 32>, grid, dim3(128), smem, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, page_size,
                scale, theta);

@@ -28,10 +28,7 @@ struct rvl_handle {
   float* dec_hidden = nullptr;
   float* stream_ws = nullptr;        // stream-K partial tiles of the weight-streaming GEMMs: [num_sms][256][256] fp32
   size_t stream_ws_bytes = 0;
-  unsigned int* stream_flags = nullptr;  // [num_sms] epoch flags
-  mutable unsigned int stream_epoch = 0;
-  unsigned int* grid_barrier = nullptr;  // arrival counter of the fused decode kernel (lives behind the flags)
-  mutable unsigned int grid_barrier_count = 0;
+  unsigned int* stream_flags = nullptr;  // [num_sms] "partial published" flags (zero between launches)
   float* partials = nullptr;             // [kMaxSplit][max_seqs][hidden] fp32 split-k partials of the decode o/down GEMMs
   int32_t *tok_seq = nullptr, *last_rows = nullptr;
   // kv
@@ -69,6 +66,34 @@ static int fail(const rvl_handle* h, int code, const std::string& msg) {
   return code;
 }
 namespace rvl {
+static Tuning g_tuning;
+static bool g_tuning_loaded = false;
+void reload_tuning() {
+  auto geti = [](const char* name, int unset) { const char* e = getenv(name); return e ? atoi(e) : unset; };
+  Tuning t;
+  t.pdl = geti("RVL_PDL", -1);
+  t.a_tiles = geti("RVL_A_TILES", 0);
+  t.stream_k = geti("RVL_STREAM_K", -1);
+  t.plan_debug = getenv("RVL_PLAN_DEBUG") ? 1 : 0;
+  t.pair = geti("RVL_PAIR", -1);
+  t.spair = geti("RVL_SPAIR", -1);
+  t.spair_streamk = geti("RVL_SPAIR_STREAMK", -1);
+  t.spair_small = geti("RVL_SPAIR_SMALL", -1);
+  t.staged = geti("RVL_STAGED", -1);
+  t.group_m = geti("RVL_GROUP_M", 0);
+  t.full_last_layer = geti("RVL_FULL_LAST_LAYER", 0);
+  const char* ad = getenv("RVL_ATTN_DECODE");
+  t.attn_decode = ad ? ad[0] : 0;
+  t.attn_ps32 = geti("RVL_ATTN_PS32", -1);
+  t.attn_prefill = geti("RVL_ATTN_PREFILL", -1);
+  t.norm_threads = geti("RVL_NORM_THREADS", 0);
+  g_tuning = t;
+  g_tuning_loaded = true;
+}
+const Tuning& tuning() {
+  if (!g_tuning_loaded) reload_tuning();
+  return g_tuning;
+}
 // error reporting for the entry points that live in other translation units (clip_encoder.cu)
 int report_error(const rvl_handle* h, int code, const char* msg) { return fail(h, code, msg); }
 }  // namespace rvl
@@ -109,6 +134,8 @@ extern "C" {
 
 int rvl_abi_version(void) { return RVL_ABI_VERSION; }
 
+void rvl_reload_env(void) { rvl::reload_tuning(); }
+
 const char* rvl_last_error(const rvl_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
 int rvl_create(const rvl_config* cfg, rvl_handle** out) {
@@ -131,6 +158,7 @@ int rvl_create(const rvl_config* cfg, rvl_handle** out) {
     return fail(nullptr, RVL_ERR_UNSUPPORTED, buf);
   }
   if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, RVL_ERR_CUDA, "rvl_create: cudaSetDevice failed");
+  rvl::tuning();                       // the RVL_* switches are read here, once (rvl_reload_env() re-reads them)
   rvl_handle* h = new rvl_handle();
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
@@ -172,9 +200,6 @@ int rvl_set_workspace(rvl_handle* h, void* ws, size_t bytes, int64_t max_tokens,
   h->stream_ws_bytes = kStreamWsBytes;
   h->stream_flags = reinterpret_cast<unsigned int*>(b + l.stream_flags);
   h->partials = reinterpret_cast<float*>(b + l.partials);
-  h->stream_epoch = 0;
-  h->grid_barrier = h->stream_flags + 200;
-  h->grid_barrier_count = 0;
   if (cudaMemset(h->stream_flags, 0, 1024) != cudaSuccess) return fail(h, RVL_ERR_CUDA, "rvl_set_workspace: cudaMemset failed");
   h->tok_seq = reinterpret_cast<int32_t*>(b + l.tok_seq); h->last_rows = reinterpret_cast<int32_t*>(b + l.last_rows);
   return RVL_OK;
@@ -220,7 +245,6 @@ static int linear(const rvl_handle* h, const void* x, const void* w, const void*
       c.split_used = split_used;
     } else if (h->stream_ws) {
       c.stream_ws = h->stream_ws; c.stream_ws_bytes = h->stream_ws_bytes; c.stream_flags = h->stream_flags;
-      c.stream_epoch = ++h->stream_epoch;
     }
   }
   std::string err;
@@ -253,7 +277,6 @@ int rvl_gemm_bf16(rvl_handle* h, const void* A, const void* W, const void* bias,
   c.out_mode = out_mode; c.flags = flags; c.rowmap = rowmap; c.split_k = split_k < 1 ? 1 : split_k;
   if ((flags & RVL_GEMM_FLAG_SWAP) && c.split_k == 1 && h->stream_ws) {
     c.stream_ws = h->stream_ws; c.stream_ws_bytes = h->stream_ws_bytes; c.stream_flags = h->stream_flags;
-    c.stream_epoch = ++h->stream_epoch;
   }
   std::string err;
   int rc = gemm_bf16(c, h->num_sms, static_cast<cudaStream_t>(stream), &err);
@@ -318,8 +341,7 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
   const int64_t T = total_tokens;
   const int H = c.hidden, I = c.intermediate;
   launch_token_seq(cu_seqlens, n_seq, h->tok_seq, h->last_rows, T, st);
-  const char* env_fl = getenv("RVL_FULL_LAST_LAYER");      // diagnostic, read per call: 1 = run the last layer on every row
-  const bool env_full_last = env_fl && atoi(env_fl) == 1;
+  const bool env_full_last = tuning().full_last_layer == 1;   // diagnostic: run the last layer on every row
   for (int l = 0; l < c.n_layers; ++l) {
     const rvl_layer_weights& w = h->layers[l];
     launch_rmsnorm(hidden, w.ln1, h->xnorm, T, H, c.rms_eps, nullptr, st);
@@ -385,71 +407,6 @@ int rvl_decode_step(rvl_handle* h, const int32_t* token_ids, int32_t* seq_lens, 
   const int64_t n = n_seq;
   float* hid = h->dec_hidden;
   launch_embed_rows(h->w.embed_tokens, token_ids, nullptr, n_seq, H, c.vocab, hid, st);
-  const char* env_fused = getenv("RVL_FUSED_DECODE");      // read per call: tests and tools toggle it
-  if (h->w.wgu_layout == 1 && n_seq <= 256 && H <= 8192 && !h->prof_on && env_fused && atoi(env_fused) == 1) {
-    // ---- EXPERIMENTAL fused path: one persistent kernel per attention boundary (csrc/decode_fused.cu).  Off by default:
-    // measured 9.56 / 3.50 ms per 7B decode step (B = 180 / 1) against 9.04 / 3.13 ms for the per-GEMM path - the five
-    // grid barriers per layer and the 4-5-way stream-K fix-up of the 32-tile o / down projections cost more than the six
-    // launches they replace.
-    auto launch = [&](FusedCall& fc) -> int {
-      fc.n_tokens = n_seq;
-      fc.stream_ws = h->stream_ws; fc.stream_ws_bytes = h->stream_ws_bytes; fc.stream_flags = h->stream_flags;
-      fc.epoch0 = h->stream_epoch + 1;
-      h->stream_epoch += fc.n_phases;
-      fc.grid_barrier = h->grid_barrier;
-      fc.grid_barrier_base = h->grid_barrier_count;
-      h->grid_barrier_count += static_cast<unsigned int>(fc.n_phases) * h->num_sms;
-      std::string err;
-      int r = decode_fused(fc, h->num_sms, st, &err);
-      return r ? fail(h, r, err) : RVL_OK;
-    };
-    // o / down projections: plain split-k into the partial buffers, summed into the residual by the RMSNorm phase that follows
-    // (a 32-tile GEMM dealt stream-K over 148 SMs needs a 4-5-way fix-up per tile: measured ~30 us per phase)
-    const int tiles_h = (H + 127) / 128;
-    int sk = h->num_sms / tiles_h;
-    if (sk > 4) sk = 4;
-    if (sk < 1) sk = 1;
-    auto norm = [&](const void* w, void* y, int n_partials) {
-      FusedPhase p; p.kind = 1; p.x = hid; p.norm_w = w; p.y = y; p.dim = H; p.eps = c.rms_eps; p.partials = h->partials; p.n_partials = n_partials;
-      return p;
-    };
-    auto resid = [&](const void* W, const void* act, int K) {
-      FusedPhase p; p.kind = 0; p.W = W; p.act = act; p.out = h->partials; p.features = H; p.K = K; p.ldc = H; p.out_kind = RVL_FUSED_OUT_F32;
-      p.split_k = (K / 64) / sk >= 4 ? sk : 1;
-      return p;
-    };
-    auto gemm = [&](const void* W, const void* act, void* out, int features, int K, int64_t ldc, int kind) {
-      FusedPhase p; p.kind = 0; p.W = W; p.act = act; p.out = out; p.features = features; p.K = K; p.ldc = ldc; p.out_kind = kind; return p;
-    };
-    {
-      FusedCall fc;
-      fc.n_phases = 2;
-      fc.ph[0] = norm(h->layers[0].ln1, h->xnorm, 0);
-      fc.ph[1] = gemm(h->layers[0].wqkv, h->xnorm, h->qkv, 3 * H, H, 3 * H, RVL_FUSED_OUT_BF16);
-      if ((rc = launch(fc))) return rc;
-    }
-    for (int l = 0; l < c.n_layers; ++l) {
-      const rvl_layer_weights& w = h->layers[l];
-      launch_attn_decode(h->qkv, h->attn, seq_lens, n_seq, page_table, max_pages, k_pages(h, l), v_pages(h, l), c.n_heads,
-                         c.kv_page_size, 1, c.rope_theta, max_kv_len, st);
-      FusedCall fc;
-      fc.n_phases = 6;
-      fc.ph[0] = resid(w.wo, h->attn, H);
-      fc.ph[1] = norm(w.ln2, h->xnorm, fc.ph[0].split_k);
-      fc.ph[2] = gemm(w.wgu, h->xnorm, h->act, 2 * I, H, I, RVL_FUSED_OUT_SWIGLU);
-      fc.ph[3] = resid(w.wdown, h->act, I);
-      if (l + 1 < c.n_layers) {
-        fc.ph[4] = norm(h->layers[l + 1].ln1, h->xnorm, fc.ph[3].split_k);
-        fc.ph[5] = gemm(h->layers[l + 1].wqkv, h->xnorm, h->qkv, 3 * H, H, 3 * H, RVL_FUSED_OUT_BF16);
-      } else {
-        fc.ph[4] = norm(h->w.final_norm, h->xlast, fc.ph[3].split_k);
-        fc.ph[5] = gemm(h->w.lm_head, h->xlast, logits_out, c.vocab, H, c.vocab, RVL_FUSED_OUT_F32);
-      }
-      if ((rc = launch(fc))) return rc;
-    }
-    launch_k(inc_kernel, dim3((n_seq + 127) / 128), dim3(128), 0, st, seq_lens, static_cast<int>(n_seq));
-    return check_cuda(h, "rvl_decode_step");
-  }
   // o_proj / down_proj leave split-k partial sums in h->partials; the next RMSNorm adds them to the residual
   const int64_t pstride = n * H;
   int pending = 0;

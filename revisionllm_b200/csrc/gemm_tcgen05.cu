@@ -65,8 +65,8 @@ struct GemmArgs {
   int prefetch_a;       // A is a bound weight no earlier kernel writes: fill the smem ring with A before pdl_wait()
   int units_per_cta;    // stream-K: k-blocks per CTA
   float* ws;            // stream-K: per-CTA fp32 partial [a_tiles*128][ws_ld]
-  unsigned int* flags;  // stream-K: per-CTA "partial written" epoch
-  unsigned int epoch;
+  unsigned int* flags;  // stream-K: per-CTA "partial published" flag; the head CTA that consumed the partial clears it again,
+                        // so the flags are zero between launches and a captured CUDA graph can be replayed unchanged
   int ws_ld;
   long long split_stride;  // > 0: split-k partial s goes to out + s * split_stride (plain stores, no atomics)
   long long ldc;
@@ -513,7 +513,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int f = 1; f <= w.followers; ++f) {
           const unsigned int* fl = args.flags + blockIdx.x + f;
           unsigned int spins = 0;
-          while (ld_acquire(fl) != args.epoch) {
+          while (ld_acquire(fl) == 0u) {
             if (++spins > (1u << 26)) mbar_timeout(nullptr, 0xdead);
           }
         }
@@ -600,6 +600,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             bulk_commit_group();
           }
         }
+        if (kStreamK && w.kind == 2) {
+          // every epilogue thread has read the followers' partials (the bar.sync above): clear their flags for the next launch
+          if (threadIdx.x == 64)
+            for (int f = 1; f <= w.followers; ++f) args.flags[blockIdx.x + f] = 0u;
+        }
         if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
         continue;
       }
@@ -656,8 +661,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // publish the partial: every epilogue thread fences its own stores, then one thread raises the flag
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) st_release(args.flags + blockIdx.x, args.epoch);
+        if (threadIdx.x == 64) st_release(args.flags + blockIdx.x, 1u);
         if (warp == 2) DBG_T(6);
+      }
+      if (kStreamK && w.kind == 2) {
+        // all four epilogue warps are done with the followers' partials: clear their flags for the next launch
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64)
+          for (int f = 1; f <= w.followers; ++f) args.flags[blockIdx.x + f] = 0u;
       }
       if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
@@ -885,7 +896,7 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc_pair(tmem_ptr, 512);
+    tmem_alloc_pair(tmem_ptr, static_cast<uint32_t>(args.tmem_cols));
     tmem_relinquish_pair();
   }
   tc_fence_before();
@@ -989,7 +1000,7 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -1028,8 +1039,8 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) st_release(args.flags + blockIdx.x, args.epoch);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (threadIdx.x == 64) st_release(args.flags + blockIdx.x, 1u);
+        if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       if (w.kind == 2) {
@@ -1037,7 +1048,7 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         for (int f = 1; f <= w.followers; ++f) {
           const unsigned int* fl = args.flags + blockIdx.x + 2 * f;
           unsigned int spins = 0;
-          while (ld_acquire(fl) != args.epoch) {
+          while (ld_acquire(fl) == 0u) {
             if (++spins > (1u << 26)) mbar_timeout(nullptr, 0xdead);
           }
         }
@@ -1106,7 +1117,9 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           bulk_commit_group();
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (w.kind == 2 && threadIdx.x == 64)                      // partials consumed (the bar.sync above): flags back to zero
+        for (int f = 1; f <= w.followers; ++f) args.flags[blockIdx.x + 2 * f] = 0u;
+      if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (threadIdx.x == 64) bulk_wait_all();
   }
@@ -1116,7 +1129,7 @@ gemm_stream_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(args.tmem_cols));
   }
 }
 
@@ -1202,10 +1215,8 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   if (c.split_k > 1 && !partials && c.out_mode != RVL_GEMM_ADD_F32) { *err = "gemm: split_k needs RVL_GEMM_ADD_F32 or a partial buffer"; return RVL_ERR_INVALID; }
   if (partials && c.out_mode != RVL_GEMM_OUT_F32) { *err = "gemm: split-k partials are fp32 (RVL_GEMM_OUT_F32)"; return RVL_ERR_INVALID; }
   const bool swap = (c.flags & RVL_GEMM_FLAG_SWAP) != 0;
-  static const char* env_at = getenv("RVL_A_TILES");      // experiment hooks
-  static const char* env_sk = getenv("RVL_STREAM_K");
-  static const char* env_dbg = getenv("RVL_PLAN_DEBUG");
-  static const char* env_pair = getenv("RVL_PAIR");
+  const Tuning& tn = tuning();                            // RVL_* experiment hooks, read once per process
+  const bool env_dbg = tn.plan_debug != 0;
   GemmArgs a{};
   a.K = static_cast<int>(c.K);
   a.k_blocks = static_cast<int>((c.K + kBK - 1) / kBK);
@@ -1235,7 +1246,7 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   // Weight streaming keeps 128-row tiles: more, smaller units balance better and the partial tiles stay small.
   // (measured on B200: 1-4 % faster in isolation, no gain inside the power-capped sweep, so it stays opt-in)
   a.a_tiles = 1;
-  if (env_at && atoi(env_at) == 2 && !swap && a.M >= 4 * kBM && a.N >= 256) a.a_tiles = 2;
+  if (tn.a_tiles == 2 && !swap && a.M >= 4 * kBM && a.N >= 256) a.a_tiles = 2;
   a.tiles_m = (a.M + a.a_tiles * kBM - 1) / (a.a_tiles * kBM);
   a.tiles_n = (a.N + a.bn - 1) / a.bn;
   // stream-K for the weight-streaming orientation: needs the workspace, a single n-tile and no explicit split
@@ -1244,11 +1255,10 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   // for less than one wave of tiles the fix-up traffic eats the gain (qkv: 34.3 vs 35.0 us).
   const int waves = (a.tiles_m + num_sms - 1) / num_sms;
   const bool ragged = a.tiles_m > num_sms && a.tiles_m < 0.7 * waves * num_sms;
-  const bool force_sk = (env_sk && atoi(env_sk) == 2) || (c.flags & RVL_GEMM_FLAG_STREAMK);
+  const bool force_sk = tn.stream_k == 2 || (c.flags & RVL_GEMM_FLAG_STREAMK);
   // many tokens: the CTA-pair weight-streaming kernel takes the GEMM (tile mode / split-k partials), no stream-K
-  const char* env_spair0 = getenv("RVL_SPAIR");              // read per call: in-process A/B
   const bool spair_candidate = swap && a.N > 64 && a.M >= 256 && (num_sms % 2 == 0) && !c.bias && !c.rowmap && !a.relu &&
-                               c.out_mode != RVL_GEMM_ADD_F32 && !force_sk && !(env_spair0 && atoi(env_spair0) == 0);
+                               c.out_mode != RVL_GEMM_ADD_F32 && !force_sk && tn.spair != 0;
   if (!spair_candidate && swap && c.stream_ws && c.stream_flags && sk == 1 && a.tiles_n == 1 && !a.rowmap && !partials && a.a_tiles == 1 &&
       (ragged || force_sk)) {
     const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
@@ -1256,12 +1266,11 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     int upc = static_cast<int>((total + ctas - 1) / ctas);
     if (upc < 8 && total >= 8) upc = 8;                                   // keep pipelines worth starting
     const size_t need = static_cast<size_t>(num_sms) * a.a_tiles * 8 * 8 * 128 * 16;
-    if (need <= c.stream_ws_bytes && (!env_sk || atoi(env_sk) != 0)) {
+    if (need <= c.stream_ws_bytes && tn.stream_k != 0) {
       a.stream_k = 1;
       a.units_per_cta = upc;
       a.ws = c.stream_ws;
       a.flags = c.stream_flags;
-      a.epoch = c.stream_epoch;
       a.ws_ld = a.sub_stride;
     }
   }
@@ -1275,13 +1284,12 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
   a.tmem_cols = pow2_at_least(a.acc_stages * a.a_tiles * a.sub_stride);
   const int stage_bytes = a.a_tiles * kATileBytes + a.bn * kBK * 2;
   // staged TMA-store epilogue for the weight-streaming orientation (plain bf16 / fp32 / SwiGLU outputs)
-  static const char* env_staged = getenv("RVL_STAGED");
   const bool out_f32 = c.out_mode != RVL_GEMM_OUT_BF16;
   const int out_es = out_f32 ? 4 : 2;
   a.staged = 0;
   if (swap && a.a_tiles == 1 && !c.bias && !c.rowmap && !a.relu && !a.atomic && c.out_mode != RVL_GEMM_ADD_F32 &&
       (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && (c.ldc * out_es) % 16 == 0 && (a.split_stride * out_es) % 16 == 0 &&
-      !(env_staged && atoi(env_staged) == 0))
+      tn.staged != 0)
     a.staged = a.swiglu ? 12 : (out_f32 ? 3 : 6);
   a.stages = (a.staged ? kSmemBudgetStaged : kSmemBudget) / stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
@@ -1291,7 +1299,7 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
             a.M, a.N, a.K, a.bn, a.a_tiles, a.stages, a.acc_stages, a.tmem_cols, a.split_k, a.stream_k, a.units_per_cta);
   // CTA-pair kernel (tcgen05 cta_group::2): token-major GEMMs with >= one wave of 256 x 256 tiles
   const bool pair_ok = !swap && a.split_k == 1 && !a.stream_k && a.N >= 256 && a.M >= 1024 && (num_sms % 2 == 0);
-  if (pair_ok && !(env_pair && atoi(env_pair) == 0)) {   // RVL_PAIR=0 falls back to the single-CTA kernel
+  if (pair_ok && tn.pair != 0) {   // RVL_PAIR=0 falls back to the single-CTA kernel
     a.a_tiles = 1;
     a.bn = 256;
     a.tiles_m = (a.M + 255) / 256;
@@ -1300,9 +1308,8 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
       // m-tiles per n-sweep (L2 reuse of the A slab against the weight streaming through).  Measured interleaved on B200 at
       // 33120 tokens (tools/prefill_gemm_ab.py): 32 is 3-4 % faster than 16 for qkv / gate|up / down, 16 is best for the
       // small o projection; the differences come from DRAM traffic (power), not from the tensor pipe.
-      const char* env_gm = getenv("RVL_GROUP_M");
       long long gm = (c.N * c.K >= (32ll << 20)) ? 32 : 16;
-      if (env_gm) gm = atoi(env_gm);
+      if (tn.group_m > 0) gm = tn.group_m;
       a.group_m = static_cast<int>(gm < 2 ? 2 : (gm > 64 ? 64 : gm));
     }
     a.stages = kSmemBudget / (kATileBytes + 128 * kBK * 2);
@@ -1329,21 +1336,18 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     return RVL_OK;
   }
   // CTA-pair weight streaming (see gemm_stream_pair_kernel): many tokens, staged outputs, no stream-K
-  const char* env_spair = getenv("RVL_SPAIR");
-  if (swap && a.staged && spair_candidate && a.tiles_n == 1 && a.a_tiles == 1 && (num_sms % 2 == 0) && a.M >= 256 &&
-      !(env_spair && atoi(env_spair) == 0)) {
+  if (swap && a.staged && spair_candidate && a.tiles_n == 1 && a.a_tiles == 1 && (num_sms % 2 == 0) && a.M >= 256 && tn.spair != 0) {
     CUtensorMap pa_map, pb_map, po_map;
     a.tiles_m = (a.M + 255) / 256;
     // a ragged last wave of 256-row tiles (gate|up: 86 tiles on 74 clusters): deal the k-blocks out evenly (stream-K).
     // Measured at 180 tokens: gate|up 39.7 us against 44.6 us in tile mode (42.1 us on the single-CTA stream-K kernel); for
     // less than one wave (qkv: 48 tiles, 26.0 vs 30.2 us) or nearly full waves (lm_head: 125 tiles, 49.9 vs 51.6 us) tile mode wins.
-    const char* env_spsk = getenv("RVL_SPAIR_STREAMK");
     const int clusters = num_sms / 2;
     const int pair_waves = (a.tiles_m + clusters - 1) / clusters;
     const bool pair_ragged = a.tiles_m > clusters && a.tiles_m < 0.7 * pair_waves * clusters;
     a.stream_k = 0;
-    if (c.stream_ws && c.stream_flags && sk == 1 && !partials && !(env_spsk && atoi(env_spsk) == 0) &&
-        static_cast<size_t>(num_sms) * 8 * 8 * 128 * 16 <= c.stream_ws_bytes && (pair_ragged || (env_spsk && atoi(env_spsk) == 2))) {
+    if (c.stream_ws && c.stream_flags && sk == 1 && !partials && tn.spair_streamk != 0 &&
+        static_cast<size_t>(num_sms) * 8 * 8 * 128 * 16 <= c.stream_ws_bytes && (pair_ragged || tn.spair_streamk == 2)) {
       const long long total = static_cast<long long>(a.tiles_m) * a.k_blocks;
       const int cl = num_sms / 2;
       int upc = static_cast<int>((total + cl - 1) / cl);
@@ -1352,13 +1356,26 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
       a.units_per_cta = upc;
       a.ws = c.stream_ws;
       a.flags = c.stream_flags;
-      a.epoch = c.stream_epoch;
       a.ws_ld = a.sub_stride;
     }
     const int half_bytes = ((a.bn / 2) * kBK * 2 + 1023) & ~1023;
     a.stages = kSmemBudgetStaged / (kATileBytes + half_bytes);
     if (a.stages > kMaxStages) a.stages = kMaxStages;
     a.acc_stages = 2;
+    a.tmem_cols = 512;
+    int stage_out_bytes = kStageOutBytes;
+    // RVL_SPAIR_SMALL=1 (experiment): half-size CTA - at most 110 KB of shared memory and 256 TMEM columns - so that the CTAs of
+    // the NEXT weight-streaming GEMM of the stream (programmatic dependent launch) become resident beside this kernel's,
+    // run their prologue and fill their ring with weight tiles while this kernel drains: the HBM stream does not stop at the
+    // kernel boundary.  One accumulator stage, a 16 KB staging buffer (2 / 1 / 4 chunks per store group).
+    if (tn.spair_small == 1 && a.sub_stride <= 256) {
+      stage_out_bytes = 16 * 1024;
+      a.staged = a.swiglu ? 4 : (out_f32 ? 1 : 2);
+      a.acc_stages = 1;
+      a.tmem_cols = pow2_at_least(a.sub_stride);
+      a.stages = (110 * 1024 - 1024 - 512 - stage_out_bytes) / (kATileBytes + half_bytes);
+      if (a.stages < 2) a.stages = 2;
+    }
     int rcp = make_tmap(&pa_map, pa, a.M, c.K, kBM, err);
     if (rcp) return rcp;
     rcp = make_tmap(&pb_map, pb, a.N, c.K, a.bn / 2, err);
@@ -1373,7 +1390,7 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
       }
       sp_attr = true;
     }
-    const int smem_sp = a.stages * (kATileBytes + half_bytes) + 1024 + 512 + kStageOutBytes;
+    const int smem_sp = a.stages * (kATileBytes + half_bytes) + 1024 + 512 + stage_out_bytes;
     const int units = a.stream_k ? static_cast<int>((static_cast<long long>(a.tiles_m) * a.k_blocks + a.units_per_cta - 1) / a.units_per_cta)
                                  : a.tiles_m * a.split_k;
     const int grid_sp = 2 * (units < num_sms / 2 ? units : num_sms / 2);

@@ -27,62 +27,48 @@ struct GemmCall {
   // stream-K workspace (weight-streaming orientation only): fp32 partial tiles and per-CTA flags
   float* stream_ws = nullptr;
   size_t stream_ws_bytes = 0;
-  unsigned int* stream_flags = nullptr;
-  unsigned int stream_epoch = 0;
+  unsigned int* stream_flags = nullptr;   // per-CTA "partial published" flags, zero between launches (the consumer clears them)
 };
 int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err);
 
-// decode_fused.cu: the per-layer chain of the decode step as one persistent kernel (see the file header)
-constexpr int kFusedMaxPhases = 6;
-enum { RVL_FUSED_OUT_BF16 = 0, RVL_FUSED_OUT_SWIGLU = 1, RVL_FUSED_OUT_ADD_F32 = 2, RVL_FUSED_OUT_F32 = 3 };
-struct FusedPhase {
-  int kind = 0;                 // 0: GEMM, 1: RMSNorm
-  // GEMM: out[token][feature] (+)= act[token][:] . W[feature][:]
-  const void* W = nullptr;      // [features, K] bf16
-  const void* act = nullptr;    // [n_tokens, K] bf16
-  void* out = nullptr;          // bf16 / fp32 [n_tokens, ldc]
-  int features = 0, K = 0;
-  int64_t ldc = 0;
-  int out_kind = RVL_FUSED_OUT_BF16;
-  int split_k = 0;              // > 0: plain split-k, fp32 partial s of the tile goes to out + s * n_tokens * ldc (RVL_FUSED_OUT_F32)
-  // RMSNorm: x += sum of n_partials partial buffers [n_tokens, dim] (written back), y = x * rsqrt(mean(x^2) + eps) * norm_w
-  float* x = nullptr;
-  const float* partials = nullptr;
-  int n_partials = 0;
-  const void* norm_w = nullptr;
-  void* y = nullptr;
-  int dim = 0;
-  float eps = 0.f;
+// Diagnostic switches ("Diagnostic switches"): the RVL_* environment variables are read ONCE - at the first
+// rvl_create of the process - into this table; nothing on the hot path calls getenv().  tools/ that flip a switch inside one
+// process call rvl_reload_env() afterwards.  -1 / 0 = "not set" where a switch has a default that depends on the problem.
+struct Tuning {
+  int pdl = -1;              // RVL_PDL bit mask (-1: GEMMs always, few-row norm / attention up to 128 rows)
+  int a_tiles = 0;           // RVL_A_TILES
+  int stream_k = -1;         // RVL_STREAM_K
+  int plan_debug = 0;        // RVL_PLAN_DEBUG
+  int pair = -1;             // RVL_PAIR
+  int spair = -1;            // RVL_SPAIR
+  int spair_streamk = -1;    // RVL_SPAIR_STREAMK
+  int spair_small = -1;      // RVL_SPAIR_SMALL: half-size CTA-pair weight-streaming kernel (two kernels co-resident per SM)
+  int staged = -1;           // RVL_STAGED
+  int group_m = 0;           // RVL_GROUP_M
+  int full_last_layer = 0;   // RVL_FULL_LAST_LAYER
+  int attn_decode = 0;       // RVL_ATTN_DECODE: 'r' / 's' / 0
+  int attn_ps32 = -1;        // RVL_ATTN_PS32
+  int attn_prefill = -1;     // RVL_ATTN_PREFILL: 0 = mma.sync kernel, 1 = tcgen05 kernel
+  int norm_threads = 0;      // RVL_NORM_THREADS: threads of the few-row RMSNorm CTA (256 / 512 / 1024)
 };
-struct FusedCall {
-  int n_phases = 0;
-  int n_tokens = 0;
-  FusedPhase ph[kFusedMaxPhases];
-  float* stream_ws = nullptr;
-  size_t stream_ws_bytes = 0;
-  unsigned int* stream_flags = nullptr;
-  unsigned int epoch0 = 0;              // phase p uses epoch0 + p
-  unsigned int* grid_barrier = nullptr; // monotonic arrival counter
-  unsigned int grid_barrier_base = 0;   // its value before this launch (advances by n_phases * num_sms)
-};
-int decode_fused(const FusedCall& c, int num_sms, cudaStream_t st, std::string* err);
+const Tuning& tuning();      // engine.cu
+void reload_tuning();
 
 // Programmatic dependent launch: RVL_PDL=0 in the environment switches it off (plain stream order).
 // Bit 0: the GEMM launches, bit 1: every other kernel.  Default 1: measured on B200 (decode step, 7B shape, B = 180 / 32)
 // 10.08 / 5.71 ms without, 9.72 / 5.18 ms with GEMMs only, 9.90 / 5.67 ms with everything - small kernels that become
 // resident early only squat on the SM while the GEMM before them is still streaming.
-// Bit 2: the few-row (decode) RMSNorm only, bit 3: the decode attention kernels only.  Read per call so that tools can A/B in
-// one process.
+// Bit 2: the few-row (decode) RMSNorm only, bit 3: the decode attention kernels only.  Tools A/B in one process through rvl_reload_env().
 inline int pdl_mask() {
-  const char* e = getenv("RVL_PDL");
-  return e ? atoi(e) : 1;
+  const int e = tuning().pdl;
+  return e >= 0 ? e : 1;
 }
 // Decode-step RMSNorm (bit 2) and attention (bit 3): early launch pays for few rows - measured per 7B decode step with both
 // on: 3.12 -> 3.01 ms at B = 1, 4.24 -> 4.13 at 23, 5.36 -> 5.08 at 56, 6.43 -> 6.28 at 96 - and costs at B = 180
 // (8.50 -> 8.77 ms: the 1024-thread RMSNorm CTAs cannot share an SM with a streaming GEMM CTA).  Default: on up to 128 rows.
 inline bool pdl_few_rows(long long rows, int bit) {
-  const char* e = getenv("RVL_PDL");
-  if (e) return (atoi(e) & (2 | bit)) != 0;
+  const int e = tuning().pdl;
+  if (e >= 0) return (e & (2 | bit)) != 0;
   return rows <= 128;
 }
 // Launch `kernel` so that it may start while the previous kernel of `st` is still running (it must call pdl_wait()

@@ -52,7 +52,80 @@ def _req(t: torch.Tensor, dtype, name: str):
     return t
 
 
-class Engine:
+class DecodeChunks:
+    """Chunks of greedy decode steps over fixed-address buffers, replayed as CUDA graphs (mixed into `Engine`; the CPU
+    stand-in of tests/test_generate_host_cpu.py mixes it in as well, so generate()'s chunk logic is the same code there)."""
+    _ws = None
+    _kv = None
+
+    def _init_chunks(self):
+        self._dec_bufs: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}   # (rows, max_pages) -> fixed-address decode buffers
+        self._dec_graphs: Dict[tuple, Tuple[object, int]] = {}                # captured decode chunks (graph, launches per replay)
+        self._dec_seen: Dict[tuple, int] = {}
+
+    DECODE_CHUNK = 8          # decode steps per captured graph = steps between two looks at the EOS flags
+
+    def decode_buffers(self, n_rows: int, max_pages: int) -> Dict[str, torch.Tensor]:
+        """Fixed-address buffers a captured decode chunk reads and writes (a CUDA graph bakes pointers in): last-row logits,
+        sequence lengths, page table, EOS flags, and the chunk's token / entropy rows.  A handful of (rows, pages) shapes is
+        kept; the oldest goes first."""
+        key = (n_rows, max_pages)
+        b = self._dec_bufs.get(key)
+        if b is None:
+            while len(self._dec_bufs) >= 6:
+                old = next(iter(self._dec_bufs))
+                del self._dec_bufs[old]
+                for gk in [gk for gk in self._dec_graphs if gk[:2] == old]:
+                    del self._dec_graphs[gk]
+            dev, K = self.device, self.DECODE_CHUNK
+            b = dict(logits=torch.empty((n_rows, self.cfg.vocab), dtype=torch.float32, device=dev),
+                     seq_lens=torch.empty(n_rows, dtype=torch.int32, device=dev),
+                     page_table=torch.empty((n_rows, max_pages), dtype=torch.int32, device=dev),
+                     unfinished=torch.empty(n_rows, dtype=torch.int32, device=dev),
+                     ring_tok=torch.empty((K, n_rows), dtype=torch.int32, device=dev),
+                     ring_ent=torch.empty((K, n_rows), dtype=torch.float32, device=dev))
+            self._dec_bufs[key] = b
+        return b
+
+    def decode_chunk(self, bufs: Dict[str, torch.Tensor], k: int, eos_id: int, pad_id: int, use_unfinished: bool, max_kv_len: int,
+                     graph: bool = True):
+        """`k` x (greedy sample of bufs.logits -> ring_tok[s] / ring_ent[s]; decode step on that token -> bufs.logits), the
+        generation loop of vtimellm_llama.py:287-369 for k tokens, as ONE CUDA-graph launch once the same chunk shape has been
+        seen before (the first occurrence runs eagerly: capture costs more than it saves for a shape used once).  Every
+        pointer the chunk touches lives in `bufs`, the bound weights, the workspace or the KV pages; the graph is dropped
+        when the workspace or the KV pages are re-allocated."""
+        n_rows, max_pages = bufs["page_table"].shape
+        unf = bufs["unfinished"] if use_unfinished else None
+
+        def body():
+            for s in range(k):
+                self.sample_greedy(bufs["logits"], bufs["ring_tok"][s], bufs["ring_ent"][s], unf, eos_id, pad_id)
+                self.decode_step(bufs["ring_tok"][s], bufs["seq_lens"], bufs["page_table"], bufs["logits"], max_kv_len=max_kv_len)
+
+        key = (n_rows, max_pages, k, eos_id, pad_id, use_unfinished, max_kv_len, self._ws.data_ptr() if self._ws is not None else 0,
+               self._kv.data_ptr() if self._kv is not None else 0)
+        hit = self._dec_graphs.get(key)
+        if hit is not None:
+            hit[0].replay()
+            self.launches += hit[1]
+            return
+        self._dec_seen[key] = self._dec_seen.get(key, 0) + 1
+        if not graph or self._dec_seen[key] < 2 or self.device.type != "cuda":
+            body()
+            return
+        for gk in [gk for gk in self._dec_graphs if gk[-2:] != key[-2:]]:      # graphs over buffers that no longer exist
+            del self._dec_graphs[gk]
+        before = self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            body()
+        self._dec_graphs[key] = (g, self.launches - before)
+        self.launches = before
+        g.replay()
+        self.launches += self._dec_graphs[key][1]
+
+
+class Engine(DecodeChunks):
     """One per (process, GPU).  Not thread-safe."""
 
     def __init__(self, cfg: EngineConfig, device: Optional[int] = None):
@@ -74,6 +147,7 @@ class Engine:
         self._kv: Optional[torch.Tensor] = None
         self.n_pages = 0
         self.launches = 0                         # kernels enqueued through this engine (bench's gpu_launches)
+        self._init_chunks()
 
     def close(self):
         if getattr(self, "h", None):

@@ -84,6 +84,8 @@ class KVState:
         self.reserve = reserve             # new tokens every sequence has pages for
         self.lengths = lengths.copy()      # host copy of the prompt lengths
         self.steps = 0                     # tokens appended since the prefill
+        self.shared_prefix = 0
+        self.n_shared = 0
 
     def get_seq_length(self) -> int:
         return int(self.lengths.max()) + self.steps
@@ -136,6 +138,7 @@ class RevisionLlamaForCausalLM:
         self.last_phase_events = None
         self.share_prefix_compute = False  # also COMPUTE that prefix once (see _share_prefix_rows); opt-in
         self.share_prefix_pages = True     # map the KV pages of a prompt prefix common to the whole batch once (see _alloc_kv)
+        self.decode_graphs = True          # replay chunks of greedy decode steps as CUDA graphs (engine.decode_chunk)
 
     # ---- placement (eval_nlq_negative.py:144-148 does `model.bfloat16().cuda()`)
     def bfloat16(self):
@@ -314,6 +317,7 @@ class RevisionLlamaForCausalLM:
         dev = self.device
         kv = KVState(torch.from_numpy(table).to(dev), torch.from_numpy(lengths.astype(np.int32)).to(dev), extra, lengths)
         kv.shared_prefix = shared_prefix
+        kv.n_shared = n_shared              # leading pages every row maps to the same physical pages
         return kv
 
     @staticmethod
@@ -386,10 +390,18 @@ class RevisionLlamaForCausalLM:
                  max_new_tokens=1024, use_cache=True, visual_memory=None, prefix_memory=None, output_scores=False,
                  return_dict_in_generate=False, output_hidden_states=False, attention_mask=None,
                  eos_token_id="config", pad_token_id=None, stopping_criteria=None, seed: int = 0,
-                 retire_finished: bool = False, **unused):
+                 retire_finished: bool = False, mask_entropy_after_eos: bool = False, **unused):
         """`seed`: key of the Philox stream used when do_sample=True.  `retire_finished`: drop rows that emitted EOS from the
         decode batch (their remaining tokens are pad, as in the reference; their per-step entropies stop at EOS instead of
-        continuing over pad inputs as the reference's do)."""
+        continuing over pad inputs as the reference's do).  `mask_entropy_after_eos`: keep every row in the batch but report
+        NaN for the entropies of the steps after a row's EOS - what the reference's one-call-per-prompt schedule (stage 2,
+        eval_nlq_retrieval_e2e2.py:353-359) measures; the default keeps them, like a batched reference call does
+        (eval_nlq_negative.py:287-297 takes the statistics over all steps of the batch).
+
+        The loop looks at the EOS flags every `engine.DECODE_CHUNK` steps instead of every step (the reference's
+        `unfinished_sequences.max() == 0` test, vtimellm_llama.py:359-362, costs one host synchronisation per token); steps
+        that ran after the last row finished are trimmed from the outputs, so the result is the reference's.  Greedy decoding
+        without per-step scores replays each chunk of steps as one CUDA graph (`decode_graphs`)."""
         self._need_engine()
         if num_beams != 1:
             raise NotImplementedError("beam search is not part of the reference path (num_beams=1, inference.py:49)")
@@ -402,6 +414,7 @@ class RevisionLlamaForCausalLM:
         dev = self.device
         eos = cfg.eos_token_id if eos_token_id == "config" else eos_token_id
         pad = pad_token_id if pad_token_id is not None else (cfg.pad_token_id if cfg.pad_token_id is not None else (eos if eos is not None else 0))
+        eos_arg = -1 if eos is None else int(eos)
         with torch.cuda.device(dev):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.record_phase_events else None
             if ev:
@@ -419,11 +432,18 @@ class RevisionLlamaForCausalLM:
             # KV pages: everything up front when small, else grow in chunks of 64 tokens as decoding proceeds
             chunk = max_new if max_new <= 64 else 64
             kv = self._alloc_kv(lengths, chunk, plan["shared_prefix"])
+            # chunks of decode steps between two looks at the EOS flags; greedy chunks without per-step outputs are captured as
+            # CUDA graphs over fixed-address buffers (engine.decode_chunk)
+            chunked = not sampling and not retire_finished and not output_scores and max_new <= 64
+            bufs = eng.decode_buffers(B, kv.page_table.shape[1]) if chunked else None
             cu_d = torch.from_numpy(cu).to(dev)
             P = int(plan["ctx_len"])
             if P:
                 # B + 1 sequences: the shared prefix (its K/V fill the shared pages), then every segment from position P on
                 ps = eng.cfg.kv_page_size
+                if kv.n_shared < P // ps:
+                    raise RvlError("share_prefix_compute needs the prefix pages mapped once for the whole batch (share_prefix_pages=True): "
+                                   f"{P // ps} prefix pages are computed once but only {kv.n_shared} are shared")
                 table = torch.zeros((B + 1, kv.page_table.shape[1]), dtype=torch.int32, device=dev)
                 table[0, : P // ps] = kv.page_table[0, : P // ps]
                 table[1:] = kv.page_table
@@ -432,9 +452,13 @@ class RevisionLlamaForCausalLM:
                 all_last = torch.empty((B + 1, cfg.vocab_size), dtype=torch.float32, device=dev)
                 eng.prefill(hidden, cu_d, B + 1, int(lengths.max()), table, all_last, all_logits=False, seq_pos0=pos0,
                             seq_ctx_row=torch.zeros(B + 1, dtype=torch.int32, device=dev))
-                logits = all_last[1:].contiguous()
+                if chunked:
+                    logits = bufs["logits"]
+                    logits.copy_(all_last[1:])
+                else:
+                    logits = all_last[1:].contiguous()
             else:
-                logits = torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                logits = bufs["logits"] if chunked else torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
                 eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
             if ev:
                 ev[2].record()
@@ -443,59 +467,105 @@ class RevisionLlamaForCausalLM:
             entropies = torch.full((max_new, B), float("nan"), dtype=torch.float32, device=dev)
             unfinished = torch.ones(B, dtype=torch.int32, device=dev) if eos is not None else None
             scores: List[torch.Tensor] = []
-            n_steps = 0
-            active = None                          # original row ids of the live decode batch once rows have been retired
-            tok_t = ent_t = None
-            for t in range(max_new):
-                n_live = logits.shape[0]
-                if active is None:
-                    tok_t, ent_t = tokens[t], entropies[t]
+            steps_run = 0
+            poll = eng.DECODE_CHUNK
+            if chunked:
+                bufs["seq_lens"].copy_(kv.seq_lens)
+                bufs["page_table"].copy_(kv.page_table)
+                kv.seq_lens, kv.page_table = bufs["seq_lens"], bufs["page_table"]
+                if unfinished is not None:
+                    bufs["unfinished"].fill_(1)
+                    unfinished = bufs["unfinished"]
+                kv_bound = int(lengths.max()) + max_new
+                t = 0
+                while t < max_new - 1:
+                    k = min(poll, max_new - 1 - t)
+                    eng.decode_chunk(bufs, k, eos_arg, int(pad), unfinished is not None, kv_bound, graph=self.decode_graphs)
+                    tokens[t: t + k].copy_(bufs["ring_tok"][:k])
+                    entropies[t: t + k].copy_(bufs["ring_ent"][:k])
+                    kv.steps += k
+                    t += k
+                    steps_run = t
+                    # one look at the EOS flags between two chunks (none after the last: the trim below sees everything)
+                    if unfinished is not None and t < max_new - 1 and int(unfinished.sum().item()) == 0:
+                        break
                 else:
-                    tok_t = torch.empty(n_live, dtype=torch.int32, device=dev)
-                    ent_t = torch.empty(n_live, dtype=torch.float32, device=dev)
-                if sampling:
-                    eng.sample_multinomial(logits, tok_t, float(temperature), seed, t, ent_t, unfinished, -1 if eos is None else eos, pad)
-                else:
-                    eng.sample_greedy(logits, tok_t, ent_t, unfinished, -1 if eos is None else eos, pad)
-                if active is not None:
-                    tokens[t].index_copy_(0, active, tok_t)
-                    entropies[t].index_copy_(0, active, ent_t)
-                if output_scores:
+                    # the last token needs no decode step after it
+                    eng.sample_greedy(logits, tokens[t], entropies[t], unfinished, eos_arg, int(pad))
+                    steps_run = t + 1
+            else:
+                active = None                          # original row ids of the live decode batch once rows have been retired
+                tok_t = ent_t = None
+                for t in range(max_new):
+                    n_live = logits.shape[0]
                     if active is None:
-                        scores.append(logits)
+                        tok_t, ent_t = tokens[t], entropies[t]
                     else:
-                        full = torch.zeros((B, cfg.vocab_size), dtype=torch.float32, device=dev)
-                        full.index_copy_(0, active, logits)
-                        scores.append(full)
-                n_steps = t + 1
-                n_unf = int(unfinished.sum().item()) if unfinished is not None else n_live
-                if unfinished is not None and n_unf == 0:     # vtimellm_llama.py:359-362
-                    break
-                if t == max_new - 1:
-                    break
-                if t + 1 > kv.reserve:
-                    kv = self._grow_kv(kv, kv.lengths, t + 1 + chunk)       # kv.lengths: the rows still in the batch
-                if retire_finished and unfinished is not None and n_unf < n_live:
-                    # per-sequence retirement from the paged batch: only rows still generating go through the next step
-                    live = torch.nonzero(unfinished, as_tuple=False).flatten()
-                    active = live if active is None else active.index_select(0, live)
-                    kv_live = KVState(kv.page_table.index_select(0, live).contiguous(), kv.seq_lens.index_select(0, live).contiguous(),
-                                      kv.reserve, kv.lengths[live.cpu().numpy()])
-                    kv_live.steps, kv_live.shared_prefix = kv.steps, getattr(kv, "shared_prefix", 0)
-                    kv = kv_live
-                    tok_t = tok_t.index_select(0, live).contiguous()
-                    unfinished = unfinished.index_select(0, live).contiguous()
-                    logits = torch.empty((live.shape[0], cfg.vocab_size), dtype=torch.float32, device=dev)
-                elif output_scores:
-                    logits = torch.empty((n_live, cfg.vocab_size), dtype=torch.float32, device=dev)
-                eng.decode_step(tok_t.contiguous(), kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
-                kv.steps += 1
+                        tok_t = torch.empty(n_live, dtype=torch.int32, device=dev)
+                        ent_t = torch.empty(n_live, dtype=torch.float32, device=dev)
+                    if sampling:
+                        eng.sample_multinomial(logits, tok_t, float(temperature), seed, t, ent_t, unfinished, eos_arg, pad)
+                    else:
+                        eng.sample_greedy(logits, tok_t, ent_t, unfinished, eos_arg, pad)
+                    if active is not None:
+                        tokens[t].index_copy_(0, active, tok_t)
+                        entropies[t].index_copy_(0, active, ent_t)
+                    if output_scores:
+                        if active is None:
+                            scores.append(logits)
+                        else:
+                            full = torch.zeros((B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                            full.index_copy_(0, active, logits)
+                            scores.append(full)
+                    steps_run = t + 1
+                    if t == max_new - 1:
+                        break
+                    n_unf = n_live
+                    if unfinished is not None and (retire_finished or (t + 1) % poll == 0):
+                        # vtimellm_llama.py:359-362 tests this every step; here every `poll` steps (every step only when rows
+                        # are retired, which needs the host to know them) - the surplus steps are trimmed below
+                        n_unf = int(unfinished.sum().item())
+                        if n_unf == 0:
+                            break
+                    if t + 1 > kv.reserve:
+                        kv = self._grow_kv(kv, kv.lengths, t + 1 + chunk)       # kv.lengths: the rows still in the batch
+                    if retire_finished and unfinished is not None and n_unf < n_live:
+                        # per-sequence retirement from the paged batch: only rows still generating go through the next step
+                        live = torch.nonzero(unfinished, as_tuple=False).flatten()
+                        active = live if active is None else active.index_select(0, live)
+                        kv_live = KVState(kv.page_table.index_select(0, live).contiguous(), kv.seq_lens.index_select(0, live).contiguous(),
+                                          kv.reserve, kv.lengths[live.cpu().numpy()])
+                        kv_live.steps, kv_live.shared_prefix, kv_live.n_shared = kv.steps, getattr(kv, "shared_prefix", 0), kv.n_shared
+                        kv = kv_live
+                        tok_t = tok_t.index_select(0, live).contiguous()
+                        unfinished = unfinished.index_select(0, live).contiguous()
+                        logits = torch.empty((live.shape[0], cfg.vocab_size), dtype=torch.float32, device=dev)
+                    elif output_scores:
+                        logits = torch.empty((n_live, cfg.vocab_size), dtype=torch.float32, device=dev)
+                    eng.decode_step(tok_t.contiguous(), kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
+                    kv.steps += 1
             if ev:
                 ev[3].record()
                 self.last_phase_events = ev      # splice start, prefill start, decode start, end (read after a synchronize)
+            n_steps = steps_run
+            if eos is not None and steps_run > 0:
+                # the reference stops right after the step in which the last row emitted EOS: trim what ran past it
+                hit = tokens[:steps_run] == int(eos)                                    # [steps, B]
+                first = torch.where(hit.any(dim=0), hit.to(torch.int32).argmax(dim=0), torch.full((B,), steps_run, device=dev))
+                if mask_entropy_after_eos:
+                    step_ix = torch.arange(steps_run, device=dev)[:, None]
+                    entropies[:steps_run] = torch.where(step_ix > first[None, :], torch.full_like(entropies[:steps_run], float("nan")),
+                                                        entropies[:steps_run])
+                last = int(first.max().item())
+                if last < steps_run:                                                     # every row finished
+                    n_steps = last + 1
+                    scores = scores[:n_steps]
             new_tokens = tokens[:n_steps].t().contiguous()
             ids_dev = input_ids.to(dev)
             sequences = torch.cat([ids_dev, new_tokens.to(ids_dev.dtype)], dim=1)     # prompt ids (placeholder echoed) + new
+            if chunked:
+                # hand back bookkeeping that does not alias the engine's reusable decode buffers
+                kv.seq_lens, kv.page_table = kv.seq_lens.clone(), kv.page_table.clone()
             out = CausalLMOutput(sequences=sequences, scores=tuple(scores) if output_scores else None,
                                  entropies=entropies[:n_steps].t().contiguous(), prompt_lengths=torch.from_numpy(lengths.copy()),
                                  past_key_values=kv)

@@ -13,10 +13,11 @@ import torch
 
 from oracle import llama_ref, splice_ref
 from revisionllm_b200 import synthetic as syn
+from revisionllm_b200.engine import DecodeChunks
 from revisionllm_b200.model import RevisionConfig, RevisionLlamaForCausalLM
 
 
-class CpuEngine:
+class CpuEngine(DecodeChunks):
     device = torch.device("cpu")
 
     def __init__(self, cfg, w):
@@ -28,6 +29,7 @@ class CpuEngine:
         self.caches = {}            # first OWN page id of a sequence -> its KV cache (pages are the sequence's identity)
         self.n_pages = 0
         self.calls = []
+        self._init_chunks()
 
     def ensure_kv(self, n_pages):
         self.n_pages = max(self.n_pages, n_pages)

@@ -144,7 +144,7 @@ PAIR_STREAM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", PAIR_STREAM_SHAPES)
-def test_gemm_pair_weight_streaming_exact(eng_ws, M, N, K, monkeypatch):
+def test_gemm_pair_weight_streaming_exact(eng_ws, M, N, K, rvl_env):
     """CTA-pair weight-streaming GEMM: integer inputs, so fp32 accumulation is exact whatever the split of the k-blocks -
     tile / split-k units, stream-K units forced on and off, against the single-CTA kernel and the fp32 reference."""
     from revisionllm_b200 import _cabi
@@ -155,18 +155,15 @@ def test_gemm_pair_weight_streaming_exact(eng_ws, M, N, K, monkeypatch):
     Ad, Wd = A.cuda(), W.cuda()
     FL = _cabi.GEMM_FLAG_SWAP | _cabi.GEMM_FLAG_W_CONST
     for sk_env in (None, "0", "2"):                        # policy default, stream-K units never, always
-        if sk_env is None:
-            monkeypatch.delenv("RVL_SPAIR_STREAMK", raising=False)
-        else:
-            monkeypatch.setenv("RVL_SPAIR_STREAMK", sk_env)
-        for rep in range(2):                               # stream-K flags are re-used with a new epoch
+        rvl_env("RVL_SPAIR_STREAMK", sk_env)
+        for rep in range(2):                               # the head CTAs clear the stream-K flags they consumed: a second launch finds them zero
             out = torch.full((M, N), float("nan"), device="cuda")
             eng_ws.gemm(Ad, Wd, out=out, out_mode=_cabi.GEMM_OUT_F32, flags=FL)
             assert torch.equal(out.cpu(), ref), f"pair stream fp32 {M}x{N}x{K} env={sk_env} rep={rep}: {(out.cpu() - ref).abs().max()}"
         outb = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
         eng_ws.gemm(Ad, Wd, out=outb, flags=FL)
         assert torch.equal(outb.cpu(), ref.to(torch.bfloat16)), f"pair stream bf16 {M}x{N}x{K} env={sk_env}"
-    monkeypatch.setenv("RVL_SPAIR", "0")                   # the single-CTA kernel gives the same bits
+    rvl_env("RVL_SPAIR", "0")                              # the single-CTA kernel gives the same bits
     out1 = eng_ws.gemm(Ad, Wd, out_mode=_cabi.GEMM_OUT_F32, flags=FL)
     assert torch.equal(out1.cpu(), ref)
 

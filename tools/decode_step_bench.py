@@ -33,6 +33,7 @@ for B in [int(b) for b in args.batches.split(",")]:
                 os.environ[AB] = AB_VAL
             else:
                 os.environ.pop(AB, None)
+            eng.lib.rvl_reload_env()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         out = model(ids[None].expand(B, -1), images=feats, logits_to_keep=1, reserve_new_tokens=64)
         kv = out.past_key_values

@@ -21,6 +21,7 @@ for i in range(13 if AB else 4):
             os.environ[AB] = AB_VAL
         else:
             os.environ.pop(AB, None)
+        model.engine.lib.rvl_reload_env()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()

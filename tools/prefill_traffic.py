@@ -14,14 +14,14 @@ def set_cfg(cfg):
     """cfg: "auto", a bare group size ("16"), or VAR=VALUE pairs joined by commas ("RVL_GROUP_M=16")."""
     for k in ("RVL_GROUP_M",):
         os.environ.pop(k, None)
-    if cfg == "auto":
-        return
-    if "=" not in cfg:
-        os.environ["RVL_GROUP_M"] = cfg
-        return
-    for kv in cfg.split(","):
-        k, v = kv.split("=")
-        os.environ[k] = v
+    if cfg != "auto":
+        if "=" not in cfg:
+            os.environ["RVL_GROUP_M"] = cfg
+        else:
+            for kv in cfg.split(","):
+                k, v = kv.split("=")
+                os.environ[k] = v
+    _cabi.load().rvl_reload_env()
 
 
 T, H, I = 33120, 4096, 11008
