@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RVL_ABI_VERSION 2
+#define RVL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RVL_API __attribute__((visibility("default")))
@@ -197,10 +197,13 @@ RVL_API int rvl_sample_multinomial(rvl_handle* h, const float* logits, int32_t n
  * quirk, 2 = none: raw dot products as in _topk_pooling itself), sims = frames . cls, top-k frames (ties -> lowest index), score = dot(sum of the
  * top-k normalised frames, cls) = sum of the top-k sims.
  *   frames   [n_rows, dim] bf16;  seg_offsets [n_seg+1] int32 (rows of each proposal)
+ *   seg_ends [n_seg] int32 or NULL: when given, proposal i is rows [seg_offsets[i], seg_ends[i]) - slices that need not
+ *            touch each other (eval_nlq_negative.py:309-310 scores `features[k][v0:v1+1]`, the predicted span of a window);
+ *            an empty slice scores 0
  *   cls      [dim] bf16;  scores_out [n_seg] fp32;  topk_idx_out [n_seg, k] int32 (-1 padded, may be NULL)
  *   max_seg_rows: upper bound on the rows of one proposal (<= 8192), k <= 16 */
-RVL_API int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, int32_t n_seg,
-                    int32_t dim, const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows,
+RVL_API int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, const int32_t* seg_ends,
+                    int32_t n_seg, int32_t dim, const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows,
                     float* scores_out, int32_t* topk_idx_out, rvl_stream stream);
 
 /* Stage-2 segment selection: indices of the k largest fp32 scores, descending, ties -> lowest

@@ -57,7 +57,7 @@ PROTOTYPES = {
     "rvl_decode_step": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "rvl_sample_greedy": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),
     "rvl_sample_multinomial": (C.c_int, [_P, _P, _I32, _I32, _F, C.c_uint64, C.c_uint32, _P, _I32, _I32, _P, _P, _P, _P]),
-    "rvl_cosine_topk": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "rvl_cosine_topk": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P]),
     "rvl_select_topk": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
     "rvl_merge_rank": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "rvl_profile_enable": (C.c_int, [_P, _I32, _I32]),

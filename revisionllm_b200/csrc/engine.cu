@@ -78,7 +78,6 @@ void reload_tuning() {
   t.pair = geti("RVL_PAIR", -1);
   t.spair = geti("RVL_SPAIR", -1);
   t.spair_streamk = geti("RVL_SPAIR_STREAMK", -1);
-  t.spair_small = geti("RVL_SPAIR_SMALL", -1);
   t.staged = geti("RVL_STAGED", -1);
   t.group_m = geti("RVL_GROUP_M", 0);
   t.full_last_layer = geti("RVL_FULL_LAST_LAYER", 0);
@@ -457,13 +456,13 @@ int rvl_sample_multinomial(rvl_handle* h, const float* logits, int32_t n_seq, in
   return check_cuda(h, "rvl_sample_multinomial");
 }
 
-int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, int32_t n_seg, int32_t dim,
-                    const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows, float* scores_out,
+int rvl_cosine_topk(rvl_handle* h, const void* frames, const int32_t* seg_offsets, const int32_t* seg_ends, int32_t n_seg,
+                    int32_t dim, const void* cls, int32_t k, int32_t norm_axis, int32_t max_seg_rows, float* scores_out,
                     int32_t* topk_idx_out, rvl_stream stream) {
   if (!h || !frames || !seg_offsets || !cls || !scores_out) return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: null argument");
   if (dim % 8 || k < 1 || k > 16 || (norm_axis < 0 || norm_axis > 2) || max_seg_rows < 1 || max_seg_rows > 8192)
     return fail(h, RVL_ERR_INVALID, "rvl_cosine_topk: need dim % 8 == 0, 1 <= k <= 16, norm_axis in {0,1,2}, max_seg_rows <= 8192");
-  launch_cosine_topk(frames, seg_offsets, n_seg, dim, cls, k, norm_axis, max_seg_rows, scores_out, topk_idx_out,
+  launch_cosine_topk(frames, seg_offsets, seg_ends, n_seg, dim, cls, k, norm_axis, max_seg_rows, scores_out, topk_idx_out,
                      static_cast<cudaStream_t>(stream));
   return check_cuda(h, "rvl_cosine_topk");
 }

@@ -1364,18 +1364,10 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     a.acc_stages = 2;
     a.tmem_cols = 512;
     int stage_out_bytes = kStageOutBytes;
-    // RVL_SPAIR_SMALL=1 (experiment): half-size CTA - at most 110 KB of shared memory and 256 TMEM columns - so that the CTAs of
-    // the NEXT weight-streaming GEMM of the stream (programmatic dependent launch) become resident beside this kernel's,
-    // run their prologue and fill their ring with weight tiles while this kernel drains: the HBM stream does not stop at the
-    // kernel boundary.  One accumulator stage, a 16 KB staging buffer (2 / 1 / 4 chunks per store group).
-    if (tn.spair_small == 1 && a.sub_stride <= 256) {
-      stage_out_bytes = 16 * 1024;
-      a.staged = a.swiglu ? 4 : (out_f32 ? 1 : 2);
-      a.acc_stages = 1;
-      a.tmem_cols = pow2_at_least(a.sub_stride);
-      a.stages = (110 * 1024 - 1024 - 512 - stage_out_bytes) / (kATileBytes + half_bytes);
-      if (a.stages < 2) a.stages = 2;
-    }
+    // Measured and dropped (round 2, tools/decode_ab.py): a half-size CTA (three 28 KB stages, 16 KB staging buffer, one 256-column
+    // accumulator) so that the NEXT weight-streaming GEMM's CTAs become resident beside this kernel's under programmatic
+    // dependent launch and fill their ring while this one drains - 8.16 against 7.12 ms per 7B decode step at B = 180 (7.71 vs
+    // 6.85 inside CUDA graphs): three stages do not cover the HBM latency, and that costs more than the hidden prologue saves.
     int rcp = make_tmap(&pa_map, pa, a.M, c.K, kBM, err);
     if (rcp) return rcp;
     rcp = make_tmap(&pb_map, pb, a.N, c.K, a.bn / 2, err);

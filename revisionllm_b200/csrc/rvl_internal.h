@@ -42,7 +42,6 @@ struct Tuning {
   int pair = -1;             // RVL_PAIR
   int spair = -1;            // RVL_SPAIR
   int spair_streamk = -1;    // RVL_SPAIR_STREAMK
-  int spair_small = -1;      // RVL_SPAIR_SMALL: half-size CTA-pair weight-streaming kernel (two kernels co-resident per SM)
   int staged = -1;           // RVL_STAGED
   int group_m = 0;           // RVL_GROUP_M
   int full_last_layer = 0;   // RVL_FULL_LAST_LAYER
@@ -133,7 +132,7 @@ void launch_sample_multinomial(const float* logits, int n_seq, int vocab, float 
                                uint32_t step, int32_t* unfinished, int eos_id, int pad_id, int32_t* next_tokens,
                                float* entropy_out, uint32_t* philox_out, cudaStream_t st);
 // scoring.cu
-void launch_cosine_topk(const void* frames, const int32_t* seg_offsets, int n_seg, int dim, const void* cls, int k,
+void launch_cosine_topk(const void* frames, const int32_t* seg_offsets, const int32_t* seg_ends, int n_seg, int dim, const void* cls, int k,
                         int norm_axis, int max_seg_rows, float* scores_out, int32_t* topk_idx_out, cudaStream_t st);
 void launch_select_topk(const float* scores, int n, int k, int32_t* idx_out, cudaStream_t st);
 void launch_merge_rank(const float* cos, const float* ent, const int32_t* keep, const int32_t* cover1, const int32_t* cover_all,

@@ -20,14 +20,15 @@ constexpr int kScoreThreads = 256;
 constexpr int kMaxK = 16;
 
 __global__ void __launch_bounds__(kScoreThreads) cosine_topk_kernel(const __nv_bfloat16* __restrict__ frames,
-                                                                     const int32_t* __restrict__ seg_offsets, int dim,
+                                                                     const int32_t* __restrict__ seg_offsets,
+                                                                     const int32_t* __restrict__ seg_ends, int dim,
                                                                      const __nv_bfloat16* __restrict__ cls, int k,
                                                                      int norm_axis, float* __restrict__ scores_out,
                                                                      int32_t* __restrict__ topk_idx_out) {
   extern __shared__ float s_w[];  // [dim] per-dimension weight: cls_d (axis 1) or cls_d / colnorm_d (axis 0); then sims
   const int seg = blockIdx.x;
-  const int r0 = seg_offsets[seg], r1 = seg_offsets[seg + 1];
-  const int n = r1 - r0;
+  const int r0 = seg_offsets[seg], r1 = seg_ends ? seg_ends[seg] : seg_offsets[seg + 1];
+  const int n = r1 > r0 ? r1 - r0 : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __nv_bfloat16* base = frames + static_cast<long long>(r0) * dim;
   for (int d = tid; d < dim; d += kScoreThreads) {
@@ -94,11 +95,11 @@ __global__ void __launch_bounds__(kScoreThreads) cosine_topk_kernel(const __nv_b
   }
 }
 
-void launch_cosine_topk(const void* frames, const int32_t* seg_offsets, int n_seg, int dim, const void* cls, int k,
+void launch_cosine_topk(const void* frames, const int32_t* seg_offsets, const int32_t* seg_ends, int n_seg, int dim, const void* cls, int k,
                         int norm_axis, int max_seg_rows, float* scores_out, int32_t* topk_idx_out, cudaStream_t st) {
   if (n_seg <= 0) return;
   cosine_topk_kernel<<<n_seg, kScoreThreads, (dim + max_seg_rows) * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(frames), seg_offsets, dim, reinterpret_cast<const __nv_bfloat16*>(cls), k,
+      reinterpret_cast<const __nv_bfloat16*>(frames), seg_offsets, seg_ends, dim, reinterpret_cast<const __nv_bfloat16*>(cls), k,
       norm_axis, scores_out, topk_idx_out);
 }
 

@@ -64,6 +64,9 @@ class DecodeChunks:
         self._dec_seen: Dict[tuple, int] = {}
 
     DECODE_CHUNK = 8          # decode steps per captured graph = steps between two looks at the EOS flags
+    GRAPH_AFTER = 3           # capture a chunk shape when it shows up for the third time: capturing + instantiating ~1800 kernel
+                              # nodes costs tens of ms (measured: a stage-2 query went from 67 to 144 ms when every call captured),
+                              # a replay saves ~0.25 ms per decode step
 
     def decode_buffers(self, n_rows: int, max_pages: int) -> Dict[str, torch.Tensor]:
         """Fixed-address buffers a captured decode chunk reads and writes (a CUDA graph bakes pointers in): last-row logits,
@@ -91,7 +94,8 @@ class DecodeChunks:
                      graph: bool = True):
         """`k` x (greedy sample of bufs.logits -> ring_tok[s] / ring_ent[s]; decode step on that token -> bufs.logits), the
         generation loop of vtimellm_llama.py:287-369 for k tokens, as ONE CUDA-graph launch once the same chunk shape has been
-        seen before (the first occurrence runs eagerly: capture costs more than it saves for a shape used once).  Every
+        seen `GRAPH_AFTER - 1` times before (the first occurrences run eagerly: capture costs more than it saves for a shape
+        used once or twice).  Every
         pointer the chunk touches lives in `bufs`, the bound weights, the workspace or the KV pages; the graph is dropped
         when the workspace or the KV pages are re-allocated."""
         n_rows, max_pages = bufs["page_table"].shape
@@ -110,7 +114,7 @@ class DecodeChunks:
             self.launches += hit[1]
             return
         self._dec_seen[key] = self._dec_seen.get(key, 0) + 1
-        if not graph or self._dec_seen[key] < 2 or self.device.type != "cuda":
+        if not graph or self._dec_seen[key] < self.GRAPH_AFTER or self.device.type != "cuda":
             body()
             return
         for gk in [gk for gk in self._dec_graphs if gk[-2:] != key[-2:]]:      # graphs over buffers that no longer exist
@@ -299,14 +303,18 @@ class Engine(DecodeChunks):
                                                     _ptr(entropy), _ptr(philox_out), _stream()), "rvl_sample_multinomial")
         self.launches += 1
 
-    def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True):
+    def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True, seg_ends=None):
+        """seg_ends None: proposal i = rows [seg_offsets[i], seg_offsets[i + 1]); else rows [seg_offsets[i], seg_ends[i])."""
         _req(frames, torch.bfloat16, "frames"); _req(seg_offsets, torch.int32, "seg_offsets"); _req(cls, torch.bfloat16, "cls")
         n_seg = seg_offsets.shape[0] - 1
+        if seg_ends is not None:
+            _req(seg_ends, torch.int32, "seg_ends")
+            n_seg = seg_ends.shape[0]
         if max_seg_rows is None:
             max_seg_rows = int(frames.shape[0])
         scores = torch.empty(n_seg, dtype=torch.float32, device=frames.device)
         idx = torch.empty((n_seg, k), dtype=torch.int32, device=frames.device) if want_idx else None
-        self._check(self.lib.rvl_cosine_topk(self.h, frames.data_ptr(), seg_offsets.data_ptr(), n_seg, frames.shape[1],
+        self._check(self.lib.rvl_cosine_topk(self.h, frames.data_ptr(), seg_offsets.data_ptr(), _ptr(seg_ends), n_seg, frames.shape[1],
                                              cls.data_ptr(), k, norm_axis, min(max_seg_rows, 8192), scores.data_ptr(),
                                              _ptr(idx), _stream()), "rvl_cosine_topk")
         self.launches += 1

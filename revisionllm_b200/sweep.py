@@ -110,17 +110,40 @@ class SweepResult:
     stage2_indices: Optional[torch.Tensor] = None
 
 
+def span_slices(spans: torch.Tensor, n_frames: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row ranges [begin, end) inside each window for the cosine score of its predicted span, as the stage-1 driver takes
+    them (/root/reference/revisionllm/eval/eval_nlq_negative.py:79-96,309-310): `features[k][from : to + 1]`, a one-frame
+    span widened by one frame on both sides (:90-92), Python slicing clamping at the window's end.  spans [n, 2] int32 with
+    -1 for windows whose answer holds no span ("Not Present") - the reference computes no cosine for those; here they score
+    over the whole window so that every record carries a value."""
+    lo, hi = spans[:, 0].to(torch.int64), spans[:, 1].to(torch.int64)
+    valid = (lo >= 0) & (hi >= 0)
+    one = valid & (lo == hi)
+    lo = torch.where(one, (lo - 1).clamp(min=0), lo)
+    hi = torch.where(one, hi + 1, hi)
+    begin = torch.where(valid, lo.clamp(max=n_frames), torch.zeros_like(lo))
+    end = torch.where(valid, (hi + 1).clamp(max=n_frames), torch.full_like(hi, n_frames))
+    return begin, torch.maximum(end, begin)
+
+
 def score_segments(model, seg_feats: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor],
                    max_new_tokens: int = 16, decode_spans: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                   batch: Optional[int] = None, eos_token_id="config", norm_axis: int = scoring.NORM_PER_FRAME,
+                   batch: Optional[int] = None, eos_token_id="config", norm_axis: int = scoring.NORM_ACROSS_FRAMES,
                    ) -> torch.Tensor:
     """Score `seg_feats` [n, F, 768] (host or device): generate up to `max_new_tokens` greedy tokens per
     segment, entropy statistics from the device-side per-step entropies, CLIP cosine top-3 score of each
-    segment against `cls` [768].  Returns packed records [n, REC_WORDS] on the model's device."""
+    segment against `cls` [768].  Returns packed records [n, REC_WORDS] on the model's device.
+
+    The cosine score follows the stage-1 driver (eval_nlq_negative.py:309-316): the frames of the PREDICTED span
+    (`decode_spans(new_tokens)` -> [n, 2] frame indices inside the window, -1 = no span; see `span_slices`), normalised
+    across the frame axis (`.norm(dim=0)`, the driver's quirk: `norm_axis` = scoring.NORM_ACROSS_FRAMES), sum of the top-3
+    similarities.  Without `decode_spans` every window is scored over all its frames."""
     eng = model.engine
     dev = model.device
     n, F, D = seg_feats.shape
-    batch = n if batch is None else batch
+    if n == 0:                      # a rank whose shard is empty (fewer windows than ranks) still joins the all-gather
+        return torch.empty((0, REC_WORDS), dtype=torch.int32, device=dev)
+    batch = n if batch is None else max(1, batch)
     recs = []
     for s in range(0, n, batch):
         feats = seg_feats[s: s + batch].to(dev, torch.bfloat16, non_blocking=True)
@@ -131,26 +154,28 @@ def score_segments(model, seg_feats: torch.Tensor, input_ids: torch.Tensor, cls:
         new_tok = out["sequences"][:, ids.shape[1]:].to(torch.int32)
         ent = out["entropies"]
         stats = scoring.entropy_stats_from_steps(ent)
+        spans = decode_spans(new_tok).to(dev) if decode_spans is not None else torch.full((b, 2), -1, dtype=torch.int32, device=dev)
         if cls is not None:
-            offs = torch.arange(0, (b + 1) * F, F, dtype=torch.int32, device=dev)
-            cos, _ = eng.cosine_topk(feats.reshape(b * F, D), offs, cls.to(dev, torch.bfloat16).contiguous(), k=3,
-                                     norm_axis=norm_axis, max_seg_rows=F)
+            base = torch.arange(0, b * F, F, dtype=torch.int64, device=dev)
+            begin, end = span_slices(spans, F)
+            cos, _ = eng.cosine_topk(feats.reshape(b * F, D), (base + begin).to(torch.int32), cls.to(dev, torch.bfloat16).contiguous(),
+                                     k=3, norm_axis=norm_axis, max_seg_rows=F, want_idx=False, seg_ends=(base + end).to(torch.int32))
         else:
             cos = torch.zeros(b, dtype=torch.float32, device=dev)
-        spans = decode_spans(new_tok) if decode_spans is not None else torch.full((b, 2), -1, dtype=torch.int32, device=dev)
-        recs.append(pack_records(new_tok, spans.to(dev), stats[:, 2], stats[:, 0], cos))
+        recs.append(pack_records(new_tok, spans, stats[:, 2], stats[:, 0], cos))
     return torch.cat(recs, dim=0)
 
 
 def stage1_sweep(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor],
                  max_new_tokens: int = 16, rank: int = 0, world: int = 1, group=None, batch: Optional[int] = None,
-                 decode_spans=None, eos_token_id="config", stage2_topk: Optional[int] = None) -> SweepResult:
+                 decode_spans=None, eos_token_id="config", stage2_topk: Optional[int] = None,
+                 norm_axis: int = scoring.NORM_ACROSS_FRAMES) -> SweepResult:
     """`segments` [W, F, 768]: all windows of the movie (every rank holds the same host tensor; only the
     local shard is copied to the GPU)."""
     W = segments.shape[0]
     mine = shard_indices(W, rank, world)
     local = score_segments(model, segments[torch.from_numpy(mine)], input_ids, cls, max_new_tokens, decode_spans, batch,
-                           eos_token_id)
+                           eos_token_id, norm_axis)
     allrec = allgather_records(local, W, rank, world, group)
     res = SweepResult(allrec, mine)
     if stage2_topk is not None:
@@ -336,7 +361,8 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
                     sel = torch.tensor([pos[qi] for (qi, _) in part])
                     qf = (qf[0][sel.to(qf[0].device)], qf[1][sel.to(qf[1].device)])
             res = model.generate(ids, images=feat, query_feats=qf, attention_mask=None if bool(am.all()) else am,
-                                 max_new_tokens=max_new_tokens, output_scores=False, return_dict_in_generate=True, eos_token_id=eos_token_id)
+                                 max_new_tokens=max_new_tokens, output_scores=False, return_dict_in_generate=True, eos_token_id=eos_token_id,
+                                 mask_entropy_after_eos=True)      # a prompt's statistics stop at its own EOS, as in the reference's one call per chunk (:353-359)
             stats_all = scoring.entropy_stats_from_steps(res["entropies"])
             for r, job in enumerate(part):
                 results[job] = dict(tokens=res["sequences"][r, L:], stats=stats_all[r])

@@ -122,10 +122,11 @@ class CpuEngine(DecodeChunks):
         o = torch.softmax(s, dim=-1) @ vh
         out.copy_(o.permute(0, 2, 1, 3).reshape(n_seq * Tq, n_heads * d).to(torch.bfloat16))
 
-    def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True):
+    def cosine_topk(self, frames, seg_offsets, cls, k=3, norm_axis=1, max_seg_rows=None, want_idx=True, seg_ends=None):
         from oracle import scoring_ref
         offs = seg_offsets.tolist()
-        scores = [scoring_ref.cosine_topk_score(frames[offs[i]:offs[i + 1]], cls, k, norm_axis=norm_axis)[0] for i in range(len(offs) - 1)]
+        ends = offs[1:] if seg_ends is None else seg_ends.tolist()
+        scores = [scoring_ref.cosine_topk_score(frames[offs[i]:ends[i]], cls, k, norm_axis=norm_axis)[0] for i in range(len(ends))]
         return torch.tensor(scores, dtype=torch.float32), None
 
     def select_topk(self, scores, k):
@@ -516,7 +517,25 @@ def test_stage1_sweep_records_over_the_cpu_model(cpu_model):
     ent = torch.stack([scoring_ref.step_entropy(s) for s in scores], dim=1)            # [n, steps]
     np.testing.assert_allclose(un["h_mean"].numpy(), ent.mean(1).numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(un["h_max"].numpy(), ent.max(1).values.numpy(), rtol=1e-4, atol=1e-5)
-    want_cos = [scoring_ref.cosine_topk_score(segs[i], cls, 3)[0] for i in range(n)]
+    # no span decoder: every window is scored over all its frames, normalised across the frame axis (eval_nlq_negative.py:311)
+    want_cos = [scoring_ref.cosine_topk_score(segs[i], cls, 3, norm_axis=0)[0] for i in range(n)]
     np.testing.assert_allclose(un["cos"].numpy(), np.array(want_cos, dtype=np.float32), rtol=1e-6)
     assert res.stage2_indices.tolist() == scoring_ref.select_topk_segments(np.array(want_cos, dtype=np.float32), 3).tolist()
     assert [c for c in m.engine.calls if c[0] == "prefill"] == [("prefill", 3), ("prefill", 3), ("prefill", 1)]
+    # with predicted spans the cosine score is taken over `features[k][from : to + 1]` (eval_nlq_negative.py:309-310): a
+    # one-frame span widened by one frame (:90-92), slices clamped at the window's end, windows without a span scored whole
+    table = torch.tensor([[1, 3], [2, 2], [0, 0], [-1, -1], [4, 9], [5, 5], [0, 5]], dtype=torch.int32)
+    rows_seen = []
+
+    def decode_spans(tok):
+        rows_seen.append(tok.shape[0])
+        start = sum(rows_seen[:-1])
+        return table[start: start + tok.shape[0]]
+    res2 = sweep.stage1_sweep(m, segs, ids, cls, max_new_tokens=4, batch=3, eos_token_id=None, decode_spans=decode_spans)
+    un2 = sweep.unpack_records(res2.records)
+    assert un2["spans"].tolist() == table.tolist()
+    slices = [(1, 4), (1, 4), (0, 2), (0, F), (4, F), (4, F), (0, F)]
+    want2 = [scoring_ref.cosine_topk_score(segs[i][a:b], cls, 3, norm_axis=0)[0] for i, (a, b) in enumerate(slices)]
+    np.testing.assert_allclose(un2["cos"].numpy(), np.array(want2, dtype=np.float32), rtol=1e-6)
+    # a rank with an empty shard (fewer windows than ranks) contributes zero records and still returns
+    assert sweep.score_segments(m, segs[:0], ids, cls, 4, eos_token_id=None).shape == (0, sweep.REC_WORDS)
