@@ -8,6 +8,7 @@ dependency on libcuda.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,12 +32,28 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(LIBDIR, "librevisionllm_b200.sources.sha256")
+
+
+def sources_digest() -> str:
+    """sha256 over every file the library is built from (csrc/*, the public header) and the compiler flags.  The shared
+    library travels to the GPU box as a built artefact; a stamp file next to it says which sources it was built from, so
+    `build()` recompiles exactly when they differ - file times mean nothing after a copy."""
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "revisionllm_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "revisionllm_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(STAMP) as f:
+        return f.read().strip() != sources_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -67,6 +84,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    with open(STAMP, "w") as f:
+        f.write(sources_digest() + "\n")
     return LIB
 
 

@@ -822,6 +822,227 @@ __global__ void __launch_bounds__(128) attn_decode_staged_kernel(const __nv_bflo
   }
 }
 
+// ------------------------------------------------------------------------------------------- decode, tensor-core tiles
+// Same arithmetic once more, few instructions per byte: inside the 1-hour sweep the power-capped SM clock (1.1 - 1.3 GHz)
+// makes the register kernel above SM-bound (115 us per layer in the step against 88 us at 1.9 GHz under ncu: every 16 bytes
+// of K / V cost ~25 issue slots of bf16 unpacking and FFMA2 there).  Here 64-key K / V tiles stream through a double-buffered
+// shared-memory ring with cp.async (straight out of the paged cache: a (page, head) chunk is 8 KB contiguous, two pages per
+// tile) and both products run on mma.sync.m16n8k16 with the single query row padded to a 16-row tile: each of the four warps
+// owns 16 keys of every tile (8 ldmatrix + 16 mma for its scores, the same for its share of P V), keeps its own online-softmax
+// state, and the four partial (max, sum, output) triples are merged once at the end.  15 of the 16 tile rows are wasted
+// tensor work - the tensor pipe is idle in a decode step anyway; the point is ~4x fewer issued instructions per byte.
+// Page size 32 only.  P is rounded to bf16 for the P V product exactly like the prefill kernel does.
+template <bool kFused>
+__global__ void __launch_bounds__(128, 3) attn_decode_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                               const int32_t* __restrict__ seq_lens,
+                                                               const int32_t* __restrict__ page_table, int max_pages,
+                                                               __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, int n_heads,
+                                                               float scale_log2, float theta) {
+  constexpr int kPS = 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sK = smem;                        // [2][64][128] bf16, swizzled like the prefill tiles
+  uint8_t* sV = smem + 32768;                // [2][64][128]
+  uint8_t* sQ = smem + 65536;                // [16][128]: row 0 = this step's query, rows 1 - 15 zero
+  float* s_o = reinterpret_cast<float*>(smem + 65536 + 4096);   // [4 warps][128] partial outputs
+  __shared__ float s_ml[8];                  // per warp: running max (log2 domain), running sum
+  __shared__ __align__(16) __nv_bfloat16 s_knew[kD];
+  pdl_trigger();
+  pdl_wait();
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pos = seq_lens[seq];
+  const int n_keys = pos + 1;
+  const int n_cached = kFused ? pos : n_keys;                 // rows that come from the cache (the fused kernel makes row `pos` itself)
+  const int H = n_heads * kD;
+  const int32_t* pt = page_table + static_cast<long long>(seq) * max_pages;
+  const __nv_bfloat16* row = qkv + static_cast<long long>(seq) * 3 * H + head * kD;
+  const int n_tiles = (n_keys + kKT - 1) / kKT;
+
+  // K / V rows of tile `t` into buffer `b`: thread -> chunk (tid & 15) of rows (tid >> 4) + 8 i of both pages of the tile
+  const int r0 = tid >> 4, c = tid & 15;
+  const uint32_t sw = static_cast<uint32_t>((c ^ r0) << 4);
+  auto load_tile = [&](int t, int b) {
+    const uint32_t kdst = smem_u32(sK) + b * 16384 + r0 * 256 + sw;
+    const uint32_t vdst = smem_u32(sV) + b * 16384 + r0 * 256 + sw;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int key_base = (t * 2 + half) * kPS;
+      const int page = key_base < n_keys ? __ldg(pt + t * 2 + half) : 0;
+      const long long chunk0 = ((static_cast<long long>(page) * n_heads + head) * kPS + r0) * kD + c * 8;
+      const __nv_bfloat16* ksrc = k_pages + chunk0;
+      const __nv_bfloat16* vsrc = v_pages + chunk0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int key = key_base + r0 + 8 * i;
+        const uint32_t off = static_cast<uint32_t>((half * 32 + 8 * i) * 256);
+        if (kFused && key == pos) {
+          // this step's own row: k' from shared memory (phase 0), v from the qkv row - never through the cache
+          const uint4 kk = reinterpret_cast<const uint4*>(s_knew)[c];
+          const uint4 vv = reinterpret_cast<const uint4*>(row + 2 * H)[c];
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kdst + off), "r"(kk.x), "r"(kk.y), "r"(kk.z), "r"(kk.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vdst + off), "r"(vv.x), "r"(vv.y), "r"(vv.z), "r"(vv.w) : "memory");
+        } else {
+          const int sz = key < n_cached ? 16 : 0;             // src-size 0 -> zero fill (rows past the context must be finite)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(kdst + off), "l"(ksrc + i * 8 * kD), "r"(sz) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vdst + off), "l"(vsrc + i * 8 * kD), "r"(sz) : "memory");
+        }
+      }
+    }
+  };
+
+  // a first tile that does not hold this step's own row can be on its way while phase 0 runs
+  const bool early = !kFused || pos >= kKT;
+  if (early) {
+    load_tile(0, 0);
+    cp_async_commit();
+  }
+  // ---- phase 0: query tile (row 0 real), RoPE of q / k, KV append
+  {
+    uint4* qz = reinterpret_cast<uint4*>(sQ);
+    qz[tid] = make_uint4(0u, 0u, 0u, 0u);
+    qz[tid + 128] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  __nv_bfloat16* q0 = reinterpret_cast<__nv_bfloat16*>(sQ);   // row 0 is stored unswizzled (row & 7 == 0)
+  if (kFused) {
+    const int page = pt[pos / kPS];
+    const long long slot = ((static_cast<long long>(page) * n_heads + head) * kPS + pos % kPS) * kD;
+    if (tid < kD / 2) {
+      const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * tid) / static_cast<float>(kD));
+      float sn, cs;
+      sincosf(static_cast<float>(pos) * inv_freq, &sn, &cs);
+      const float qa = __bfloat162float(row[tid]), qb = __bfloat162float(row[tid + 64]);
+      const float ka = __bfloat162float(row[H + tid]), kb = __bfloat162float(row[H + tid + 64]);
+      q0[tid] = __float2bfloat16(qa * cs - qb * sn);
+      q0[tid + 64] = __float2bfloat16(qb * cs + qa * sn);
+      const __nv_bfloat16 k0 = __float2bfloat16(ka * cs - kb * sn), k1 = __float2bfloat16(kb * cs + ka * sn);
+      s_knew[tid] = k0;
+      s_knew[tid + 64] = k1;
+      k_pages[slot + tid] = k0;
+      k_pages[slot + tid + 64] = k1;
+    } else if (tid < kD / 2 + 16) {
+      reinterpret_cast<uint4*>(v_pages + slot)[tid - kD / 2] = reinterpret_cast<const uint4*>(row + 2 * H)[tid - kD / 2];
+    }
+  } else {
+    q0[tid] = row[tid];
+  }
+  __syncthreads();
+  if (!early) {
+    load_tile(0, 0);
+    cp_async_commit();
+  }
+  uint32_t qf[8][4];
+  {
+    const int r = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ) + tile_off(r, ks * 2 + (lane >> 4)));
+  }
+  float o[16][2];                                  // row 0 of this warp's partial output lives in lanes 0 - 3
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const int t4 = lane & 3;
+  const bool row0 = lane < 4;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_tiles) {
+      load_tile(j + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t kaddr = smem_u32(sK) + buf * 16384;
+    const uint32_t vaddr = smem_u32(sV) + buf * 16384;
+    const int key0 = j * kKT + warp * 16;
+    if (key0 < n_keys) {                           // warp-uniform: a warp whose 16 keys lie past the context skips the tile
+      float s[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        uint32_t b[4];
+        ldmatrix_x4(b, kaddr + tile_off(warp * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1)));
+        mma_bf16_16816(s[0], qf[ks], b[0], b[1]);
+        mma_bf16_16816(s[1], qf[ks], b[2], b[3]);
+      }
+      // row 0 of the score tile: lanes 0 - 3 hold keys key0 + nt * 8 + t4 * 2 + {0, 1} in s[nt][0 .. 1]
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = key0 + nt * 8 + t4 * 2 + e;
+          if (key >= n_keys) s[nt][e] = -INFINITY;
+          mx = fmaxf(mx, s[nt][e]);
+        }
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = __shfl_sync(0xffffffffu, mx, 0);        // the maximum of row 0 (key0 < n_keys: at least one key is valid)
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      const float corr = ex2_approx(m_run - m_new);             // first tile: 2^-inf = 0
+      m_run = m_new;
+      float p[2][2];
+      float rs = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          p[nt][e] = ex2_approx(fmaf(s[nt][e], scale_log2, -m_new));
+          rs += p[nt][e];
+        }
+      }
+      l_run = l_run * corr + rs;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
+      uint32_t pa[4];
+      pa[0] = row0 ? pack_bf16x2(p[0][0], p[0][1]) : 0u;        // row g = 0 only; the other 15 rows of P are zero
+      pa[1] = 0u;
+      pa[2] = row0 ? pack_bf16x2(p[1][0], p[1][1]) : 0u;
+      pa[3] = 0u;
+#pragma unroll
+      for (int dp = 0; dp < 8; ++dp) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, vaddr + tile_off(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)));
+        // accumulator halves of rows 8 - 15 stay zero (their P rows are zero): two throw-away registers per mma
+        float acc0[4] = {o[2 * dp][0], o[2 * dp][1], 0.f, 0.f};
+        float acc1[4] = {o[2 * dp + 1][0], o[2 * dp + 1][1], 0.f, 0.f};
+        mma_bf16_16816(acc0, pa, b[0], b[1]);
+        mma_bf16_16816(acc1, pa, b[2], b[3]);
+        o[2 * dp][0] = acc0[0]; o[2 * dp][1] = acc0[1];
+        o[2 * dp + 1][0] = acc1[0]; o[2 * dp + 1][1] = acc1[1];
+      }
+    }
+    __syncthreads();                               // the buffer is refilled two tiles later
+  }
+  // ---- merge the four warps' (max, sum, output) of row 0
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (lane == 0) { s_ml[warp] = m_run; s_ml[4 + warp] = l_run; }
+  if (row0) {
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      s_o[warp * kD + nt * 8 + t4 * 2] = o[nt][0];
+      s_o[warp * kD + nt * 8 + t4 * 2 + 1] = o[nt][1];
+    }
+  }
+  __syncthreads();
+  {
+    const float m = fmaxf(fmaxf(s_ml[0], s_ml[1]), fmaxf(s_ml[2], s_ml[3]));
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float f = ex2_approx(s_ml[w] - m);     // a warp that saw no key: 2^-inf = 0
+      num += f * s_o[w * kD + tid];
+      den += f * s_ml[4 + w];
+    }
+    out[static_cast<long long>(seq) * H + head * kD + tid] = __float2bfloat16(num / den);
+  }
+}
+
 // fused != 0: qkv holds the un-rotated q, k of this step; the kernel applies RoPE at position seq_lens[i] and appends
 // k', v to the cache itself (the decode step of the engine).  fused == 0: qkv is post-RoPE and the cache already
 // holds this step's token (after rvl_rope_kv).
@@ -840,7 +1061,24 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
   // 3.50 ms per 7B decode step); many rows: 8 register-staged CTAs per SM overlap better than 2 staged ones (B = 180: 9.4
   // vs 9.9 ms).  RVL_ATTN_DECODE = "regs" / "staged" forces one of them.
   const int forced = tuning().attn_decode;
-  const char mode = forced ? static_cast<char>(forced) : (n_seq * n_heads >= 1024 ? 'r' : 's');
+  // many rows: the tensor-core tile kernel ('m', page size 32) - RVL_ATTN_DECODE = regs / staged / mma forces one
+  char mode = forced ? static_cast<char>(forced) : (n_seq * n_heads >= 1024 ? (page_size == 32 ? 'm' : 'r') : 's');
+  if (mode == 'm' && page_size != 32) mode = 'r';
+  if (mode == 'm') {
+    constexpr int smem_m = 65536 + 4096 + 4 * kD * 4;
+    static bool attr_m = false;
+    if (!attr_m) {
+      cudaFuncSetAttribute(attn_decode_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m);
+      cudaFuncSetAttribute(attn_decode_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m);
+      attr_m = true;
+    }
+    const float scale_log2 = 1.4426950408889634f * scale;
+    if (fused)
+      launch_pdl(pdl_dec, attn_decode_mma_kernel<true>, grid, dim3(128), smem_m, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, scale_log2, theta);
+    else
+      launch_pdl(pdl_dec, attn_decode_mma_kernel<false>, grid, dim3(128), smem_m, st, q, o, seq_lens, page_table, max_pages, kp, vp, n_heads, scale_log2, theta);
+    return;
+  }
   if (mode == 's') {
     // staged kernel: K and V rows of the whole context (or of a 432-key chunk) in shared memory.  Up to 220 keys two
     // CTAs share an SM (one computes while the other's copies are in flight).

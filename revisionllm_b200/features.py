@@ -31,7 +31,7 @@ def dumps_npz(arrays: Mapping[str, np.ndarray], compress: bool = True) -> bytes:
 
 def loads_npz(blob: bytes) -> Dict[str, np.ndarray]:
     with io.BytesIO(blob) as r:
-        z = np.load(r, allow_pickle=True)
+        z = np.load(r, allow_pickle=False)          # plain float arrays only: a feature store is data, never code
         return {k: z[k] for k in z.files}
 
 
@@ -82,11 +82,14 @@ class WindowLoader:
         self.dim = dim
         self._pinned = torch.empty((max_frames, dim), dtype=torch.float32).pin_memory()
         self._stream = torch.cuda.Stream(device=engine.device)
+        self._copied = None                # event after the last host->device copy out of the pinned buffer
 
     def upload(self, features: np.ndarray) -> torch.Tensor:
         """host [T, D] (any float dtype) -> device fp32 [T, D]; the copy runs on the loader's stream and the caller's
         current stream waits for it."""
         T = features.shape[0]
+        if self._copied is not None:
+            self._copied.synchronize()     # the previous upload may still be reading the pinned buffer
         if T > self._pinned.shape[0]:
             self._pinned = torch.empty((T, self.dim), dtype=torch.float32).pin_memory()
         stage = self._pinned[:T]
@@ -94,6 +97,8 @@ class WindowLoader:
         cur = torch.cuda.current_stream(self.engine.device)
         with torch.cuda.stream(self._stream):
             dev = stage.to(self.engine.device, non_blocking=True)
+            self._copied = torch.cuda.Event()
+            self._copied.record(self._stream)
         cur.wait_stream(self._stream)
         dev.record_stream(cur)
         return dev

@@ -33,14 +33,8 @@ def inference(model, image, query_feats, query, tokenizer, visual_memory=None, p
             input_ids, images=image, query_feats=query_feats, do_sample=do_sample, temperature=temperature, seed=seed, num_beams=1,
             max_new_tokens=max_new_tokens, use_cache=True, visual_memory=visual_memory, prefix_memory=prefix_memory,
             output_scores=output_scores, return_dict_in_generate=True, output_hidden_states=False)
-    output_ids = model_output["sequences"]
-    input_token_len = input_ids.shape[1]
-    outputs = tokenizer.batch_decode(output_ids[:, input_token_len:].cpu(), skip_special_tokens=True)
-    for i in range(len(outputs)):
-        outputs[i] = outputs[i].strip()
-        if outputs[i].endswith(stop_str):
-            outputs[i] = outputs[i][: -len(stop_str)]
-        outputs[i] = outputs[i].strip()
-    if len(outputs) == 1 and not return_list:
-        outputs = outputs[0]
-    return outputs, model_output
+    # the answer = what follows the prompt ids, decoded, with the conversation's stop string and surrounding blanks removed
+    generated = model_output["sequences"][:, input_ids.shape[1]:].cpu()
+    answers = [text.strip().removesuffix(stop_str).strip() for text in tokenizer.batch_decode(generated, skip_special_tokens=True)]
+    single = len(answers) == 1 and not return_list
+    return (answers[0] if single else answers), model_output

@@ -252,7 +252,7 @@ def _page_table(lengths, ps, extra=0):
     return table, nxt
 
 
-def test_rope_kv_and_attention_prefill_and_decode(eng):
+def test_rope_kv_and_attention_prefill_and_decode(eng, rvl_env):
     cfg = syn.TINY
     H, nh, d, ps = cfg.hidden, cfg.n_heads, 128, eng.cfg.kv_page_size
     lengths = [70, 1, 129, 64]
@@ -289,33 +289,36 @@ def test_rope_kv_and_attention_prefill_and_decode(eng):
         ref = (torch.softmax(att, -1) @ vh).transpose(0, 1).reshape(L, H)
         err = _relerr(out_d[cu[s]:cu[s + 1]].float().cpu(), ref)
         assert err < 2e-2, f"prefill attention seq {s} (L={L}): rel err {err}"      # P and O rounded to bf16
-    # ---- one decode step on top of that cache
+    # ---- one decode step on top of that cache, through each of the three decode kernels: register-staged ("regs"),
+    # whole context in shared memory by bulk copies ("staged"), 64-key tiles on mma.sync ("mma": the many-rows default)
     B = len(lengths)
     new = _rand((B, 3 * H), 11)
-    new_d = new.cuda()
     seq_lens = torch.tensor(lengths, dtype=torch.int32).cuda()
-    eng.rope_kv(new_d, table_d, layer=1, positions=seq_lens)
-    dec = eng.attn_decode(new_d, seq_lens, table_d, layer=1)
-    torch.cuda.synchronize()
-    for s, L in enumerate(lengths):
-        got_new = new_d[s].float().cpu().view(3, nh, d)
-        keys = torch.stack([kc[table[s, t // ps], :, t % ps].float().cpu() for t in range(L + 1)])     # [L+1, nh, d]
-        vals = torch.stack([vc[table[s, t // ps], :, t % ps].float().cpu() for t in range(L + 1)])
-        assert torch.equal(keys[L], got_new[1])
-        att = torch.einsum("hd,lhd->hl", got_new[0], keys) / math.sqrt(d)
-        ref = torch.einsum("hl,lhd->hd", torch.softmax(att, -1), vals).reshape(H)
-        err = _relerr(dec[s].float().cpu(), ref)
-        assert err < 1e-2, f"decode attention seq {s}: rel err {err}"
-    # ---- the same step through the fused kernel (RoPE + KV append inside the attention kernel, as rvl_decode_step runs
-    # it): identical cache contents and identical output bits, because both paths round q', k' to bf16 the same way
-    k_ref, v_ref = kc.clone(), vc.clone()
-    for s, L in enumerate(lengths):                                                   # wipe the appended slot
-        kc[table[s, L // ps], :, L % ps] = 0
-        vc[table[s, L // ps], :, L % ps] = 0
-    dec2 = eng.attn_decode(new.cuda(), seq_lens, table_d, layer=1, fused_rope=True)
-    torch.cuda.synchronize()
-    assert torch.equal(kc, k_ref) and torch.equal(vc, v_ref)
-    assert torch.equal(dec2, dec)
+    for mode in ("regs", "staged", "mma"):
+        rvl_env("RVL_ATTN_DECODE", mode)
+        new_d = new.cuda()
+        eng.rope_kv(new_d, table_d, layer=1, positions=seq_lens)
+        dec = eng.attn_decode(new_d, seq_lens, table_d, layer=1)
+        torch.cuda.synchronize()
+        for s, L in enumerate(lengths):
+            got_new = new_d[s].float().cpu().view(3, nh, d)
+            keys = torch.stack([kc[table[s, t // ps], :, t % ps].float().cpu() for t in range(L + 1)])     # [L+1, nh, d]
+            vals = torch.stack([vc[table[s, t // ps], :, t % ps].float().cpu() for t in range(L + 1)])
+            assert torch.equal(keys[L], got_new[1])
+            att = torch.einsum("hd,lhd->hl", got_new[0], keys) / math.sqrt(d)
+            ref = torch.einsum("hl,lhd->hd", torch.softmax(att, -1), vals).reshape(H)
+            err = _relerr(dec[s].float().cpu(), ref)
+            assert err < 1e-2, f"decode attention ({mode}) seq {s}: rel err {err}"
+        # ---- the same step through the fused kernel (RoPE + KV append inside the attention kernel, as rvl_decode_step runs
+        # it): identical cache contents and identical output bits, because both paths round q', k' to bf16 the same way
+        k_ref, v_ref = kc.clone(), vc.clone()
+        for s, L in enumerate(lengths):                                                   # wipe the appended slot
+            kc[table[s, L // ps], :, L % ps] = 0
+            vc[table[s, L // ps], :, L % ps] = 0
+        dec2 = eng.attn_decode(new.cuda(), seq_lens, table_d, layer=1, fused_rope=True)
+        torch.cuda.synchronize()
+        assert torch.equal(kc, k_ref) and torch.equal(vc, v_ref), mode
+        assert torch.equal(dec2, dec), mode
 
 
 # ------------------------------------------------------------------------------------------- sampling / scoring

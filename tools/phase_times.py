@@ -15,13 +15,15 @@ AB_VAL = "0"
 if AB and ":" in AB:
     AB, AB_VAL = AB.split(":")
 acc = {0: [], 1: []}
-for i in range(13 if AB else 4):
+graphs = {0: {}, 1: {}}                 # captured decode chunks bake the switches in: one graph cache per arm
+for i in range(21 if AB else 6):
     if AB:
         if i % 2:
             os.environ[AB] = AB_VAL
         else:
             os.environ.pop(AB, None)
         model.engine.lib.rvl_reload_env()
+        model.engine._dec_graphs = graphs[i % 2]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -34,7 +36,7 @@ for i in range(13 if AB else 4):
     print(f"step {i}: total {e0.elapsed_time(e1):7.2f} ms (host enqueue {1e3 * t_host:6.1f} ms) | before generate {e0.elapsed_time(ev[0]):6.2f} | "
           f"splice {ev[0].elapsed_time(ev[1]):6.2f} | prefill {ev[1].elapsed_time(ev[2]):7.2f} | decode {ev[2].elapsed_time(ev[3]):7.2f} | "
           f"tail {ev[3].elapsed_time(e1):6.2f}", flush=True)
-    if AB and i > 0:
+    if AB and i >= 9:                    # every arm has captured its graphs by then (third sight of the chunk shapes)
         acc[i % 2].append((ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), e0.elapsed_time(e1)))
 if AB:
     for k, name in ((0, "default"), (1, AB + "=" + AB_VAL)):
