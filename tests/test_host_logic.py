@@ -850,3 +850,33 @@ def test_plan_splice_with_several_placeholders_per_row_equals_oracle():
         cu = plan["cu_seqlens"]
         for b in range(B):
             assert torch.equal(packed[cu[b]:cu[b + 1]], want[b]), (case, b)
+
+
+def test_pad_sequences_1d_matches_the_reference_fixture(golden_dir):
+    """tests/golden/pad_sequences.npz holds what the reference's own pad_sequences_1d returned (make_golden_pad.py) for ragged
+    torch / numpy inputs, nested lists, a fixed length and the stage-1 driver's call (eval_nlq_negative.py:286)."""
+    import importlib.util
+    from revisionllm_b200.tensor_utils import pad_sequences_1d
+    spec = importlib.util.spec_from_file_location("make_golden_pad_cases", os.path.join(golden_dir, "make_golden_pad.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    exec(compile(src[src.index("def cases():"): src.index("def main():")], spec.origin, "exec"), {"torch": torch, "np": np}, ns)
+    g = np.load(os.path.join(golden_dir, "pad_sequences.npz"))
+    for name, (seqs, kw) in ns["cases"]().items():
+        padded, mask = pad_sequences_1d(seqs, **kw)
+        assert isinstance(padded, torch.Tensor) == bool(g[name + "/is_torch"]) and isinstance(mask, torch.Tensor) == bool(g[name + "/is_torch"])
+        got_p = padded.numpy() if isinstance(padded, torch.Tensor) else padded
+        got_m = mask.numpy() if isinstance(mask, torch.Tensor) else mask
+        assert got_p.dtype == g[name + "/padded"].dtype and got_m.dtype == np.float32
+        np.testing.assert_array_equal(got_p, g[name + "/padded"])
+        np.testing.assert_array_equal(got_m, g[name + "/mask"])
+    with pytest.raises(AssertionError):
+        pad_sequences_1d([torch.zeros(2, 3)], dtype=np.float32)          # mismatched container / dtype: same assertion as the reference
+
+
+def test_build_stamp_tracks_the_sources():
+    """`build()` decides by content, not by file times: the stamp next to the library is the digest of csrc/*, the header
+    and the flags (the library reaches the GPU box by copy, where every mtime is new)."""
+    from revisionllm_b200 import build as b
+    assert os.path.exists(b.STAMP) and open(b.STAMP).read().strip() == b.sources_digest()
+    assert not b.needs_build()
