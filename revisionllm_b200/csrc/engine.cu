@@ -520,6 +520,21 @@ int rvl_profile_read(rvl_handle* h, int32_t category, double* total_ms, double* 
   return RVL_OK;
 }
 
+// tools/ only: SM clock seen by a kernel at this point of the stream (cycles and nanoseconds of a ~20 us spin on one thread)
+__global__ void sm_clock_probe_kernel(unsigned long long* out) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < 20000ull);
+  out[0] = static_cast<unsigned long long>(clock64() - c0);
+  out[1] = t1 - t0;
+}
+void rvl_debug_sm_clock(unsigned long long* out_dev, rvl_stream stream) {
+  if (out_dev) sm_clock_probe_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(out_dev);
+}
+
 // ------------------------------------------------------------------------------------------ single kernels
 int rvl_rmsnorm(rvl_handle* h, const float* x, const void* w, void* y, int64_t n_rows, int32_t dim, float eps,
                 const int32_t* rows, rvl_stream stream) {

@@ -462,6 +462,9 @@ class RevisionLlamaForCausalLM:
                 eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
             if ev:
                 ev[2].record()
+            probe = getattr(self, "debug_clock_probe", None)          # tools/phase_times.py: uint64 [3, 2] on the device
+            if probe is not None:
+                eng.lib.rvl_debug_sm_clock(probe[0].data_ptr(), torch.cuda.current_stream().cuda_stream)
             del hidden
             tokens = torch.full((max_new, B), int(pad), dtype=torch.int32, device=dev)
             entropies = torch.full((max_new, B), float("nan"), dtype=torch.float32, device=dev)
@@ -486,6 +489,8 @@ class RevisionLlamaForCausalLM:
                     kv.steps += k
                     t += k
                     steps_run = t
+                    if probe is not None and t == k:
+                        eng.lib.rvl_debug_sm_clock(probe[1].data_ptr(), torch.cuda.current_stream().cuda_stream)
                     # one look at the EOS flags between two chunks (none after the last: the trim below sees everything)
                     if unfinished is not None and t < max_new - 1 and int(unfinished.sum().item()) == 0:
                         break
@@ -544,6 +549,8 @@ class RevisionLlamaForCausalLM:
                         logits = torch.empty((n_live, cfg.vocab_size), dtype=torch.float32, device=dev)
                     eng.decode_step(tok_t.contiguous(), kv.seq_lens, kv.page_table, logits, max_kv_len=kv.get_seq_length() + 1)
                     kv.steps += 1
+            if probe is not None:
+                eng.lib.rvl_debug_sm_clock(probe[2].data_ptr(), torch.cuda.current_stream().cuda_stream)
             if ev:
                 ev[3].record()
                 self.last_phase_events = ev      # splice start, prefill start, decode start, end (read after a synchronize)

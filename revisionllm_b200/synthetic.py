@@ -46,12 +46,18 @@ class SynthConfig:
     plant_gain: float = 1.0         # 0 disables the planted successor structure
     perm_mult: int = 7919           # successor(t) = 3 + ((t-3)*mult + add) mod (vocab-3)
     perm_add: int = 104729
+    # > 0: the planted continuation also depends on the VISUAL input (see `plant_visual_classes`): features carry one of
+    # `visual_classes` directions, a layer-0 attention head averages it into the residual stream, lm_head reads it
+    visual_classes: int = 0
+    class_amp: float = 8.0          # amplitude of the class direction in every frame of a segment (frame noise has norm ~27.7)
+    class_gain: float = 1.0         # weight of the class read-out in lm_head, relative to plant_gain
 
     def dict(self):
         return asdict(self)
 
 
 VICUNA_7B = SynthConfig()
+VICUNA_7B_VIS = SynthConfig(visual_classes=4)      # the benchmark / full-size parity weights: four visually selected token chains
 TINY = SynthConfig(hidden=256, n_layers=2, n_heads=2, head_dim=128, intermediate=512, vocab=512, max_pos=1024)
 SMALL = SynthConfig(hidden=512, n_layers=4, n_heads=4, head_dim=128, intermediate=1024, vocab=2048, max_pos=2048)
 
@@ -67,6 +73,70 @@ def successor_table(cfg: SynthConfig) -> torch.Tensor:
     succ = 3 + ((t - 3).clamp(min=0) * mult + cfg.perm_add) % n
     succ[:3] = 3
     return succ
+
+
+def class_successor_table(cfg: SynthConfig) -> torch.Tensor:
+    """[K, vocab] int64: successor of token t when the segment shows class k.  Class k's successors all lie in
+    A_k = {v >= 3 : (v - 3) % K == k}, so the K candidate successors of a token are distinct and the class read-out of
+    lm_head (a bonus for every token of A_k) picks one of them."""
+    K = cfg.visual_classes
+    per = (cfg.vocab - 3) // K
+    mult = cfg.perm_mult
+    while math.gcd(mult, per) != 1:
+        mult += 1
+    t = torch.arange(cfg.vocab, dtype=torch.int64)
+    rows = []
+    for k in range(K):
+        slot = ((t - 3).clamp(min=0) * mult + cfg.perm_add + 7 * k) % per
+        rows.append(3 + K * slot + k)
+    return torch.stack(rows)
+
+
+def class_directions(cfg: SynthConfig, seed: int = 0) -> torch.Tensor:
+    """[K, adapter_dim] fp32 orthonormal feature-space directions, one per visual class (fixed by `seed`)."""
+    g = torch.Generator().manual_seed(seed + 7777)
+    q, _ = torch.linalg.qr(torch.randn(cfg.adapter_dim, cfg.visual_classes, generator=g))
+    return q.t().contiguous()
+
+
+def plant_visual_classes(cfg: SynthConfig, w: Dict[str, torch.Tensor], seed: int) -> None:
+    """Make the greedy continuation depend on the visual input, through the model's own arithmetic:
+
+      * every frame of a segment of class k carries `class_amp * c_k` (make_features(classes=...)); mm_projector maps it
+        to p_k = P c_k in every visual position of the prompt;
+      * in layer 0 the LAST attention head gets W_q = 0 (all scores 0: it averages its values over the causal context),
+        value rows that read out the K directions p_k / |p_k|, and output columns that write K fixed random vectors r_k
+        (embedding-sized) into the residual stream - so every position behind the video, at prefill and at every decode
+        step, carries ~1.5 r_k for the class it saw;
+      * lm_head: row v of A_k (class_successor_table) = noise + plant_gain * (sum of the embeddings of the tokens whose
+        class-k successor is v) + class_gain * r_k.  For the current token a and class k the row succ_k(a) collects both
+        bonuses, every other row at most one: the chain is succ_k(succ_k(...)) - four different chains for four classes,
+        with a margin of the size of the planted bonus itself.
+    Replaces the single successor permutation of plant_gain (the reference weights are random-init either way)."""
+    K, H, V, d = cfg.visual_classes, cfg.hidden, cfg.vocab, cfg.head_dim
+    dev = w["lm_head.weight"].device
+    g = torch.Generator().manual_seed(seed + 4242)
+    r = torch.randn(K, H, generator=g).to(dev)                                        # r_k, rms 1 like an embedding
+    P = w["model.mm_projector.weight"].float()                                        # [H, adapter_dim]
+    p = class_directions(cfg, seed).to(dev) @ P.t()                                    # [K, H]
+    p_hat = p / p.norm(dim=1, keepdim=True)
+    h0 = (cfg.n_heads - 1) * d
+    wq, wv, wo = (w[f"model.layers.0.self_attn.{n}_proj.weight"] for n in ("q", "v", "o"))
+    wq[h0:h0 + d] = 0
+    wv[h0:h0 + d] = 0
+    # value = beta_v * (p_hat . normed x): ~ beta_v * class_amp * |p| / rms(x) on a visual row of the class, ~ beta_v * N(0,1) elsewhere
+    beta_v, beta_o = 0.25, 0.75
+    wv[h0:h0 + K] = (beta_v * p_hat).to(wv.dtype)
+    wo[:, h0:h0 + d] = 0
+    wo[:, h0:h0 + K] = (beta_o * r.t()).to(wo.dtype)
+    succ = class_successor_table(cfg).to(dev)                                          # [K, V]
+    emb = w["model.embed_tokens.weight"].float() / cfg.embed_std
+    head = torch.randn((V, H), generator=torch.Generator().manual_seed(seed + 99), dtype=torch.float32).to(dev)
+    for k in range(K):
+        head.index_add_(0, succ[k, 3:], cfg.plant_gain * emb[3:])                      # row succ_k(a) += embed[a]
+        rows = torch.arange(3 + k, V, K, device=dev)
+        head[rows] += cfg.class_gain * r[k]
+    w["lm_head.weight"] = (head * cfg.init_std).to(torch.bfloat16)
 
 
 def _randn(shape, std, gen, device, dtype=torch.bfloat16):
@@ -115,6 +185,8 @@ def make_llama_weights(cfg: SynthConfig, seed: int = 0, device: str = "cpu") -> 
     w["lm_head.weight"] = (head * cfg.init_std).to(torch.bfloat16)
     w["model.mm_projector.weight"] = _randn((H, cfg.adapter_dim), 1.0 / math.sqrt(cfg.adapter_dim), gen, device)
     w["model.mm_projector.bias"] = _randn((H,), 0.1, gen, device)
+    if cfg.visual_classes > 0:
+        plant_visual_classes(cfg, w, seed)
     return w
 
 
@@ -154,11 +226,36 @@ def make_clip_encoder_weights(hidden: int, seed: int = 0, device: str = "cpu") -
     return p
 
 
-def make_features(n_segments: int, n_frames: int, dim: int = 768, seed: int = 0, device: str = "cpu") -> torch.Tensor:
-    """Synthetic CLIP frame features ~ N(0,1), bf16."""
+def make_features(n_segments: int, n_frames: int, dim: int = 768, seed: int = 0, device: str = "cpu",
+                  class_cfg: "SynthConfig" = None, weight_seed: int = 0) -> torch.Tensor:
+    """Synthetic CLIP frame features ~ N(0,1), bf16.  With `class_cfg` (a config with
+    visual_classes > 0) every frame of segment i additionally carries the direction of class `segment_class(i, K)`
+    (plant_visual_classes: the weights made with `weight_seed` read it back out)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + 17)
-    return torch.randn((n_segments, n_frames, dim), generator=gen, device=device, dtype=torch.float32).to(torch.bfloat16)
+    x = torch.randn((n_segments, n_frames, dim), generator=gen, device=device, dtype=torch.float32)
+    if class_cfg is not None and class_cfg.visual_classes > 0:
+        dirs = class_directions(class_cfg, weight_seed).to(device)
+        cls = segment_classes(n_segments, class_cfg.visual_classes).to(device)
+        x = x + class_cfg.class_amp * dirs[cls][:, None, :]
+    return x.to(torch.bfloat16)
+
+
+def segment_classes(n_segments: int, n_classes: int) -> torch.Tensor:
+    """Visual class of each synthetic segment: a fixed pseudo-random pattern (not i % K, so neighbours differ irregularly)."""
+    i = torch.arange(n_segments, dtype=torch.int64)
+    return ((i * 2654435761) >> 7) % n_classes
+
+
+def expected_chain(cfg: SynthConfig, last_prompt_token: int, steps: int, visual_class: int = 0) -> list:
+    """The planted greedy continuation: successor chain of the last prompt token (of class `visual_class` when the weights
+    carry visual classes)."""
+    table = class_successor_table(cfg)[visual_class] if cfg.visual_classes > 0 else successor_table(cfg)
+    out, cur = [], int(last_prompt_token)
+    for _ in range(steps):
+        cur = int(table[cur])
+        out.append(cur)
+    return out
 
 
 def make_prompt_ids(cfg: SynthConfig, n_pre: int = 38, n_post: int = 46, seed: int = 0) -> torch.Tensor:

@@ -50,6 +50,8 @@ for B in [int(b) for b in args.batches.split(",")]:
     bufs["page_table"].copy_(kv.page_table)
     bufs["logits"].copy_(out.logits[:, 0])
     graphs = {name: {} for name, _, _ in variants}
+    probe = torch.zeros(2, dtype=torch.int64, device="cuda")
+    mhz = {}
     times = {name: [] for name, _, _ in variants}
     for rep in range(args.reps + 2):
         for name, env, g in variants:
@@ -62,7 +64,9 @@ for B in [int(b) for b in args.batches.split(",")]:
             for _ in range(2):
                 eng.decode_chunk(bufs, K, -1, 0, False, L + 64, graph=g)
             e1.record()
+            eng.lib.rvl_debug_sm_clock(probe.data_ptr(), torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
+            mhz[name] = 1e3 * probe[0].item() / max(probe[1].item(), 1)
             if rep >= 2:                                   # rep 0: eager warm-up, rep 1: capture
                 times[name].append(e0.elapsed_time(e1) / (2 * K))
     bytes_step = 13.214e9 + B * 0.524288e6 * (L + K + 1)
@@ -71,7 +75,7 @@ for B in [int(b) for b in args.batches.split(",")]:
         med = t[len(t) // 2]
         results[f"B={B} {name}"] = {"ms_per_step_median": med, "min": t[0], "max": t[-1], "gbs": bytes_step / med / 1e6,
                                     "frac_hbm": bytes_step / med / 1e6 / peak}
-        print(f"B={B:4d} {name:55s} median {med:7.3f} ms/step (min {t[0]:.3f} max {t[-1]:.3f})  {bytes_step / med / 1e6:6.0f} GB/s = {bytes_step / med / 1e6 / peak:.3f} of HBM", flush=True)
+        print(f"B={B:4d} {name:55s} median {med:7.3f} ms/step (min {t[0]:.3f} max {t[-1]:.3f})  {bytes_step / med / 1e6:6.0f} GB/s = {bytes_step / med / 1e6 / peak:.3f} of HBM   SM clock after the run {mhz[name]:.0f} MHz", flush=True)
 set_env({})
 if args.out:
     json.dump(results, open(args.out, "w"), indent=1)

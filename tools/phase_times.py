@@ -7,6 +7,7 @@ from revisionllm_b200.model import RevisionConfig, RevisionLlamaForCausalLM
 cfg = syn.VICUNA_7B
 model = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg), syn.make_llama_weights(cfg, seed=0, device="cuda")).bfloat16().cuda()
 model.record_phase_events = True
+model.debug_clock_probe = torch.zeros((3, 2), dtype=torch.int64, device="cuda")     # SM clock at decode start / after 8 steps / at the end
 feats = syn.make_features(180, 100, 768, seed=1).cuda()
 ids = syn.make_prompt_ids(cfg, seed=2).cuda()
 cls = torch.randn(768, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
@@ -35,7 +36,8 @@ for i in range(21 if AB else 6):
     ev = model.last_phase_events
     print(f"step {i}: total {e0.elapsed_time(e1):7.2f} ms (host enqueue {1e3 * t_host:6.1f} ms) | before generate {e0.elapsed_time(ev[0]):6.2f} | "
           f"splice {ev[0].elapsed_time(ev[1]):6.2f} | prefill {ev[1].elapsed_time(ev[2]):7.2f} | decode {ev[2].elapsed_time(ev[3]):7.2f} | "
-          f"tail {ev[3].elapsed_time(e1):6.2f}", flush=True)
+          f"tail {ev[3].elapsed_time(e1):6.2f} | SM MHz at decode start / mid / end "
+          + " / ".join(f"{1e3 * c / max(n, 1):.0f}" for c, n in model.debug_clock_probe.cpu().tolist()), flush=True)
     if AB and i >= 9:                    # every arm has captured its graphs by then (third sight of the chunk shapes)
         acc[i % 2].append((ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), e0.elapsed_time(e1)))
 if AB:
