@@ -1061,8 +1061,11 @@ void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int
   // 3.50 ms per 7B decode step); many rows: 8 register-staged CTAs per SM overlap better than 2 staged ones (B = 180: 9.4
   // vs 9.9 ms).  RVL_ATTN_DECODE = "regs" / "staged" forces one of them.
   const int forced = tuning().attn_decode;
-  // many rows: the tensor-core tile kernel ('m', page size 32) - RVL_ATTN_DECODE = regs / staged / mma forces one
-  char mode = forced ? static_cast<char>(forced) : (n_seq * n_heads >= 1024 ? (page_size == 32 ? 'm' : 'r') : 's');
+  // Page size 32 (every shipped configuration): the tensor-core tile kernel 'm' at every batch size - measured per 7B decode
+  // step inside CUDA graphs (tools/decode_ab.py, mma / regs / staged): B = 1: 2.87 / 3.04 / 2.93 ms, 8: 2.93 / 3.19 / 3.17,
+  // 23: 3.22 / 3.42 / 3.83, 56: 3.85 / 4.05 / 3.89, 180: 6.51 / 6.76 / 11.5.  Other page sizes: staged for few rows, registers for
+  // many.  RVL_ATTN_DECODE = regs / staged / mma forces one.
+  char mode = forced ? static_cast<char>(forced) : (page_size == 32 ? 'm' : (n_seq * n_heads >= 1024 ? 'r' : 's'));
   if (mode == 'm' && page_size != 32) mode = 'r';
   if (mode == 'm') {
     constexpr int smem_m = 65536 + 4096 + 4 * kD * 4;

@@ -370,3 +370,112 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
     for qi in mine:
         out[qi] = _stage2_finish(plans[qi], [results[(qi, ci)] for ci in range(len(plans[qi]))], queries[qi]["grounding_windows"], answer_number)
     return out
+
+
+# ------------------------------------------------------------------------------------------ one movie, end to end
+@dataclass
+class MovieConfig:
+    """Geometry and scoring switches of the two evaluation scripts (their argparse defaults)."""
+    clip_length: int = 250            # stage-1 window length in feature frames (debug_window * feature_fps)
+    num_frames: int = 100             # frames sampled per stage-1 window
+    stage2_clip_length: int = 250     # stage-2 window length in feature frames
+    stage2_num_frames: int = 250      # frames per stage-2 window (through the ClipEncoder)
+    stride: int = 5                   # stage-2 windows start every clip_length // stride frames
+    batch: int = 100                  # stage-2 windows per query ("top-100"; 33 for stage2_long_33)
+    zooms: Tuple[int, ...] = (4, 2, 1)
+    max_new_tokens: int = 16
+    score_merge: str = "multiply"     # eval_nlq_negative.py --score_merge
+    normalize: bool = True
+    perm_seed: Optional[int] = 0
+    stage1_batch: Optional[int] = None
+
+
+@dataclass
+class MovieResult:
+    records: torch.Tensor                       # stage-1 records of every window, global order (on every rank)
+    answers: List[str]                          # stage-1 answer per window
+    clip_frames: Dict[int, Tuple[int, int]]     # window -> predicted span (windows whose answer names one)
+    ious: List[float]
+    grounding_windows: List[int]                # stage-2 windows chosen from the stage-1 answers
+    stage2: Optional[List[Dict]]                # one entry per stage-2 generate() call (None on ranks that did not run it)
+    stage2_answers: Optional[List[str]]
+    stage2_frames: Optional[Dict[int, Tuple[int, int]]]
+    ranked: Optional[Dict[str, list]]           # proposals best first: windows / scores / ious
+
+
+def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok: Callable[[torch.Tensor], List[str]],
+              gt: Tuple[float, float], cfg: MovieConfig = MovieConfig(), query_feats=None, stage2_input_ids: Optional[torch.Tensor] = None,
+              detok_stage2: Optional[Callable[[torch.Tensor], List[str]]] = None, rank: int = 0, world: int = 1, group=None,
+              stage2_rank: int = 0, eos_token_id="config") -> MovieResult:
+    """One movie-query through the whole recursive path, as ONE call on `world` GPUs - what the reference spreads over three
+    scripts and their JSONL files:
+
+      stage 1  (/root/reference/revisionllm/eval/eval_nlq_negative.py:221-336)   half-overlapping windows -> generate ->
+               answers + entropy statistics -> predicted spans -> cosine score of each span; windows dealt round-robin to the
+               ranks, one all-gather of the fixed-size records;
+      select   (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:262-294)  stage-2 window grid, windows of the
+               positive stage-1 answers padded evenly to `batch`;
+      stage 2  (:337-386)  zoom levels 4 / 2 / 1 over the chosen windows through the ClipEncoder, on ONE rank (`stage2_rank`;
+               north star: one GPU per query);
+      rank     (/root/reference/revisionllm/eval/metric_retrieval_forward.py:96-199)  stage-1 proposals kept where stage 2
+               looked, merged cosine / entropy score, best first (`rvl_merge_rank`).
+
+    `features` [T, 768] fp32 (host numpy or torch); `detok(tokens [n, T'])` -> answer strings (a tokenizer's batch_decode with
+    the reference's strip / stop-string rule); `gt` = (start, end) as fractions of the movie.  Every rank returns the stage-1
+    part; stage-2 results and the ranking live on `stage2_rank` (the other ranks return None there - no second exchange)."""
+    from . import metrics
+    from .features import WindowLoader
+    eng, dev = model.engine, model.device
+    feats_np = features.numpy() if isinstance(features, torch.Tensor) else np.asarray(features)
+    T = feats_np.shape[0]
+    loader = getattr(model, "_window_loader", None)                                        # pinned staging buffer, kept across movies
+    if loader is None or loader.dim != feats_np.shape[1]:
+        loader = model._window_loader = WindowLoader(eng, max_frames=max(T, 1 << 15), dim=feats_np.shape[1])
+    movie = loader.upload(feats_np)                                                        # fp32 [T, 768] on the device, once
+    idx1 = scoring.stage1_windows(T, cfg.clip_length, cfg.num_frames)
+    if idx1.shape[0] == 0:                                                                 # shorter than one window: one uniform sample
+        idx1 = np.linspace(0, T - 1, cfg.num_frames, dtype=np.int32)[None]
+    W = idx1.shape[0]
+    mine = shard_indices(W, rank, world)
+    win1 = eng.gather_windows(movie, torch.from_numpy(np.ascontiguousarray(idx1[mine])).to(dev)) if len(mine) else \
+        torch.empty((0, cfg.num_frames, feats_np.shape[1]), dtype=torch.bfloat16, device=dev)
+
+    def decode_spans(tok):
+        spans = torch.full((tok.shape[0], 2), -1, dtype=torch.int32)
+        for i, text in enumerate(detok(tok.cpu())):
+            sp = scoring.parse_span(text)
+            if sp is not None:
+                spans[i, 0], spans[i, 1] = sp
+        return spans
+    local = score_segments(model, win1, input_ids, cls, cfg.max_new_tokens, decode_spans, cfg.stage1_batch, eos_token_id)
+    records = allgather_records(local, W, rank, world, group)
+    un = unpack_records(records.cpu())
+    answers = detok(un["tokens"][:, : int(un["n_tokens"].max())])
+    num_frames_video = int(T * cfg.num_frames / cfg.clip_length)
+    clip_frames, ious, ent = metrics.iou(answers, gt, cfg.num_frames, num_frames_video, un["h_mean"].tolist())
+    cos = [float(un["cos"][w]) for w in clip_frames]
+    # ---- stage-2 selection (every rank computes the same list; only stage2_rank uses it)
+    idx2, _ = scoring.stage2_windows(T, cfg.stage2_clip_length, cfg.stage2_num_frames, cfg.stride)
+    grounding = scoring.stage2_select_windows(answers, idx2.shape[0], cfg.batch, cfg.stride) if idx2.shape[0] else []
+    res = MovieResult(records, answers, clip_frames, ious, grounding, None, None, None, None)
+    if rank != stage2_rank or not grounding or model.clip_encoder is None:
+        return res
+    gw = np.asarray(grounding, dtype=np.int64)                                             # negative ids index from the end, as in the reference
+    win2 = eng.gather_windows(movie, torch.from_numpy(np.ascontiguousarray(idx2[gw])).to(dev))
+    dt2 = detok_stage2 or detok
+
+    def answer_number(tok):
+        return scoring.parse_first_int(dt2(tok[None].cpu())[0])
+    ids2 = stage2_input_ids if stage2_input_ids is not None else input_ids
+    calls = stage2_pass(model, win2, query_feats, ids2, grounding, cfg.batch, cfg.zooms, cfg.max_new_tokens, cfg.perm_seed,
+                        answer_number, eos_token_id)
+    answers2 = [dt2(torch.tensor(c["tokens"])[None])[0] for c in calls]
+    frames2, _hit = metrics.stage2_frames(answers2, gt, cfg.batch, [c["start"] for c in calls], [c["perm"] for c in calls],
+                                          [c["zoom"] for c in calls], grounding)
+    res.stage2, res.stage2_answers, res.stage2_frames = calls, answers2, frames2
+    if clip_frames:
+        # rank_query expects one entry per answered window in window order - `present` there is defined by the answer strings
+        present = [i for i, a in enumerate(answers) if a != "Not Present" and a != "From 249 to 249."]
+        if present == list(clip_frames):
+            res.ranked = metrics.rank_query(eng, answers, cos, ent, ious, stage2_frames=frames2, mode=cfg.score_merge, normalize=cfg.normalize)
+    return res

@@ -60,6 +60,7 @@ VICUNA_7B = SynthConfig()
 VICUNA_7B_VIS = SynthConfig(visual_classes=4)      # the benchmark / full-size parity weights: four visually selected token chains
 TINY = SynthConfig(hidden=256, n_layers=2, n_heads=2, head_dim=128, intermediate=512, vocab=512, max_pos=1024)
 SMALL = SynthConfig(hidden=512, n_layers=4, n_heads=4, head_dim=128, intermediate=1024, vocab=2048, max_pos=2048)
+MEDIUM = SynthConfig(hidden=1024, n_layers=8, n_heads=8, head_dim=128, intermediate=2816, vocab=8192, max_pos=2048)
 
 
 def successor_table(cfg: SynthConfig) -> torch.Tensor:
@@ -337,3 +338,23 @@ class StubTokenizer:
                 prev_digit = tok.isdigit()
             out.append(s)
         return out
+
+
+def synthetic_answers(tokens, n_frames: int):
+    """Stand-in for `tokenizer.batch_decode` on random-init weights (no vocabulary offline): a deterministic map from a row of
+    generated token ids to one of the answer strings the fine-tuned model produces - "Not Present" or "From a to b." with a
+    span inside the window - so that the parse -> select -> stage-2 -> rank chain has something to chew on."""
+    out = []
+    for row in (tokens.tolist() if hasattr(tokens, "tolist") else tokens):
+        if row[0] % 5 == 0:
+            out.append("Not Present")
+        else:
+            a = row[1 % len(row)] % n_frames
+            b = min(n_frames - 1, a + row[2 % len(row)] % 23)
+            out.append(f"From {a} to {b}.")
+    return out
+
+
+def synthetic_answers_stage2(tokens):
+    """Stage-2 answers name a (zoomed, permuted) window number: here the first generated id modulo 97."""
+    return [str(row[0] % 97) for row in (tokens.tolist() if hasattr(tokens, "tolist") else tokens)]

@@ -878,5 +878,12 @@ def test_build_stamp_tracks_the_sources():
     """`build()` decides by content, not by file times: the stamp next to the library is the digest of csrc/*, the header
     and the flags (the library reaches the GPU box by copy, where every mtime is new)."""
     from revisionllm_b200 import build as b
+    b.build()                                   # compiles only when the stamp and the sources disagree
     assert os.path.exists(b.STAMP) and open(b.STAMP).read().strip() == b.sources_digest()
     assert not b.needs_build()
+    stamp = open(b.STAMP).read()
+    try:
+        open(b.STAMP, "w").write("0" * 64 + "\n")
+        assert b.needs_build()                  # a library built from other sources is rebuilt whatever its file time says
+    finally:
+        open(b.STAMP, "w").write(stamp)
