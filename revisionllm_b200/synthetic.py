@@ -349,7 +349,7 @@ def synthetic_answers(tokens, n_frames: int):
         if row[0] % 5 == 0:
             out.append("Not Present")
         else:
-            a = row[1 % len(row)] % n_frames
+            a = row[1 % len(row)] % (n_frames - 1)           # never the "From F-1 to F-1." sentinel the drivers drop
             b = min(n_frames - 1, a + row[2 % len(row)] % 23)
             out.append(f"From {a} to {b}.")
     return out
