@@ -536,7 +536,7 @@ def main():
             movie = synthetic_movie(cfg, 18000, seed=31).numpy()
             gq = torch.Generator().manual_seed(8)
             q_feats = (torch.randn(1, 32, cfg.adapter_dim, generator=gq).to(torch.bfloat16), torch.ones(1, 32))
-            mc = sweep.MovieConfig(clip_length=200, num_frames=N_FRAMES, stage2_clip_length=250, stage2_num_frames=250, stride=5, batch=100,
+            mc = sweep.MovieConfig(clip_length=200, num_frames=N_FRAMES, stage2_clip_length=200, stage2_num_frames=250, stride=5, batch=100,
                                    zooms=(4, 2, 1), max_new_tokens=NEW_TOKENS)
             ids_s2 = syn.make_prompt_ids(cfg, seed=9)
 

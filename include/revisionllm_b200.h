@@ -289,9 +289,11 @@ RVL_API int rvl_rope_kv(rvl_handle* h, void* qkv, int64_t n_tokens, const int32_
 RVL_API int rvl_swiglu(rvl_handle* h, const void* gu, void* act, int64_t n_tokens, int32_t intermediate,
                rvl_stream stream);
 
-/* Causal varlen attention over qkv [T, 3*hidden] (post-RoPE) -> out [T, hidden] bf16. */
+/* Causal varlen attention over qkv [total_tokens, 3*hidden] (post-RoPE) -> out [total_tokens, hidden] bf16.
+ * tcgen05 kernel (TMA-staged Q / K / V tiles, S and O in TMEM, fp32 online softmax); replaces the eager attention of
+ * transformers' Llama reached from vtimellm_llama.py:79-90. */
 RVL_API int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const int32_t* cu_seqlens,
-                     int32_t n_seq, int32_t max_seqlen, rvl_stream stream);
+                     int32_t n_seq, int32_t max_seqlen, int64_t total_tokens, rvl_stream stream);
 
 /* Paged-KV decode attention: q from qkv [n_seq, 3*hidden], keys 0..seq_lens[i] (inclusive of this
  * step's token) -> out [n_seq, hidden] bf16.

@@ -69,7 +69,7 @@ PROTOTYPES = {
     "rvl_rmsnorm": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _P, _P]),
     "rvl_rope_kv": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I32, _I32, _P]),
     "rvl_swiglu": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
-    "rvl_attn_prefill": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),
+    "rvl_attn_prefill": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _P]),
     "rvl_attn_decode": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P]),
     "rvl_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P]),
     "rvl_mha96": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librevisionllm_b200.so")
-SOURCES = ["engine.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "sampling.cu", "scoring.cu", "clip_encoder.cu"]
+SOURCES = ["engine.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "attention_tcgen05.cu", "sampling.cu", "scoring.cu", "clip_encoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false",

@@ -272,8 +272,14 @@ __global__ void __launch_bounds__(128, 3) attn_prefill_kernel(const __nv_bfloat1
 }
 
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
-                         cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row, int only_last) {
+                         cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row, int only_last, int64_t total_tokens,
+                         int num_sms) {
   if (n_seq <= 0 || max_seqlen <= 0) return;
+  // tcgen05 kernel (attention_tcgen05.cu) unless the sequences name an external context (shared-prefix compute: a K tile would
+  // straddle two row ranges) or RVL_ATTN_PREFILL=0 asks for the mma.sync kernel below
+  if (tuning().attn_prefill != 0 && !seq_pos0 && !seq_ctx_row && total_tokens > 0 && num_sms > 0 &&
+      launch_attn_prefill_tc(qkv, out, cu_seqlens, n_seq, total_tokens, max_seqlen, n_heads, num_sms, st, only_last))
+    return;
   static bool attr = false;
   constexpr int smem = 16384 * 4;
   if (!attr) {

@@ -354,7 +354,8 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
     {
       // causal FLOPs need the per-sequence lengths (device side); use the uniform-length bound T*max_seqlen
       ProfScope ps(h, st, RVL_PROF_ATTN_PREFILL, 2.0 * T * max_seqlen * H, 2.0 * T * 4 * H);
-      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row, last_only ? 1 : 0);
+      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row, last_only ? 1 : 0, T,
+                          h->num_sms);
     }
     if (last_only) {
       const int64_t n = n_seq;
@@ -563,9 +564,10 @@ int rvl_swiglu(rvl_handle* h, const void* gu, void* act, int64_t n_tokens, int32
 }
 
 int rvl_attn_prefill(rvl_handle* h, const void* qkv, void* out, const int32_t* cu_seqlens, int32_t n_seq,
-                     int32_t max_seqlen, rvl_stream stream) {
+                     int32_t max_seqlen, int64_t total_tokens, rvl_stream stream) {
   if (!h || !qkv || !out || !cu_seqlens) return fail(h, RVL_ERR_INVALID, "rvl_attn_prefill: null argument");
-  launch_attn_prefill(qkv, out, cu_seqlens, n_seq, max_seqlen, h->cfg.n_heads, static_cast<cudaStream_t>(stream));
+  launch_attn_prefill(qkv, out, cu_seqlens, n_seq, max_seqlen, h->cfg.n_heads, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0,
+                      total_tokens, h->num_sms);
   return check_cuda(h, "rvl_attn_prefill");
 }
 

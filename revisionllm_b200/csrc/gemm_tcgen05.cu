@@ -1201,6 +1201,10 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t n_feat, int6
   return RVL_OK;
 }
 
+int make_tmap_bf16_2d(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err) {
+  return make_tmap(tm, base, rows, cols, box_rows, err);
+}
+
 static int pow2_at_least(int x) {
   int c = 32;
   while (c < x) c <<= 1;

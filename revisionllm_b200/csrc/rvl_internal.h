@@ -10,6 +10,8 @@
 
 #include "../../include/revisionllm_b200.h"
 
+struct CUtensorMap_st;          // CUDA driver API tensor map (cuda.h), used by pointer only here
+
 namespace rvl {
 
 struct GemmCall {
@@ -115,9 +117,14 @@ void launch_gather_last_rows(const void* attn, const float* hidden, const int32_
 void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaStream_t st);
 void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, int32_t* last_rows, int64_t total,
                       cudaStream_t st);
-// attention.cu
+// gemm_tcgen05.cu: 2D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], 128-byte swizzle, OOB -> zeros
+int make_tmap_bf16_2d(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err);
+// attention.cu / attention_tcgen05.cu
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
-                         cudaStream_t st, const int32_t* seq_pos0 = nullptr, const int32_t* seq_ctx_row = nullptr, int only_last = 0);
+                         cudaStream_t st, const int32_t* seq_pos0 = nullptr, const int32_t* seq_ctx_row = nullptr, int only_last = 0,
+                         int64_t total_tokens = 0, int num_sms = 0);
+bool launch_attn_prefill_tc(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int64_t total_tokens, int max_seqlen,
+                            int n_heads, int num_sms, cudaStream_t st, int only_last);
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
                         int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused, float theta,
                         int max_kv_len, cudaStream_t st);

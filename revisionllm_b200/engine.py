@@ -396,7 +396,7 @@ class Engine(DecodeChunks):
         _req(qkv, torch.bfloat16, "qkv")
         out = torch.empty((qkv.shape[0], self.cfg.hidden), dtype=torch.bfloat16, device=qkv.device)
         self._check(self.lib.rvl_attn_prefill(self.h, qkv.data_ptr(), out.data_ptr(), cu_seqlens.data_ptr(), n_seq,
-                                              max_seqlen, _stream()), "rvl_attn_prefill")
+                                              max_seqlen, qkv.shape[0], _stream()), "rvl_attn_prefill")
         self.launches += 1
         return out
 

@@ -457,6 +457,9 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
     # ---- stage-2 selection (every rank computes the same list; only stage2_rank uses it)
     idx2, _ = scoring.stage2_windows(T, cfg.stage2_clip_length, cfg.stage2_num_frames, cfg.stride)
     grounding = scoring.stage2_select_windows(answers, idx2.shape[0], cfg.batch, cfg.stride) if idx2.shape[0] else []
+    # the mapping of :281-283 assumes both stages cut windows of the same length; with other geometries it can name windows past
+    # the end of the stage-2 grid (the reference then fails on `clip_feats[i]` and its bare `except` drops the query): leave them out
+    grounding = [w for w in grounding if -idx2.shape[0] <= w < idx2.shape[0]]
     res = MovieResult(records, answers, clip_frames, ious, grounding, None, None, None, None)
     if rank != stage2_rank or not grounding or model.clip_encoder is None:
         return res

@@ -265,7 +265,10 @@ def test_rope_kv_and_attention_prefill_and_decode(eng, rvl_env):
     cu_d, table_d = torch.from_numpy(cu).cuda(), torch.from_numpy(table).cuda()
     tok_seq = torch.from_numpy(np.repeat(np.arange(len(lengths)), lengths).astype(np.int32)).cuda()
     eng.rope_kv(qkv_d, table_d, layer=1, tok_seq=tok_seq, cu_seqlens=cu_d)
-    out_d = eng.attn_prefill(qkv_d, cu_d, len(lengths), max(lengths))
+    out_d = eng.attn_prefill(qkv_d, cu_d, len(lengths), max(lengths))          # tcgen05 kernel (default)
+    rvl_env("RVL_ATTN_PREFILL", "0")
+    out_mma = eng.attn_prefill(qkv_d, cu_d, len(lengths), max(lengths))        # round-1 mma.sync kernel (still used for shared-prefix compute)
+    rvl_env("RVL_ATTN_PREFILL", None)
     torch.cuda.synchronize()
     kc, vc = eng.kv_view(1)
     for s, L in enumerate(lengths):
@@ -287,8 +290,9 @@ def test_rope_kv_and_attention_prefill_and_decode(eng, rvl_env):
         att = qh @ kh.transpose(1, 2) / math.sqrt(d)
         att = att + torch.triu(torch.full((L, L), float("-inf")), 1)
         ref = (torch.softmax(att, -1) @ vh).transpose(0, 1).reshape(L, H)
-        err = _relerr(out_d[cu[s]:cu[s + 1]].float().cpu(), ref)
-        assert err < 2e-2, f"prefill attention seq {s} (L={L}): rel err {err}"      # P and O rounded to bf16
+        for name, o in (("tcgen05", out_d), ("mma.sync", out_mma)):
+            err = _relerr(o[cu[s]:cu[s + 1]].float().cpu(), ref)
+            assert err < 2e-2, f"prefill attention ({name}) seq {s} (L={L}): rel err {err}"      # P and O rounded to bf16
     # ---- one decode step on top of that cache, through each of the three decode kernels: register-staged ("regs"),
     # whole context in shared memory by bulk copies ("staged"), 64-key tiles on mma.sync ("mma": the many-rows default)
     B = len(lengths)
