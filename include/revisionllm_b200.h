@@ -242,6 +242,9 @@ RVL_API int rvl_profile_read(rvl_handle* h, int32_t category, double* total_ms, 
 /* tools/gemm_timeline.py only: per-CTA clock64 timestamps of the GEMM roles (8 x uint64 per CTA, up to 160 CTAs).
  * Reads the previous launch's stamps into `out` (n entries) when out != NULL, then switches stamping on/off. */
 RVL_API void rvl_debug_gemm_timestamps(int enable, unsigned long long* out, int n);
+/* tools/attn_timeline.py only: globaltimer stamps of CTA 0 of the tcgen05 prefill attention kernel, [4 roles][256 events][4]
+ * uint64 (see csrc/attention_tcgen05.cu); reads the previous launch's stamps into `out`, then switches stamping on / off. */
+RVL_API void rvl_debug_attn_timestamps(int enable, unsigned long long* out, int n);
 /* tools/phase_times.py only: enqueue a one-thread kernel that spins ~20 us and writes {SM cycles, nanoseconds} to out_dev
  * (2 x uint64, device memory): the SM clock the stream's kernels see at that point (the power-capped clock inside a sweep). */
 RVL_API void rvl_debug_sm_clock(unsigned long long* out_dev, rvl_stream stream);

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "rvl_debug_gemm_timestamps": (None, [C.c_int, _P, C.c_int]),
     "rvl_reload_env": (None, []),
     "rvl_debug_sm_clock": (None, [_P, _P]),
+    "rvl_debug_attn_timestamps": (None, [C.c_int, _P, C.c_int]),
     "rvl_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I32, _I32, _P, _I32, _P]),
     "rvl_rmsnorm": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _P, _P]),
     "rvl_rope_kv": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I32, _I32, _P]),

@@ -3,21 +3,25 @@
 // Replaces the eager `matmul -> softmax(fp32) -> matmul` attention of transformers' Llama that the reference reaches from
 // revisionllm/model/vtimellm_llama.py:79-90 (and, in round 1 of this repo, an mma.sync flash kernel: attention.cu).
 //
+// Work item = (sequence, head, PAIR of 128-row query tiles).  The two query tiles are two independent "slots" of the CTA
+// that share every K / V tile (the later tile needs a superset of the keys of the earlier one):
 //   S = Q K^T  : tcgen05.mma, M = 128 query rows x N = 64 keys x K = 128 dims, Q and K tiles K-major in shared memory
-//                (TMA, 128-byte swizzle), S in TMEM (two 64-column buffers: QK^T of tile j + 1 overlaps the softmax of tile j)
-//   softmax    : four warps, thread = query row = TMEM lane; tcgen05.ld of the row's 64 scores, causal / length mask, online
-//                max and sum in fp32 registers (base 2, the scale rides in the FFMA in front of ex2), P rounded to bf16 and
-//                written to shared memory in the K-major 128-byte-swizzled layout the next MMA reads
+//                (TMA, 128-byte swizzle), S in TMEM (two 64-column buffers per slot: QK^T of tile j + 1 overlaps the softmax
+//                of tile j)
+//   softmax    : four warps per slot, thread = query row = TMEM lane; tcgen05.ld of the row's 64 scores, causal / length mask,
+//                online max and sum in fp32 registers (base 2, the scale rides in the FFMA in front of ex2), P rounded to
+//                bf16 and written to shared memory in the K-major 128-byte-swizzled layout the next MMA reads
 //   O += P V   : tcgen05.mma, M = 128 x N = 128 dims x K = 64 keys, V straight from its TMA tile as an MN-major operand
-//                (keys are rows of the tile), O accumulates in TMEM (128 columns); when a row's running maximum grows by more
-//                than 2^8 the row of O is rescaled in TMEM by its own thread (tcgen05.ld / st), otherwise the old maximum is
-//                kept (P <= 256 is exact enough in bf16 and the final division by the running sum is unaffected)
-//   epilogue   : O row / running sum -> bf16 -> global
-// Roles per CTA (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2 - 5 softmax / correction / epilogue.
-// CTAs are persistent over (sequence, head, 128-row query tile) work items; 256 TMEM columns and ~113 KB of shared memory
-// per CTA, so two CTAs share an SM and one's softmax overlaps the other's loads and MMAs.
-// A warp whose 32 rows lie past the sequence end, or entirely above the tile's first key (causal), skips the tile's
-// exponentials and stores zeros for P.
+//                (keys are rows of the tile), O accumulates in TMEM (128 columns per slot); when a row's running maximum
+//                grows by more than 2^8 the row of O is rescaled in TMEM by its own thread (tcgen05.ld / st), otherwise the
+//                old maximum is kept (P <= 256 is exact enough in bf16, the final division by the running sum is unaffected)
+//   epilogue   : O row / running sum -> bf16 -> the warp's own rows of the P buffer -> coalesced 16-byte global stores
+// Roles (one CTA per SM, persistent over the items): a TMA producer warp (runs up to four K / V tiles and one item's Q tiles
+// ahead), an MMA issuer warp (polls: whichever of the four possible MMAs - QK^T / PV of either slot - has its inputs ready
+// goes out), four softmax / correction / epilogue warps per slot.
+// At L = 184 the kernel is bound by HBM, not by the tensor pipe: a layer reads the 814 MB qkv stream once and writes 271 MB
+// (46 FLOP per byte); what the structure buys is enough loads in flight (224 KB of shared memory per SM) to cover the
+// ~1.5 us a tile takes from issue to arrival.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,23 +32,43 @@
 
 namespace rvl {
 
+// tools/attn_timeline.py: globaltimer stamps of CTA 0 - [role][event index][kind]; role 0 producer (kind 0 = K/V tile issued),
+// role 1 MMA (0 / 1 = QK issued for slot 0 / 1, 2 / 3 = PV issued), role 2 first softmax warp of slot 0 and role 3 of slot 1
+// (0 = scores ready, 1 = exponentials done, 2 = previous PV seen done, 3 = P published); events are indexed by the CTA's
+// running K/V tile counter (roles 0, 1) or the slot's running tile counter (roles 2, 3)
+constexpr int kDbgEvents = 256;
+__device__ unsigned long long g_attn_dbg[4][kDbgEvents][4];
+__device__ int g_attn_dbg_on = 0;
+__device__ __forceinline__ void dbg_stamp(int role, uint32_t idx, int kind) {
+  if (g_attn_dbg_on && blockIdx.x == 0 && idx < kDbgEvents && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_attn_dbg[role][idx][kind] = t;
+  }
+}
+
 namespace {
 
 constexpr int kHD = 128;          // head_dim
-constexpr int kQTile = 128;       // query rows per work item (UMMA M)
+constexpr int kQTile = 128;       // query rows per slot (UMMA M)
 constexpr int kKTile = 64;        // keys per tile (UMMA N of QK^T, K of PV)
-constexpr int kAttnThreads = 192;
+constexpr int kSlots = 2;
+// warps 0 - 3: softmax of slot 0, 4 - 7: slot 1 (TMEM lane quarter = warp % 4), 8: TMA producer, 9: unused, 10 / 11: MMA issuer
+// of slot 0 / 1.  The two polling warps sit on schedulers 2 and 3 on purpose: in the common item (L = 184: the later query tile
+// holds rows 128 - 183) the softmax warps that do the work are quarters 0 and 1, i.e. schedulers 0 and 1.
+constexpr int kAttnThreads = 12 * 32;
+constexpr int kProducerWarp = 8, kMmaWarp = 11;
 constexpr int kQBytes = kQTile * kHD * 2;          // 32 KB: two [128 x 64] halves
-constexpr int kKVBytes = kKTile * kHD * 2;         // 16 KB: two [64 x 64] halves
+constexpr int kKVBytes = kKTile * kHD * 2;         // 16 KB: two [64 x 64] halves (K; the same again for V)
 constexpr int kPBytes = kQTile * kKTile * 2;       // 16 KB: [128 x 64] bf16
-constexpr int kKVStages = 2;
-constexpr int kAttnSmem = 1024 + kQBytes + kKVStages * 2 * kKVBytes + kPBytes + 256;   // 115,968 B: two CTAs per SM
-constexpr uint32_t kTmemCols = 256;                // S0 [0, 64) | S1 [64, 128) | O [128, 256)
+constexpr int kKVStages = 4;
+constexpr int kAttnSmem = 1024 + kSlots * (kQBytes + kPBytes) + kKVStages * 2 * kKVBytes + 256;   // 230,656 B: one CTA per SM
+constexpr uint32_t kTmemCols = 512;                // per slot: S0 [0, 64) | S1 [64, 128) | O [128, 256)
 
 struct AttnArgs {
   const int32_t* cu_seqlens;
   __nv_bfloat16* out;
-  int n_seq, n_heads, n_qt;       // n_qt = query tiles per sequence (from max_seqlen)
+  int n_seq, n_heads, n_pairs;    // n_pairs = pairs of query tiles per sequence (from max_seqlen)
   int only_last;                  // only the query tile that holds the last position of each sequence
   float scale_log2;               // log2(e) / sqrt(head_dim)
 };
@@ -86,62 +110,77 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// work item -> (sequence, head, query tile); false when the item has nothing to do (tile past the end of the sequence, or
-// not the last tile under only_last).  Every role evaluates it identically.
+// work item -> (sequence, head, pair of query tiles); false when the item has nothing to do.  Every role evaluates it
+// identically.  nt[s] = K / V tiles slot s consumes (0: the slot sits this item out); the item loads max(nt) tiles.
 struct Item {
-  int seq, head, qt, s0, L, q0, n_tiles;
+  int seq, head, s0, L;
+  int q0[kSlots], nt[kSlots], n_tiles;
 };
-__device__ __forceinline__ bool decode_item(const AttnArgs& a, int item, Item& it) {
-  it.qt = item % a.n_qt;
-  const int r = item / a.n_qt;
+// `flip`: which slot takes the earlier query tile alternates from one item of the CTA to the next - the slot that ran the short
+// chain (earlier tile: fewer keys) released its Q buffer early, so the NEXT item's long chain can have its Q loaded while the
+// current item is still computing.
+__device__ __forceinline__ bool decode_item(const AttnArgs& a, int item, int flip, Item& it) {
+  // the pair index is the SLOW index and runs backwards: every CTA of the grid-stride loop gets the same mix of long (late
+  // query tiles: more keys) and short items, the long ones first
+  const int per_pair = a.n_seq * a.n_heads;
+  const int pp = a.n_pairs - 1 - item / per_pair;
+  const int r = item - (item / per_pair) * per_pair;
   it.head = r % a.n_heads;
   it.seq = r / a.n_heads;
-  it.s0 = a.cu_seqlens[it.seq];
-  it.L = a.cu_seqlens[it.seq + 1] - it.s0;
-  it.q0 = it.qt * kQTile;
-  if (it.q0 >= it.L) return false;
-  if (a.only_last && it.q0 + kQTile < it.L) return false;
-  const int last_key = min(it.L, it.q0 + kQTile);         // causal: keys < q0 + 128
-  it.n_tiles = (last_key + kKTile - 1) / kKTile;
-  return true;
+  it.s0 = __ldg(a.cu_seqlens + it.seq);
+  it.L = __ldg(a.cu_seqlens + it.seq + 1) - it.s0;
+  it.n_tiles = 0;
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int q0 = (pp * kSlots + (s ^ flip)) * kQTile;
+    it.q0[s] = q0;
+    const bool on = q0 < it.L && !(a.only_last && q0 + kQTile < it.L);
+    it.nt[s] = on ? (min(it.L, q0 + kQTile) + kKTile - 1) / kKTile : 0;      // causal: keys < q0 + 128
+    it.n_tiles = max(it.n_tiles, it.nt[s]);
+  }
+  return it.n_tiles > 0;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                        // [2 halves][128 rows][128 B]
-  uint8_t* sK = sQ + kQBytes;                                // [stage][2 halves][64 rows][128 B]
+  uint8_t* sQ = smem;                                        // [slot][2 halves][128 rows][128 B]
+  uint8_t* sP = sQ + kSlots * kQBytes;                       // [slot][128 rows][128 B]
+  uint8_t* sK = sP + kSlots * kPBytes;                       // [stage][2 halves][64 rows][128 B]
   uint8_t* sV = sK + kKVStages * kKVBytes;                   // same
-  uint8_t* sP = sV + kKVStages * kKVBytes;                   // [128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
-  uint64_t* q_full = bars;               // TMA -> MMA: the item's Q tile landed
-  uint64_t* q_empty = bars + 1;          // MMA -> TMA: every QK^T of the item has read Q
-  uint64_t* kv_full = bars + 2;          // [2]
-  uint64_t* kv_empty = bars + 4;         // [2]  PV of the tile done: K and V slot free
-  uint64_t* s_full = bars + 6;           // [2]  QK^T done: scores in TMEM
-  uint64_t* s_empty = bars + 8;          // [2]  softmax has read the scores (4 warps)
-  uint64_t* p_full = bars + 10;          // softmax wrote P (and rescaled O) (4 warps)
-  uint64_t* o_done = bars + 11;          // PV done: O updated, P free
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kKVBytes);
+  uint64_t* kv_full = bars;              // [4]  TMA -> MMA
+  uint64_t* kv_empty = bars + 4;         // [4]  both slots' PV of the tile done (count 2)
+  uint64_t* q_full = bars + 8;           // [slot]
+  uint64_t* q_empty = bars + 10;         // [slot] every QK^T of the item has read the slot's Q
+  uint64_t* s_full = bars + 12;          // [slot][2]  QK^T done: scores in TMEM
+  uint64_t* s_empty = bars + 16;         // [slot][2]  softmax has read the scores (4 warps)
+  uint64_t* p_full = bars + 20;          // [slot] softmax wrote P (and rescaled O) (4 warps)
+  uint64_t* o_done = bars + 22;          // [slot] PV done: O updated, P free
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = args.n_heads * kHD;
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&kv_empty[i], 2);
     }
-    mbar_init(p_full, 4);
-    mbar_init(o_done, 1);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_done[s], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[s * 2 + i], 1);
+        mbar_init(&s_empty[s * 2 + i], 4);
+      }
+    }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_ptr, kTmemCols);
     tmem_relinquish();
   }
@@ -151,29 +190,42 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
   const uint32_t tmem_base = *tmem_ptr;
   pdl_trigger();
   pdl_wait();
-  const int n_items = args.n_seq * args.n_heads * args.n_qt;
+  const int n_items = args.n_seq * args.n_heads * args.n_pairs;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
-    uint32_t n_q = 0, n_kv = 0;                    // items / tiles issued so far (barrier phases)
+    uint32_t n_kv = 0, n_it = 0;                   // K/V tiles issued so far; items so far
+    uint32_t n_q[kSlots] = {0, 0};                 // items each slot took part in so far
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       Item it;
-      if (!decode_item(args, item, it)) continue;
-      if (n_q > 0) mbar_wait(q_empty, (n_q - 1) & 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, kQBytes);
-        const int row = it.s0 + it.q0, col = it.head * kHD;
+      if (!decode_item(args, item, n_it & 1, it)) continue;
+      ++n_it;
+      const int s_long_dbg = it.nt[1] > it.nt[0] ? 1 : 0;
+      auto load_q = [&](int s) {
+        if (it.nt[s] == 0) return;
+        if (n_q[s] > 0) mbar_wait(&q_empty[s], (n_q[s] - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[s], kQBytes);
+          const int row = it.s0 + it.q0[s], col = it.head * kHD;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int g = 0; g < 2; ++g)
-            tma_load_2d(sQ + h * (kQBytes / 2) + g * (64 * 128), &tmap_qkv, q_full, col + h * 64, row + g * 64);
-      }
-      __syncwarp();
-      ++n_q;
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d(sQ + s * kQBytes + h * (kQBytes / 2) + g * (64 * 128), &tmap_qkv, &q_full[s], col + h * 64, row + g * 64);
+        }
+        __syncwarp();
+        dbg_stamp(0, 128 + n_it, s == s_long_dbg ? 1 : 2);      // Q issued (index 128 + item): kind 1 long chain, 2 short chain
+        ++n_q[s];
+      };
+      // in the order the buffers come free: the Q buffer of the slot with the long chain (it ran the short one last time),
+      // two K/V tiles, the other Q buffer, the remaining tiles
+      const int s_long = it.nt[1] > it.nt[0] ? 1 : 0;
+      load_q(s_long);
       for (int j = 0; j < it.n_tiles; ++j, ++n_kv) {
-        const int st = n_kv & 1;
-        if (n_kv >= kKVStages) mbar_wait(&kv_empty[st], ((n_kv >> 1) - 1) & 1);
+        if (j == 2) load_q(s_long ^ 1);
+        const int st = n_kv % kKVStages;
+        const uint32_t use = n_kv / kKVStages;
+        if (use > 0) mbar_wait(&kv_empty[st], (use - 1) & 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[st], 2 * kKVBytes);
           const int row = it.s0 + j * kKTile;
@@ -184,107 +236,158 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
           }
         }
         __syncwarp();
+        dbg_stamp(0, n_kv, 0);
       }
+      if (it.n_tiles <= 2) load_q(s_long ^ 1);
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == kMmaWarp || warp == kMmaWarp - 1) {
+    // ------------------------------------------------------------------ MMA issuer of one slot (two warps, one per slot)
     constexpr uint32_t idesc_qk = attn_idesc(kQTile, kKTile, 0);
     constexpr uint32_t idesc_pv = attn_idesc(kQTile, kHD, 1);
-    const uint64_t q_desc = umma_desc_k_sw128(smem_u32(sQ));
-    const uint64_t p_desc = umma_desc_k_sw128(smem_u32(sP));
-    uint32_t n_q = 0, n_t = 0;                     // items / tiles so far
+    const int s = warp - (kMmaWarp - 1);           // the slot this warp serves
+    uint32_t n_kv = 0, idle = 0, n_it = 0;         // K/V tiles of finished items; items so far
+    uint32_t n_q = 0, n_ts = 0;                    // the slot's items / tiles so far
+    const uint64_t q_desc = umma_desc_k_sw128(smem_u32(sQ + s * kQBytes));
+    const uint64_t p_desc = umma_desc_k_sw128(smem_u32(sP + s * kPBytes));
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       Item it;
-      if (!decode_item(args, item, it)) continue;
-      mbar_wait(q_full, n_q & 1);
-      tc_fence_after();
-      // S(j) = Q K_j^T into S buffer (tile counter & 1); issued one tile ahead of the PV that consumes P(j)
-      auto issue_qk = [&](uint32_t t) {
-        const int st = t & 1;
-        mbar_wait(&kv_full[st], (t >> 1) & 1);
-        if (t >= 2) mbar_wait(&s_empty[st], ((t >> 1) - 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK + st * kKVBytes));
+      if (!decode_item(args, item, n_it & 1, it)) continue;
+      ++n_it;
+      if (s == 0) dbg_stamp(1, 128 + n_it, 0);                  // the MMA warp starts polling for this item
+      const int n_my = it.nt[s], n_other = it.nt[s ^ 1];
+      int qk_next = 0, pv_next = 0;
+      // QK^T of a tile goes out as soon as its K tile has landed, the slot's Q is there and the softmax warps have drained the
+      // S buffer it writes (two tiles back); PV as soon as its P is published.  The conditions are POLLED, four lanes testing
+      // the four barriers at once (non-blocking test_wait): with a fixed issue order the timeline showed PV(t) waiting ~0.9 us
+      // behind the K/V load of tile t + 1, and with one warp polling both slots lane by lane ~0.5 us between two issues.
+      while (pv_next < n_my) {
+        const uint32_t seq_q = n_kv + qk_next, ts_q = n_ts + qk_next;
+        const int st_q = seq_q % kKVStages, sb_q = ts_q & 1;
+        const uint32_t ts_p = n_ts + pv_next;
+        bool ok = true;
+        if (lane == 0) ok = qk_next > 0 || mbar_test_wait(&q_full[s], n_q & 1);
+        else if (lane == 1) ok = qk_next < n_my && mbar_test_wait(&kv_full[st_q], (seq_q / kKVStages) & 1);
+        else if (lane == 2) ok = ts_q < 2 || mbar_test_wait(&s_empty[s * 2 + sb_q], ((ts_q >> 1) - 1) & 1);
+        else if (lane == 3) ok = pv_next < qk_next && mbar_test_wait(&p_full[s], ts_p & 1);
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        const bool qk_ready = qk_next < n_my && (m & 7u) == 7u;
+        const bool pv_ready = (m & 8u) != 0;
+        if (pv_ready) {                                          // PV first: it is what the softmax warps are waiting for
+          const uint32_t seq = n_kv + pv_next;
+          const int st = seq % kKVStages;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t v_desc = umma_desc_mn_sw128(smem_u32(sV + st * kKVBytes), kKVBytes / 2);
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k) {
-            // 16 dims = 32 B inside the 128-byte swizzle row: + 2 in the (addr >> 4) field; dims 64 .. 127 live in the second half
-            const uint64_t qa = q_desc + ((k >> 2) * ((kQBytes / 2) >> 4)) + 2 * (k & 3);
-            const uint64_t kb = k_desc + ((k >> 2) * ((kKVBytes / 2) >> 4)) + 2 * (k & 3);
-            umma_bf16(tmem_base + st * kKTile, qa, kb, idesc_qk, k > 0 ? 1u : 0u);
+            for (int k = 0; k < kKTile / 16; ++k)     // 16 keys = two 8-row groups = 2048 B of the V tile; 32 B of a P row
+              umma_bf16(tmem_base + s * 256 + 2 * kKTile, p_desc + 2 * k, v_desc + k * (2048 >> 4), idesc_pv, (pv_next > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&kv_empty[st]);
+            // kv_empty counts two arrivals (one per slot): a tile the other slot does not use is released on its behalf by
+            // the same MMAs' completion - never by a plain arrive, which could land in the phase of the stage's previous tile
+            if (pv_next >= n_other) umma_commit(&kv_empty[st]);
+            umma_commit(&o_done[s]);
           }
-          umma_commit(&s_full[st]);
+          __syncwarp();
+          dbg_stamp(1, seq, 2 + s);
+          ++pv_next;
         }
-        __syncwarp();
-      };
-      issue_qk(n_t);
-      for (int j = 0; j < it.n_tiles; ++j) {
-        const uint32_t t = n_t + j;
-        if (j + 1 < it.n_tiles) issue_qk(t + 1);
-        else if (elect_one()) umma_commit(q_empty);            // the item's last QK^T: Q may be overwritten once it completes
-        __syncwarp();
-        mbar_wait(p_full, t & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const int st = t & 1;
-          const uint64_t v_desc = umma_desc_mn_sw128(smem_u32(sV + st * kKVBytes), kKVBytes / 2);
+        if (qk_ready) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK + st_q * kKVBytes));
 #pragma unroll
-          for (int k = 0; k < kKTile / 16; ++k)     // 16 keys = two 8-row groups = 2048 B of the V tile; 32 B of a P row
-            umma_bf16(tmem_base + 2 * kKTile, p_desc + 2 * k, v_desc + k * (2048 >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&kv_empty[st]);
-          umma_commit(o_done);
+            for (int k = 0; k < kHD / 16; ++k) {
+              // 16 dims = 32 B inside the 128-byte swizzle row: + 2 in the (addr >> 4) field; dims 64 .. 127: second half
+              const uint64_t qa = q_desc + ((k >> 2) * ((kQBytes / 2) >> 4)) + 2 * (k & 3);
+              const uint64_t kb = k_desc + ((k >> 2) * ((kKVBytes / 2) >> 4)) + 2 * (k & 3);
+              umma_bf16(tmem_base + s * 256 + sb_q * kKTile, qa, kb, idesc_qk, k > 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[s * 2 + sb_q]);
+            if (qk_next + 1 == n_my) umma_commit(&q_empty[s]);    // the item's last QK^T of the slot: its Q may be overwritten
+          }
+          __syncwarp();
+          dbg_stamp(1, seq_q, s);
+          ++qk_next;
         }
-        __syncwarp();
+        if (pv_ready || qk_ready) {
+          idle = 0;
+        } else {
+          __nanosleep(20);                                        // leave the issue slots of this scheduler to the softmax warps
+          if (++idle > (1u << 24)) mbar_timeout(nullptr, 0xa77);
+        }
       }
-      n_t += it.n_tiles;
-      ++n_q;
+      n_kv += it.n_tiles;
+      n_ts += n_my;
+      if (n_my) ++n_q;
     }
-  } else {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ softmax, correction, epilogue (thread = query row)
+    const int slot = warp >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // row inside the query tile = TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t p_row = smem_u32(sP) + r * 128;
+    const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16) + slot * 256;
+    const uint32_t p_base = smem_u32(sP + slot * kPBytes);
+    const uint32_t p_row = p_base + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    uint32_t n_t = 0;
+    const bool stamp = (warp & 3) == 0;
+    uint64_t* my_s_full = s_full + slot * 2;
+    uint64_t* my_s_empty = s_empty + slot * 2;
+    uint32_t n_t = 0, n_it = 0;                              // the slot's tiles so far; the CTA's items so far
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       Item it;
-      if (!decode_item(args, item, it)) continue;
-      const int q_pos = it.q0 + r;                           // position of this thread's query inside the sequence
-      const int warp_first = it.q0 + quarter * 32;           // first query position of the warp
+      if (!decode_item(args, item, n_it & 1, it)) continue;
+      ++n_it;
+      const int n_my = it.nt[slot];
+      if (n_my == 0) continue;
+      const int q0 = it.q0[slot];
+      const int q_pos = q0 + r;                              // position of this thread's query inside the sequence
+      const int warp_first = q0 + quarter * 32;              // first query position of the warp
+      const int lim_row = min(q_pos, it.L - 1);              // last key this row may see
       float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < it.n_tiles; ++j) {
+      for (int j = 0; j < n_my; ++j) {
         const uint32_t t = n_t + j;
-        const int st = t & 1;
+        const int sb = t & 1;
         const int k0 = j * kKTile;
-        mbar_wait(&s_full[st], (t >> 1) & 1);
+        mbar_wait(&my_s_full[sb], (t >> 1) & 1);
         tc_fence_after();
+        if (stamp) dbg_stamp(2 + slot, t, 0);
         // the warp has nothing to exponentiate when all its rows lie past the sequence or above every key of the tile
         const bool skip = warp_first >= it.L || k0 > warp_first + 31;
         uint32_t pk[32];                                     // the row's 64 probabilities as bf16 pairs
         float corr = 1.f;
         if (!skip) {
-          uint32_t sr[32];
+          uint32_t sr0[32], sr1[32];
           float p[64];
-          tmem_ld_32x32(tmem_base + lane_addr + st * kKTile, sr);
+          tmem_ld_32x32(tmem_base + lane_addr + sb * kKTile, sr0);
+          tmem_ld_32x32(tmem_base + lane_addr + sb * kKTile + 32, sr1);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) p[i] = __uint_as_float(sr[i]);
-          tmem_ld_32x32(tmem_base + lane_addr + st * kKTile + 32, sr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) p[32 + i] = __uint_as_float(sr[i]);
+          for (int i = 0; i < 32; ++i) { p[i] = __uint_as_float(sr0[i]); p[32 + i] = __uint_as_float(sr1[i]); }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[st]);
-          if (k0 + kKTile - 1 > warp_first || k0 + kKTile > it.L) {       // diagonal or tail tile
+          if (lane == 0) mbar_arrive(&my_s_empty[sb]);
+          // keys k0 + i with i > lim are masked for this row (causal, sequence end); groups of 16 keys that are masked for EVERY
+          // row of the warp (i > lim_w, warp-uniform) are left out of the maximum and of the exponentials altogether - on a
+          // diagonal tile that is up to half of the work of a unit (MUFU) that the two slots' warps of a scheduler share
+          const int lim = lim_row - k0;
+          const int lim_w = min(min(warp_first + 31, it.L - 1) - k0, kKTile - 1);
+          if (lim_w < kKTile - 1 || k0 + kKTile - 1 > warp_first) {
 #pragma unroll
             for (int i = 0; i < 64; ++i)
-              if (k0 + i > q_pos || k0 + i >= it.L) p[i] = -INFINITY;
+              if (i > lim) p[i] = -INFINITY;
           }
-          float mx = p[0];
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (few warps per scheduler: latency is exposed)
 #pragma unroll
-          for (int i = 1; i < 64; ++i) mx = fmaxf(mx, p[i]);
+          for (int g = 0; g < 4; ++g) {
+            if (16 * g <= lim_w) {
+#pragma unroll
+              for (int i = 16 * g; i < 16 * g + 16; i += 4) {
+                mx4[0] = fmaxf(mx4[0], p[i]); mx4[1] = fmaxf(mx4[1], p[i + 1]);
+                mx4[2] = fmaxf(mx4[2], p[i + 2]); mx4[3] = fmaxf(mx4[3], p[i + 3]);
+              }
+            }
+          }
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
           const float m_tile = mx * args.scale_log2;          // -inf when the row has no key in this tile (rows past the end)
           float m_use = m_run;
           if (m_tile > m_run + 8.f || m_run == -INFINITY) {   // lazy rescale: keep the old maximum while P stays <= 2^8
@@ -292,28 +395,38 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
             corr = (m_run == -INFINITY) ? 1.f : ex2f(m_run - m_use);   // first tile: O is overwritten, nothing to rescale
           }
           const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
-          float rs = 0.f;
+          float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            const float a = ex2f(fmaf(p[i], args.scale_log2, -m_sub));
-            const float b = ex2f(fmaf(p[i + 1], args.scale_log2, -m_sub));
-            rs += a + b;
-            pk[i >> 1] = pack_bf16x2(a, b);
+          for (int g = 0; g < 4; ++g) {
+            if (16 * g <= lim_w) {
+#pragma unroll
+              for (int i = 16 * g; i < 16 * g + 16; i += 2) {
+                const float a = ex2f(fmaf(p[i], args.scale_log2, -m_sub));
+                const float b = ex2f(fmaf(p[i + 1], args.scale_log2, -m_sub));
+                rs4[(i >> 1) & 3] += a + b;
+                pk[i >> 1] = pack_bf16x2(a, b);
+              }
+            } else {
+#pragma unroll
+              for (int i = 8 * g; i < 8 * g + 8; ++i) pk[i] = 0u;
+            }
           }
-          l_run = l_run * corr + rs;
+          l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
           m_run = m_use;
         } else {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[st]);
+          if (lane == 0) mbar_arrive(&my_s_empty[sb]);
 #pragma unroll
           for (int i = 0; i < 32; ++i) pk[i] = 0u;
         }
+        if (stamp) dbg_stamp(2 + slot, t, 1);
         // PV of the previous tile must be complete before its P is overwritten and before O is rescaled
         if (j > 0) {
-          mbar_wait(o_done, (t - 1) & 1);
+          mbar_wait(&o_done[slot], (t - 1) & 1);
           tc_fence_after();
         }
+        if (stamp) dbg_stamp(2 + slot, t, 2);
         if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
 #pragma unroll 1
           for (int c = 0; c < kHD / 32; ++c) {
@@ -334,41 +447,60 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
         fence_proxy_async();                                  // generic-proxy writes of P -> visible to the tensor core's reads
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[slot]);
+        if (stamp) dbg_stamp(2 + slot, t, 3);
       }
       // ---- epilogue: O row / l -> bf16 -> out
-      const uint32_t t_last = n_t + it.n_tiles - 1;
-      mbar_wait(o_done, t_last & 1);
+      const uint32_t t_last = n_t + n_my - 1;
+      mbar_wait(&o_done[slot], t_last & 1);
       tc_fence_after();
+      // Each thread owns one 256-byte output row: stored directly, a warp-level 16-byte store touches 32 different lines.
+      // Instead the warp's 32 rows go through ITS OWN 4 KB of the slot's P buffer (free: the last PV has completed), 64 dims
+      // at a time, and leave as 4 rows x 128 B per warp-level store.
       const bool live = q_pos < it.L;
       const float inv = live ? 1.f / l_run : 0.f;
-      __nv_bfloat16* dst = args.out + (static_cast<long long>(it.s0) + q_pos) * H + it.head * kHD;
+      const int rows_valid = min(32, it.L - warp_first);                  // rows of this warp inside the sequence (<= 0: none)
+      __nv_bfloat16* dst_warp = args.out + (static_cast<long long>(it.s0) + warp_first) * H + it.head * kHD;
+      const uint32_t p_warp = p_base + quarter * 32 * 128;
+      if (rows_valid > 0) {
 #pragma unroll 1
-      for (int c = 0; c < kHD / 32; ++c) {
-        uint32_t orow[32];
-        tmem_ld_32x32(tmem_base + lane_addr + 2 * kKTile + c * 32, orow);
-        tmem_ld_wait();
-        if (live) {
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o0[32], o1[32];
+          tmem_ld_32x32(tmem_base + lane_addr + 2 * kKTile + half * 64, o0);
+          tmem_ld_32x32(tmem_base + lane_addr + 2 * kKTile + half * 64 + 32, o1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(orow[8 * q]) * inv, __uint_as_float(orow[8 * q + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(orow[8 * q + 2]) * inv, __uint_as_float(orow[8 * q + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(orow[8 * q + 4]) * inv, __uint_as_float(orow[8 * q + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(orow[8 * q + 6]) * inv, __uint_as_float(orow[8 * q + 7]) * inv);
-            reinterpret_cast<uint4*>(dst + c * 32)[q] = o;
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t* src = c < 4 ? o0 + 8 * c : o1 + 8 * (c - 4);
+            const uint32_t w0 = pack_bf16x2(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+            const uint32_t w1 = pack_bf16x2(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+            const uint32_t w2 = pack_bf16x2(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+            const uint32_t w3 = pack_bf16x2(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((static_cast<uint32_t>(c) ^ sw) << 4)), "r"(w0), "r"(w1),
+                         "r"(w2), "r"(w3)
+                         : "memory");
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), cc = lane & 7;             // row inside the warp's block, 16-byte chunk of the half row
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(p_warp + rr * 128 + ((static_cast<uint32_t>(cc) ^ static_cast<uint32_t>(rr & 7)) << 4)));
+            if (rr < rows_valid) *reinterpret_cast<uint4*>(dst_warp + static_cast<long long>(rr) * H + half * 64 + cc * 8) = v;
+          }
+          __syncwarp();
         }
       }
-      // the next item's first PV overwrites O: all four warps must be done reading it.  Their next p_full arrival is what lets
-      // that PV start, and it comes after these loads (tcgen05.wait::ld above + the fence before the arrive).
-      n_t += it.n_tiles;
+      // The next item's first PV of this slot overwrites O: all four warps must be done reading it.  Their next p_full arrival
+      // is what lets that PV start, and it comes after these loads (tcgen05.wait::ld above + the fence before the arrive).
+      n_t += n_my;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -394,12 +526,17 @@ bool launch_attn_prefill_tc(const void* qkv, void* out, const int32_t* cu_seqlen
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.n_seq = n_seq;
   a.n_heads = n_heads;
-  a.n_qt = (max_seqlen + kQTile - 1) / kQTile;
+  a.n_pairs = (max_seqlen + kSlots * kQTile - 1) / (kSlots * kQTile);
   a.only_last = only_last;
   a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHD));
-  const long long items = static_cast<long long>(n_seq) * n_heads * a.n_qt;
-  const int grid = static_cast<int>(items < 2LL * num_sms ? items : 2LL * num_sms);
+  const long long items = static_cast<long long>(n_seq) * n_heads * a.n_pairs;
+  const int grid = static_cast<int>(items < num_sms ? items : num_sms);
   return launch_k(attn_prefill_tc_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, st, tm, a) == cudaSuccess;
 }
 
 }  // namespace rvl
+
+extern "C" void rvl_debug_attn_timestamps(int enable, unsigned long long* out, int n) {
+  if (out && n > 0) cudaMemcpyFromSymbol(out, rvl::g_attn_dbg, sizeof(unsigned long long) * n);
+  cudaMemcpyToSymbol(rvl::g_attn_dbg_on, &enable, sizeof(int));
+}

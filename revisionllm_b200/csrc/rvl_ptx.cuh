@@ -52,6 +52,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test (try_wait may suspend the thread for a system-dependent time when the phase is not complete yet: fine
+// for a wait, wrong for a thread that polls several barriers and must react to whichever completes first)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug turns into a trap (reported as a CUDA error) instead of a hang
 // that would wedge the GPU.  try_wait itself suspends for a HW time slice, so the bound is seconds.
 static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
