@@ -227,6 +227,17 @@ RVL_API int rvl_merge_rank(rvl_handle* h, const float* cos, const float* ent, co
                    const int32_t* cover1, const int32_t* cover_all, int32_t n, int32_t mode, int32_t normalize,
                    int32_t minmax, double* scores_out, int32_t* order_out, int32_t* n_out, rvl_stream stream);
 
+/* `n_steps` tokens of the greedy generation loop in one call (vtimellm_llama.py:287-369 for n_steps iterations): for
+ * s = 0 .. n_steps - 1: token_ring[s] / entropy_ring[s] = greedy sample (+ entropy, EOS / pad bookkeeping as in
+ * rvl_sample_greedy) of `logits`, then one rvl_decode_step on that token writes the next logits back to `logits`.
+ * Every pointer is fixed for the whole call, so the call can be captured as ONE CUDA graph and replayed (what
+ * engine.decode_chunk does); nothing synchronises.
+ *   logits        [n_seq, vocab] fp32, in/out        token_ring   [n_steps, n_seq] int32 out
+ *   entropy_ring  [n_steps, n_seq] fp32 out or NULL   unfinished   [n_seq] int32 in/out or NULL */
+RVL_API int rvl_decode_n(rvl_handle* h, int32_t n_steps, float* logits, int32_t* token_ring, float* entropy_ring,
+                 int32_t* unfinished, int32_t eos_id, int32_t pad_id, int32_t* seq_lens, int32_t n_seq,
+                 const int32_t* page_table, int32_t max_pages, int32_t max_kv_len, rvl_stream stream);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 #define RVL_PROF_GEMM 0          /* tcgen05 GEMM, token-major (prefill) */
 #define RVL_PROF_GEMM_SMALL_M 1  /* tcgen05 GEMM, weight-streaming orientation (decode / last rows) */

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "rvl_splice_rows": (C.c_int, [_P, _P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
     "rvl_prefill": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P]),
     "rvl_decode_step": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P]),
+    "rvl_decode_n": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _I32, _P, _I32, _I32, _P]),
     "rvl_sample_greedy": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),
     "rvl_sample_multinomial": (C.c_int, [_P, _P, _I32, _I32, _F, C.c_uint64, C.c_uint32, _P, _I32, _I32, _P, _P, _P, _P]),
     "rvl_cosine_topk": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P]),

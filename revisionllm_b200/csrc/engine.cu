@@ -439,6 +439,22 @@ int rvl_sample_greedy(rvl_handle* h, const float* logits, int32_t n_seq, int32_t
   return check_cuda(h, "rvl_sample_greedy");
 }
 
+int rvl_decode_n(rvl_handle* h, int32_t n_steps, float* logits, int32_t* token_ring, float* entropy_ring, int32_t* unfinished,
+                 int32_t eos_id, int32_t pad_id, int32_t* seq_lens, int32_t n_seq, const int32_t* page_table, int32_t max_pages,
+                 int32_t max_kv_len, rvl_stream stream) {
+  int rc = ready(h, "rvl_decode_n");
+  if (rc) return rc;
+  if (!logits || !token_ring || !seq_lens || !page_table || n_steps <= 0) return fail(h, RVL_ERR_INVALID, "rvl_decode_n: bad argument");
+  for (int s = 0; s < n_steps; ++s) {
+    int32_t* tok = token_ring + static_cast<size_t>(s) * n_seq;
+    launch_sample_greedy(logits, n_seq, h->cfg.vocab, unfinished, eos_id, pad_id, tok,
+                         entropy_ring ? entropy_ring + static_cast<size_t>(s) * n_seq : nullptr, nullptr, nullptr,
+                         static_cast<cudaStream_t>(stream));
+    if ((rc = rvl_decode_step(h, tok, seq_lens, n_seq, page_table, max_pages, max_kv_len, logits, stream))) return rc;
+  }
+  return RVL_OK;
+}
+
 int rvl_gather_windows(rvl_handle* h, const float* features, int32_t n_frames, int32_t dim, const int32_t* frame_idx, int32_t n_rows,
                        void* out, rvl_stream stream) {
   if (!h || !features || !frame_idx || !out) return fail(h, RVL_ERR_INVALID, "rvl_gather_windows: null argument");

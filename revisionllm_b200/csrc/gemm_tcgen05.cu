@@ -1310,9 +1310,12 @@ int gemm_bf16(const GemmCall& c, int num_sms, cudaStream_t st, std::string* err)
     a.tiles_n = (a.N + 255) / 256;
     {
       // m-tiles per n-sweep (L2 reuse of the A slab against the weight streaming through).  Measured interleaved on B200 at
-      // 33120 tokens (tools/prefill_gemm_ab.py): 32 is 3-4 % faster than 16 for qkv / gate|up / down, 16 is best for the
-      // small o projection; the differences come from DRAM traffic (power), not from the tensor pipe.
-      long long gm = (c.N * c.K >= (32ll << 20)) ? 32 : 16;
+      // 33120 tokens (tools/prefill_gemm_ab.py, groups 4 / 6 / 8 / 12 / 16 / 32, round 2): qkv 2.56 / 2.56 / 2.60 / 2.65 / 2.63 /
+      // 2.54 ms, gate|up 4.54 / 4.56 / 4.52 / 4.51 / 4.45 / 4.36, o 0.974 / 0.973 / 0.973 / 0.985 / 0.991 / 0.991, down 2.49 / 2.56 /
+      // 2.60 / 2.64 / 2.69 / 2.54 - everything within 3 %: 32 for the wide outputs, 8 for the small o projection, 4 for the
+      // long-K down projection (a 256-row A tile is 5.6 MB there).  The differences come from DRAM traffic (power), not from
+      // the tensor pipe, which is 97 - 99.7 % active either way.
+      long long gm = (c.N * c.K < (32ll << 20)) ? 8 : (c.K > 2 * c.N ? 4 : 32);
       if (tn.group_m > 0) gm = tn.group_m;
       a.group_m = static_cast<int>(gm < 2 ? 2 : (gm > 64 ? 64 : gm));
     }

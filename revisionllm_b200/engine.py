@@ -102,9 +102,8 @@ class DecodeChunks:
         unf = bufs["unfinished"] if use_unfinished else None
 
         def body():
-            for s in range(k):
-                self.sample_greedy(bufs["logits"], bufs["ring_tok"][s], bufs["ring_ent"][s], unf, eos_id, pad_id)
-                self.decode_step(bufs["ring_tok"][s], bufs["seq_lens"], bufs["page_table"], bufs["logits"], max_kv_len=max_kv_len)
+            self.decode_n(k, bufs["logits"], bufs["ring_tok"], bufs["ring_ent"], unf, eos_id, pad_id, bufs["seq_lens"], bufs["page_table"],
+                          max_kv_len)
 
         key = (n_rows, max_pages, k, eos_id, pad_id, use_unfinished, max_kv_len, self._ws.data_ptr() if self._ws is not None else 0,
                self._kv.data_ptr() if self._kv is not None else 0)
@@ -286,6 +285,20 @@ class Engine(DecodeChunks):
         self._check(self.lib.rvl_decode_step(self.h, token_ids.data_ptr(), seq_lens.data_ptr(), n, page_table.data_ptr(),
                                              page_table.shape[1], max_kv_len, logits_out.data_ptr(), _stream()), "rvl_decode_step")
         self.launches += 1 + (7 if self.wgu_interleaved else 8) * self.cfg.n_layers + 3
+
+    def decode_n(self, n_steps, logits, token_ring, entropy_ring, unfinished, eos_id, pad_id, seq_lens, page_table, max_kv_len: int = 0):
+        """`n_steps` x (greedy sample of `logits` -> token_ring[s] / entropy_ring[s]; decode step on that token -> `logits`) in one
+        C call (rvl_decode_n)."""
+        _req(logits, torch.float32, "logits"); _req(token_ring, torch.int32, "token_ring"); _req(seq_lens, torch.int32, "seq_lens")
+        _req(page_table, torch.int32, "page_table")
+        n = logits.shape[0]
+        if token_ring.shape[0] < n_steps or token_ring.shape[1] != n:
+            raise RvlError("decode_n: token_ring must be [>= n_steps, n_seq]")
+        self.ensure_workspace(n, n)
+        self._check(self.lib.rvl_decode_n(self.h, n_steps, logits.data_ptr(), token_ring.data_ptr(), _ptr(entropy_ring), _ptr(unfinished),
+                                          eos_id, pad_id, seq_lens.data_ptr(), n, page_table.data_ptr(), page_table.shape[1], max_kv_len,
+                                          _stream()), "rvl_decode_n")
+        self.launches += n_steps * (2 + (7 if self.wgu_interleaved else 8) * self.cfg.n_layers + 3)
 
     def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
         _req(logits, torch.float32, "logits"); _req(next_tokens, torch.int32, "next_tokens")

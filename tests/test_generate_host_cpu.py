@@ -146,6 +146,11 @@ class CpuEngine(DecodeChunks):
             unfinished.copy_(unf.to(unfinished.dtype))
         next_tokens.copy_(nxt.to(next_tokens.dtype))
 
+    def decode_n(self, n_steps, logits, token_ring, entropy_ring, unfinished, eos_id, pad_id, seq_lens, page_table, max_kv_len=0):
+        for s in range(n_steps):                         # rvl_decode_n: the loop the C entry point runs
+            self.sample_greedy(logits, token_ring[s], None if entropy_ring is None else entropy_ring[s], unfinished, eos_id, pad_id)
+            self.decode_step(token_ring[s], seq_lens, page_table, logits, max_kv_len=max_kv_len)
+
     def sample_greedy(self, logits, next_tokens, entropy=None, unfinished=None, eos_id=2, pad_id=2):
         nxt = torch.argmax(logits, dim=-1)
         if entropy is not None:
