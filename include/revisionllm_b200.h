@@ -319,7 +319,53 @@ RVL_API int rvl_attn_decode(rvl_handle* h, const void* qkv, void* out, const int
                     const int32_t* page_table, int32_t max_pages, int32_t layer, int32_t fused_rope,
                     int32_t max_kv_len /* as in rvl_decode_step */, rvl_stream stream);
 
-/* ---- stage-2 adapter (ClipEncoder) kernels; the host composes them with rvl_gemm_bf16 ------------ */
+/* ---- stage-2 adapter (ClipEncoder) ------------------------------------------------------------- */
+
+/* One encoder layer of the adapter (nn.MultiheadAttention + FFN + two LayerNorms; transformer.py:188-305), all bf16. */
+typedef struct rvl_clip_layer {
+  const void* in_proj_w;   /* [3*768, 768]: q | k | v */
+  const void* in_proj_b;   /* [3*768] */
+  const void* out_proj_w;  /* [768, 768] */
+  const void* out_proj_b;
+  const void* linear1_w;   /* [2048, 768] */
+  const void* linear1_b;
+  const void* linear2_w;   /* [768, 2048] */
+  const void* linear2_b;
+  const void* norm1_w;
+  const void* norm1_b;
+  const void* norm2_w;
+  const void* norm2_b;
+} rvl_clip_layer;
+
+typedef struct rvl_clip_weights {
+  rvl_clip_layer t2v[2];        /* text -> video cross-attention layers (t2v_encoder.layers.{0,1}) */
+  rvl_clip_layer enc[2];        /* self-attention layers over [global token ; frames] (encoder.layers.{0,1}) */
+  const void* global_token;     /* bf16 [768]  (global_rep_token) */
+  const float* pos;             /* fp32 [T, 768]: PositionEmbeddingSine(normalize=True) of T frames (transformer.py:35-57) */
+  const float* pos_global;      /* fp32 [T + 1, 768]: global_rep_pos followed by `pos` */
+  const void* proj_w;           /* bf16 [hidden, 768]  (mm_projector.weight of the adapter) */
+  const void* proj_b;           /* bf16 [hidden] */
+  int32_t hidden;
+} rvl_clip_weights;
+
+/* Bytes of scratch rvl_clip_encoder needs for V segments of T frames and Q texts of Lq tokens. */
+RVL_API size_t rvl_clip_encoder_workspace_bytes(int32_t n_seg, int32_t n_frames, int32_t n_text, int32_t text_len);
+
+/* The whole stage-2 adapter in one call.  Replaces ClipEncoder.forward (transformer.py:94-145: two text->video
+ * cross-attention layers :271-305, prepend the global token, two post-norm self-attention layers :210-223 over 1 + T tokens,
+ * CLS row -> Linear(768 -> hidden)) as reached from the hierarchy branch of vtimellm_arch.py:114-121.
+ *   frames        [n_seg, n_frames, 768] bf16      text       [n_text, text_len, 768] bf16
+ *   text_mask     [n_text, text_len] fp32, 1 = valid
+ *   seg_text_idx  [n_seg] int32 or NULL (n_text == n_seg, one to one): the text each segment attends to - the reference
+ *                 repeats the query once per segment (vtimellm_arch.py:116-119), here the keys / values of a text are
+ *                 projected once
+ *   ws            scratch of at least rvl_clip_encoder_workspace_bytes(...) bytes, 256-byte aligned
+ *   out           [n_seg, hidden] bf16: one projected CLS row per segment */
+RVL_API int rvl_clip_encoder(rvl_handle* h, const rvl_clip_weights* w, const void* frames, const void* text,
+                     const float* text_mask, const int32_t* seg_text_idx, int32_t n_seg, int32_t n_frames,
+                     int32_t n_text, int32_t text_len, void* ws, size_t ws_bytes, void* out, rvl_stream stream);
+
+/* the kernels the adapter is made of (unit parity tests) */
 
 /* LayerNorm over the last dim (<= 1024, biased variance, like nn.LayerNorm; transformer.py:199-200):
  * y = (x - mean) * rsqrt(var + eps) * w + b, or y = x when w == b == NULL.  Any of the outputs may be

@@ -31,6 +31,16 @@ class rvl_layer_weights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wo", "wgu", "wdown", "ln1", "ln2")]
 
 
+class rvl_clip_layer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "linear1_w", "linear1_b", "linear2_w",
+                                          "linear2_b", "norm1_w", "norm1_b", "norm2_w", "norm2_b")]
+
+
+class rvl_clip_weights(C.Structure):
+    _fields_ = [("t2v", rvl_clip_layer * 2), ("enc", rvl_clip_layer * 2), ("global_token", C.c_void_p), ("pos", C.c_void_p),
+                ("pos_global", C.c_void_p), ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("hidden", C.c_int32)]
+
+
 class rvl_weights(C.Structure):
     _fields_ = [("embed_tokens", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p),
                 ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("layers", C.POINTER(rvl_layer_weights)),
@@ -73,6 +83,8 @@ PROTOTYPES = {
     "rvl_swiglu": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "rvl_attn_prefill": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _P]),
     "rvl_attn_decode": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P]),
+    "rvl_clip_encoder_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
+    "rvl_clip_encoder": (C.c_int, [_P, C.POINTER(rvl_clip_weights), _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _SZ, _P, _P]),
     "rvl_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P]),
     "rvl_mha96": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
 }

@@ -51,11 +51,46 @@ class ClipEncoder:
             self._pos_cache[T] = (pos.contiguous(), torch.cat([gpos, pos], dim=0).contiguous())
         return self._pos_cache[T]
 
+    def _c_weights(self, T: int):
+        """The adapter's parameters as the `rvl_clip_weights` table of the C entry point (pointers into self.p)."""
+        from . import _cabi
+        pos, pos_g = self._pos(T)
+        w = _cabi.rvl_clip_weights()
+
+        def layer(pre):
+            names = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+                     "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")
+            return _cabi.rvl_clip_layer(*[self.p[pre + n].data_ptr() for n in names])
+        for i in range(NL):
+            w.t2v[i] = layer(f"t2v_encoder.layers.{i}.")
+            w.enc[i] = layer(f"encoder.layers.{i}.")
+        w.global_token = self.p["global_rep_token"].data_ptr()
+        w.pos, w.pos_global = pos.data_ptr(), pos_g.data_ptr()
+        w.proj_w, w.proj_b = self.p["mm_projector.weight"].data_ptr(), self.p["mm_projector.bias"].data_ptr()
+        w.hidden = self.hidden
+        return w
+
     def __call__(self, frames: torch.Tensor, text: torch.Tensor, text_mask: torch.Tensor,
                  seg_text_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         """frames [V, T, 768] bf16; text [Q, Lq, 768] bf16; text_mask [Q, Lq] (1 = valid);
         seg_text_idx int32 [V]: which text each segment attends to (None: Q == V, one to one).
-        Returns the projected CLS rows [V, hidden] bf16."""
+        Returns the projected CLS rows [V, hidden] bf16.  One call into the C ABI (rvl_clip_encoder); `composed()` is the same
+        sequence of kernels driven from here, kept for the unit test that compares the two bit for bit."""
+        if not hasattr(self.eng, "clip_encoder"):
+            return self.composed(frames, text, text_mask, seg_text_idx)       # engines without the one-call entry (test stand-ins)
+        dev = self.eng.device
+        V, T, d = frames.shape
+        Q, Lq, _ = text.shape
+        assert d == D
+        if seg_text_idx is None and Q != V:
+            raise ValueError("seg_text_idx is required when the number of texts differs from the number of segments")
+        out = torch.empty((V, self.hidden), dtype=torch.bfloat16, device=dev)
+        return self.eng.clip_encoder(self._c_weights(T), frames.to(dev, torch.bfloat16).contiguous(), text.to(dev, torch.bfloat16).contiguous(),
+                                     text_mask.to(dev, torch.float32).contiguous(),
+                                     None if seg_text_idx is None else seg_text_idx.to(dev, torch.int32).contiguous(), out)
+
+    def composed(self, frames: torch.Tensor, text: torch.Tensor, text_mask: torch.Tensor,
+                 seg_text_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         eng, p = self.eng, self.p
         dev = eng.device
         V, T, d = frames.shape

@@ -151,6 +151,7 @@ class Engine(DecodeChunks):
         self.n_pages = 0
         self.launches = 0                         # kernels enqueued through this engine (bench's gpu_launches)
         self._init_chunks()
+        self._clip_ws: Optional[torch.Tensor] = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -420,6 +421,21 @@ class Engine(DecodeChunks):
                                              page_table.data_ptr(), page_table.shape[1], layer, 1 if fused_rope else 0, max_kv_len, _stream()),
                     "rvl_attn_decode")
         self.launches += 1
+        return out
+
+    def clip_encoder(self, weights, frames, text, text_mask, seg_text_idx, out):
+        """rvl_clip_encoder: the whole stage-2 adapter in one C call.  `weights`: a filled _cabi.rvl_clip_weights."""
+        _req(frames, torch.bfloat16, "frames"); _req(text, torch.bfloat16, "text"); _req(text_mask, torch.float32, "text_mask")
+        V, T, _ = frames.shape
+        Q, Lq, _ = text.shape
+        nbytes = self.lib.rvl_clip_encoder_workspace_bytes(V, T, Q, Lq)
+        if self._clip_ws is None or self._clip_ws.numel() < nbytes:
+            self._clip_ws = None
+            self._clip_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.rvl_clip_encoder(self.h, C.byref(weights), frames.data_ptr(), text.data_ptr(), text_mask.data_ptr(),
+                                              _ptr(seg_text_idx), V, T, Q, Lq, self._clip_ws.data_ptr(), self._clip_ws.numel(),
+                                              out.data_ptr(), _stream()), "rvl_clip_encoder")
+        self.launches += 3 + 2 * 8 + 1 + 2 * 8 + 2 + 1
         return out
 
     def layernorm(self, x, w=None, b=None, y_f32=None, y_bf16=None, pos=None, y_pos_bf16=None, period=0, eps=1e-5):

@@ -14,7 +14,7 @@ g = torch.Generator().manual_seed(8)
 q_tok = torch.randn(1, 32, cfg.adapter_dim, generator=g).to(torch.bfloat16)
 q_mask = torch.ones(1, 32)
 ids = syn.make_prompt_ids(cfg, seed=9)
-for i in range(3):
+for i in range(6):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     sweep.stage2_pass(model, wins, (q_tok, q_mask), ids, grounding_windows=list(range(100)), batch=100, zooms=(4, 2, 1), max_new_tokens=16,
