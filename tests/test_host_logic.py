@@ -526,7 +526,7 @@ def test_every_entry_point_rejects_a_null_handle_without_a_gpu():
     rvl_status and leaves a message in rvl_last_error - no crash, no CUDA call, so this runs on the CPU-only box."""
     lib = _cabi.load()
     skipped = {"rvl_abi_version", "rvl_last_error", "rvl_destroy", "rvl_create", "rvl_workspace_bytes", "rvl_kv_bytes",
-               "rvl_debug_gemm_timestamps", "rvl_reload_env", "rvl_debug_sm_clock", "rvl_debug_attn_timestamps"}
+               "rvl_debug_gemm_timestamps", "rvl_reload_env", "rvl_debug_sm_clock", "rvl_debug_attn_timestamps", "rvl_clip_encoder_workspace_bytes"}
     checked = 0
     for name, (restype, argtypes) in _cabi.PROTOTYPES.items():
         if name in skipped:
