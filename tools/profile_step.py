@@ -14,10 +14,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--segments", type=int, default=180)
 ap.add_argument("--new-tokens", type=int, default=16)
 args = ap.parse_args()
-cfg = syn.VICUNA_7B
+cfg = syn.VICUNA_7B_VIS
 sd = syn.make_llama_weights(cfg, seed=0, device="cuda")
 model = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg), sd).bfloat16().cuda()
-feats = syn.make_features(args.segments, 100, 768, seed=1).cuda()
+feats = syn.make_features(args.segments, 100, 768, seed=1, class_cfg=cfg).cuda()
 ids = syn.make_prompt_ids(cfg, seed=2)
 cls = torch.randn(768, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
 sweep.score_segments(model, feats, ids, cls, args.new_tokens, eos_token_id=None)
