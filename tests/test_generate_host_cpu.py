@@ -368,6 +368,29 @@ def test_stage2_pass_schedules_agree_on_the_cpu_model(monkeypatch):
         assert key(fast) == key(slow), n_windows
         assert n_fast == 1 and n_slow == len(slow)                              # one batched generate() against one per chunk
         assert all(r["window"] in kw["grounding_windows"] for r in fast)
+    # with EOS on: a chunk's entropy statistics stop at its own EOS whatever else shares the batch (the reference's one
+    # generate() per chunk, eval_nlq_retrieval_e2e2.py:353-359).  Three queries with different prompts answer differently; the
+    # EOS id is the second token of the first query's answer, which the other two never emit.
+    qs = []
+    for k in range(3):
+        n_windows = 5 + k
+        qs.append(dict(windows=syn.make_features(n_windows, 5, 768, seed=60 + k), query_feats=q, input_ids=syn.make_prompt_ids(cfg, 6, 9, seed=20 + k),
+                       grounding_windows=list(range(10, 10 + n_windows)), perm_seed=1))
+    args = (4, (2, 1), 5, lambda t: int(t[0]) % 4)
+    free = sweep.stage2_pass_queries(m, qs, *args, None)
+    eos = int(free[0][0]["tokens"][1])
+    assert all(eos not in r["tokens"] for res in free[1:] for r in res), "pick other prompt seeds"
+    fast = sweep.stage2_pass_queries(m, qs, *args, eos)
+    slow = sweep.stage2_pass_queries(m, qs, *args, eos, 1, dedup=False)
+    assert all(r["tokens"][1] == eos for r in slow[0]) and all(eos not in r["tokens"] for res in slow[1:] for r in res)
+    for qa, qb, qf in zip(fast, slow, free):
+        for a, b, f in zip(qa, qb, qf):
+            # (fp32 CPU matmuls are not batch-invariant to the last bit; a statistic over the wrong steps differs in the first digits)
+            assert (a["inv_max_entropy"], a["inv_mean_entropy"]) == pytest.approx((b["inv_max_entropy"], b["inv_mean_entropy"]), rel=1e-4), (a, b)
+            cut = b["tokens"].index(eos) + 1 if eos in b["tokens"] else len(b["tokens"])
+            assert a["tokens"][:cut] == b["tokens"][:cut] and a["window"] == b["window"]
+    # and the statistics of the stopped chunks are NOT those of the full five steps
+    assert all(a["inv_mean_entropy"] != pytest.approx(f["inv_mean_entropy"], rel=1e-3) for a, f in zip(fast[0], free[0]))
 
 
 def test_shared_prefix_compute_changes_nothing_but_the_rows_computed(cpu_model):
