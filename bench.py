@@ -302,11 +302,18 @@ def main():
     attn_d = eng.profile_read(3)
     # decode step t reads K and V of (seq_len + t + 1) tokens per sequence, all layers
     attn_d_bytes = sum(n_local * KV_BYTES_PER_TOKEN * (seq_len + t + 1) for t in range(NEW_TOKENS - 1))
+    # which measured peak: the GEMMs of a 1-hour sweep run back to back for hundreds of ms at the power-capped clock (the
+    # sustained cuBLAS figure); a rank's share at N >= 4 is a < 100 ms burst between decode phases at nearly the full clock
+    # (the burst figure).  Both are MEASURED_PEAKS.json numbers; the choice is by the time the GEMMs take in the step.
+    sustained = gemm["ms"] >= 120.0
+    tf_peak = pk["tf_sust"] if sustained else pk["tf_burst"]
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_pair_kernel (token-major tcgen05 GEMMs of the prefill: qkv, o, gate|up + SwiGLU, down, projector)",
         "achieved": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else None,
-        "peak": pk["tf_sust"], "unit": "TFLOP/s", "peak_source": pk["src"] + ", sustained bf16",
-        "frac": (gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / pk["tf_sust"]) if gemm["ms"] > 0 else None,
+        "peak": tf_peak, "unit": "TFLOP/s",
+        "peak_source": pk["src"] + (", sustained bf16 (GEMMs run >= 120 ms back to back in the step)" if sustained else
+                                    ", burst bf16 (the GEMMs of this rank's share last < 120 ms)"),
+        "frac": (gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / tf_peak) if gemm["ms"] > 0 else None,
         "traffic": None, "launches": gemm["launches"], "ms_in_step": gemm["ms"],
         "decode_gemm": {"bound": "hbm", "achieved": gemm_small["bytes"] / (gemm_small["ms"] * 1e-3) / 1e9 if gemm_small["ms"] > 0 else None,
                         "peak": pk["hbm"], "unit": "GB/s", "ms_in_step": gemm_small["ms"], "launches": gemm_small["launches"],
@@ -328,7 +335,7 @@ def main():
     tf_prefill = (n_local * seq_len * FLOP_PER_TOKEN - skipped) / (phase_ms["prefill"] * 1e-3) / 1e12
     roofline["phases"] = {
         "splice_ms": phase_ms["splice"], "prefill_ms": phase_ms["prefill"], "decode_ms": phase_ms["decode"],
-        "prefill": {"bound": "tensor", "achieved": tf_prefill, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf_prefill / pk["tf_sust"],
+        "prefill": {"bound": "tensor", "achieved": tf_prefill, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_prefill / tf_peak,
                     "note": "all of prefill (GEMMs + attention + RMSNorm + RoPE/KV write + lm_head on last rows) against the executed GEMM FLOPs only"},
         "decode": {"bound": "hbm", "ms_per_step": phase_ms["decode"] / dec_steps, "achieved": dec_bytes / (phase_ms["decode"] * 1e-3) / 1e9,
                    "peak": pk["hbm"], "unit": "GB/s", "frac": dec_bytes / (phase_ms["decode"] * 1e-3) / 1e9 / pk["hbm"],

@@ -1,4 +1,4 @@
-"""Batch-of-1 vs batch-of-6 logits at the 7B shape (run with RVL_FUSED_DECODE=0/1)."""
+"""Batch-of-1 vs batch-of-6 logits at the 7B shape."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,5 +16,5 @@ rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
 s6, t6 = run(feats)
 s1, t1 = run(feats[2:3])
 s6b, _ = run(feats)
-print(os.environ.get("RVL_FUSED_DECODE"), "B=1 vs B=6 per step:", [round(rel(s1[t, 0], s6[t, 2]), 5) for t in range(steps)], "tokens equal", t1[0].tolist() == t6[2].tolist(),
+print("B=1 vs B=6 per step:", [round(rel(s1[t, 0], s6[t, 2]), 5) for t in range(steps)], "tokens equal", t1[0].tolist() == t6[2].tolist(),
       "| run-to-run B=6:", rel(s6b, s6))
