@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RVL_ABI_VERSION 3
+#define RVL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define RVL_API __attribute__((visibility("default")))
@@ -150,6 +150,7 @@ RVL_API int rvl_splice_rows(rvl_handle* h, const void* vis, const int32_t* vis_d
  *                [0, seq_pos0[i]) are the rows [seq_ctx_row[i], +seq_pos0[i]) of the same packed stream - a prompt prefix
  *                shared by the batch that is embedded, projected and written to (shared) KV pages ONCE, as its own
  *                sequence, and attended to by every sequence that names it (max_seqlen counts positions, context included).
+ *                seq_pos0[i] must be a multiple of the KV page size: a shared prefix consists of whole pages.
  *   seq_ctx_row  optional int32 [n_seq] device, see seq_pos0 (both NULL: every sequence is self-contained) */
 RVL_API int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t n_seq,
                 int64_t total_tokens, int32_t max_seqlen, const int32_t* page_table, int32_t max_pages,
@@ -380,10 +381,13 @@ RVL_API int rvl_layernorm(rvl_handle* h, const float* x, const void* w, const vo
  *   out[s*Tq + t, a*96:(a+1)*96] = softmax_j(q[s*Tq + t] . k[kv(s)*Tk + j] / sqrt(96) + mask) v[kv(s)*Tk + j]
  * q/k/v/out are bf16 with explicit row strides (elements), so they can be column slices of fused
  * projections.  kv_seq_idx int32 [n_seq] (NULL: kv(s) = s) lets many query sequences share one key/value
- * sequence (the text of a query is shared by all its segments).  key_mask fp32 [n_kv_seq, Tk], 0 = padded. */
+ * sequence (the text of a query is shared by all its segments); n_kv_seq = number of key / value sequences
+ * (rows of k and v = n_kv_seq * Tk; ignored when kv_seq_idx is NULL).  key_mask fp32 [n_kv_seq, Tk], 0 = padded.
+ * Runs on tcgen05 (TMA-staged Q / K / V tiles, scores and output in TMEM) when q, k, v, out are 16-byte aligned and
+ * out_stride is a multiple of 8; otherwise on an mma.sync kernel. */
 RVL_API int rvl_mha96(rvl_handle* h, const void* q, int64_t q_stride, const void* k, int64_t k_stride, const void* v,
               int64_t v_stride, void* out, int64_t out_stride, int32_t n_seq, int32_t n_heads, int32_t Tq,
-              int32_t Tk, const int32_t* kv_seq_idx, const float* key_mask, rvl_stream stream);
+              int32_t Tk, const int32_t* kv_seq_idx, int32_t n_kv_seq, const float* key_mask, rvl_stream stream);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,7 @@ PROTOTYPES = {
     "rvl_clip_encoder_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "rvl_clip_encoder": (C.c_int, [_P, C.POINTER(rvl_clip_weights), _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _SZ, _P, _P]),
     "rvl_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P]),
-    "rvl_mha96": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "rvl_mha96": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
 }
 
 _lib = None

@@ -275,10 +275,11 @@ void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, 
                          cudaStream_t st, const int32_t* seq_pos0, const int32_t* seq_ctx_row, int only_last, int64_t total_tokens,
                          int num_sms) {
   if (n_seq <= 0 || max_seqlen <= 0) return;
-  // tcgen05 kernel (attention_tcgen05.cu) unless the sequences name an external context (shared-prefix compute: a K tile would
-  // straddle two row ranges) or RVL_ATTN_PREFILL=0 asks for the mma.sync kernel below
-  if (tuning().attn_prefill != 0 && !seq_pos0 && !seq_ctx_row && total_tokens > 0 && num_sms > 0 &&
-      launch_attn_prefill_tc(qkv, out, cu_seqlens, n_seq, total_tokens, max_seqlen, n_heads, num_sms, st, only_last))
+  // tcgen05 kernel (attention_tcgen05.cu) unless RVL_ATTN_PREFILL=0 asks for the mma.sync kernel below (= 2: only for
+  // sequences that name an external context, the round-2 state before the tensor-core kernel learnt to follow one)
+  const int mode = tuning().attn_prefill;
+  if (mode != 0 && !(mode == 2 && (seq_pos0 || seq_ctx_row)) && total_tokens > 0 && num_sms > 0 &&
+      launch_attn_prefill_tc(qkv, out, cu_seqlens, n_seq, total_tokens, max_seqlen, n_heads, num_sms, st, only_last, seq_pos0, seq_ctx_row))
     return;
   static bool attr = false;
   constexpr int smem = 16384 * 4;
@@ -465,7 +466,13 @@ __global__ void __launch_bounds__(128) mha96_mma_kernel(const __nv_bfloat16* __r
 
 int launch_mha96(const void* q, long long q_stride, const void* k, long long k_stride, const void* v, long long v_stride, void* out,
                  long long out_stride, int n_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx, const float* key_mask,
-                 cudaStream_t st) {
+                 cudaStream_t st, int n_kv_seq, int num_sms) {
+  // tcgen05 kernel (attention_tcgen05.cu, the head_dim-96 instantiation) when the caller says how many key / value sequences
+  // there are (the tensor maps need the row count) and the operands are 16-byte aligned; RVL_ATTN_MHA96=0: the kernel above
+  if (!kv_seq_idx) n_kv_seq = n_seq;
+  if (tuning().attn_mha96 != 0 && n_kv_seq > 0 && num_sms > 0 &&
+      launch_mha96_tc(q, q_stride, k, k_stride, v, v_stride, out, out_stride, n_seq, n_kv_seq, n_heads, Tq, Tk, kv_seq_idx, key_mask, num_sms, st))
+    return cudaGetLastError() == cudaSuccess ? RVL_OK : RVL_ERR_CUDA;
   static bool attr = false;
   constexpr int smem = 16384 * 4;
   if (!attr) {

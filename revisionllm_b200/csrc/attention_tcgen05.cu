@@ -1,7 +1,14 @@
-// Causal varlen prefill attention on the 5th-gen tensor cores (head_dim 128, no GQA).
-//
-// Replaces the eager `matmul -> softmax(fp32) -> matmul` attention of transformers' Llama that the reference reaches from
-// revisionllm/model/vtimellm_llama.py:79-90 (and, in round 1 of this repo, an mma.sync flash kernel: attention.cu).
+// Attention on the 5th-gen tensor cores, two instantiations of one kernel:
+//   * causal varlen prefill, head_dim 128, no GQA: replaces the eager `matmul -> softmax(fp32) -> matmul` attention of
+//     transformers' Llama that the reference reaches from revisionllm/model/vtimellm_llama.py:79-90 (and, in round 1 of this
+//     repo, an mma.sync flash kernel: attention.cu).  A sequence may name an external context (`seq_pos0` / `seq_ctx_row` of
+//     rvl_prefill: the prompt prefix shared by the batch, projected once): its first keys are then rows of another part of
+//     the packed stream, and the K / V tiles are loaded as two 32-key boxes each so that a tile may straddle the two ranges.
+//   * non-causal, head_dim 96, fixed Tq / Tk, optional key-padding mask and shared key / value sequences: the
+//     nn.MultiheadAttention core of the stage-2 ClipEncoder (revisionllm/model/adapter/transformer.py:216-217, :288-289).
+//     The tiles keep the 128-dim geometry: the second 64-column box of a head holds its dims 64 .. 95 and 32 columns of the
+//     neighbouring head (or zeros past the matrix); QK^T stops after six 16-dim steps, so they are never read, and the 32
+//     surplus columns of O are never stored.
 //
 // Work item = (sequence, head, PAIR of 128-row query tiles).  The two query tiles are two independent "slots" of the CTA
 // that share every K / V tile (the later tile needs a superset of the keys of the earlier one):
@@ -49,7 +56,7 @@ __device__ __forceinline__ void dbg_stamp(int role, uint32_t idx, int kind) {
 
 namespace {
 
-constexpr int kHD = 128;          // head_dim
+constexpr int kHD = 128;          // dims per tile row (head_dim 128; head_dim 96 uses the first 96)
 constexpr int kQTile = 128;       // query rows per slot (UMMA M)
 constexpr int kKTile = 64;        // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int kSlots = 2;
@@ -66,9 +73,17 @@ constexpr int kAttnSmem = 1024 + kSlots * (kQBytes + kPBytes) + kKVStages * 2 * 
 constexpr uint32_t kTmemCols = 512;                // per slot: S0 [0, 64) | S1 [64, 128) | O [128, 256)
 
 struct AttnArgs {
-  const int32_t* cu_seqlens;
+  const int32_t* cu_seqlens;      // causal: rows [cu[i], cu[i + 1]) of the packed stream are sequence i
+  const int32_t* seq_pos0;        // causal, optional: the sequence's own rows start at this position ...
+  const int32_t* seq_ctx_row;     // ... and its positions [0, pos0) are the rows [ctx_row, ctx_row + pos0) (multiple of 32)
+  const int32_t* kv_seq_idx;      // non-causal, optional: key / value sequence of query sequence i
+  const float* key_mask;          // non-causal, optional: fp32 [n_kv_seq, Tk], 0 = padded key
   __nv_bfloat16* out;
-  int n_seq, n_heads, n_pairs;    // n_pairs = pairs of query tiles per sequence (from max_seqlen)
+  long long out_stride;           // elements between output rows
+  int n_seq, n_heads, n_pairs;    // n_pairs = pairs of query tiles per sequence (from the longest sequence)
+  int Tq, Tk;                     // non-causal: rows per query / key sequence
+  int q_col0, k_col0, v_col0;     // column of head 0 in the q / k / v tensor maps
+  int kv_box32;                   // K / V tensor maps have 32-row boxes (external context: a tile = two boxes)
   int only_last;                  // only the query tile that holds the last position of each sequence
   float scale_log2;               // log2(e) / sqrt(head_dim)
 };
@@ -112,13 +127,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // work item -> (sequence, head, pair of query tiles); false when the item has nothing to do.  Every role evaluates it
 // identically.  nt[s] = K / V tiles slot s consumes (0: the slot sits this item out); the item loads max(nt) tiles.
+// Query rows are counted from the sequence's own first row; keys by POSITION (context first: P positions, then the own rows).
 struct Item {
-  int seq, head, s0, L;
+  int seq, head, kv_seq;
+  int q_row0, kv_row0, ctx_row0;  // first own row of the queries / keys; first row of the external context
+  int P, Lq, Lk;                  // context positions, query rows, key positions (causal: Lk = P + Lq)
   int q0[kSlots], nt[kSlots], n_tiles;
 };
 // `flip`: which slot takes the earlier query tile alternates from one item of the CTA to the next - the slot that ran the short
 // chain (earlier tile: fewer keys) released its Q buffer early, so the NEXT item's long chain can have its Q loaded while the
 // current item is still computing.
+template <bool kCausal>
 __device__ __forceinline__ bool decode_item(const AttnArgs& a, int item, int flip, Item& it) {
   // the pair index is the SLOW index and runs backwards: every CTA of the grid-stride loop gets the same mix of long (late
   // query tiles: more keys) and short items, the long ones first
@@ -127,22 +146,41 @@ __device__ __forceinline__ bool decode_item(const AttnArgs& a, int item, int fli
   const int r = item - (item / per_pair) * per_pair;
   it.head = r % a.n_heads;
   it.seq = r / a.n_heads;
-  it.s0 = __ldg(a.cu_seqlens + it.seq);
-  it.L = __ldg(a.cu_seqlens + it.seq + 1) - it.s0;
+  if (kCausal) {
+    const int s0 = __ldg(a.cu_seqlens + it.seq);
+    it.Lq = __ldg(a.cu_seqlens + it.seq + 1) - s0;
+    it.q_row0 = it.kv_row0 = s0;
+    it.P = a.seq_pos0 ? __ldg(a.seq_pos0 + it.seq) : 0;
+    it.ctx_row0 = a.seq_ctx_row ? __ldg(a.seq_ctx_row + it.seq) : 0;
+    it.Lk = it.P + it.Lq;
+    it.kv_seq = it.seq;
+  } else {
+    it.kv_seq = a.kv_seq_idx ? __ldg(a.kv_seq_idx + it.seq) : it.seq;
+    it.q_row0 = it.seq * a.Tq;
+    it.kv_row0 = it.kv_seq * a.Tk;
+    it.ctx_row0 = 0;
+    it.P = 0;
+    it.Lq = a.Tq;
+    it.Lk = a.Tk;
+  }
   it.n_tiles = 0;
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
     const int q0 = (pp * kSlots + (s ^ flip)) * kQTile;
     it.q0[s] = q0;
-    const bool on = q0 < it.L && !(a.only_last && q0 + kQTile < it.L);
-    it.nt[s] = on ? (min(it.L, q0 + kQTile) + kKTile - 1) / kKTile : 0;      // causal: keys < q0 + 128
+    const bool on = q0 < it.Lq && !(a.only_last && q0 + kQTile < it.Lq);
+    const int keys = kCausal ? it.P + min(it.Lq, q0 + kQTile) : it.Lk;         // causal: key positions < P + q0 + 128
+    it.nt[s] = on ? (keys + kKTile - 1) / kKTile : 0;
     it.n_tiles = max(it.n_tiles, it.nt[s]);
   }
   return it.n_tiles > 0;
 }
 
+template <int HD, bool kCausal>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               const __grid_constant__ CUtensorMap tmap_v, const AttnArgs args) {
+  static_assert(HD == 128 || HD == 96, "head_dim 128 (Llama) or 96 (ClipEncoder)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                        // [slot][2 halves][128 rows][128 B]
@@ -161,9 +199,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = args.n_heads * kHD;
   if (warp == kProducerWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
     for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 2);
@@ -198,7 +237,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
     uint32_t n_q[kSlots] = {0, 0};                 // items each slot took part in so far
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       Item it;
-      if (!decode_item(args, item, n_it & 1, it)) continue;
+      if (!decode_item<kCausal>(args, item, n_it & 1, it)) continue;
       ++n_it;
       const int s_long_dbg = it.nt[1] > it.nt[0] ? 1 : 0;
       auto load_q = [&](int s) {
@@ -206,12 +245,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
         if (n_q[s] > 0) mbar_wait(&q_empty[s], (n_q[s] - 1) & 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&q_full[s], kQBytes);
-          const int row = it.s0 + it.q0[s], col = it.head * kHD;
+          const int row = it.q_row0 + it.q0[s], col = args.q_col0 + it.head * HD;
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int g = 0; g < 2; ++g)
-              tma_load_2d(sQ + s * kQBytes + h * (kQBytes / 2) + g * (64 * 128), &tmap_qkv, &q_full[s], col + h * 64, row + g * 64);
+              tma_load_2d(sQ + s * kQBytes + h * (kQBytes / 2) + g * (64 * 128), &tmap_q, &q_full[s], col + h * 64, row + g * 64);
         }
         __syncwarp();
         dbg_stamp(0, 128 + n_it, s == s_long_dbg ? 1 : 2);      // Q issued (index 128 + item): kind 1 long chain, 2 short chain
@@ -228,11 +267,30 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
         if (use > 0) mbar_wait(&kv_empty[st], (use - 1) & 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[st], 2 * kKVBytes);
-          const int row = it.s0 + j * kKTile;
+          const int kc = args.k_col0 + it.head * HD, vc = args.v_col0 + it.head * HD;
+          if (kCausal && args.kv_box32) {
+            // two 32-key boxes per tile and 64-dim half: positions below P are rows of the context, the others own rows
+            if (it.P & 31) {
+              printf("rvl attention: seq_pos0 = %d is not a multiple of 32\n", it.P);
+              __trap();
+            }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tma_load_2d(sK + st * kKVBytes + h * (kKVBytes / 2), &tmap_qkv, &kv_full[st], H + it.head * kHD + h * 64, row);
-            tma_load_2d(sV + st * kKVBytes + h * (kKVBytes / 2), &tmap_qkv, &kv_full[st], 2 * H + it.head * kHD + h * 64, row);
+            for (int g = 0; g < 2; ++g) {
+              const int pos = j * kKTile + g * 32;
+              const int row = pos < it.P ? it.ctx_row0 + pos : it.kv_row0 + pos - it.P;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                tma_load_2d(sK + st * kKVBytes + h * (kKVBytes / 2) + g * (32 * 128), &tmap_k, &kv_full[st], kc + h * 64, row);
+                tma_load_2d(sV + st * kKVBytes + h * (kKVBytes / 2) + g * (32 * 128), &tmap_v, &kv_full[st], vc + h * 64, row);
+              }
+            }
+          } else {
+            const int row = it.kv_row0 + j * kKTile;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_load_2d(sK + st * kKVBytes + h * (kKVBytes / 2), &tmap_k, &kv_full[st], kc + h * 64, row);
+              tma_load_2d(sV + st * kKVBytes + h * (kKVBytes / 2), &tmap_v, &kv_full[st], vc + h * 64, row);
+            }
           }
         }
         __syncwarp();
@@ -251,7 +309,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
     const uint64_t p_desc = umma_desc_k_sw128(smem_u32(sP + s * kPBytes));
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       Item it;
-      if (!decode_item(args, item, n_it & 1, it)) continue;
+      if (!decode_item<kCausal>(args, item, n_it & 1, it)) continue;
       ++n_it;
       if (s == 0) dbg_stamp(1, 128 + n_it, 0);                  // the MMA warp starts polling for this item
       const int n_my = it.nt[s], n_other = it.nt[s ^ 1];
@@ -296,7 +354,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
           if (elect_one()) {
             const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK + st_q * kKVBytes));
 #pragma unroll
-            for (int k = 0; k < kHD / 16; ++k) {
+            for (int k = 0; k < HD / 16; ++k) {
               // 16 dims = 32 B inside the 128-byte swizzle row: + 2 in the (addr >> 4) field; dims 64 .. 127: second half
               const uint64_t qa = q_desc + ((k >> 2) * ((kQBytes / 2) >> 4)) + 2 * (k & 3);
               const uint64_t kb = k_desc + ((k >> 2) * ((kKVBytes / 2) >> 4)) + 2 * (k & 3);
@@ -335,14 +393,15 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
     uint32_t n_t = 0, n_it = 0;                              // the slot's tiles so far; the CTA's items so far
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       Item it;
-      if (!decode_item(args, item, n_it & 1, it)) continue;
+      if (!decode_item<kCausal>(args, item, n_it & 1, it)) continue;
       ++n_it;
       const int n_my = it.nt[slot];
       if (n_my == 0) continue;
       const int q0 = it.q0[slot];
-      const int q_pos = q0 + r;                              // position of this thread's query inside the sequence
-      const int warp_first = q0 + quarter * 32;              // first query position of the warp
-      const int lim_row = min(q_pos, it.L - 1);              // last key this row may see
+      const int q_idx = q0 + r;                              // this thread's query row inside the sequence
+      const int warp_first = q0 + quarter * 32;              // first query row of the warp
+      const int pos_first = it.P + warp_first;               // its position
+      const int lim_row = kCausal ? it.P + min(q_idx, it.Lq - 1) : it.Lk - 1;   // last key position this row may see
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_my; ++j) {
         const uint32_t t = n_t + j;
@@ -352,7 +411,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
         tc_fence_after();
         if (stamp) dbg_stamp(2 + slot, t, 0);
         // the warp has nothing to exponentiate when all its rows lie past the sequence or above every key of the tile
-        const bool skip = warp_first >= it.L || k0 > warp_first + 31;
+        const bool skip = warp_first >= it.Lq || (kCausal && k0 > pos_first + 31);
         uint32_t pk[32];                                     // the row's 64 probabilities as bf16 pairs
         float corr = 1.f;
         if (!skip) {
@@ -370,11 +429,21 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
           // row of the warp (i > lim_w, warp-uniform) are left out of the maximum and of the exponentials altogether - on a
           // diagonal tile that is up to half of the work of a unit (MUFU) that the two slots' warps of a scheduler share
           const int lim = lim_row - k0;
-          const int lim_w = min(min(warp_first + 31, it.L - 1) - k0, kKTile - 1);
-          if (lim_w < kKTile - 1 || k0 + kKTile - 1 > warp_first) {
+          const int lim_w = kCausal ? min(min(pos_first + 31, it.Lk - 1) - k0, kKTile - 1) : min(it.Lk - 1 - k0, kKTile - 1);
+          if (lim_w < kKTile - 1 || (kCausal && k0 + kKTile - 1 > pos_first)) {
 #pragma unroll
             for (int i = 0; i < 64; ++i)
               if (i > lim) p[i] = -INFINITY;
+          }
+          if (!kCausal && args.key_mask) {                    // key padding: one bit per key of the tile, the same for every row
+            const float* mrow = args.key_mask + static_cast<long long>(it.kv_seq) * it.Lk + k0;
+            const uint32_t lo = __ballot_sync(0xffffffffu, k0 + lane < it.Lk && __ldg(mrow + lane) != 0.f);
+            const uint32_t hi = __ballot_sync(0xffffffffu, k0 + 32 + lane < it.Lk && __ldg(mrow + 32 + lane) != 0.f);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (!((lo >> i) & 1u)) p[i] = -INFINITY;
+              if (!((hi >> i) & 1u)) p[32 + i] = -INFINITY;
+            }
           }
           float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (few warps per scheduler: latency is exposed)
 #pragma unroll
@@ -457,10 +526,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
       // Each thread owns one 256-byte output row: stored directly, a warp-level 16-byte store touches 32 different lines.
       // Instead the warp's 32 rows go through ITS OWN 4 KB of the slot's P buffer (free: the last PV has completed), 64 dims
       // at a time, and leave as 4 rows x 128 B per warp-level store.
-      const bool live = q_pos < it.L;
+      const bool live = q_idx < it.Lq;
       const float inv = live ? 1.f / l_run : 0.f;
-      const int rows_valid = min(32, it.L - warp_first);                  // rows of this warp inside the sequence (<= 0: none)
-      __nv_bfloat16* dst_warp = args.out + (static_cast<long long>(it.s0) + warp_first) * H + it.head * kHD;
+      const int rows_valid = min(32, it.Lq - warp_first);                 // rows of this warp inside the sequence (<= 0: none)
+      __nv_bfloat16* dst_warp = args.out + (static_cast<long long>(it.q_row0) + warp_first) * args.out_stride + it.head * HD;
       const uint32_t p_warp = p_base + quarter * 32 * 128;
       if (rows_valid > 0) {
 #pragma unroll 1
@@ -487,7 +556,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
             uint4 v;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                          : "r"(p_warp + rr * 128 + ((static_cast<uint32_t>(cc) ^ static_cast<uint32_t>(rr & 7)) << 4)));
-            if (rr < rows_valid) *reinterpret_cast<uint4*>(dst_warp + static_cast<long long>(rr) * H + half * 64 + cc * 8) = v;
+            if (rr < rows_valid && half * 64 + cc * 8 < HD)
+              *reinterpret_cast<uint4*>(dst_warp + static_cast<long long>(rr) * args.out_stride + half * 64 + cc * 8) = v;
           }
           __syncwarp();
         }
@@ -508,30 +578,74 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
 
 }  // namespace
 
-// false: the tensor-core kernel does not take this call (the caller falls back to the mma.sync kernel)
-bool launch_attn_prefill_tc(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int64_t total_tokens, int max_seqlen,
-                            int n_heads, int num_sms, cudaStream_t st, int only_last) {
-  if (n_seq <= 0 || max_seqlen <= 0 || total_tokens <= 0) return true;
-  const int H = n_heads * kHD;
-  CUtensorMap tm;
-  std::string err;
-  if (make_tmap_bf16_2d(&tm, qkv, total_tokens, 3LL * H, 64, &err) != RVL_OK) return false;
-  static bool attr = false;
+template <int HD, bool kCausal>
+static bool launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& a, int num_sms, cudaStream_t st) {
+  static bool attr = false;                 // one flag per instantiation
   if (!attr) {
-    if (cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(attn_tc_kernel<HD, kCausal>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) != cudaSuccess) return false;
     attr = true;
   }
-  AttnArgs a;
+  const long long items = static_cast<long long>(a.n_seq) * a.n_heads * a.n_pairs;
+  const int grid = static_cast<int>(items < num_sms ? items : num_sms);
+  return launch_k(attn_tc_kernel<HD, kCausal>, dim3(grid), dim3(kAttnThreads), kAttnSmem, st, tq, tk, tv, a) == cudaSuccess;
+}
+
+// false: the tensor-core kernel does not take this call (the caller falls back to the mma.sync kernel)
+bool launch_attn_prefill_tc(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int64_t total_tokens, int max_seqlen,
+                            int n_heads, int num_sms, cudaStream_t st, int only_last, const int32_t* seq_pos0,
+                            const int32_t* seq_ctx_row) {
+  if (n_seq <= 0 || max_seqlen <= 0 || total_tokens <= 0) return true;
+  if ((seq_pos0 != nullptr) != (seq_ctx_row != nullptr)) return false;
+  const int H = n_heads * kHD;
+  CUtensorMap tm, tm_kv;
+  std::string err;
+  if (make_tmap_bf16_2d(&tm, qkv, total_tokens, 3LL * H, 64, &err) != RVL_OK) return false;
+  tm_kv = tm;
+  if (seq_pos0 && make_tmap_bf16_2d(&tm_kv, qkv, total_tokens, 3LL * H, 32, &err) != RVL_OK) return false;
+  AttnArgs a{};
   a.cu_seqlens = cu_seqlens;
+  a.seq_pos0 = seq_pos0;
+  a.seq_ctx_row = seq_ctx_row;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.out_stride = H;
   a.n_seq = n_seq;
   a.n_heads = n_heads;
-  a.n_pairs = (max_seqlen + kSlots * kQTile - 1) / (kSlots * kQTile);
+  a.n_pairs = (max_seqlen + kSlots * kQTile - 1) / (kSlots * kQTile);      // max_seqlen counts positions: an upper bound of the own rows
+  a.q_col0 = 0;
+  a.k_col0 = H;
+  a.v_col0 = 2 * H;
+  a.kv_box32 = seq_pos0 ? 1 : 0;
   a.only_last = only_last;
-  a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHD));
-  const long long items = static_cast<long long>(n_seq) * n_heads * a.n_pairs;
-  const int grid = static_cast<int>(items < num_sms ? items : num_sms);
-  return launch_k(attn_prefill_tc_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, st, tm, a) == cudaSuccess;
+  a.scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+  return launch_tc<128, true>(tm, tm_kv, tm_kv, a, num_sms, st);
+}
+
+// nn.MultiheadAttention core of the ClipEncoder (head_dim 96, non-causal); false: not taken (operands not 16-byte aligned)
+bool launch_mha96_tc(const void* q, long long q_stride, const void* k, long long k_stride, const void* v, long long v_stride, void* out,
+                     long long out_stride, int n_seq, int n_kv_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx,
+                     const float* key_mask, int num_sms, cudaStream_t st) {
+  if (n_seq <= 0 || Tq <= 0 || Tk <= 0) return true;
+  if (num_sms <= 0 || n_kv_seq <= 0 || out_stride % 8 || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
+  const long long D = 96LL * n_heads;
+  if (q_stride < D || k_stride < D || v_stride < D) return false;
+  CUtensorMap tq, tk, tv;
+  std::string err;
+  // the column extent stops at the last head: what a head's second 64-column box reads past it comes back as zeros
+  if (make_tmap_bf16_2d(&tq, q, static_cast<int64_t>(n_seq) * Tq, D, 64, &err, q_stride) != RVL_OK) return false;
+  if (make_tmap_bf16_2d(&tk, k, static_cast<int64_t>(n_kv_seq) * Tk, D, 64, &err, k_stride) != RVL_OK) return false;
+  if (make_tmap_bf16_2d(&tv, v, static_cast<int64_t>(n_kv_seq) * Tk, D, 64, &err, v_stride) != RVL_OK) return false;
+  AttnArgs a{};
+  a.kv_seq_idx = kv_seq_idx;
+  a.key_mask = key_mask;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.out_stride = out_stride;
+  a.n_seq = n_seq;
+  a.n_heads = n_heads;
+  a.n_pairs = (Tq + kSlots * kQTile - 1) / (kSlots * kQTile);
+  a.Tq = Tq;
+  a.Tk = Tk;
+  a.scale_log2 = 1.4426950408889634f / sqrtf(96.f);
+  return launch_tc<96, false>(tq, tk, tv, a, num_sms, st);
 }
 
 }  // namespace rvl

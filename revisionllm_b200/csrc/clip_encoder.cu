@@ -192,7 +192,7 @@ int rvl_clip_encoder(rvl_handle* h, const rvl_clip_weights* w, const void* frame
     void* q = sg + l.a_q; void* kv = sg + l.a_kv; void* att = sg + l.a_att; void* xbf = sg + l.a_xbf; void* hb = sg + l.a_h;
     if ((rc = gemm(sg + l.a_xpbf, L.in_proj_w, L.in_proj_b, q, rows, D, D, RVL_GEMM_OUT_BF16, 0))) return rc;                     // Q = (x + pos) Wq^T + bq
     if ((rc = gemm(text, bf(L.in_proj_w, 1LL * D * D), bf(L.in_proj_b, D), kv, 1LL * Q * Lq, 2 * D, D, RVL_GEMM_OUT_BF16, 0))) return rc;   // K | V of the text, once per query
-    if ((rc = rvl_mha96(h, q, D, kv, 2 * D, bf(kv, D), 2 * D, att, D, V, kClipHeads, T, Lq, seg_text_idx, text_mask, stream))) return rc;
+    if ((rc = rvl_mha96(h, q, D, kv, 2 * D, bf(kv, D), 2 * D, att, D, V, kClipHeads, T, Lq, seg_text_idx, Q, text_mask, stream))) return rc;
     if ((rc = gemm(att, L.out_proj_w, L.out_proj_b, x, rows, D, D, RVL_GEMM_ADD_F32, 0))) return rc;                             // src2 = x + attn
     if ((rc = rvl_layernorm(h, x, L.norm1_w, L.norm1_b, nullptr, xbf, nullptr, nullptr, rows, D, 0, 1e-5f, stream))) return rc;
     if ((rc = gemm(xbf, L.linear1_w, L.linear1_b, hb, rows, F, D, RVL_GEMM_OUT_BF16, RVL_GEMM_FLAG_RELU))) return rc;
@@ -208,7 +208,7 @@ int rvl_clip_encoder(rvl_handle* h, const rvl_clip_weights* w, const void* frame
     const rvl_clip_layer& L = w->enc[i];
     if ((rc = gemm(x1pbf, L.in_proj_w, L.in_proj_b, qk, rows1, 2 * D, D, RVL_GEMM_OUT_BF16, 0))) return rc;                      // q = k = x + pos
     if ((rc = gemm(x1bf, bf(L.in_proj_w, 2LL * D * D), bf(L.in_proj_b, 2 * D), vb, rows1, D, D, RVL_GEMM_OUT_BF16, 0))) return rc;   // v = x
-    if ((rc = rvl_mha96(h, qk, 2 * D, bf(qk, D), 2 * D, vb, D, att1, D, V, kClipHeads, T1, T1, nullptr, nullptr, stream))) return rc;
+    if ((rc = rvl_mha96(h, qk, 2 * D, bf(qk, D), 2 * D, vb, D, att1, D, V, kClipHeads, T1, T1, nullptr, 0, nullptr, stream))) return rc;
     if ((rc = gemm(att1, L.out_proj_w, L.out_proj_b, x1, rows1, D, D, RVL_GEMM_ADD_F32, 0))) return rc;
     if ((rc = rvl_layernorm(h, x1, L.norm1_w, L.norm1_b, x1, x1bf, nullptr, nullptr, rows1, D, 0, 1e-5f, stream))) return rc;
     if ((rc = gemm(x1bf, L.linear1_w, L.linear1_b, h1, rows1, F, D, RVL_GEMM_OUT_BF16, RVL_GEMM_FLAG_RELU))) return rc;
@@ -236,12 +236,13 @@ int rvl_layernorm(rvl_handle* h, const float* x, const void* w, const void* b, f
 
 int rvl_mha96(rvl_handle* h, const void* q, int64_t q_stride, const void* k, int64_t k_stride, const void* v,
               int64_t v_stride, void* out, int64_t out_stride, int32_t n_seq, int32_t n_heads, int32_t Tq, int32_t Tk,
-              const int32_t* kv_seq_idx, const float* key_mask, rvl_stream stream) {
+              const int32_t* kv_seq_idx, int32_t n_kv_seq, const float* key_mask, rvl_stream stream) {
   if (!q || !k || !v || !out || n_seq <= 0 || Tq <= 0 || Tk <= 0) return report_error(h, RVL_ERR_INVALID, "rvl_mha96: null argument");
   if (q_stride % 8 || k_stride % 8 || v_stride % 8 || out_stride % 2)
     return report_error(h, RVL_ERR_INVALID, "rvl_mha96: q / k / v row strides must be multiples of 8 elements, the out stride of 2");
+  if (kv_seq_idx && n_kv_seq <= 0) return report_error(h, RVL_ERR_INVALID, "rvl_mha96: kv_seq_idx needs n_kv_seq, the number of key / value sequences");
   return launch_mha96(q, q_stride, k, k_stride, v, v_stride, out, out_stride, n_seq, n_heads, Tq, Tk, kv_seq_idx, key_mask,
-                      static_cast<cudaStream_t>(stream));
+                      static_cast<cudaStream_t>(stream), kv_seq_idx ? n_kv_seq : n_seq, handle_num_sms(h));
 }
 
 }  // extern "C"

@@ -85,6 +85,7 @@ void reload_tuning() {
   t.attn_decode = ad ? ad[0] : 0;
   t.attn_ps32 = geti("RVL_ATTN_PS32", -1);
   t.attn_prefill = geti("RVL_ATTN_PREFILL", -1);
+  t.attn_mha96 = geti("RVL_ATTN_MHA96", -1);
   t.norm_threads = geti("RVL_NORM_THREADS", 0);
   g_tuning = t;
   g_tuning_loaded = true;
@@ -95,6 +96,7 @@ const Tuning& tuning() {
 }
 // error reporting for the entry points that live in other translation units (clip_encoder.cu)
 int report_error(const rvl_handle* h, int code, const char* msg) { return fail(h, code, msg); }
+int handle_num_sms(const rvl_handle* h) { return h ? h->num_sms : 0; }
 }  // namespace rvl
 static int check_cuda(const rvl_handle* h, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -354,8 +356,11 @@ int rvl_prefill(rvl_handle* h, float* hidden, const int32_t* cu_seqlens, int32_t
     {
       // causal FLOPs need the per-sequence lengths (device side); use the uniform-length bound T*max_seqlen
       ProfScope ps(h, st, RVL_PROF_ATTN_PREFILL, 2.0 * T * max_seqlen * H, 2.0 * T * 4 * H);
-      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row, last_only ? 1 : 0, T,
-                          h->num_sms);
+      // an external context must end on a 32-key boundary for the tcgen05 kernel (it loads 32-key boxes); contexts are whole
+      // KV pages, so any page size that is a multiple of 32 guarantees it - otherwise total_tokens = 0 selects the mma.sync kernel
+      const bool ctx_ok = !seq_pos0 || c.kv_page_size % 32 == 0;
+      launch_attn_prefill(h->qkv, h->attn, cu_seqlens, n_seq, max_seqlen, c.n_heads, st, seq_pos0, seq_ctx_row, last_only ? 1 : 0,
+                          ctx_ok ? T : 0, h->num_sms);
     }
     if (last_only) {
       const int64_t n = n_seq;

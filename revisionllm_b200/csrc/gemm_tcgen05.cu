@@ -1152,15 +1152,17 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle, OOB -> zeros.
-static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err) {
+// `ld` (elements): row pitch when the matrix is a column slice of a wider one (0: the rows are dense, pitch = cols)
+static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err, int64_t ld = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { *err = "cuTensorMapEncodeTiled entry point not available"; return RVL_ERR_CUDA; }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (cols * 2) % 16) {
+  if (ld <= 0) ld = cols;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) {
     *err = "GEMM operand must be 16-byte aligned with a row pitch that is a multiple of 16 bytes";
     return RVL_ERR_INVALID;
   }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
@@ -1201,8 +1203,8 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t n_feat, int6
   return RVL_OK;
 }
 
-int make_tmap_bf16_2d(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err) {
-  return make_tmap(tm, base, rows, cols, box_rows, err);
+int make_tmap_bf16_2d(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err, int64_t ld) {
+  return make_tmap(tm, base, rows, cols, box_rows, err, ld);
 }
 
 static int pow2_at_least(int x) {

@@ -49,7 +49,8 @@ struct Tuning {
   int full_last_layer = 0;   // RVL_FULL_LAST_LAYER
   int attn_decode = 0;       // RVL_ATTN_DECODE: 'r' / 's' / 0
   int attn_ps32 = -1;        // RVL_ATTN_PS32
-  int attn_prefill = -1;     // RVL_ATTN_PREFILL: 0 = mma.sync kernel, 1 = tcgen05 kernel
+  int attn_prefill = -1;     // RVL_ATTN_PREFILL: 0 = mma.sync kernel, 2 = mma.sync only with an external context, else tcgen05
+  int attn_mha96 = -1;       // RVL_ATTN_MHA96: 0 = mma.sync kernel, else tcgen05
   int norm_threads = 0;      // RVL_NORM_THREADS: threads of the few-row RMSNorm CTA (256 / 512 / 1024)
 };
 const Tuning& tuning();      // engine.cu
@@ -99,6 +100,7 @@ inline cudaError_t launch_gemm_k(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 // engine.cu: sets rvl_last_error (handle and thread) and returns `code`
 int report_error(const rvl_handle* h, int code, const char* msg);
+int handle_num_sms(const rvl_handle* h);   // SM count of the handle's device (0 for a null handle)
 
 // elementwise.cu
 // y = rmsnorm(x + sum_p partials[p]) ; when x_out != null the summed row is written back (residual update)
@@ -117,20 +119,25 @@ void launch_gather_last_rows(const void* attn, const float* hidden, const int32_
 void launch_swiglu(const void* gu, void* act, int64_t n_tokens, int inter, cudaStream_t st);
 void launch_token_seq(const int32_t* cu_seqlens, int n_seq, int32_t* tok_seq, int32_t* last_rows, int64_t total,
                       cudaStream_t st);
-// gemm_tcgen05.cu: 2D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], 128-byte swizzle, OOB -> zeros
-int make_tmap_bf16_2d(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err);
+// gemm_tcgen05.cu: 2D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], 128-byte swizzle, OOB -> zeros;
+// ld = row pitch in elements when the matrix is a column slice of a wider one (0: dense rows)
+int make_tmap_bf16_2d(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int box_rows, std::string* err, int64_t ld = 0);
 // attention.cu / attention_tcgen05.cu
 void launch_attn_prefill(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int n_heads,
                          cudaStream_t st, const int32_t* seq_pos0 = nullptr, const int32_t* seq_ctx_row = nullptr, int only_last = 0,
                          int64_t total_tokens = 0, int num_sms = 0);
 bool launch_attn_prefill_tc(const void* qkv, void* out, const int32_t* cu_seqlens, int n_seq, int64_t total_tokens, int max_seqlen,
-                            int n_heads, int num_sms, cudaStream_t st, int only_last);
+                            int n_heads, int num_sms, cudaStream_t st, int only_last, const int32_t* seq_pos0 = nullptr,
+                            const int32_t* seq_ctx_row = nullptr);
+bool launch_mha96_tc(const void* q, long long q_stride, const void* k, long long k_stride, const void* v, long long v_stride, void* out,
+                     long long out_stride, int n_seq, int n_kv_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx,
+                     const float* key_mask, int num_sms, cudaStream_t st);
 void launch_attn_decode(const void* qkv, void* out, const int32_t* seq_lens, int n_seq, const int32_t* page_table,
                         int max_pages, void* k_pages, void* v_pages, int n_heads, int page_size, int fused, float theta,
                         int max_kv_len, cudaStream_t st);
 int launch_mha96(const void* q, long long q_stride, const void* k, long long k_stride, const void* v, long long v_stride, void* out,
                  long long out_stride, int n_seq, int n_heads, int Tq, int Tk, const int32_t* kv_seq_idx, const float* key_mask,
-                 cudaStream_t st);
+                 cudaStream_t st, int n_kv_seq = 0, int num_sms = 0);
 // sampling.cu
 void launch_sample_greedy(const float* logits, int n_seq, int vocab, int32_t* unfinished, int eos_id, int pad_id,
                           int32_t* next_tokens, float* entropy_out, int32_t* seq_lens, int32_t* n_unfinished,

@@ -466,7 +466,7 @@ class Engine(DecodeChunks):
                 raise RvlError(f"mha96: {n} must be a CUDA bf16 matrix with unit column stride")
         self._check(self.lib.rvl_mha96(self.h, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                                        out.data_ptr(), out.stride(0), n_seq, n_heads, Tq, Tk, _ptr(kv_seq_idx),
-                                       _ptr(key_mask), _stream()), "rvl_mha96")
+                                       k.shape[0] // Tk, _ptr(key_mask), _stream()), "rvl_mha96")
         self.launches += 1
 
     def kv_view(self, layer: int):

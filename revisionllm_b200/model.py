@@ -438,6 +438,7 @@ class RevisionLlamaForCausalLM:
             bufs = eng.decode_buffers(B, kv.page_table.shape[1]) if chunked else None
             cu_d = torch.from_numpy(cu).to(dev)
             P = int(plan["ctx_len"])
+            self.last_shared_prefix = P         # positions of the prompt prefix computed once for the batch (0: none), for tests / tools
             if P:
                 # B + 1 sequences: the shared prefix (its K/V fill the shared pages), then every segment from position P on
                 ps = eng.cfg.kv_page_size

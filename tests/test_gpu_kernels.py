@@ -325,6 +325,47 @@ def test_rope_kv_and_attention_prefill_and_decode(eng, rvl_env):
         assert torch.equal(dec2, dec), mode
 
 
+@pytest.mark.parametrize("Tq,Tk,shared_kv", [(251, 251, False), (250, 12, True), (300, 70, True), (64, 130, False)])
+def test_mha96_tcgen05_and_mma_against_torch(eng, rvl_env, Tq, Tk, shared_kv):
+    """`rvl_mha96` (nn.MultiheadAttention core of the ClipEncoder, transformer.py:216-217 / :288-289): 8 heads x 96 dims, no causal
+    mask, key padding, key / value sequences shared between query sequences, operands as column slices of fused projections.
+    The tcgen05 instantiation (default) and the mma.sync kernel (RVL_ATTN_MHA96=0) against fp32 torch on the same bf16 inputs."""
+    nh, d, D = 8, 96, 768
+    n_seq = 5
+    n_kv = 2 if shared_kv else n_seq
+    g = torch.Generator().manual_seed(Tq * 1000 + Tk)
+    qk = (torch.randn(n_seq * Tq, 2 * D, generator=g) * 0.7).to(torch.bfloat16)        # q = left half of a fused [q | k] projection
+    kvb = (torch.randn(n_kv * Tk, 2 * D, generator=g) * 0.7).to(torch.bfloat16)        # k | v of the key sequences
+    idx = torch.tensor([0, 1, 1, 0, 1], dtype=torch.int32) if shared_kv else None
+    mask = None
+    if shared_kv:
+        mask = torch.ones(n_kv, Tk)
+        mask[0, Tk - 3:] = 0                                                          # padding at the end ...
+        mask[1, 1] = 0                                                                # ... and a hole
+    q = qk[:, :D].float().view(n_seq, Tq, nh, d)
+    k = kvb[:, :D].float().view(n_kv, Tk, nh, d)
+    v = kvb[:, D:].float().view(n_kv, Tk, nh, d)
+    sel = idx.long() if idx is not None else torch.arange(n_seq)
+    att = torch.einsum("sqhd,skhd->shqk", q, k[sel]) / math.sqrt(d)
+    if mask is not None:
+        att = att.masked_fill(mask[sel][:, None, None, :] == 0, float("-inf"))
+    ref = torch.einsum("shqk,skhd->sqhd", torch.softmax(att, -1), v[sel]).reshape(n_seq * Tq, D)
+    qk_d, kv_d = qk.cuda(), kvb.cuda()
+    idx_d = idx.cuda() if idx is not None else None
+    mask_d = mask.cuda() if mask is not None else None
+    outs = {}
+    for name, env in (("tcgen05", None), ("mma.sync", "0")):
+        rvl_env("RVL_ATTN_MHA96", env)
+        out = torch.full((n_seq * Tq, D), float("nan"), dtype=torch.bfloat16, device="cuda")
+        eng.mha96(qk_d[:, :D], kv_d[:, :D], kv_d[:, D:], out, n_seq, nh, Tq, Tk, kv_seq_idx=idx_d, key_mask=mask_d)
+        torch.cuda.synchronize()
+        outs[name] = out.float().cpu()
+        assert torch.isfinite(outs[name]).all(), name
+        err = _relerr(outs[name], ref)
+        assert err < 1.5e-2, f"mha96 ({name}) Tq={Tq} Tk={Tk}: rel err {err}"           # P and O rounded to bf16
+    assert _relerr(outs["tcgen05"], outs["mma.sync"]) < 1.5e-2
+
+
 # ------------------------------------------------------------------------------------------- sampling / scoring
 def test_sample_greedy_entropy_and_eos(eng):
     g = torch.Generator().manual_seed(5)
