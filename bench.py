@@ -560,10 +560,16 @@ def main():
             barrier()
             mv_ms = 1e3 * max_over_ranks(time.perf_counter() - t0) / 2
             line["movie_e2e_ms"] = mv_ms
+            phases = {}                            # one more run with the device synchronised at the phase boundaries (rank 0's view)
+            sweep.run_movie(model, movie, ids, cls_host, partial(syn.synthetic_answers, n_frames=N_FRAMES), (0.40, 0.45), mc,
+                            query_feats=q_feats, stage2_input_ids=ids_s2, detok_stage2=syn.synthetic_answers_stage2,
+                            rank=rank, world=world, eos_token_id=None, timings=phases)
+            barrier()
             line["movie_e2e"] = {"ms": mv_ms, "stage1_windows": int(mres.records.shape[0]), "frames_per_window": N_FRAMES,
                                  "stage1_answers_with_span": len(mres.clip_frames), "stage2_windows": len(mres.grounding_windows),
                                  "stage2_generate_calls": len(mres.stage2) if mres.stage2 else 0,
                                  "ranked_proposals": len(mres.ranked["windows"]) if mres.ranked else 0,
+                                 "phases_ms": {k: round(v, 2) for k, v in phases.items()},
                                  "note": "wall clock, host features in -> ranked proposals out on rank 0: upload + window gather + stage 1 on N ranks + "
                                          "all-gather + parse + select + stage-2 top-100 (ClipEncoder + zooms 4/2/1) on rank 0 + merge/rank kernel"}
         except Exception as e:

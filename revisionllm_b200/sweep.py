@@ -269,7 +269,8 @@ def _stage2_finish(calls: List[Dict], results: List[Dict], grounding_windows: Se
 def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tensor, grounding_windows: Sequence[int],
                 batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16, perm_seed: Optional[int] = 0,
                 answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config",
-                max_calls_per_batch: int = 16, dedup: bool = True) -> List[Dict]:
+                max_calls_per_batch: int = 16, dedup: bool = True, rank: int = 0, world: int = 1, shard_calls: bool = False,
+                group=None) -> List[Dict]:
     """Stage-2 hierarchical pass (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:337-386).
 
     `windows` [N, T, 768]: the selected stage-2 windows (already restricted to `grounding_windows`).  For each
@@ -284,12 +285,16 @@ def stage2_pass(model, windows: torch.Tensor, query_feats, input_ids: torch.Tens
     Returns one dict per chunk (the reference's generate() calls, in its order): tokens, entropy stats (1/max, 1/mean as in
     :356-359), picked window."""
     q = dict(windows=windows, query_feats=query_feats, input_ids=input_ids, grounding_windows=grounding_windows, perm_seed=perm_seed)
-    return stage2_pass_queries(model, [q], batch, zooms, max_new_tokens, answer_number, eos_token_id, max_calls_per_batch, dedup=dedup)[0]
+    if not shard_calls:
+        rank, world = 0, 1                                   # one query: it runs on the calling rank
+    return stage2_pass_queries(model, [q], batch, zooms, max_new_tokens, answer_number, eos_token_id, max_calls_per_batch, rank, world,
+                               dedup=dedup, shard_calls=shard_calls, group=group)[0]
 
 
 def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms: Sequence[int] = (4, 2, 1), max_new_tokens: int = 16,
                         answer_number: Optional[Callable[[torch.Tensor], Optional[int]]] = None, eos_token_id="config",
-                        max_calls_per_batch: int = 64, rank: int = 0, world: int = 1, dedup: bool = True) -> List[Optional[List[Dict]]]:
+                        max_calls_per_batch: int = 64, rank: int = 0, world: int = 1, dedup: bool = True,
+                        shard_calls: bool = False, group=None) -> List[Optional[List[Dict]]]:
     """Stage 2 for SEVERAL queries at once (north star: "one GPU per query, batched across queries").
 
     Each entry of `queries` holds what `stage2_pass` takes for one query: `windows` [N, T, 768], `query_feats`
@@ -300,8 +305,12 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
     per decode step for all of them instead of once per chunk.  Prompts of different lengths are right-padded and masked;
     query features of different lengths are padded with masked rows.  Per query the result equals `stage2_pass`'s.
     `dedup` (default): the ClipEncoder adapter sees every distinct (query, window) pair once instead of once per zoom repeat
-    and per chunk (7 x fewer adapter rows for zooms (4, 2, 1)); False feeds the stacked copies like the reference."""
-    mine = [qi for qi in range(len(queries)) if qi % world == rank]
+    and per chunk (7 x fewer adapter rows for zooms (4, 2, 1)); False feeds the stacked copies like the reference.
+    `shard_calls` (fewer queries than ranks - one movie-query on 8 GPUs): every rank holds every query, the generate() calls
+    of all queries are dealt round-robin to the ranks instead, and one all-gather of fixed-size records (the stage-1 record
+    layout: tokens, entropy mean / max) gives every rank every call's result; needs max_new_tokens <= REC_TOKENS."""
+    shard_calls = bool(shard_calls) and world > 1 and max_new_tokens <= REC_TOKENS
+    mine = [qi for qi in range(len(queries)) if shard_calls or qi % world == rank]
     jobs: List[Tuple[int, int]] = []                       # (query, call)
     plans: Dict[int, List[Dict]] = {}
     for qi in mine:
@@ -310,6 +319,9 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
         gen = torch.Generator().manual_seed(seed) if seed is not None else None
         plans[qi] = _stage2_plan(int(q["windows"].shape[0]), batch, zooms, gen)
         jobs += [(qi, ci) for ci in range(len(plans[qi]))]
+    all_jobs = jobs
+    if shard_calls:
+        jobs = all_jobs[rank::world]
     results: Dict[Tuple[int, int], Dict] = {}
     groups: Dict[Tuple[int, int, bool], List[Tuple[int, int]]] = {}
     for (qi, ci) in jobs:                                   # one generate() needs equal visual rows / frames per row
@@ -366,6 +378,27 @@ def stage2_pass_queries(model, queries: Sequence[Dict], batch: int = 100, zooms:
             stats_all = scoring.entropy_stats_from_steps(res["entropies"])
             for r, job in enumerate(part):
                 results[job] = dict(tokens=res["sequences"][r, L:], stats=stats_all[r])
+    if shard_calls:
+        dev = model.device
+        n_loc = len(jobs)
+        tok = torch.full((n_loc, REC_TOKENS), -1, dtype=torch.int32, device=dev)
+        st = torch.zeros((n_loc, 4), dtype=torch.float32, device=dev)
+        width = torch.zeros(n_loc, dtype=torch.int32, device=dev)
+        for i, job in enumerate(jobs):
+            t = results[job]["tokens"]
+            tok[i, : t.shape[0]] = t.to(dev, torch.int32)
+            width[i] = int(t.shape[0])
+            st[i] = torch.as_tensor(results[job]["stats"], dtype=torch.float32).to(dev)
+        local = pack_records(tok, torch.full((n_loc, 2), -1, dtype=torch.int32, device=dev), st[:, 2], st[:, 0], st[:, 1])
+        local[:, REC_TOKENS] = width                        # pack_records stores the buffer width; a call may have produced fewer tokens
+        shards = [np.arange(r, len(all_jobs), world, dtype=np.int64) for r in range(world)]
+        un = unpack_records(allgather_indexed(local, shards, rank, world, group).cpu())
+        results = {}
+        for i, job in enumerate(all_jobs):
+            n_t = int(un["n_tokens"][i])
+            # stats in entropy_stats_from_steps order (max, min, mean, std): the consumers read max and mean
+            stats = torch.stack([un["h_max"][i], un["cos"][i], un["h_mean"][i], torch.zeros(())])
+            results[job] = dict(tokens=un["tokens"][i, :n_t].to(torch.int64), stats=stats)
     out: List[Optional[List[Dict]]] = [None] * len(queries)
     for qi in mine:
         out[qi] = _stage2_finish(plans[qi], [results[(qi, ci)] for ci in range(len(plans[qi]))], queries[qi]["grounding_windows"], answer_number)
@@ -388,6 +421,8 @@ class MovieConfig:
     normalize: bool = True
     perm_seed: Optional[int] = 0
     stage1_batch: Optional[int] = None
+    stage2_calls_per_batch: int = 64  # stage-2 chunks (all zoom levels) that share one batched generate()
+    stage2_shard_calls: bool = True   # world > 1: deal the stage-2 generate() calls of the query to all ranks (one more all-gather)
 
 
 @dataclass
@@ -406,7 +441,7 @@ class MovieResult:
 def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok: Callable[[torch.Tensor], List[str]],
               gt: Tuple[float, float], cfg: MovieConfig = MovieConfig(), query_feats=None, stage2_input_ids: Optional[torch.Tensor] = None,
               detok_stage2: Optional[Callable[[torch.Tensor], List[str]]] = None, rank: int = 0, world: int = 1, group=None,
-              stage2_rank: int = 0, eos_token_id="config") -> MovieResult:
+              stage2_rank: int = 0, eos_token_id="config", timings: Optional[Dict[str, float]] = None) -> MovieResult:
     """One movie-query through the whole recursive path, as ONE call on `world` GPUs - what the reference spreads over three
     scripts and their JSONL files:
 
@@ -415,17 +450,29 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
                ranks, one all-gather of the fixed-size records;
       select   (/root/reference/revisionllm/eval/eval_nlq_retrieval_e2e2.py:262-294)  stage-2 window grid, windows of the
                positive stage-1 answers padded evenly to `batch`;
-      stage 2  (:337-386)  zoom levels 4 / 2 / 1 over the chosen windows through the ClipEncoder, on ONE rank (`stage2_rank`;
-               north star: one GPU per query);
+      stage 2  (:337-386)  zoom levels 4 / 2 / 1 over the chosen windows through the ClipEncoder: the independent generate()
+               calls of the query dealt to the ranks + one all-gather of their records (`cfg.stage2_shard_calls`), or all on
+               `stage2_rank` (north star: one GPU per query);
       rank     (/root/reference/revisionllm/eval/metric_retrieval_forward.py:96-199)  stage-1 proposals kept where stage 2
                looked, merged cosine / entropy score, best first (`rvl_merge_rank`).
 
     `features` [T, 768] fp32 (host numpy or torch); `detok(tokens [n, T'])` -> answer strings (a tokenizer's batch_decode with
     the reference's strip / stop-string rule); `gt` = (start, end) as fractions of the movie.  Every rank returns the stage-1
-    part; stage-2 results and the ranking live on `stage2_rank` (the other ranks return None there - no second exchange)."""
+    part; the ranking lives on `stage2_rank`, the stage-2 calls on every rank (on `stage2_rank` only without call sharding).
+    `timings`: a dict that receives the wall-clock ms of each phase (the device is synchronised at the phase boundaries: a
+    diagnostic, it serialises what otherwise overlaps)."""
+    import time
     from . import metrics
     from .features import WindowLoader
     eng, dev = model.engine, model.device
+    t_prev = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + 1e3 * (now - t_prev[0])
+            t_prev[0] = now
     feats_np = features.numpy() if isinstance(features, torch.Tensor) else np.asarray(features)
     T = feats_np.shape[0]
     loader = getattr(model, "_window_loader", None)                                        # pinned staging buffer, kept across movies
@@ -439,6 +486,7 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
     mine = shard_indices(W, rank, world)
     win1 = eng.gather_windows(movie, torch.from_numpy(np.ascontiguousarray(idx1[mine])).to(dev)) if len(mine) else \
         torch.empty((0, cfg.num_frames, feats_np.shape[1]), dtype=torch.bfloat16, device=dev)
+    lap("upload_and_window_gather")
 
     def decode_spans(tok):
         spans = torch.full((tok.shape[0], 2), -1, dtype=torch.int32)
@@ -448,6 +496,7 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
                 spans[i, 0], spans[i, 1] = sp
         return spans
     local = score_segments(model, win1, input_ids, cls, cfg.max_new_tokens, decode_spans, cfg.stage1_batch, eos_token_id)
+    lap("stage1")
     records = allgather_records(local, W, rank, world, group)
     un = unpack_records(records.cpu())
     answers = detok(un["tokens"][:, : int(un["n_tokens"].max())])
@@ -461,7 +510,11 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
     # the end of the stage-2 grid (the reference then fails on `clip_feats[i]` and its bare `except` drops the query): leave them out
     grounding = [w for w in grounding if -idx2.shape[0] <= w < idx2.shape[0]]
     res = MovieResult(records, answers, clip_frames, ious, grounding, None, None, None, None)
-    if rank != stage2_rank or not grounding or model.clip_encoder is None:
+    lap("allgather_parse_select")
+    # one query has up to ~24 independent stage-2 prompts (chunks x zoom levels): with several ranks they are dealt out and the
+    # per-call records all-gathered, so every rank holds the stage-2 calls and `stage2_rank` ranks them
+    sharded = cfg.stage2_shard_calls and world > 1 and cfg.max_new_tokens <= REC_TOKENS
+    if (rank != stage2_rank and not sharded) or not grounding or model.clip_encoder is None:
         return res
     gw = np.asarray(grounding, dtype=np.int64)                                             # negative ids index from the end, as in the reference
     win2 = eng.gather_windows(movie, torch.from_numpy(np.ascontiguousarray(idx2[gw])).to(dev))
@@ -470,15 +523,19 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
     def answer_number(tok):
         return scoring.parse_first_int(dt2(tok[None].cpu())[0])
     ids2 = stage2_input_ids if stage2_input_ids is not None else input_ids
+    lap("stage2_window_gather")
     calls = stage2_pass(model, win2, query_feats, ids2, grounding, cfg.batch, cfg.zooms, cfg.max_new_tokens, cfg.perm_seed,
-                        answer_number, eos_token_id)
+                        answer_number, eos_token_id, max_calls_per_batch=cfg.stage2_calls_per_batch, rank=rank, world=world,
+                        shard_calls=sharded, group=group)
+    lap("stage2_pass")
     answers2 = [dt2(torch.tensor(c["tokens"])[None])[0] for c in calls]
     frames2, _hit = metrics.stage2_frames(answers2, gt, cfg.batch, [c["start"] for c in calls], [c["perm"] for c in calls],
                                           [c["zoom"] for c in calls], grounding)
     res.stage2, res.stage2_answers, res.stage2_frames = calls, answers2, frames2
-    if clip_frames:
+    if clip_frames and rank == stage2_rank:
         # rank_query expects one entry per answered window in window order - `present` there is defined by the answer strings
         present = [i for i, a in enumerate(answers) if a != "Not Present" and a != "From 249 to 249."]
         if present == list(clip_frames):
             res.ranked = metrics.rank_query(eng, answers, cos, ent, ious, stage2_frames=frames2, mode=cfg.score_merge, normalize=cfg.normalize)
+    lap("merge_rank")
     return res

@@ -203,3 +203,56 @@ def test_stage1_sweep_driver_world2_gloo_equals_one_rank():
     assert got[0][1] == [0, 2, 4, 6, 8, 10] and got[1][1] == [1, 3, 5, 7, 9]
     un = sweep.unpack_records(alone.records)
     assert un["tokens"].shape[0] == 11 and torch.isfinite(un["h_mean"]).all()
+
+
+class _FakeStage2Model:
+    """generate() stand-in for the stage-2 driver: tokens and entropies are a function of each prompt's stacked windows."""
+    engine = None
+    device = torch.device("cpu")
+
+    def generate(self, ids, images=None, max_new_tokens=4, **kw):
+        code = images.float().sum(dim=(1, 2, 3)) + ids.clamp(min=0).sum(dim=1).float()
+        new = torch.stack([(code * (t + 1)).round().long() % 83 for t in range(max_new_tokens)], dim=1)
+        ent = (code[:, None] % 7 + 1.0) * torch.arange(1, max_new_tokens + 1)[None] * 0.125
+        return {"sequences": torch.cat([ids, new], dim=1), "entropies": ent}
+
+
+def _stage2_inputs():
+    g = torch.Generator().manual_seed(12)
+    wins = torch.randint(-3, 4, (11, 5, 8), generator=g).to(torch.bfloat16)
+    ids = torch.randint(3, 300, (9,), generator=g)
+    kw = dict(grounding_windows=list(range(20, 31)), batch=4, zooms=(4, 2, 1), max_new_tokens=5, perm_seed=3,
+              answer_number=lambda t: int(t[0]) % 4, eos_token_id=None)
+    return wins, ids, kw
+
+
+def _worker_stage2(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wins, ids, kw = _stage2_inputs()
+        calls = sweep.stage2_pass(_FakeStage2Model(), wins, None, ids, rank=rank, world=world, shard_calls=True, **kw)
+        q.put((rank, calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stage2_calls_dealt_to_two_ranks_equal_one_rank():
+    """One query's stage-2 generate() calls (chunks x zoom levels) dealt round-robin to two ranks + the all-gather of their
+    records: every rank ends with the list of calls - tokens, entropy statistics, chosen window - that one rank computes alone."""
+    wins, ids, kw = _stage2_inputs()
+    alone = sweep.stage2_pass(_FakeStage2Model(), wins, None, ids, **kw)
+    assert len(alone) == 11 + 6 + 3
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_stage2, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1] == alone
