@@ -535,7 +535,7 @@ def main():
         except Exception as e:      # stage 2 is reported, never allowed to take the headline number down
             line["stage2_top100"] = {"error": repr(e)[:200]}
     # ---- north_star "Target": ONE synthetic one-hour MAD-shaped movie through stage 1 (segment-sharded over the N ranks, one
-    # all-gather) + answer parsing + stage-2 window selection + the stage-2 top-100 pass on one rank + merge / ranking, as one
+    # all-gather) + answer parsing + stage-2 window selection + the stage-2 top-100 pass (calls dealt to the ranks) + merge / ranking, as one
     # chained call from HOST features (sweep.run_movie).  Windows: 200 feature frames sampled to 100, stride 100 -> 179 segments.
     if not args.no_movie_e2e:
         try:
@@ -571,7 +571,9 @@ def main():
                                  "ranked_proposals": len(mres.ranked["windows"]) if mres.ranked else 0,
                                  "phases_ms": {k: round(v, 2) for k, v in phases.items()},
                                  "note": "wall clock, host features in -> ranked proposals out on rank 0: upload + window gather + stage 1 on N ranks + "
-                                         "all-gather + parse + select + stage-2 top-100 (ClipEncoder + zooms 4/2/1) on rank 0 + merge/rank kernel"}
+                                         "all-gather + parse + select + stage-2 top-100 (ClipEncoder + zooms 4/2/1; its independent generate() calls dealt to the N ranks, "
+                                         "one all-gather of their records) + merge/rank kernel on rank 0; phases_ms: one extra run with the device synchronised "
+                                         "at the phase boundaries"}
         except Exception as e:
             line["movie_e2e"] = {"error": repr(e)[:300]}
     # ---- BASELINE.json configs[4]: VidChapters-shaped ragged batch - videos of 1-60 min at 2 fps, 500 s windows with 250 s
