@@ -707,6 +707,45 @@ def main():
             del sc, out
         except Exception as e:
             line.setdefault("parity_full_size", {})["fixture_error"] = repr(e)[:200]
+    # ---- the same for stage 2 (BASELINE.json configs[3]; tests/golden/stage2_7b.npz from make_golden_7b_stage2.py): three prompts of
+    # 100 ClipEncoder CLS tokens (zoom 1 / 2 / 4) over 100 windows x 250 frames, adapter weights from the CPU generator
+    fix2 = os.path.join(ROOT, "tests", "golden", "stage2_7b.npz")
+    if rank == 0 and world == 1 and not args.no_stage2 and os.path.exists(fix2):
+        try:
+            import importlib.util
+            from revisionllm_b200.clip_encoder import ClipEncoder
+            spec = importlib.util.spec_from_file_location("make_golden_7b_stage2", os.path.join(ROOT, "tests", "golden", "make_golden_7b_stage2.py"))
+            gen2 = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(gen2)
+            g2 = np.load(fix2)
+            wins2 = syn.make_features(gen2.V, gen2.T, cfg.adapter_dim, seed=41)
+            gq2 = torch.Generator().manual_seed(42)
+            qt2 = torch.randn(1, gen2.LQ, cfg.adapter_dim, generator=gq2).to(torch.bfloat16)
+            qm2 = torch.ones(1, gen2.LQ)
+            qm2[0, gen2.LQ - 5:] = 0
+            ids2 = syn.make_prompt_ids(cfg, seed=9)
+            rows2 = [torch.arange(gen2.V), torch.arange(gen2.V // 2).repeat_interleave(2), torch.arange(gen2.V // 4).repeat_interleave(4)]
+            keep_enc = model.clip_encoder
+            model.clip_encoder = ClipEncoder(eng, syn.make_clip_encoder_weights(cfg.hidden, seed=0))
+            n2, steps2 = g2["tokens"].shape
+            o2 = model.generate(ids2[None].repeat(n2, 1), images=torch.stack([wins2[r] for r in rows2]), query_feats=(qt2.repeat(n2, 1, 1), qm2.repeat(n2, 1)),
+                                max_new_tokens=steps2, output_scores=True, return_dict_in_generate=True, eos_token_id=None)
+            model.clip_encoder = keep_enc
+            tok2 = o2["sequences"][:, ids2.shape[0]:].cpu()
+            sc2 = torch.stack(o2["scores"]).float().cpu()
+            worst2 = 0.0
+            for i in range(n2):
+                got = torch.gather(sc2[:, i], 1, torch.from_numpy(g2["top_ids"][i].astype(np.int64)))
+                err = (got - torch.from_numpy(g2["top_vals"][i])).abs().amax(dim=1) / torch.from_numpy(g2["row_absmax"][i])
+                got_p = sc2[:, i][:, torch.from_numpy(g2["probe_ids"].astype(np.int64))]
+                err_p = (got_p - torch.from_numpy(g2["probe_vals"][i])).abs().amax(dim=1) / torch.from_numpy(g2["row_absmax"][i])
+                worst2 = max(worst2, float(err.max()), float(err_p.max()))
+            line.setdefault("parity_full_size", {})["stage2"] = {
+                "prompts_checked": int(n2), "tokens_identical": int(sum(tok2[i].tolist() == g2["tokens"][i].tolist() for i in range(n2))),
+                "logit_max_rel_err_per_row": worst2, "tolerance": 3e-2,
+                "oracle": "cached fp32 CPU oracle (tests/golden/stage2_7b.npz): ClipEncoder over 100 windows x 250 frames + 100 CLS tokens in a 7B prompt, zoom 1 / 2 / 4"}
+        except Exception as e:
+            line.setdefault("parity_full_size", {})["stage2"] = {"error": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
