@@ -86,6 +86,7 @@ class KVState:
         self.steps = 0                     # tokens appended since the prefill
         self.shared_prefix = 0
         self.n_shared = 0
+        self.group = None                  # rows with the same entry share their first n_shared pages (None: the whole batch)
 
     def get_seq_length(self) -> int:
         return int(self.lengths.max()) + self.steps
@@ -216,39 +217,61 @@ class RevisionLlamaForCausalLM:
         return images.to(dev, torch.bfloat16).reshape(B * F, D).contiguous(), [F] * B, False
 
     def _share_prefix_rows(self, plan) -> None:
-        """Opt-in (`share_prefix_compute`): the whole pages of a text prefix common to every sequence of the batch are computed
-        ONCE.  The packed stream becomes [prefix (P rows) | seq 0 from position P | seq 1 from position P | ...]; the prefix is
-        one more sequence whose K/V go to the shared pages, and every real sequence names it as its attention context
-        (`seq_pos0` / `seq_ctx_row` of rvl_prefill).  Row-wise kernels (GEMMs, norms, SwiGLU) never see the difference and the
-        attention tiles stay aligned to absolute positions, so every logit keeps its bits - (B - 1) * P rows of work disappear
-        (32 of 184 positions for the 1-hour sweep).  Off by default: the headline benchmark computes every segment in full,
-        like the reference."""
+        """Opt-in (`share_prefix_compute`): the whole pages of a prompt prefix common to several sequences are computed ONCE.
+        Sequences are grouped (`plan["group"]`: one group for the whole batch when only the text in front of <video> is
+        common; one group per distinct visual input when `image_index` says which rows show the same segment - then the
+        visual positions are common too).  The packed stream becomes [context of group 0 (P rows) | context of group 1 | ... |
+        seq 0 from position P | seq 1 from position P | ...]; each context is one more sequence whose K/V go to the pages its
+        group shares, and every real sequence names its group's context as its attention context (`seq_pos0` / `seq_ctx_row`
+        of rvl_prefill).  Row-wise kernels (GEMMs, norms, SwiGLU) never see the difference and the attention tiles stay
+        aligned to absolute positions, so every logit keeps its bits - (B - G) * P rows of work disappear (32 of 184 positions
+        for the 1-hour sweep of one query; 128 of 184 for every further query on the same movie).  Off by default: the
+        headline benchmark computes every segment in full, like the reference."""
         ps = self.engine.cfg.kv_page_size
         lengths = plan["lengths"].astype(np.int64)
         B = lengths.shape[0]
+        group = np.asarray(plan.get("group", np.zeros(B, dtype=np.int64)), dtype=np.int64)
+        uniq, first, inv = np.unique(group, return_index=True, return_inverse=True)      # leader = first member of each group
+        G = uniq.shape[0]
         P = (min(int(plan["shared_prefix"]), int(lengths.min()) - 1) // ps) * ps
-        if B < 2 or P < ps:
+        if B < 2 or G == B or P < ps:
             return
         cu = plan["cu_seqlens"].astype(np.int64)
-        new_start = np.concatenate([[P], P + np.cumsum(lengths - P)])                  # first own row of sequence b; [-1] = total
+        own_start = np.concatenate([[G * P], G * P + np.cumsum(lengths - P)])          # first own row of sequence b; [-1] = total
+        leader = np.zeros(B, dtype=bool)
+        leader[first] = True
         def remap(dst):
             b = np.searchsorted(cu, dst, side="right") - 1
             pos = dst - cu[b]
-            keep = (pos >= P) | (b == 0)
-            return keep, np.where(pos < P, pos, new_start[b] + pos - P)
+            keep = (pos >= P) | leader[b]
+            return keep, np.where(pos < P, inv[b] * P + pos, own_start[b] + pos - P)
         kt, nt = remap(plan["text_dst"].astype(np.int64))
         kv_, nv = remap(plan["vis_dst"].astype(np.int64))
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         plan["text_ids"], plan["text_dst"] = i32(plan["text_ids"][kt]), i32(nt[kt])
         plan["vis_src"], plan["vis_dst"] = i32(plan["vis_src"][kv_]), i32(nv[kv_])
-        plan["cu_seqlens"] = i32(np.concatenate([[0], new_start]))                     # B + 1 sequences: the prefix first
+        plan["cu_seqlens"] = i32(np.concatenate([np.arange(G) * P, own_start]))        # G + B sequences: the contexts first
         plan["ctx_len"] = P
+        plan["ctx_groups"] = G
+        plan["group_of"] = inv                                                          # dense group number of every sequence
+        plan["group_leader"] = first
 
     def _splice(self, input_ids, attention_mask, images, query_feats, visual_memory=None, prefix_memory=None,
-                share_compute: bool = False):
-        """Projector + splice into a packed fp32 residual stream.  Returns (hidden [T, H], plan)."""
+                share_compute: bool = False, image_index=None):
+        """Projector + splice into a packed fp32 residual stream.  Returns (hidden [T, H], plan).
+        `image_index` (int [B]): row b shows `images[image_index[b]]` - several prompts (queries) over the same segments
+        without repeating the features; rows that share a segment form a group for `share_prefix_compute`."""
         eng = self.engine
         rows, n_vis, projected = self._visual_blocks(images, query_feats)
+        idx_np = None
+        if image_index is not None:
+            if projected or isinstance(images, (list, tuple)) or visual_memory is not None:
+                raise RvlError("image_index is defined for stage-1 `images` [S, F, D] (Linear projector, no visual_memory)")
+            idx_np = np.asarray(image_index.detach().cpu().numpy() if isinstance(image_index, torch.Tensor) else image_index, dtype=np.int64)
+            if idx_np.shape[0] != input_ids.shape[0] or idx_np.min() < 0 or idx_np.max() >= len(n_vis):
+                raise RvlError("image_index needs one entry per prompt, each naming a row of `images`")
+            n_src = n_vis
+            n_vis = [n_src[i] for i in idx_np]                                          # visual rows of every prompt
         ids_np = input_ids.detach().cpu().numpy().astype(np.int64)
         am_np = None if attention_mask is None else attention_mask.detach().cpu().numpy().astype(bool)
         if visual_memory is not None:
@@ -276,8 +299,19 @@ class RevisionLlamaForCausalLM:
             rows = torch.cat([rows.view(B, F, D), vm.to(self.device, torch.bfloat16)], dim=1).reshape(B * (F + M), D).contiguous()
             n_vis = [n for _ in range(B) for n in (F, M)]
         plan = plan_splice(ids_np, n_vis, am_np, self.config.tokenizer_model_max_length, constants.IMAGE_TOKEN_INDEX)
-        plan["shared_prefix"] = min(self._common_text_prefix(ids_np, am_np), int(plan["lengths"].min()))
+        pre = self._common_text_prefix(ids_np, am_np)
+        plan["shared_prefix"] = min(pre, int(plan["lengths"].min()))
         plan["ctx_len"] = 0
+        if idx_np is not None:
+            # plan["vis_src"] counts the visual rows prompt by prompt: point them at the rows of the segment each prompt shows
+            F = n_src[0]
+            src = plan["vis_src"].astype(np.int64)
+            plan["vis_src"] = np.ascontiguousarray(idx_np[src // F] * F + src % F, dtype=np.int32)
+            # the same text up to a <video> placeholder at the same place in every row: prompts on the same segment also share
+            # its visual positions
+            if ids_np.shape[0] > 1 and pre < ids_np.shape[1] and bool((ids_np[:, pre] == constants.IMAGE_TOKEN_INDEX).all()):
+                plan["group"] = idx_np
+                plan["shared_prefix"] = min(pre + F, int(plan["lengths"].min()))
         if share_compute:
             self._share_prefix_rows(plan)
         dev = self.device
@@ -294,30 +328,35 @@ class RevisionLlamaForCausalLM:
             eng.project_splice(rows, vis_dst, text_ids, text_dst, hidden)
         return hidden, plan
 
-    def _alloc_kv(self, lengths: np.ndarray, extra: int, shared_prefix: int = 0) -> KVState:
+    def _alloc_kv(self, lengths: np.ndarray, extra: int, shared_prefix: int = 0, group: Optional[np.ndarray] = None) -> KVState:
         """Page table of one live batch.  `shared_prefix` = number of leading prompt positions whose tokens are identical
         in every sequence (the system prompt in front of <video>): causal attention makes their K/V identical too, so
         the whole pages they fill are mapped to the SAME physical pages for all sequences.  Every sequence still
         computes and writes them at prefill (identical bits); what changes is that the 180 x 32 decode-attention CTAs
-        of a step read one copy that stays in the 126 MB L2 instead of 180 copies from HBM."""
+        of a step read one copy that stays in the 126 MB L2 instead of 180 copies from HBM.
+        `group` (int [B]): the positions are identical only among rows of the same group (prompts on the same segment,
+        `image_index`): each group gets its own copy of the shared pages."""
         eng = self.engine
         ps = eng.cfg.kv_page_size
         n_shared = (shared_prefix // ps) if (self.share_prefix_pages and len(lengths) > 1) else 0
         pages_per = [int(math.ceil((int(l) + extra) / ps)) for l in lengths]
         n_shared = min([n_shared] + [int(l) // ps for l in lengths])
+        gid = np.zeros(len(lengths), dtype=np.int64) if group is None else np.unique(np.asarray(group), return_inverse=True)[1]
+        n_groups = int(gid.max()) + 1 if len(lengths) else 0
         max_pages = max(pages_per)
-        total = n_shared + sum(n - n_shared for n in pages_per)
+        total = n_groups * n_shared + sum(n - n_shared for n in pages_per)
         eng.ensure_kv(total)
         table = np.zeros((len(lengths), max_pages), dtype=np.int32)
-        nxt = n_shared
+        nxt = n_groups * n_shared
         for i, n in enumerate(pages_per):
-            table[i, :n_shared] = np.arange(n_shared, dtype=np.int32)
+            table[i, :n_shared] = gid[i] * n_shared + np.arange(n_shared, dtype=np.int32)
             table[i, n_shared:n] = np.arange(nxt, nxt + n - n_shared, dtype=np.int32)
             nxt += n - n_shared
         dev = self.device
         kv = KVState(torch.from_numpy(table).to(dev), torch.from_numpy(lengths.astype(np.int32)).to(dev), extra, lengths)
         kv.shared_prefix = shared_prefix
-        kv.n_shared = n_shared              # leading pages every row maps to the same physical pages
+        kv.n_shared = n_shared              # leading pages every row of a group maps to the same physical pages
+        kv.group = None if group is None else np.asarray(group)
         return kv
 
     @staticmethod
@@ -390,7 +429,7 @@ class RevisionLlamaForCausalLM:
                  max_new_tokens=1024, use_cache=True, visual_memory=None, prefix_memory=None, output_scores=False,
                  return_dict_in_generate=False, output_hidden_states=False, attention_mask=None,
                  eos_token_id="config", pad_token_id=None, stopping_criteria=None, seed: int = 0,
-                 retire_finished: bool = False, mask_entropy_after_eos: bool = False, **unused):
+                 retire_finished: bool = False, mask_entropy_after_eos: bool = False, image_index=None, **unused):
         """`seed`: key of the Philox stream used when do_sample=True.  `retire_finished`: drop rows that emitted EOS from the
         decode batch (their remaining tokens are pad, as in the reference; their per-step entropies stop at EOS instead of
         continuing over pad inputs as the reference's do).  `mask_entropy_after_eos`: keep every row in the batch but report
@@ -401,7 +440,10 @@ class RevisionLlamaForCausalLM:
         The loop looks at the EOS flags every `engine.DECODE_CHUNK` steps instead of every step (the reference's
         `unfinished_sequences.max() == 0` test, vtimellm_llama.py:359-362, costs one host synchronisation per token); steps
         that ran after the last row finished are trimmed from the outputs, so the result is the reference's.  Greedy decoding
-        without per-step scores replays each chunk of steps as one CUDA graph (`decode_graphs`)."""
+        without per-step scores replays each chunk of steps as one CUDA graph (`decode_graphs`).
+        `image_index` (int [B]): prompt b shows `images[image_index[b]]` ([S, F, D] stage-1 features) - several queries over
+        the same segments in one batch; with `share_prefix_compute` the system text and the visual positions of a segment are
+        computed once for all its prompts."""
         self._need_engine()
         if num_beams != 1:
             raise NotImplementedError("beam search is not part of the reference path (num_beams=1, inference.py:49)")
@@ -420,7 +462,7 @@ class RevisionLlamaForCausalLM:
             if ev:
                 ev[0].record()
             hidden, plan = self._splice(input_ids, attention_mask, images, query_feats, visual_memory, prefix_memory,
-                                        share_compute=self.share_prefix_compute)
+                                        share_compute=self.share_prefix_compute, image_index=image_index)
             if ev:
                 ev[1].record()
             lengths, cu = plan["lengths"], plan["cu_seqlens"]
@@ -431,7 +473,7 @@ class RevisionLlamaForCausalLM:
             max_new = min(int(max_new_tokens), room)
             # KV pages: everything up front when small, else grow in chunks of 64 tokens as decoding proceeds
             chunk = max_new if max_new <= 64 else 64
-            kv = self._alloc_kv(lengths, chunk, plan["shared_prefix"])
+            kv = self._alloc_kv(lengths, chunk, plan["shared_prefix"], plan.get("group"))
             # chunks of decode steps between two looks at the EOS flags; greedy chunks without per-step outputs are captured as
             # CUDA graphs over fixed-address buffers (engine.decode_chunk)
             chunked = not sampling and not retire_finished and not output_scores and max_new <= 64
@@ -440,24 +482,28 @@ class RevisionLlamaForCausalLM:
             P = int(plan["ctx_len"])
             self.last_shared_prefix = P         # positions of the prompt prefix computed once for the batch (0: none), for tests / tools
             if P:
-                # B + 1 sequences: the shared prefix (its K/V fill the shared pages), then every segment from position P on
+                # G + B sequences: the context of every group (its K/V fill the pages the group shares), then every prompt from
+                # position P on, naming its group's context rows
                 ps = eng.cfg.kv_page_size
                 if kv.n_shared < P // ps:
-                    raise RvlError("share_prefix_compute needs the prefix pages mapped once for the whole batch (share_prefix_pages=True): "
+                    raise RvlError("share_prefix_compute needs the prefix pages mapped once per group (share_prefix_pages=True): "
                                    f"{P // ps} prefix pages are computed once but only {kv.n_shared} are shared")
-                table = torch.zeros((B + 1, kv.page_table.shape[1]), dtype=torch.int32, device=dev)
-                table[0, : P // ps] = kv.page_table[0, : P // ps]
-                table[1:] = kv.page_table
-                pos0 = torch.full((B + 1,), P, dtype=torch.int32, device=dev)
-                pos0[0] = 0
-                all_last = torch.empty((B + 1, cfg.vocab_size), dtype=torch.float32, device=dev)
-                eng.prefill(hidden, cu_d, B + 1, int(lengths.max()), table, all_last, all_logits=False, seq_pos0=pos0,
-                            seq_ctx_row=torch.zeros(B + 1, dtype=torch.int32, device=dev))
+                G = int(plan["ctx_groups"])
+                lead = torch.from_numpy(np.ascontiguousarray(plan["group_leader"], dtype=np.int64)).to(dev)
+                table = torch.zeros((G + B, kv.page_table.shape[1]), dtype=torch.int32, device=dev)
+                table[:G, : P // ps] = kv.page_table.index_select(0, lead)[:, : P // ps]
+                table[G:] = kv.page_table
+                pos0 = torch.full((G + B,), P, dtype=torch.int32, device=dev)
+                pos0[:G] = 0
+                ctx_row = torch.zeros(G + B, dtype=torch.int32, device=dev)
+                ctx_row[G:] = torch.from_numpy(np.ascontiguousarray(plan["group_of"] * P, dtype=np.int32)).to(dev)
+                all_last = torch.empty((G + B, cfg.vocab_size), dtype=torch.float32, device=dev)
+                eng.prefill(hidden, cu_d, G + B, int(lengths.max()), table, all_last, all_logits=False, seq_pos0=pos0, seq_ctx_row=ctx_row)
                 if chunked:
                     logits = bufs["logits"]
-                    logits.copy_(all_last[1:])
+                    logits.copy_(all_last[G:])
                 else:
-                    logits = all_last[1:].contiguous()
+                    logits = all_last[G:].contiguous()
             else:
                 logits = bufs["logits"] if chunked else torch.empty((B, cfg.vocab_size), dtype=torch.float32, device=dev)
                 eng.prefill(hidden, cu_d, B, int(lengths.max()), kv.page_table, logits, all_logits=False)
@@ -542,6 +588,7 @@ class RevisionLlamaForCausalLM:
                         kv_live = KVState(kv.page_table.index_select(0, live).contiguous(), kv.seq_lens.index_select(0, live).contiguous(),
                                           kv.reserve, kv.lengths[live.cpu().numpy()])
                         kv_live.steps, kv_live.shared_prefix, kv_live.n_shared = kv.steps, getattr(kv, "shared_prefix", 0), kv.n_shared
+                        kv_live.group = None if getattr(kv, "group", None) is None else kv.group[live.cpu().numpy()]
                         kv = kv_live
                         tok_t = tok_t.index_select(0, live).contiguous()
                         unfinished = unfinished.index_select(0, live).contiguous()
@@ -588,7 +635,7 @@ class RevisionLlamaForCausalLM:
         c = eng.cfg
         eng._kv = None
         eng.n_pages = 0
-        new = self._alloc_kv(lengths, extra, getattr(kv, "shared_prefix", 0))
+        new = self._alloc_kv(lengths, extra, getattr(kv, "shared_prefix", 0), getattr(kv, "group", None))
         per_old = old_pages * c.n_heads * c.kv_page_size * c.head_dim
         per_new = eng.n_pages * c.n_heads * c.kv_page_size * c.head_dim
         src, dst = old_kv.view(torch.bfloat16), eng._kv.view(torch.bfloat16)

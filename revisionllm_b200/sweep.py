@@ -166,6 +166,80 @@ def score_segments(model, seg_feats: torch.Tensor, input_ids: torch.Tensor, cls:
     return torch.cat(recs, dim=0)
 
 
+def score_segments_queries(model, seg_feats: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor],
+                           max_new_tokens: int = 16, decode_spans: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                           batch_segments: Optional[int] = None, eos_token_id="config", norm_axis: int = scoring.NORM_ACROSS_FRAMES,
+                           attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Several queries over the same segments in one pass - the reference's evaluation loop asks every query of a movie about
+    every window of that movie (/root/reference/revisionllm/eval/eval_nlq_negative.py:183-337 runs once per query; MAD has
+    hundreds of queries per movie), and SURVEY.md section 8e names batching the queries' sweeps as the way to keep the decode
+    batch large when a movie is spread over many GPUs.
+
+    `seg_feats` [S, F, 768]; `input_ids` [Q, Ltxt] (right-padded, `attention_mask` [Q, Ltxt] when the queries differ in
+    length); `cls` [Q, 768] or None.  Rows are segment-major - (segment s, query q) is row s * Q + q - so the prompts that
+    share a segment sit next to each other: the features travel once (`image_index`), the decode batch is Q times larger for
+    the same weight stream, and with `model.share_prefix_compute` the system text and the visual positions of a segment run
+    through the decoder once for all Q prompts.  Returns records [S * Q, REC_WORDS] in that row order."""
+    eng, dev = model.engine, model.device
+    S, F, D = seg_feats.shape
+    Q = input_ids.shape[0]
+    if S == 0 or Q == 0:
+        return torch.empty((0, REC_WORDS), dtype=torch.int32, device=dev)
+    step = S if batch_segments is None else max(1, batch_segments)
+    recs = []
+    for s0 in range(0, S, step):
+        feats = seg_feats[s0: s0 + step].to(dev, torch.bfloat16, non_blocking=True)
+        b = feats.shape[0]
+        ids = input_ids.repeat(b, 1)                                                   # row = segment * Q + query
+        am = None if attention_mask is None else attention_mask.repeat(b, 1)
+        index = torch.arange(b).repeat_interleave(Q)
+        out = model.generate(ids, images=feats, image_index=index, attention_mask=am, max_new_tokens=max_new_tokens, output_scores=False,
+                             return_dict_in_generate=True, eos_token_id=eos_token_id)
+        new_tok = out["sequences"][:, ids.shape[1]:].to(torch.int32)
+        stats = scoring.entropy_stats_from_steps(out["entropies"])
+        n = b * Q
+        spans = decode_spans(new_tok).to(dev) if decode_spans is not None else torch.full((n, 2), -1, dtype=torch.int32, device=dev)
+        cos = torch.zeros(n, dtype=torch.float32, device=dev)
+        if cls is not None:
+            base = torch.arange(0, b * F, F, dtype=torch.int64, device=dev)
+            flat = feats.reshape(b * F, D)
+            for q in range(Q):                                                         # one launch per query: its own text vector
+                begin, end = span_slices(spans[q::Q], F)
+                c, _ = eng.cosine_topk(flat, (base + begin).to(torch.int32), cls[q].to(dev, torch.bfloat16).contiguous(), k=3,
+                                       norm_axis=norm_axis, max_seg_rows=F, want_idx=False, seg_ends=(base + end).to(torch.int32))
+                cos[q::Q] = c
+        recs.append(pack_records(new_tok, spans, stats[:, 2], stats[:, 0], cos))
+    return torch.cat(recs, dim=0)
+
+
+def stage1_sweep_queries(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor], max_new_tokens: int = 16,
+                         rank: int = 0, world: int = 1, group=None, batch_segments: Optional[int] = None, decode_spans=None,
+                         eos_token_id="config", attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`score_segments_queries` on `world` ranks: segment i -> rank i mod world (each rank runs all Q queries on its segments),
+    one all-gather.  Returns records [W * Q, REC_WORDS] on every rank, row = segment * Q + query."""
+    W, Q = segments.shape[0], input_ids.shape[0]
+    mine = shard_indices(W, rank, world)
+    local = score_segments_queries(model, segments[torch.from_numpy(mine)], input_ids, cls, max_new_tokens, decode_spans, batch_segments,
+                                   eos_token_id, attention_mask=attention_mask)
+    if world == 1:
+        return local
+    # the record gather works on whole segments: Q records of a segment travel together
+    wide = allgather_wide(local.view(len(mine), Q * REC_WORDS), W, rank, world, group)
+    return wide.view(W * Q, REC_WORDS)
+
+
+def allgather_wide(local: torch.Tensor, n_total: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """`allgather_records` for rows of any width (round-robin shards: rank r, slot j -> global row j * world + r)."""
+    import torch.distributed as dist
+    width = local.shape[1]
+    per = (n_total + world - 1) // world
+    buf = torch.full((per, width), -1, dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = torch.empty((world * per, width), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out.view(world, per, width).transpose(0, 1).reshape(world * per, width)[:n_total].contiguous()
+
+
 def stage1_sweep(model, segments: torch.Tensor, input_ids: torch.Tensor, cls: Optional[torch.Tensor],
                  max_new_tokens: int = 16, rank: int = 0, world: int = 1, group=None, batch: Optional[int] = None,
                  decode_spans=None, eos_token_id="config", stage2_topk: Optional[int] = None,

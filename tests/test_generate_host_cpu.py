@@ -50,6 +50,7 @@ class CpuEngine(DecodeChunks):
     def prefill(self, hidden, cu, n_seq, max_seqlen, page_table, logits_out, all_logits=False, seq_pos0=None, seq_ctx_row=None):
         self.calls.append(("prefill", n_seq))
         self.prefill_rows = int(cu[n_seq])
+        self.caches.clear()                              # a prefill starts a new batch: page ids of the previous one mean nothing now
         for b in range(n_seq):
             x = hidden[int(cu[b]):int(cu[b + 1])][None]
             if seq_pos0 is not None and int(seq_pos0[b]) > 0:
@@ -414,6 +415,83 @@ def test_shared_prefix_compute_changes_nothing_but_the_rows_computed(cpu_model):
     assert m.engine.calls.count(("prefill", B + 1)) == 1                    # the prefix went through as one more sequence
     table = shared["past_key_values"].page_table
     assert (table[:, 0] == table[0, 0]).all() and len(set(table[:, 1].tolist())) == B
+
+
+def test_several_queries_on_the_same_segments_share_the_visual_context(cpu_model):
+    """`image_index`: Q prompts (queries) per segment in one batch without repeating the features; with `share_prefix_compute`
+    the system text AND the visual positions of a segment are embedded / run through the decoder once per segment (one context
+    sequence per group of prompts).  Same tokens and logits - to the bit on the CPU stand-in - as the batch in which every
+    prompt carries its own copy of the features, fewer rows through the prefill, the context pages mapped once per segment."""
+    m, w, cfg = cpu_model
+    S, Q, F, n_pre = 3, 2, 40, 30                                             # 30 text ids + 40 frames in front of the query: P = 64
+    feats = syn.make_features(S, F, cfg.adapter_dim, seed=18)
+    base = syn.make_prompt_ids(cfg, n_pre, 7, seed=19)
+    g = torch.Generator().manual_seed(20)
+    ids = []
+    for s_ in range(S):                                                        # segment-major rows: (segment, query)
+        for q_ in range(Q):
+            row = base.clone()
+            row[n_pre + 1:] = torch.randint(3, cfg.vocab, (row.shape[0] - n_pre - 1,), generator=torch.Generator().manual_seed(100 + q_))
+            ids.append(row)
+    ids = torch.stack(ids)
+    index = torch.arange(S).repeat_interleave(Q)
+    kw = dict(max_new_tokens=3, output_scores=True, return_dict_in_generate=True, eos_token_id=None)
+    plain = m.generate(ids, images=feats[index], **kw)                         # every prompt with its own copy of the features
+    rows_plain = m.engine.prefill_rows
+    indexed = m.generate(ids, images=feats, image_index=index, **kw)           # same batch, features stored once
+    assert indexed["sequences"].tolist() == plain["sequences"].tolist()
+    assert torch.equal(torch.stack(indexed["scores"]), torch.stack(plain["scores"]))
+    m.share_prefix_compute = True
+    shared = m.generate(ids, images=feats, image_index=index, **kw)
+    rows_shared = m.engine.prefill_rows
+    m.share_prefix_compute = False
+    assert m.last_shared_prefix == 64
+    assert shared["sequences"].tolist() == plain["sequences"].tolist()
+    assert torch.equal(torch.stack(shared["scores"]), torch.stack(plain["scores"]))
+    assert rows_plain - rows_shared == (S * Q - S) * 64                       # one context per segment instead of one per prompt
+    assert m.engine.calls.count(("prefill", S + S * Q)) == 1
+    table = shared["past_key_values"].page_table
+    for s_ in range(S):                                                        # the two context pages: one copy per segment
+        rows = table[s_ * Q:(s_ + 1) * Q, :2]
+        assert (rows == rows[0]).all()
+    assert len({tuple(r) for r in table[:, :2].tolist()}) == S and len(set(table[:, 2].tolist())) == S * Q
+    # queries of different lengths (masked tails) in the same batch
+    am = torch.ones_like(ids, dtype=torch.bool)
+    am[1::2, -2:] = False
+    plain_m = m.generate(ids, images=feats[index], attention_mask=am, **kw)
+    m.share_prefix_compute = True
+    shared_m = m.generate(ids, images=feats, image_index=index, attention_mask=am, **kw)
+    m.share_prefix_compute = False
+    assert torch.equal(torch.stack(shared_m["scores"]), torch.stack(plain_m["scores"]))
+    assert shared_m["prompt_lengths"].tolist() == plain_m["prompt_lengths"].tolist()
+
+
+def test_multi_query_sweep_equals_one_sweep_per_query(cpu_model):
+    """sweep.score_segments_queries (Q queries over S segments in one pass, rows segment-major, features stored once, shared
+    visual context) returns for every (segment, query) the record that sweep.score_segments returns for that query alone:
+    same tokens, entropy statistics, spans and span-sliced cosine scores."""
+    from revisionllm_b200 import sweep
+    m, w, cfg = cpu_model
+    S, Q, F = 5, 3, 40
+    feats = syn.make_features(S, F, cfg.adapter_dim, seed=28)
+    base = syn.make_prompt_ids(cfg, 30, 7, seed=29)
+    ids = base[None].repeat(Q, 1)
+    for q_ in range(1, Q):
+        ids[q_, 31:] = torch.randint(3, cfg.vocab, (ids.shape[1] - 31,), generator=torch.Generator().manual_seed(200 + q_))
+    cls = torch.randn(Q, cfg.adapter_dim, generator=torch.Generator().manual_seed(30)).to(torch.bfloat16)
+    spans_of = lambda tok: torch.stack([tok[:, 0] % 7, tok[:, 0] % 7 + tok[:, 1] % 5], dim=1).to(torch.int32)    # a deterministic "parser"
+    single = [sweep.score_segments(m, feats, ids[q_], cls[q_], 3, spans_of, None, None) for q_ in range(Q)]
+    for share in (False, True):
+        m.share_prefix_compute = share
+        multi = sweep.score_segments_queries(m, feats, ids, cls, 3, spans_of, batch_segments=2, eos_token_id=None)
+        m.share_prefix_compute = False
+        assert multi.shape == (S * Q, sweep.REC_WORDS)
+        for q_ in range(Q):
+            a, b = sweep.unpack_records(multi[q_::Q]), sweep.unpack_records(single[q_])
+            assert a["tokens"].tolist() == b["tokens"].tolist() and a["spans"].tolist() == b["spans"].tolist(), (share, q_)
+            for k in ("h_mean", "h_max", "cos"):
+                assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), (share, q_, k)
+    assert m.last_shared_prefix == 64 or m.last_shared_prefix == 0
 
 
 class PagedCpuEngine(CpuEngine):

@@ -326,6 +326,66 @@ def test_shared_prefix_plan_remap_is_a_compact_relabelling():
     assert small["ctx_len"] == 0 and np.array_equal(small["cu_seqlens"], keep)
 
 
+def test_shared_context_plan_with_groups_of_prompts():
+    """model._share_prefix_rows with `plan["group"]` (several prompts per segment): one context sequence per group in front
+    of the packed stream, carrying the group leader's first P items; every prompt keeps its items from position P on; every row
+    of the new stream is written exactly once.  And the page table gives each group its own copy of the shared pages."""
+    from types import SimpleNamespace
+    from revisionllm_b200.model import RevisionLlamaForCausalLM as M
+    S, Q, F, ps, n_pre = 3, 4, 50, 32, 20
+    g = np.random.default_rng(7)
+    pre = g.integers(3, 900, size=n_pre)
+    ids = np.stack([np.concatenate([pre, [-200], g.integers(3, 900, size=9)]) for _ in range(S * Q)]).astype(np.int64)
+    group = np.repeat(np.array([7, 2, 5]), Q)                            # arbitrary labels, segment-major rows
+    plan = plan_splice(ids, [F] * (S * Q))
+    plan["shared_prefix"], plan["ctx_len"], plan["group"] = n_pre + F, 0, group
+    before = {k: plan[k].copy() for k in ("cu_seqlens", "text_ids", "text_dst", "vis_src", "vis_dst", "lengths")}
+    M._share_prefix_rows(SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps))), plan)
+    P, G = plan["ctx_len"], plan["ctx_groups"]
+    assert (P, G) == (64, 3)
+    lengths = before["lengths"].astype(np.int64)
+    cu = plan["cu_seqlens"]
+    assert cu.tolist() == np.concatenate([np.arange(G) * P, G * P + np.concatenate([[0], np.cumsum(lengths - P)])]).tolist()
+    dst = np.concatenate([plan["text_dst"], plan["vis_dst"]])
+    assert sorted(dst.tolist()) == list(range(int(cu[-1])))
+    assert plan["group_of"].tolist() == np.repeat([2, 0, 1], Q).tolist() and sorted(plan["group_leader"].tolist()) == [0, 4, 8]
+    ocu = before["cu_seqlens"].astype(np.int64)
+    for gi in range(G):                                                 # context gi = the first P items of its leader
+        b = int(plan["group_leader"][gi])
+        old = sorted([(d - ocu[b], "t", t) for d, t in zip(before["text_dst"], before["text_ids"]) if ocu[b] <= d < ocu[b] + P] +
+                     [(d - ocu[b], "v", v) for d, v in zip(before["vis_dst"], before["vis_src"]) if ocu[b] <= d < ocu[b] + P])
+        new = sorted([(d - cu[gi], "t", t) for d, t in zip(plan["text_dst"], plan["text_ids"]) if cu[gi] <= d < cu[gi + 1]] +
+                     [(d - cu[gi], "v", v) for d, v in zip(plan["vis_dst"], plan["vis_src"]) if cu[gi] <= d < cu[gi + 1]])
+        assert old == new, gi
+    for b in range(S * Q):                                              # own rows: the items from position P on, in order
+        lo, hi = ocu[b] + P, ocu[b + 1]
+        old = sorted([(d - lo, t) for d, t in zip(before["text_dst"], before["text_ids"]) if lo <= d < hi] +
+                     [(d - lo, -1 - v) for d, v in zip(before["vis_dst"], before["vis_src"]) if lo <= d < hi])
+        new = sorted([(d - cu[G + b], t) for d, t in zip(plan["text_dst"], plan["text_ids"]) if cu[G + b] <= d < cu[G + b + 1]] +
+                     [(d - cu[G + b], -1 - v) for d, v in zip(plan["vis_dst"], plan["vis_src"]) if cu[G + b] <= d < cu[G + b + 1]])
+        assert old == new, b
+    # one prompt per group: nothing to share
+    solo = plan_splice(ids[:3], [F] * 3)
+    solo["shared_prefix"], solo["ctx_len"], solo["group"] = n_pre + F, 0, np.array([0, 1, 2])
+    M._share_prefix_rows(SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps))), solo)
+    assert solo["ctx_len"] == 0
+    # page table: two shared pages per group, disjoint between groups, own pages disjoint everywhere
+    asked = []
+    stub = SimpleNamespace(engine=SimpleNamespace(cfg=SimpleNamespace(kv_page_size=ps), ensure_kv=asked.append),
+                           device=torch.device("cpu"), share_prefix_pages=True)
+    kv = M._alloc_kv(stub, lengths, extra=16, shared_prefix=n_pre + F, group=group)
+    t = kv.page_table.numpy()
+    need = int(np.ceil((int(lengths[0]) + 16) / ps))
+    for gi in range(S):
+        rows = t[gi * Q:(gi + 1) * Q]
+        assert (rows[:, :2] == rows[0, :2]).all()
+    shared = {tuple(r[:2]) for r in t}
+    assert len(shared) == S and len({p for pair in shared for p in pair}) == 2 * S
+    own = t[:, 2:need].reshape(-1).tolist()
+    assert len(own) == len(set(own)) and not set(own) & {p for pair in shared for p in pair}
+    assert asked == [2 * S + len(own)]
+
+
 def test_kv_page_table_shares_whole_prefix_pages_only():
     """model._alloc_kv: pages filled entirely by the common prompt prefix are mapped once for all sequences; every other page
     belongs to exactly one sequence; every sequence can hold its prompt plus the reserved new tokens."""
