@@ -176,6 +176,7 @@ def main():
                     help="also time a VidChapters-shaped ragged batch (BASELINE.json configs[4]: stage 1 + stage 2) of this many videos, "
                          "sharded over the ranks; default: 1024 on 8 GPUs, none otherwise")
     ap.add_argument("--no-movie-e2e", action="store_true", help="skip the chained stage-1 -> stage-2 -> rank measurement")
+    ap.add_argument("--no-multi-query", action="store_true", help="skip the 8-queries-per-movie measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -444,6 +445,42 @@ def main():
         line["shared_prefix_compute"] = {"error": repr(e)[:200]}
     finally:
         model.share_prefix_compute = False
+    # ---- several queries of the SAME movie in one pass (reported beside the headline, NOT part of `value`): the reference asks every
+    # query of a movie about every window, one sweep per query (eval_nlq_negative.py:183-337; MAD has hundreds of queries per
+    # movie), and SURVEY.md section 8e names batching the queries' sweeps as the way to keep the decode batch large when a movie is
+    # spread over many GPUs.  8 queries x 180 segments: rows segment-major, features stored once (`image_index`), the system text
+    # and the visual positions of a segment (128 of 184 positions) computed once per segment (`share_prefix_compute`), segments
+    # dealt to the ranks, one all-gather.  Same tokens as one sweep per query.
+    if strong and n_seg == N_SEG and not args.no_multi_query:
+        try:
+            from revisionllm_b200 import constants
+            Qm = 8
+            n_pre = int((ids == constants.IMAGE_TOKEN_INDEX).nonzero()[0])
+            ids_q = ids[None].repeat(Qm, 1)
+            for q in range(1, Qm):              # same system text, another query text behind <video> (the last ids stay: same planted chain)
+                ids_q[q, n_pre + 1:-4] = torch.randint(3, cfg.vocab, (ids.shape[0] - n_pre - 5,), generator=torch.Generator().manual_seed(500 + q))
+            cls_q = torch.randn(Qm, cfg.adapter_dim, generator=torch.Generator().manual_seed(6)).to(torch.bfloat16).to(dev)
+            model.share_prefix_compute = True
+            mq = lambda: sweep.stage1_sweep_queries(model, feats_dev, ids_q, cls_q, NEW_TOKENS, rank, world, batch_segments=90, eos_token_id=None)
+            for _ in range(3):
+                rec_q = mq()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                rec_q = mq()
+            barrier()
+            mq_ms = 1e3 * max_over_ranks(time.perf_counter() - t0) / 2
+            tok_q = sweep.unpack_records(rec_q)["tokens"].view(n_seg, Qm, -1)
+            tok_1 = sweep.unpack_records(rec)["tokens"][:n_seg]
+            line["multi_query"] = {"queries": Qm, "segments": n_seg, "ms": mq_ms, "ms_per_query": mq_ms / Qm, "value": n_seg * Qm / (mq_ms * 1e-3),
+                                   "unit": "segment-queries/s", "vs_one_sweep_per_query": (dev_ms / args.steps * Qm) / mq_ms,
+                                   "shared_positions": int(model.last_shared_prefix), "rows_per_rank": int(len(sweep.shard_indices(n_seg, rank, world)) * Qm),
+                                   "query0_tokens_identical_to_headline_run": bool((tok_q[:, 0] == tok_1).all()),
+                                   "note": "8 queries on the headline's movie in one pass against 8 x the headline's step time; opt-in batching + shared visual context"}
+        except Exception as e:
+            line["multi_query"] = {"error": repr(e)[:300]}
+        finally:
+            model.share_prefix_compute = False
     # ---- the reference's own windowing of a 1-hour MAD movie (eval_nlq_negative.py:226-235: 250 frames per window, stride
     # half a window -> 57 windows, L = 334), reported beside the headline, not part of `value`
     try:

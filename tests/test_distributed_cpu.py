@@ -256,3 +256,59 @@ def test_stage2_calls_dealt_to_two_ranks_equal_one_rank():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got[0] == got[1] == alone
+
+
+class _FakeIndexedModel:
+    """generate() stand-in for the multi-query sweep: tokens are a function of the segment a row shows and of its prompt."""
+    engine = None
+    device = torch.device("cpu")
+
+    def generate(self, ids, images=None, image_index=None, max_new_tokens=4, **kw):
+        code = images.float().sum(dim=(1, 2))[image_index] + ids.clamp(min=0).sum(dim=1).float()
+        new = torch.stack([(code * (t + 1)).round().long() % 83 for t in range(max_new_tokens)], dim=1)
+        ent = (code[:, None] % 7 + 1.0) * torch.arange(1, max_new_tokens + 1)[None] * 0.125
+        return {"sequences": torch.cat([ids, new], dim=1), "entropies": ent}
+
+
+def _multi_query_inputs():
+    g = torch.Generator().manual_seed(14)
+    segs = torch.randint(-3, 4, (11, 6, 8), generator=g).to(torch.bfloat16)
+    ids = torch.randint(3, 300, (3, 9), generator=g)                    # three queries
+    return segs, ids
+
+
+def _worker_multi_query(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        segs, ids = _multi_query_inputs()
+        rec = sweep.stage1_sweep_queries(_FakeIndexedModel(), segs, ids, None, max_new_tokens=4, rank=rank, world=world, batch_segments=2,
+                                         eos_token_id=None)
+        q.put((rank, rec.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multi_query_sweep_world2_gloo_equals_one_rank():
+    """sweep.stage1_sweep_queries on two ranks: segment i -> rank i mod 2 with all its queries, the Q records of a segment travel
+    together through one all-gather; every rank ends with the [W * Q] table (row = segment * Q + query) one rank computes."""
+    segs, ids = _multi_query_inputs()
+    alone = sweep.stage1_sweep_queries(_FakeIndexedModel(), segs, ids, None, max_new_tokens=4, batch_segments=4, eos_token_id=None).numpy()
+    assert alone.shape == (11 * 3, sweep.REC_WORDS)
+    # row = segment * Q + query: the same segment with another query differs, the same query on another segment differs
+    tok = sweep.unpack_records(torch.from_numpy(alone))["tokens"][:, :4]
+    assert not torch.equal(tok[0], tok[1]) and not torch.equal(tok[0], tok[3])
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_multi_query, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(got[0], got[1])
+    np.testing.assert_array_equal(got[0], alone)
