@@ -309,7 +309,8 @@ class RevisionLlamaForCausalLM:
             plan["vis_src"] = np.ascontiguousarray(idx_np[src // F] * F + src % F, dtype=np.int32)
             # the same text up to a <video> placeholder at the same place in every row: prompts on the same segment also share
             # its visual positions
-            if ids_np.shape[0] > 1 and pre < ids_np.shape[1] and bool((ids_np[:, pre] == constants.IMAGE_TOKEN_INDEX).all()):
+            if np.unique(idx_np).shape[0] < idx_np.shape[0] and pre < ids_np.shape[1] and \
+                    bool((ids_np[:, pre] == constants.IMAGE_TOKEN_INDEX).all()):
                 plan["group"] = idx_np
                 plan["shared_prefix"] = min(pre + F, int(plan["lengths"].min()))
         if share_compute:

@@ -613,3 +613,112 @@ def run_movie(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok
             res.ranked = metrics.rank_query(eng, answers, cos, ent, ious, stage2_frames=frames2, mode=cfg.score_merge, normalize=cfg.normalize)
     lap("merge_rank")
     return res
+
+
+def run_movie_queries(model, features, input_ids: torch.Tensor, cls: torch.Tensor, detok: Callable[[torch.Tensor], List[str]],
+                      gts: Sequence[Tuple[float, float]], cfg: MovieConfig = MovieConfig(), query_feats: Optional[Sequence] = None,
+                      stage2_input_ids: Optional[torch.Tensor] = None, detok_stage2: Optional[Callable[[torch.Tensor], List[str]]] = None,
+                      rank: int = 0, world: int = 1, group=None, eos_token_id="config",
+                      timings: Optional[Dict[str, float]] = None) -> List[MovieResult]:
+    """`run_movie` for Q queries on the SAME movie in one call - the reference runs its three scripts once per query.
+
+      stage 1  every window with every query in one pass (`score_segments_queries`: features stored once per window, with
+               `model.share_prefix_compute` the system text + visual positions of a window computed once for its Q prompts);
+               windows dealt round-robin to the ranks, one all-gather (the Q records of a window travel together);
+      select   per query, on every rank, from the gathered records;
+      stage 2  whole queries dealt to the ranks and batched across the queries of a rank (`stage2_pass_queries`; north star: one
+               GPU per query, batched across queries) - with fewer queries than ranks the generate() calls are dealt instead;
+      rank     per query, on the rank that ran its stage 2.
+
+    `input_ids` [Q, Ltxt] (same length; the system text in front of <video> is common), `cls` [Q, 768], `gts[q]` = (start, end)
+    fractions, `query_feats[q]` = (tokens [1, Lq, 768], mask [1, Lq]), `stage2_input_ids` [Q, L2] or [L2].  Returns one
+    MovieResult per query; `stage2` / `ranked` are filled on the rank that owns the query (query q -> rank q mod world), on every
+    rank when the calls were dealt."""
+    import time
+    from . import metrics
+    from .features import WindowLoader
+    eng, dev = model.engine, model.device
+    t_prev = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + 1e3 * (now - t_prev[0])
+            t_prev[0] = now
+    Q = int(input_ids.shape[0])
+    feats_np = features.numpy() if isinstance(features, torch.Tensor) else np.asarray(features)
+    T = feats_np.shape[0]
+    loader = getattr(model, "_window_loader", None)
+    if loader is None or loader.dim != feats_np.shape[1]:
+        loader = model._window_loader = WindowLoader(eng, max_frames=max(T, 1 << 15), dim=feats_np.shape[1])
+    movie = loader.upload(feats_np)
+    idx1 = scoring.stage1_windows(T, cfg.clip_length, cfg.num_frames)
+    if idx1.shape[0] == 0:
+        idx1 = np.linspace(0, T - 1, cfg.num_frames, dtype=np.int32)[None]
+    W = idx1.shape[0]
+    mine = shard_indices(W, rank, world)
+    win1 = eng.gather_windows(movie, torch.from_numpy(np.ascontiguousarray(idx1[mine])).to(dev)) if len(mine) else \
+        torch.empty((0, cfg.num_frames, feats_np.shape[1]), dtype=torch.bfloat16, device=dev)
+    lap("upload_and_window_gather")
+
+    def decode_spans(tok):
+        spans = torch.full((tok.shape[0], 2), -1, dtype=torch.int32)
+        for i, text in enumerate(detok(tok.cpu())):
+            sp = scoring.parse_span(text)
+            if sp is not None:
+                spans[i, 0], spans[i, 1] = sp
+        return spans
+    local = score_segments_queries(model, win1, input_ids, cls, cfg.max_new_tokens, decode_spans, cfg.stage1_batch, eos_token_id)
+    lap("stage1")
+    records = local if world == 1 else allgather_wide(local.view(len(mine), Q * REC_WORDS), W, rank, world, group).view(W * Q, REC_WORDS)
+    rec_cpu = records.cpu()
+    num_frames_video = int(T * cfg.num_frames / cfg.clip_length)
+    idx2, _ = scoring.stage2_windows(T, cfg.stage2_clip_length, cfg.stage2_num_frames, cfg.stride)
+    results: List[MovieResult] = []
+    per_q = []
+    for q in range(Q):
+        un = unpack_records(rec_cpu[q::Q])
+        answers = detok(un["tokens"][:, : int(un["n_tokens"].max())])
+        clip_frames, ious, ent = metrics.iou(answers, gts[q], cfg.num_frames, num_frames_video, un["h_mean"].tolist())
+        cos = [float(un["cos"][w]) for w in clip_frames]
+        grounding = scoring.stage2_select_windows(answers, idx2.shape[0], cfg.batch, cfg.stride) if idx2.shape[0] else []
+        grounding = [w for w in grounding if -idx2.shape[0] <= w < idx2.shape[0]]
+        results.append(MovieResult(records[q::Q], answers, clip_frames, ious, grounding, None, None, None, None))
+        per_q.append((cos, ent))
+    lap("allgather_parse_select")
+    if model.clip_encoder is None or query_feats is None:
+        return results
+    live = [q for q in range(Q) if results[q].grounding_windows]
+    deal_calls = cfg.stage2_shard_calls and world > 1 and len(live) < world and cfg.max_new_tokens <= REC_TOKENS
+    dt2 = detok_stage2 or detok
+    queries = []
+    for q in live:
+        gw = np.asarray(results[q].grounding_windows, dtype=np.int64)
+        owned = deal_calls or (len(queries) % world == rank)                    # only the owner gathers the query's windows
+        win2 = eng.gather_windows(movie, torch.from_numpy(np.ascontiguousarray(idx2[gw])).to(dev)) if owned else None
+        ids2 = input_ids[q] if stage2_input_ids is None else (stage2_input_ids if stage2_input_ids.dim() == 1 else stage2_input_ids[q])
+        queries.append(dict(windows=win2, query_feats=query_feats[q], input_ids=ids2, grounding_windows=results[q].grounding_windows,
+                            perm_seed=cfg.perm_seed))
+    lap("stage2_window_gather")
+    answer_number = lambda tok: scoring.parse_first_int(dt2(tok[None].cpu())[0])
+    passes = stage2_pass_queries(model, queries, cfg.batch, cfg.zooms, cfg.max_new_tokens, answer_number, eos_token_id,
+                                 cfg.stage2_calls_per_batch, rank, world, shard_calls=deal_calls, group=group)
+    lap("stage2_pass")
+    for n, q in enumerate(live):
+        calls = passes[n]
+        if calls is None:
+            continue
+        res = results[q]
+        answers2 = [dt2(torch.tensor(c["tokens"])[None])[0] for c in calls]
+        frames2, _hit = metrics.stage2_frames(answers2, gts[q], cfg.batch, [c["start"] for c in calls], [c["perm"] for c in calls],
+                                              [c["zoom"] for c in calls], res.grounding_windows)
+        res.stage2, res.stage2_answers, res.stage2_frames = calls, answers2, frames2
+        if res.clip_frames and (not deal_calls or rank == 0):
+            present = [i for i, a in enumerate(res.answers) if a != "Not Present" and a != "From 249 to 249."]
+            if present == list(res.clip_frames):
+                cos, ent = per_q[q]
+                res.ranked = metrics.rank_query(eng, res.answers, cos, ent, res.ious, stage2_frames=frames2, mode=cfg.score_merge,
+                                                normalize=cfg.normalize)
+    lap("merge_rank")
+    return results
