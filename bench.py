@@ -611,8 +611,45 @@ def main():
                                          "all-gather + parse + select + stage-2 top-100 (ClipEncoder + zooms 4/2/1; its independent generate() calls dealt to the N ranks, "
                                          "one all-gather of their records) + merge/rank kernel on rank 0; phases_ms: one extra run with the device synchronised "
                                          "at the phase boundaries"}
+            # the same chain for 8 queries on that movie in one call (sweep.run_movie_queries: stage 1 in one pass with the visual
+            # context of a window shared by its 8 prompts, stage 2 one GPU per query / batched across queries)
+            if not args.no_multi_query:
+                Qm = 8
+                n_pre = int((ids == -200).nonzero()[0])
+                ids_q = ids[None].repeat(Qm, 1)
+                for q in range(1, Qm):
+                    ids_q[q, n_pre + 1:-4] = torch.randint(3, cfg.vocab, (ids.shape[0] - n_pre - 5,), generator=torch.Generator().manual_seed(500 + q))
+                cls_q = torch.randn(Qm, cfg.adapter_dim, generator=torch.Generator().manual_seed(6)).to(torch.bfloat16)
+                qf_q = [(torch.randn(1, 32, cfg.adapter_dim, generator=torch.Generator().manual_seed(700 + q)).to(torch.bfloat16), torch.ones(1, 32))
+                        for q in range(Qm)]
+                gts_q = [(0.05 + 0.1 * q, 0.10 + 0.1 * q) for q in range(Qm)]
+                mcq = sweep.MovieConfig(clip_length=200, num_frames=N_FRAMES, stage2_clip_length=200, stage2_num_frames=250, stride=5, batch=100,
+                                        zooms=(4, 2, 1), max_new_tokens=NEW_TOKENS, stage1_batch=90)
+                model.share_prefix_compute = True
+                try:
+                    mq_call = lambda t=None: sweep.run_movie_queries(model, movie, ids_q, cls_q, partial(syn.synthetic_answers, n_frames=N_FRAMES), gts_q, mcq,
+                                                                     query_feats=qf_q, stage2_input_ids=ids_s2, detok_stage2=syn.synthetic_answers_stage2,
+                                                                     rank=rank, world=world, eos_token_id=None, timings=t)
+                    for _ in range(3):
+                        mq_res = mq_call()
+                    barrier()
+                    t0 = time.perf_counter()
+                    for _ in range(2):
+                        mq_res = mq_call()
+                    barrier()
+                    mq_e2e = 1e3 * max_over_ranks(time.perf_counter() - t0) / 2
+                    ph_q = {}
+                    mq_call(ph_q)
+                    barrier()
+                    line["movie_e2e_queries"] = {"queries": Qm, "ms": mq_e2e, "ms_per_query": mq_e2e / Qm, "vs_one_call_per_query": mv_ms * Qm / mq_e2e,
+                                                 "stage2_queries_on_this_rank": sum(1 for r in mq_res if r.stage2 is not None),
+                                                 "phases_ms": {k: round(v, 2) for k, v in ph_q.items()},
+                                                 "note": "8 queries on the movie of movie_e2e in one sweep.run_movie_queries call (opt-in: shared visual context in "
+                                                         "stage 1; stage 2 one GPU per query, batched across the queries of a rank), wall clock, max over ranks"}
+                finally:
+                    model.share_prefix_compute = False
         except Exception as e:
-            line["movie_e2e"] = {"error": repr(e)[:300]}
+            line.setdefault("movie_e2e", {})["error"] = repr(e)[:300]
     # ---- BASELINE.json configs[4]: VidChapters-shaped ragged batch - videos of 1-60 min at 2 fps, 500 s windows with 250 s
     # stride sampled to <= 100 frames, queries of 8-32 tokens; stage 1 varlen-packed, windows dealt to the ranks by length
     # (sweep.shard_balanced), one all-gather of the records; then stage 2 (ClipEncoder + zooms 4/2/1 over each video's windows,
