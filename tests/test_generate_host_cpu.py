@@ -536,14 +536,18 @@ class PagedCpuEngine(CpuEngine):
         return cache
 
     def prefill(self, hidden, cu, n_seq, max_seqlen, page_table, logits_out, all_logits=False, seq_pos0=None, seq_ctx_row=None):
-        assert seq_pos0 is None and not all_logits
+        assert not all_logits
         self.calls.append(("prefill", n_seq))
         for b in range(n_seq):
             x = hidden[int(cu[b]):int(cu[b + 1])][None]
+            p0 = int(seq_pos0[b]) if seq_pos0 is not None else 0
+            if p0:                                       # positions [0, p0) are the context rows; only the own positions are stored
+                c0 = int(seq_ctx_row[b])
+                x = torch.cat([hidden[c0:c0 + p0][None], x], dim=1)
             cache = llama_ref.KVCache(self.shape.n_layers)
             h = llama_ref.decoder_stack(self.w, self.shape, x, cache)
             logits_out[b] = llama_ref.lm_head(self.w, h[:, -1])[0]
-            self._store(page_table[b], cache, 0)
+            self._store(page_table[b], cache, p0)
 
     def decode_step(self, tok, seq_lens, page_table, logits, max_kv_len=0):
         self.calls.append(("decode", tok.shape[0]))
@@ -581,6 +585,39 @@ def test_paged_kv_tables_shared_pages_and_growth_past_the_first_reservation(monk
             table = out["past_key_values"].page_table
             assert (len(set(table[:, 0].tolist())) == 1) == share
             assert table.shape[1] * 32 >= ids.shape[1] - 1 + 5 + steps
+
+
+def test_paged_kv_tables_with_one_shared_context_per_segment(monkeypatch):
+    """Several prompts per segment over the paged stand-in (`image_index` + `share_prefix_compute`): the context pages of a
+    segment are written once, by its context sequence, and read by all its prompts through the page table; 70 new tokens
+    re-page the pool mid-generation with the groups intact.  Tokens equal the un-paged oracle loop on the repeated features."""
+    cfg = syn.TINY
+    w = syn.make_llama_weights(cfg, seed=0)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    S, Q, F = 2, 3, 30
+    feats = syn.make_features(S, F, cfg.adapter_dim, seed=22)
+    base = syn.make_prompt_ids(cfg, 40, 6, seed=23)                               # 40 + 30 positions in front of the query: P = 64
+    ids = base[None].repeat(S * Q, 1)
+    for r in range(S * Q):
+        if r % Q:
+            ids[r, 41:-2] = torch.randint(3, cfg.vocab, (ids.shape[1] - 43,), generator=torch.Generator().manual_seed(700 + r % Q))
+    index = torch.arange(S).repeat_interleave(Q)
+    for steps in (5, 70):
+        want, _ = _oracle(w, cfg, ids, feats[index], steps, stop_on_eos=False)
+        m = RevisionLlamaForCausalLM(RevisionConfig.from_synth(cfg), dict(w))
+        m.engine = PagedCpuEngine(cfg, w)
+        m.device = torch.device("cpu")
+        m.share_prefix_compute = True
+        out = m.generate(ids, images=feats, image_index=index, max_new_tokens=steps, return_dict_in_generate=True, eos_token_id=None)
+        assert m.last_shared_prefix == 64 and m.engine.calls[0] == ("prefill", S + S * Q)
+        got = out["sequences"][:, ids.shape[1]:]
+        same = (got == want).all(dim=0).long().cumprod(0).sum().item()
+        assert same == steps, (steps, same)
+        table = out["past_key_values"].page_table
+        for s_ in range(S):
+            blk = table[s_ * Q:(s_ + 1) * Q, :2]
+            assert (blk == blk[0]).all()
+        assert len({tuple(r) for r in table[:, :2].tolist()}) == S
 
 
 def test_sampling_arguments_reach_the_engine(cpu_model):
