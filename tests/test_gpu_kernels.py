@@ -325,7 +325,7 @@ def test_rope_kv_and_attention_prefill_and_decode(eng, rvl_env):
         assert torch.equal(dec2, dec), mode
 
 
-@pytest.mark.parametrize("Tq,Tk,shared_kv", [(251, 251, False), (250, 12, True), (300, 70, True), (64, 130, False)])
+@pytest.mark.parametrize("Tq,Tk,shared_kv", [(251, 251, False), (250, 12, True), (300, 70, True), (64, 130, False), (520, 330, False), (1, 5, True)])
 def test_mha96_tcgen05_and_mma_against_torch(eng, rvl_env, Tq, Tk, shared_kv):
     """`rvl_mha96` (nn.MultiheadAttention core of the ClipEncoder, transformer.py:216-217 / :288-289): 8 heads x 96 dims, no causal
     mask, key padding, key / value sequences shared between query sequences, operands as column slices of fused projections.
