@@ -425,7 +425,7 @@ def main():
     extras = world == 1                       # the side measurements below belong to the 1-GPU line; N > 1 runs stay short
     try:
         if not extras:
-            raise RuntimeError("1-GPU run only")
+            raise RuntimeError("reported by the 1-GPU run only")
         model.share_prefix_compute = True
         for _ in range(2):
             resident_step()
@@ -442,7 +442,7 @@ def main():
                                          "tokens_identical_to_headline_run": same,
                                          "note": "opt-in: common 32-position prompt prefix computed once per step instead of once per segment"}
     except Exception as e:
-        line["shared_prefix_compute"] = {"error": repr(e)[:200]}
+        line["shared_prefix_compute"] = {"skipped": str(e)} if not extras else {"error": repr(e)[:200]}
     finally:
         model.share_prefix_compute = False
     # ---- several queries of the SAME movie in one pass (reported beside the headline, NOT part of `value`): the reference asks every
@@ -485,7 +485,7 @@ def main():
     # half a window -> 57 windows, L = 334), reported beside the headline, not part of `value`
     try:
         if not extras:
-            raise RuntimeError("1-GPU run only")
+            raise RuntimeError("reported by the 1-GPU run only")
         feats_mad = syn.make_features(57, 250, cfg.adapter_dim, seed=21, class_cfg=cfg).to(dev)
         for _ in range(3):                    # new batch shape: the third sight captures its decode chunks
             sweep.score_segments(model, feats_mad, ids_dev, cls_dev, NEW_TOKENS, eos_token_id=None)
@@ -500,7 +500,7 @@ def main():
                                       "note": "one rank, 57 windows x 250 frames x 16 greedy tokens (the reference's MAD windowing)"}
         del feats_mad
     except Exception as e:
-        line["mad_windows_57x250"] = {"error": repr(e)[:200]}
+        line["mad_windows_57x250"] = {"skipped": str(e)} if not extras else {"error": repr(e)[:200]}
     # ---- stage 2 (BASELINE.json configs[3], reported beside the headline, not part of `value`): top-100 segments by
     # cosine score -> 250-frame windows through the ClipEncoder adapter (one CLS token per window) -> one ~180-token
     # prompt per zoom level (4, 2, 1), 16 greedy tokens each.  One query per rank.
