@@ -381,6 +381,27 @@ def main():
             roofline["traffic_source"] = t.get("source")
             roofline["algorithmic_bytes_per_launch"] = t.get("prefill_gemm_algorithmic_bytes_per_launch")
             break
+    # The power-capped SM clock differs from box to box (1.08 - 1.26 GHz seen), and MEASURED_PEAKS.json was taken on one of them:
+    # the same library call it used (torch.matmul, bf16 8192^3, back to back until the power cap bites) is timed HERE as well,
+    # for information - `frac` above stays relative to the driver-written peak.
+    if rank == 0 and world == 1 and roofline["achieved"]:
+        try:
+            a8 = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+            b8 = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+            for _ in range(300):
+                torch.matmul(a8, b8)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(1200):
+                torch.matmul(a8, b8)
+            c1.record()
+            torch.cuda.synchronize()
+            live = 1200 * 2.0 * 8192 ** 3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
+            roofline["cublas_sustained_on_this_box"] = {"tflops": live, "frac": roofline["achieved"] / live,
+                                                        "note": "torch.matmul bf16 8192^3 x 1200 back to back after 300 warm-up calls, this process, after the timed region"}
+            del a8, b8
+        except Exception as e:
+            roofline["cublas_sustained_on_this_box"] = {"error": repr(e)[:200]}
     if roofline["decode_gemm"]["achieved"]:
         roofline["decode_gemm"]["frac"] = roofline["decode_gemm"]["achieved"] / pk["hbm"]
     if roofline["decode_attention"]["achieved"]:
